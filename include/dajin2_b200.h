@@ -1,0 +1,211 @@
+/*
+ * dajin2_b200 — C ABI of the B200-native read-level numeric core for DAJIN2.
+ *
+ * The reference (akikuno/DAJIN2 v0.9.3) is pure Python and has no FFI: the seams this library plugs into are
+ * plain Python functions.  Each entry point below names the reference function(s) whose
+ * read-scale loop it replaces (paths relative to src/DAJIN2/).  The Python shim in dajin2_b200/ binds these
+ * with ctypes and keeps the reference's signatures; INTEGRATION.md shows the stub a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the boundary.
+ *   - Every pointer is a DEVICE pointer unless the parameter name starts with h_.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous on that
+ *     stream unless stated otherwise; buffers are owned by the caller.
+ *   - Return value: 0 on success, non-zero on failure; dj_last_error() returns a thread-local message.
+ *   - There is no CPU fallback anywhere in this library.
+ *
+ * Read x locus code matrix (the encoding every later stage consumes), one byte per MIDSV token:
+ *     bit 7      token is an insertion "+X|+Y|...|<anchor>"; the low bits then describe the anchor
+ *     bits 6..0  anchor id a:
+ *                  0..9    "=B"   a = 5*lower + b          b: A=0 C=1 G=2 T=3 N=4
+ *                  10..19  "-B"   a = 10 + 5*lower + b
+ *                  20..69  "*RB"  a = 20 + 25*lower + 5*r + b   (ref base r, read base b; same case)
+ *                  127     token outside the supported grammar (flag bit DJ_FLAG_BAD_TOKEN is raised)
+ * "lower" marks an all-lowercase token (inside an inversion).  Insertions must have the case of their anchor.
+ */
+#ifndef DAJIN2_B200_H
+#define DAJIN2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DJ_ABI_VERSION 1
+
+#define DJ_CODE_INVALID 0x7F
+#define DJ_CODE_INS 0x80
+
+/* per-read flag bits written by dj_encode */
+#define DJ_FLAG_TOKEN_COUNT 1u /* number of tokens != n_loci */
+#define DJ_FLAG_BAD_TOKEN 2u   /* a token outside the supported grammar */
+
+/* bytes of text one warp iteration of the encoder covers; checkpoint granularity of the token index */
+#define DJ_ENC_CHUNK 512
+
+/* rows of dj_hist output: counts[DJ_HIST_ROWS][n_loci] (int32) */
+#define DJ_HIST_MATCH 0   /* '=' with the N / lowercase skip rule   (indel_counter.py:15-31)            */
+#define DJ_HIST_INS 1     /* '+'  "                                                                    */
+#define DJ_HIST_DEL 2     /* '-'  "                                                                    */
+#define DJ_HIST_SUB 3     /* '*'  "                                                                    */
+#define DJ_HIST_SW_INS_P 4 /* startswith('+'), '+' strand, no skip rule (error_correction/strand_bias_handler.py:18-33) */
+#define DJ_HIST_SW_DEL_P 5
+#define DJ_HIST_SW_SUB_P 6
+#define DJ_HIST_SW_INS_M 7 /* same, '-' strand */
+#define DJ_HIST_SW_DEL_M 8
+#define DJ_HIST_SW_SUB_M 9
+#define DJ_HIST_ROWS 10
+
+/* bits of the per-locus mask describing mutation_loci[i] (list[set[str]] in the reference) */
+#define DJ_MASK_INS 1
+#define DJ_MASK_DEL 2
+#define DJ_MASK_SUB 4
+
+/* One distinct 3-mer observed at a selected locus (record exported by dj_kmer_export).
+ * The reference's key is the string "prev,cur,next" (clustering/kmer_generator.py:35-56). */
+typedef struct {
+    uint32_t sel_index;     /* index into the `sel` array passed to dj_kmer_count                    */
+    uint16_t prev;          /* 0..255 code byte, 256 = '@', 257 = raw (uncompressed) insertion token */
+    uint16_t cur;           /* code byte of the centre token                                         */
+    uint16_t next;          /* as prev                                                               */
+    uint16_t reserved;
+    uint32_t count_sample;  /* reads of file 0 carrying this 3-mer at this locus                     */
+    uint32_t count_control; /* reads of file 1                                                       */
+    uint32_t example;       /* (file << 31) | smallest read index seen: lets the host print raw tokens */
+    uint32_t slot;          /* slot in the device table (index for slot_value_id in dj_annotate)     */
+} DjKmerRecord;
+
+/* One distinct score row found by dj_dedup_rows. */
+typedef struct {
+    uint32_t slot;       /* slot in the device table; dj_dedup_rows wrote it to slot_of_row[]   */
+    uint32_t count;      /* number of rows equal to this one                                    */
+    uint32_t count_plus; /* ... of which '+' strand                                             */
+    uint32_t first_row;  /* smallest row position (in the order given to dj_dedup_rows)         */
+} DjRowRecord;
+
+int dj_abi_version(void);
+const char *dj_last_error(void);
+/* h_out[0]=SM count, [1]=cc major, [2]=cc minor.  Fails when no CUDA device is usable. */
+int dj_device_info(int32_t *h_out);
+
+/* Row pitch (bytes) of the code matrix for n_loci tokens per read (multiple of 32). */
+int32_t dj_code_pitch(int32_t n_loci);
+/* Number of uint32 checkpoints per read for rows of at most max_row_len bytes. */
+int32_t dj_ckpt_pitch(int32_t max_row_len);
+
+/*
+ * MIDSV text -> code matrix (+ per-read scalars).  Replaces the `json.loads` + `split(",")` every reference
+ * pass starts with (utils/fileio.py:49-52) and computes, in the same pass,
+ *   match_score[r]  = calc_match(MIDSV)                      (classification/classifier.py:11-24)
+ *   n_tokens[r], flags[r]                                     (validation; the reference assumes n_loci tokens)
+ *   ckpt[r][j]      = number of tokens that start before byte j*DJ_ENC_CHUNK - (row_off[r] & 15) of the row
+ * Read r's text is text[row_off[r] .. row_off[r]+row_len[r]); 16 readable bytes must follow the last row.
+ */
+int dj_encode(const uint8_t *text, const int64_t *row_off, const int32_t *row_len, int64_t n_reads,
+              int32_t n_loci, int32_t code_pitch, int32_t ckpt_pitch, uint8_t *codes, int32_t *match_score,
+              int32_t *n_tokens, uint32_t *flags, uint32_t *ckpt, void *stream);
+
+/*
+ * Per-locus histograms of the code matrix over `rows` (NULL = all n_rows reads in order).
+ * counts[DJ_HIST_ROWS][n_loci] is zeroed and filled.  Replaces count_indels (indel_counter.py:15-31) and the
+ * second full pass of count_strandless_of_indels (error_correction/strand_bias_handler.py:18-33).
+ */
+int dj_hist(const uint8_t *codes, int32_t code_pitch, const uint8_t *strand, const int32_t *rows,
+            int64_t n_rows, int32_t n_loci, int32_t *counts, void *stream);
+
+/*
+ * 10-wide window cosine distances of is_dissimilar_loci (mutation_processing/anomaly_detector.py:28-58):
+ * dist[i] = cosine_distance(sample[i:i+10], control[i:i+10]), dist_tail[i] = the same on [i+1:i+10].
+ */
+int dj_window_cosine(const double *sample, const double *control, int32_t n_loci, double *dist,
+                     double *dist_tail, void *stream);
+
+/* Bytes of device memory a 3-mer table with `capacity` slots (power of two) needs. */
+int64_t dj_kmer_table_bytes(uint32_t capacity);
+int dj_kmer_table_clear(void *table, uint32_t capacity, void *stream);
+
+/*
+ * Count the distinct 3-mers at the selected loci (generate_mutation_kmers + call_count,
+ * clustering/kmer_generator.py:35-56, clustering/score_handler.py:15-16).  "@,@,@" is not stored: its count is
+ * n_rows minus the stored counts of that locus.  `which` = 0 (sample file) or 1 (control file).
+ * sel[] holds loci in [1, n_loci-2] whose mask is non-zero, ascending.
+ */
+int dj_kmer_count(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, int64_t n_rows,
+                  const uint8_t *text, const int64_t *row_off, const int32_t *row_len, const uint32_t *ckpt,
+                  int32_t ckpt_pitch, const uint8_t *locimask, int32_t n_loci, const int32_t *sel,
+                  int32_t n_sel, int32_t which, void *table, uint32_t capacity, void *stream);
+
+/* Synchronous: copies the occupied slots to the HOST array h_out (at most max_records). */
+int dj_kmer_export(const void *table, uint32_t capacity, DjKmerRecord *h_out, uint32_t max_records,
+                   uint32_t *h_n_records, void *stream);
+
+/*
+ * Score rows (annotate_score, clustering/score_handler.py:136-148) as value ids:
+ * ids[t][c] for row t (read rows[t]) and column c (locus col_locus[c]).  col_sel[c] is the index of that locus
+ * in the `sel` array used for counting, or -1 when the locus can only carry "@,@,@".  A 3-mer found in the
+ * table yields slot_value_id[slot]; "@,@,@" yields col_at_id[c]; control rows (is_control) get 0 for every
+ * stored 3-mer, exactly as score_handler.py:143-144 does.
+ */
+int dj_annotate(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, int64_t n_rows,
+                const uint8_t *text, const int64_t *row_off, const int32_t *row_len, const uint32_t *ckpt,
+                int32_t ckpt_pitch, const uint8_t *locimask, int32_t n_loci, const int32_t *col_locus,
+                const int32_t *col_sel, const uint16_t *col_at_id, int32_t n_cols, int32_t is_control,
+                const void *table, uint32_t capacity, const uint16_t *slot_value_id, uint16_t *ids,
+                void *stream);
+
+/* Raw text of token loci[k] of read reads[k] -> out[k][0..out_len[k]) (truncated to max_len). */
+int dj_fetch_tokens(const uint8_t *text, const int64_t *row_off, const int32_t *row_len, const uint32_t *ckpt,
+                    int32_t ckpt_pitch, const int32_t *reads, const int32_t *loci, int32_t n, uint8_t *out,
+                    int32_t *out_len, int32_t max_len, void *stream);
+
+/* Row de-duplication of the id matrix: slot_of_row[t] = table slot of row t's content. */
+int64_t dj_row_table_bytes(uint32_t capacity);
+int dj_row_table_clear(void *table, uint32_t capacity, void *stream);
+int dj_dedup_rows(const uint16_t *ids, int64_t n_rows, int32_t n_cols, const uint8_t *strand,
+                  const int32_t *rows, void *table, uint32_t capacity, int32_t *slot_of_row, void *stream);
+int dj_dedup_export(const void *table, uint32_t capacity, DjRowRecord *h_out, uint32_t max_records,
+                    uint32_t *h_n_records, void *stream);
+
+/*
+ * One bisection of sklearn's BisectingKMeans on weighted points (sklearn/cluster/_bisect_k_means.py:298-363,
+ * Lloyd: sklearn/cluster/_kmeans.py:630-758, sparse kernels sklearn/cluster/_k_means_lloyd.pyx:221-420,
+ * _k_means_common.pyx:55-312).  Points whose leaf[] equals `target` are split in two starting from the points
+ * seed0 / seed1.  sub_label[p] in {0,1} is written for those points (untouched elsewhere).
+ * stats[0..1] = inertia of the two halves, stats[2] = iterations, stats[3..4] = weights of the halves.
+ * The call that call site clustering/clustering.py:35,68 makes through scikit-learn.
+ */
+int dj_bisect(const double *X, const double *weight, int32_t n_points, int32_t n_cols, const int32_t *leaf,
+              int32_t target, int32_t seed0, int32_t seed1, double tol, int32_t max_iter, int8_t *sub_label,
+              double *centers, double *stats, void *stream);
+
+/*
+ * Brute-force read x centroid assignment for n_rows score rows given as value ids (no de-duplication):
+ * label[t] = argmin_j |x_t - c_j|^2, plus per-centroid weighted sums.  Diagnostic / evidence path for the
+ * dense contraction; the production path clusters the de-duplicated points with dj_bisect.
+ */
+int dj_assign_rows(const uint16_t *ids, int64_t n_rows, int32_t n_cols, const double *value_of_id,
+                   const double *centers, int32_t n_centers, int32_t *label, double *sums, double *counts,
+                   void *stream);
+
+/*
+ * Weighted silhouette score (sklearn/metrics/cluster/_unsupervised.py:59-300) of points with multiplicities:
+ * every point stands for weight[p] identical rows.  h-less: score[0] receives the mean over all rows.
+ */
+int dj_silhouette(const double *X, const double *weight, const int32_t *label, int32_t n_points,
+                  int32_t n_cols, int32_t n_clusters, double *score, void *stream);
+
+/* j-th member selection for sklearn's random init: members of leaf `target` in row order. */
+int dj_member_counts(const int32_t *slot_of_row, int64_t n_rows, const int32_t *leaf_of_slot, int32_t target,
+                     int32_t *block_counts, void *stream); /* one count per 1024 rows */
+int dj_member_locate(const int32_t *slot_of_row, int64_t n_rows, const int32_t *leaf_of_slot, int32_t target,
+                     int32_t block, int32_t rank_in_block, int32_t *out_row, void *stream);
+
+/* labels[t] = label_of_slot[slot_of_row[t]] */
+int dj_gather_labels(const int32_t *slot_of_row, int64_t n_rows, const int32_t *label_of_slot,
+                     int32_t *labels, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAJIN2_B200_H */

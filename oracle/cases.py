@@ -1,0 +1,119 @@
+"""Parity cases shared by ``oracle/make_golden.py`` (runs the real reference) and ``tests/`` (runs the oracle and
+the CUDA path).  TEST INFRASTRUCTURE — see the header of ``oracle/dajin2_oracle.py``.
+
+A case is a dict ``{"sequence", "sample": rows/strands/qnames, "control": ..., "knockin": set | None}`` for one
+FASTA allele; multi-allele cases hold one such dict per FASTA allele under ``"alleles"``.  Synthetic rows come
+from the deterministic C generator (``dajin2_b200.synth``), so only the recipe is stored with the golden
+vectors plus a SHA-256 of the generated text.
+"""
+
+from __future__ import annotations
+
+import gzip
+import hashlib
+import json
+from pathlib import Path
+
+from dajin2_b200 import synth
+
+GOLDEN_DIR = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _pack(batch) -> dict:
+    rows = [batch.midsv(r) for r in range(batch.n_reads)]
+    return {
+        "rows": rows,
+        "strands": [chr(s) for s in batch.strand],
+        "qnames": [q.decode("ascii") for q in batch.qnames()],
+    }
+
+
+def digest(part: dict) -> str:
+    h = hashlib.sha256()
+    for row, s in zip(part["rows"], part["strands"]):
+        h.update(row.encode("ascii"))
+        h.update(s.encode("ascii"))
+    return h.hexdigest()
+
+
+def synthetic_case(length: int, n_sample: int, n_control: int, profile: str, kind: str = "throughput",
+                   fraction: float = 0.1) -> dict:
+    if kind == "throughput":
+        pop = synth.throughput_population(length, profile)
+    elif kind == "inversion":
+        pop = synth.inversion_population(length, profile)
+    elif kind == "point":
+        pop = synth.point_mutation_population(length, fraction, profile)
+    else:
+        raise ValueError(kind)
+    ctrl = synth.control_population(length, profile, reference=pop.reference)
+    sample = synth.generate(pop, n_sample, seed=synth.SEED + 1)
+    control = synth.generate(ctrl, n_control, seed=synth.SEED + 99)
+    return {"sequence": pop.reference, "sample": _pack(sample), "control": _pack(control), "knockin": None}
+
+
+def flox_like_case(n_sample: int = 400, n_control: int = 300, profile: str = "r10") -> dict:
+    """Two FASTA alleles (control, flox = control + two knock-in insertions); sample = flox and flox+1-nt deletion."""
+    base = synth.random_reference(1000)
+    ins_a = synth.random_reference(46, seed=7)
+    ins_b = synth.random_reference(62, seed=8)
+    flox = base[:400] + ins_a + base[400:700] + ins_b + base[700:]
+    knockin = set(range(400, 446)) | set(range(746, 808))
+    fr = [0.5, 0.5]
+    S, D, I = synth.SUB, synth.DEL, synth.INS  # noqa: E741
+    # the same two true alleles expressed against each FASTA allele
+    vs_control = synth.Population(base, [[(I, 400, 46), (I, 700, 62)], [(I, 400, 46), (I, 700, 62), (D, 850, 1)]], fr,
+                                  profile, rname="control")
+    vs_flox = synth.Population(flox, [[], [(D, 850 + 108, 1)]], fr, profile, rname="flox")
+    ctrl_vs_control = synth.Population(base, [[]], [1.0], profile, rname="control")
+    ctrl_vs_flox = synth.Population(flox, [[(D, 400, 46), (D, 746, 62)]], [1.0], profile, rname="flox")
+    out = {"alleles": {}}
+    for name, seq, ps, pc, kin in (("control", base, vs_control, ctrl_vs_control, None),
+                                   ("flox", flox, vs_flox, ctrl_vs_flox, knockin)):
+        out["alleles"][name] = {
+            "sequence": seq,
+            "sample": _pack(synth.generate(ps, n_sample, seed=synth.SEED + 1)),
+            "control": _pack(synth.generate(pc, n_control, seed=synth.SEED + 99)),
+            "knockin": kin,
+        }
+    return out
+
+
+def kat_case() -> dict:
+    """SURVEY.md §8c extra known-answer case (quirk ii: '@,@,@' is a scored k-mer)."""
+    sample = ["=A,=C,-G,+T|+T|=T,=A,=C"] * 3 + ["=A,=C,-G,+A|=T,=A,=C"] * 2 + ["=A,=C,=G,=T,=A,=C"] * 5
+    control = ["=A,=C,=G,=T,*AG,=C"] * 4 + ["=A,=C,=G,=T,=A,=C"] * 6
+    mk = lambda rows: {"rows": rows, "strands": ["+", "-"] * (len(rows) // 2),  # noqa: E731
+                       "qnames": [f"read{i:04d}" for i in range(len(rows))]}
+    return {"sequence": "ACGTAC", "sample": mk(sample), "control": mk(control), "knockin": None,
+            "loci": ["", "", "-", "+", "*", ""]}
+
+
+RECIPES = {
+    # name: (builder, kwargs)
+    "tp_L1000_N2000_r10": (synthetic_case, dict(length=1000, n_sample=2000, n_control=1000, profile="r10")),
+    "tp_L1000_N1200_r9": (synthetic_case, dict(length=1000, n_sample=1200, n_control=800, profile="r9")),
+    "inv_L2724_N300": (synthetic_case, dict(length=2724, n_sample=300, n_control=300, profile="r10", kind="inversion")),
+    "point_L900_N1500": (synthetic_case, dict(length=900, n_sample=1500, n_control=1000, profile="r10", kind="point",
+                                              fraction=0.1)),
+    "flox_like": (flox_like_case, dict()),
+    "kat": (kat_case, dict()),
+}
+
+
+def build_case(name: str) -> dict:
+    fn, kw = RECIPES[name]
+    return fn(**kw)
+
+
+def load_golden(name: str) -> dict:
+    with gzip.open(GOLDEN_DIR / f"{name}.json.gz", "rt") as f:
+        return json.load(f)
+
+
+def save_golden(name: str, payload: dict) -> Path:
+    GOLDEN_DIR.mkdir(parents=True, exist_ok=True)
+    path = GOLDEN_DIR / f"{name}.json.gz"
+    with gzip.GzipFile(path, "wb", mtime=0) as gz:
+        gz.write(json.dumps(payload, sort_keys=True).encode("ascii"))
+    return path

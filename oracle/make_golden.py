@@ -1,0 +1,176 @@
+"""Generate ``tests/golden/*.json.gz`` by running the REAL reference (read-only checkout at /root/reference).
+
+Build-container only: the GPU box has no /root/reference, so tests read the committed vectors instead.
+Run as ``python oracle/make_golden.py [case ...]`` from the repo root.  The reference is imported unmodified
+with empty stand-ins for the third-party modules that are absent here (``oracle/ref_stubs``); BLAS/OpenMP are
+pinned to one thread exactly as the reference's ``main.py:5-9`` does.
+TEST INFRASTRUCTURE — see the header of ``oracle/dajin2_oracle.py``.
+"""
+
+from __future__ import annotations
+
+import os
+
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ[_v] = "1"
+
+import json
+import pickle
+import sys
+import tempfile
+from pathlib import Path
+from types import SimpleNamespace
+
+HERE = Path(__file__).resolve().parent
+sys.path[:0] = [str(HERE / "ref_stubs"), "/root/reference/src", str(HERE.parent)]
+
+from DAJIN2.core import classification, clustering, preprocess  # noqa: E402
+from DAJIN2.core.classification import classifier  # noqa: E402
+from DAJIN2.core.clustering import score_handler  # noqa: E402
+from DAJIN2.core.clustering import clustering as ref_clustering  # noqa: E402
+from DAJIN2.core.clustering.strand_bias_handler import count_strand_distribution  # noqa: E402
+from DAJIN2.core.preprocess.error_correction import strand_bias_handler as ref_strand  # noqa: E402
+from DAJIN2.utils.allele_handler import to_allele_key  # noqa: E402
+
+from oracle import cases  # noqa: E402
+
+FIXTURE = Path("/root/reference/tests/data/clustering/find_knockin_loci/midsv/barcode42_flox_midsv.jsonl")
+FIXTURE_SEQ = Path("/root/reference/tests/data/clustering/find_knockin_loci/design_cables2.jsonl")
+
+
+def fixture_case() -> dict:
+    """The only real MIDSV file in the reference: 100 control reads against the 2832-nt flox allele."""
+    recs = [json.loads(line) for line in FIXTURE.read_text().splitlines()]
+    rows = [r["MIDSV"] for r in recs]
+    n_loci = len(rows[0].split(","))
+    # reference base per locus recovered from the reads themselves (majority of '=X' tokens)
+    seq = []
+    for col in zip(*(r.split(",") for r in rows)):
+        votes = [t[1].upper() for t in col if t[0] == "=" and t[1] in "ACGTacgt"]
+        seq.append(max(set(votes), key=votes.count) if votes else "N")
+    sequence = "".join(seq)
+    assert len(sequence) == n_loci
+    qn = [r["QNAME"] for r in recs]
+    strands = ["+" if i % 2 == 0 else "-" for i in range(len(rows))]
+    # sample = the same reads, 60 % of them carrying one substitution and one 1-nt deletion
+    sample_rows = []
+    for i, row in enumerate(rows):
+        toks = row.split(",")
+        if i % 5 < 3:
+            for pos, new in ((1000, "*{}T"), (1500, "-{}")):
+                ref = sequence[pos]
+                alt = "T" if ref != "T" else "A"
+                toks[pos] = new.format(ref).replace("T", alt) if new.startswith("*") else new.format(ref)
+                if new.startswith("*"):
+                    toks[pos] = f"*{ref}{alt}"
+        sample_rows.append(",".join(toks))
+    return {
+        "sequence": sequence,
+        "sample": {"rows": sample_rows, "strands": strands, "qnames": [q + "-s" for q in qn]},
+        "control": {"rows": rows, "strands": strands, "qnames": qn},
+        "knockin": None,
+    }
+
+
+def write_jsonl(path: Path, part: dict, rname: str) -> None:
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "w") as f:
+        for q, row, s in zip(part["qnames"], part["rows"], part["strands"]):
+            f.write(json.dumps({"QNAME": q, "RNAME": rname, "MIDSV": row, "STRAND": s, "PRESET": "map-ont"}) + "\n")
+
+
+def unique_rows(rows) -> dict:
+    """Sparse unique rows + per-read index (score rows are >99 % zeros and heavily duplicated)."""
+    table, index = {}, []
+    for row in rows:
+        key = tuple((i, float(v)) for i, v in enumerate(row) if v != 0)
+        index.append(table.setdefault(key, len(table)))
+    return {"unique": [[[i, v.hex()] for i, v in key] for key in table], "index": index}
+
+
+def run_reference(alleles: dict, given_loci=None) -> dict:
+    """alleles: FASTA-ordered {name: {"sequence","sample","control","knockin"}} -> golden payload."""
+    out = {"alleles": {}}
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = Path(tmp)
+        sname, cname = "sample", "ctrl"
+        fasta = {name: a["sequence"] for name, a in alleles.items()}
+        for name, a in alleles.items():
+            key = to_allele_key(name)
+            write_jsonl(tmp / sname / "midsv" / key / f"{sname}_midsv.jsonl", a["sample"], name)
+            write_jsonl(tmp / cname / "midsv" / key / f"{cname}_midsv.jsonl", a["control"], name)
+            if a.get("knockin") is not None:
+                p = tmp / sname / "knockin_loci" / key / "knockin.pickle"
+                p.parent.mkdir(parents=True, exist_ok=True)
+                p.write_bytes(pickle.dumps(set(a["knockin"])))
+            (tmp / sname / "clustering").mkdir(parents=True, exist_ok=True)
+        args = SimpleNamespace(tempdir=tmp, sample_name=sname, control_name=cname, fasta_alleles=fasta)
+        if given_loci is None:
+            preprocess.cache_mutation_loci(args, is_control=True)
+            preprocess.cache_mutation_loci(args, is_control=False)
+        for name, a in alleles.items():
+            key = to_allele_key(name)
+            g = {"sha_sample": cases.digest(a["sample"]), "sha_control": cases.digest(a["control"])}
+            p_s = tmp / sname / "midsv" / key / f"{sname}_midsv.jsonl"
+            p_c = tmp / cname / "midsv" / key / f"{cname}_midsv.jsonl"
+            if given_loci is None:
+                d = tmp / sname / "mutation_loci" / key
+                g["count_sample"] = pickle.loads((d / f"{sname}_count.pickle").read_bytes())
+                norm = pickle.loads((d / f"{sname}_normalized.pickle").read_bytes())
+                g["norm_sample"] = {k: [float(x).hex() for x in v] for k, v in norm.items()}
+                g["count_control"] = pickle.loads(
+                    (tmp / cname / "mutation_loci" / key / f"{cname}_count.pickle").read_bytes())
+                loci = pickle.loads((d / "mutation_loci.pickle").read_bytes())
+            else:
+                loci = [set(s) for s in given_loci]
+            g["mutation_loci"] = ["".join(sorted(s)) for s in loci]
+            g["strand_counts"] = {str(i): v for i, v in ref_strand.count_strandless_of_indels(p_s, loci).items()}
+            g["calc_match"] = [classifier.calc_match(r) for r in a["sample"]["rows"]]
+            knock = set(a["knockin"]) if a.get("knockin") is not None else set()
+            score = score_handler.make_score(p_s, p_c, loci, knock)
+            g["make_score"] = {str(i): {k: float(v).hex() for k, v in d.items()} for i, d in enumerate(score) if d}
+            xs = list(score_handler.annotate_score(p_s, score, loci))
+            xc = list(score_handler.annotate_score(p_c, score, loci, is_control=True))
+            g["rows_sample"] = unique_rows(xs)
+            g["rows_control"] = unique_rows(xc)
+            if any(loci) and len(xs) >= 5:
+                ps, pc = tmp / "xs.jsonl", tmp / "xc.jsonl"
+                ps.write_text("".join(json.dumps(r) + "\n" for r in xs))
+                pc.write_text("".join(json.dumps(r) + "\n" for r in xc))
+                strand_all = count_strand_distribution(tmp / sname / "midsv" / to_allele_key("control")
+                                                       / f"{sname}_midsv.jsonl") if "control" in alleles else \
+                    count_strand_distribution(p_s)
+                g["return_labels"] = [int(x) for x in ref_clustering.return_labels(ps, pc, p_s, strand_all)]
+            out["alleles"][name] = g
+        if given_loci is None and "control" in alleles:
+            classif = classification.classify_alleles(tmp, fasta, sname)
+            out["classify"] = [[c["QNAME"], c["ALLELE"]] for c in classif]
+            labels = clustering.extract_labels(classif, tmp, sname, cname)
+            out["extract_labels_order"] = [c["QNAME"] for c in classif]
+            out["extract_labels"] = [int(x) for x in labels]
+            clust = clustering.update_labels(clustering.add_percent(clustering.add_readnum(
+                clustering.add_labels(classif, labels))))
+            out["final"] = [[c["QNAME"], c["ALLELE"], int(c["LABEL"]), int(c["READNUM"]), c["PERCENT"]] for c in clust]
+    return out
+
+
+def main(names) -> None:
+    for name in names:
+        if name == "fixture_flox100":
+            case = fixture_case()
+            payload = run_reference({"control": case})
+            payload["inputs"] = {"control": {**case, "knockin": None}}
+        else:
+            case = cases.build_case(name)
+            if "alleles" in case:
+                payload = run_reference(case["alleles"])
+            elif "loci" in case:
+                payload = run_reference({"control": case}, given_loci=case["loci"])
+            else:
+                payload = run_reference({"control": case})
+        path = cases.save_golden(name, payload)
+        print(name, "->", path, path.stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or list(cases.RECIPES) + ["fixture_flox100"])
