@@ -1,0 +1,475 @@
+#!/usr/bin/env python
+"""bench.py — reads/s of the DAJIN2 hot path (encode -> score -> cluster) on B200.
+
+``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line (rank 0).  A step is one pass of the
+whole hot path over one batch of synthetic nanopore-like reads (SURVEY.md §8d workload: 8 alleles at
+40/25/15/10/5/2/2/1 %, L = 5000, R10-like errors, 10^4 control reads); weak scaling: every GPU processes
+``--reads`` sample reads (default 10^6) and the per-locus counts, 3-mer tables and distinct score rows are
+combined across ranks, so the job classifies N x reads reads.
+
+  value      whole-job reads/s with the text already resident in HBM (encode ... labels on the device)
+  e2e        the same through ``dajin2_b200.pipeline.run_host``: pinned host buffers -> H2D -> path -> labels D2H
+  roofline   the encoder (dominant kernel): algorithmic bytes (text + codes + scalars) / CUDA-event time, against
+             the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the oracle port of the reference's Python path on one host core, on a bounded sample
+
+``--impl reference`` times the oracle port of the reference's CPU path with every host core on bounded samples.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "reads_per_sec_encode_score_cluster"
+UNIT = "reads/s"
+N_CONTROL = 10_000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="sample reads per GPU")
+    ap.add_argument("--loci", type=int, default=5000)
+    ap.add_argument("--profile", default="r10")
+    ap.add_argument("--cpu-sample", type=int, default=600, help="sample reads of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args) -> str:
+    return (f"synthetic nanopore-like reads x {args.loci} nt amplicon, 8 alleles at 40/25/15/10/5/2/2/1 %, "
+            f"{args.profile} error profile, {args.reads} sample reads per GPU + {N_CONTROL} control reads")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+_CLOCK_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+                "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+
+class ClockSampler:
+    def __init__(self, gpu_index: int):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={_CLOCK_QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        rows = [ln.split(",") for ln in Path(self.file.name).read_text().splitlines() if ln.count(",") >= 8]
+        os.unlink(self.file.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any("Active" == r[5 + k].strip() for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------------------
+
+
+def make_workload(args, rank: int, world: int, pinned: bool):
+    import numpy as np
+    import torch
+
+    from dajin2_b200 import synth
+    from dajin2_b200.ingest import HostReads
+
+    pop = synth.throughput_population(args.loci, args.profile)
+    keep = []
+
+    def alloc(nbytes):
+        t = torch.empty(nbytes, dtype=torch.uint8, pin_memory=pinned)
+        keep.append(t)
+        return t.numpy()
+
+    bs = synth.generate(pop, args.reads, seed=synth.SEED + 1, first_read=rank, stride=world, text_alloc=alloc)
+    bc = synth.generate(synth.control_population(args.loci, args.profile, reference=pop.reference), N_CONTROL,
+                        seed=synth.SEED + 99, text_alloc=alloc)
+    hs = HostReads(bs.text, bs.row_off, bs.row_len, bs.strand, bs.qnames())
+    hc = HostReads(bc.text, bc.row_off, bc.row_len, bc.strand, bc.qnames())
+    return pop, hs, hc, keep
+
+
+def rows_of(host, n):
+    return [host.text[o : o + ln].tobytes().decode("ascii") for o, ln in zip(host.row_off[:n], host.row_len[:n])]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU legs (the oracle is the thing timed here, never part of the product path)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def oracle_pass(rows_s, strands_s, qn_s, rows_c, sequence) -> dict:
+    """The reference's hot path for one allele, restated by the oracle: every pass the reference makes."""
+    from oracle import dajin2_oracle as orc
+
+    L = len(sequence)
+    t = {}
+    t0 = time.perf_counter()
+    cs = orc.count_indels(rows_s, L)
+    cc = orc.count_indels(rows_c, L)
+    ns, nc = orc.normalize_indels(cs), orc.normalize_indels(cc)
+    t["summarize_indels"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    loci = orc.extract_mutation_loci(rows_s, strands_s, sequence, ns, nc)
+    t["extract_mutation_loci"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    _ = [orc.calc_match(r) for r in rows_s]
+    order = sorted(range(len(rows_s)), key=lambda i: qn_s[i])
+    rows_sorted = [rows_s[i] for i in order]
+    t["classify"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    score = orc.make_score(rows_sorted, rows_c, loci, set())
+    t["make_score"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    xs = list(orc.annotate_score(rows_sorted, score, loci))
+    xc = list(orc.annotate_score(rows_c, score, loci, True))
+    t["annotate_score"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    st = [strands_s[i] for i in order]
+    if any(loci):
+        labels = orc.return_labels(xs, xc, st, {"+": st.count("+"), "-": st.count("-")})
+    else:
+        labels = [1] * len(xs)
+    t["return_labels"] = time.perf_counter() - t0
+    t["n_clusters"] = len(set(labels))
+    return t
+
+
+def cpu_baseline(args, hs, hc, sequence) -> dict:
+    n_s = min(args.cpu_sample, hs.n_reads)
+    n_c = min(max(n_s // 2, 50), hc.n_reads)
+    rows_s, rows_c = rows_of(hs, n_s), rows_of(hc, n_c)
+    strands = [chr(x) for x in hs.strand[:n_s]]
+    qn = [q.decode() for q in hs.qnames[:n_s]]
+    t0 = time.perf_counter()
+    parts = oracle_pass(rows_s, strands, qn, rows_c, sequence)
+    dt = time.perf_counter() - t0
+    return {"value": n_s / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_s} sample + {n_c} control reads of the same workload, oracle port of the reference's "
+                      f"Python path, 1 process, BLAS threads = 1 (as the reference runs a sample), {dt:.1f} s",
+            "seconds": dt, "stage_seconds": {k: round(v, 3) for k, v in parts.items() if k != "n_clusters"}}
+
+
+def _ref_worker(job):
+    """Linear passes of the reference path on one shard of reads (process-pool worker)."""
+    from oracle import dajin2_oracle as orc
+
+    kind, payload = job
+    if kind == "count":
+        rows, L = payload
+        return orc.count_indels(rows, L), [orc.calc_match(r) for r in rows]
+    if kind == "strand":
+        rows, strands, loci_t = payload
+        return orc.count_strand_of_indels(rows, strands, loci_t)
+    if kind == "kmers":
+        rows, loci_t = payload
+        from collections import Counter
+
+        return [Counter(col) for col in zip(*orc.mutation_kmers(rows, loci_t))]
+    if kind == "annotate":
+        rows, score, loci_t, is_control = payload
+        return list(orc.annotate_score(rows, score, loci_t, is_control))
+    raise ValueError(kind)
+
+
+def run_reference_arm(args):
+    """The reference's CPU path (oracle port) with every host core: read-parallel passes in a process pool,
+    per-locus reductions and clustering in the parent, on bounded samples of the workload."""
+    import multiprocessing as mp
+    from collections import Counter
+
+    import numpy as np
+
+    from oracle import dajin2_oracle as orc
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    n_s = max(200, 120 * workers)
+    n_c = max(100, n_s // 4)
+    small = argparse.Namespace(**{**vars(args), "reads": n_s})
+    pop, hs, hc, _ = make_workload(small, 0, 1, pinned=False)
+    sequence = pop.reference
+    L = len(sequence)
+    rows_s, rows_c = rows_of(hs, n_s), rows_of(hc, n_c)
+    strands = [chr(x) for x in hs.strand[:n_s]]
+    qn = [q.decode() for q in hs.qnames[:n_s]]
+
+    def shards(seq, k):
+        step = (len(seq) + k - 1) // k
+        return [seq[i : i + step] for i in range(0, len(seq), step)]
+
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        def step():
+            res = pool.map(_ref_worker, [("count", (sh, L)) for sh in shards(rows_s, workers)])
+            cs = {op: np.sum([r[0][op] for r in res], axis=0).tolist() for op in "=+-*"}
+            resc = pool.map(_ref_worker, [("count", (sh, L)) for sh in shards(rows_c, workers)])
+            cc = {op: np.sum([r[0][op] for r in resc], axis=0).tolist() for op in "=+-*"}
+            ns, nc = orc.normalize_indels(cs), orc.normalize_indels(cc)
+            ncm = orc.minimize_mutation_counts(nc, ns)
+            loci = orc.extract_anomal_loci(ns, ncm, {"*": 0.1, "-": 0.1, "+": 0.1})
+            homo = orc.homopolymer_errors(sequence, ns, ncm, loci)
+            loci_t = orc.transpose_loci(loci, L)
+            # strand pass, sharded (the Fisher tests stay in the parent)
+            from scipy.stats import fisher_exact
+
+            tabs = pool.map(_ref_worker, [("strand", (sh, st, loci_t)) for sh, st in
+                                          zip(shards(rows_s, workers), shards(strands, workers))])
+            merged: dict = {}
+            for tab in tabs:
+                for i, per in tab.items():
+                    for op, c in per.items():
+                        cell = merged.setdefault(i, {}).setdefault(op, {"+": 0, "-": 0})
+                        cell["+"] += c["+"]
+                        cell["-"] += c["-"]
+            n_plus = strands.count("+")
+            bias = {op: set() for op in "+-*"}
+            for i, per in merged.items():
+                for op, c in per.items():
+                    ratio = c["+"] / (c["+"] + c["-"])
+                    if not (0.2 < ratio < 0.8) and fisher_exact([[c["+"], c["-"]], [n_plus, n_s - n_plus]]).pvalue < 0.01:
+                        bias[op].add(i)
+            loci = orc.discard_errors(orc.discard_errors(loci, homo), bias)
+            loci_t = orc.transpose_loci(orc.merge_consecutive_indels(loci), L)
+            order = sorted(range(n_s), key=lambda i: qn[i])
+            rows_sorted = [rows_s[i] for i in order]
+            # make_score with sharded k-mer counting; the percentage arithmetic is the oracle's
+            ks = pool.map(_ref_worker, [("kmers", (sh, loci_t)) for sh in shards(rows_sorted, workers)])
+            kc = pool.map(_ref_worker, [("kmers", (sh, loci_t)) for sh in shards(rows_c, workers)])
+
+            def pct(parts, total):
+                out = []
+                for cols in zip(*parts):
+                    c = Counter()
+                    for x in cols:
+                        c.update(x)
+                    out.append({k: round(v / total * 100, 3) for k, v in c.items()})
+                return out
+
+            ps, pc = pct(ks, n_s), pct(kc, n_c)
+            saved = orc.kmer_percentages
+            try:
+                it = iter([ps, pc])
+                orc.kmer_percentages = lambda rows, lt: next(it)
+                score = orc.make_score(rows_sorted, rows_c, loci_t, set())
+            finally:
+                orc.kmer_percentages = saved
+            xs = [r for part in pool.map(_ref_worker, [("annotate", (sh, score, loci_t, False))
+                                                        for sh in shards(rows_sorted, workers)]) for r in part]
+            xc = [r for part in pool.map(_ref_worker, [("annotate", (sh, score, loci_t, True))
+                                                        for sh in shards(rows_c, workers)]) for r in part]
+            st = [strands[i] for i in order]
+            if any(loci_t):
+                orc.return_labels(xs, xc, st, {"+": st.count("+"), "-": st.count("-")})
+
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = time.perf_counter() - t0
+    value = n_s * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_per_step": f"{n_s} sample + {n_c} control reads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
+                         "sample": f"{n_s} sample + {n_c} control reads per step; read-parallel passes of the oracle "
+                                   f"port in a {workers}-process pool, reductions + sklearn clustering in the parent"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # noqa: PLC0415
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as entry
+
+    if rank == 0:
+        entry.build()
+    if dist is not None:
+        dist.barrier()
+
+    from dajin2_b200 import _cabi, engine, pipeline
+    from dajin2_b200 import distributed as djdist
+
+    pop, hs, hc, keep = make_workload(args, rank, world, pinned=True)
+    sequence = pop.reference
+    comm = djdist.Communicator(dist) if dist is not None else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm -------------------------------------------------------------------------------
+    enc_s = engine.EncodedReads(hs, len(sequence), validate=False, encode=False)
+    enc_c = engine.EncodedReads(hc, len(sequence), validate=False, encode=False)
+    order = pipeline.qname_order(hs.qnames) if world == 1 else None
+    text_bytes = int(hs.row_len.astype(np.int64).sum())
+    enc_bytes = text_bytes + hs.n_reads * (len(sequence) + 16)
+
+    def device_step():
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+        enc_s.encode()
+        ev[1].record()
+        enc_c.encode()
+        res = pipeline.run_device(enc_s, enc_c, sequence, None, None if comm else order, fetch_labels=False,
+                                  reencode=False, comm=comm)
+        return res, ev
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _cabi.launch_count
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    enc_events, stage = [], {}
+    last = None
+    for _ in range(args.steps):
+        last, ev = device_step()
+        enc_events.append(ev)
+        for k, v in last.timings.items():
+            if isinstance(v, float):
+                stage[k] = stage.get(k, 0.0) + v
+    end.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    launches = _cabi.launch_count - launches0
+    ms = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    enc_ms = float(np.mean([a.elapsed_time(b) for a, b in enc_events]))
+
+    # ---- end-to-end arm: pinned host buffers -> H2D -> path -> labels D2H ----------------------------------
+    del enc_s, enc_c
+    torch.cuda.empty_cache()
+
+    def e2e_step():
+        return pipeline.run_host(hs, hc, sequence, None, None, comm=comm)
+
+    e2e_steps = max(2, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(e2e_steps):
+        r2 = e2e_step()
+    e2.record()
+    barrier()
+    ms2 = torch.tensor([s2.elapsed_time(e2)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(ms2.item()) / e2e_steps
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = enc_bytes / (enc_ms * 1e-3) / 1e9
+    total_reads = args.reads * world
+    line = {
+        "metric": METRIC, "value": total_reads * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": workload_name(args), "reads_per_gpu": args.reads, "control_reads": N_CONTROL,
+                   "n_loci": args.loci, "parallelism": f"reads sharded x{world}",
+                   "l2": f"inputs ({text_bytes / 1e9:.1f} GB text per GPU) are larger than the 126 MB L2",
+                   "clusters": last.cluster_sizes, "percentages": last.percentages,
+                   "selected_loci": int(sum(1 for m in last.mutation_loci if m))},
+        "clocks": clocks,
+        "e2e": {"value": total_reads / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                "h2d_bytes_per_step": int(r2.timings.get("h2d_bytes", 0)),
+                "d2h_bytes_per_step": int(r2.timings.get("d2h_bytes", 0))},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "encode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "algorithmic_bytes_per_launch": enc_bytes, "ms_per_launch": enc_ms},
+        "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage.items()},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, hs, hc, sequence)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

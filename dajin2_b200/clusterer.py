@@ -1,0 +1,309 @@
+"""Clustering of the score rows (``return_labels`` / ``optimize_labels`` of the reference,
+``src/DAJIN2/core/clustering/clustering.py:24-90``) on the device.
+
+The N score rows are collapsed to U distinct weighted points by ``dj_dedup_rows``; scikit-learn's
+BisectingKMeans / silhouette arithmetic then runs on those points in float64 inside ``dj_bisect`` /
+``dj_silhouette``.  What stays on the host is control flow that is O(U) or O(k): the bisecting tree, the greedy
+silhouette stop rule, numpy's legacy ``RandomState`` (the seeds scikit-learn draws are row *indices*, so the
+draws are mapped back to points with ``dj_member_counts`` / ``dj_member_locate``), Fisher tests and the rare
+decision-tree re-allocation of strand-biased clusters.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from collections import Counter
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .engine import KmerModel, _next_pow2, _p, _stream, require_cuda
+
+TOL = 1e-4  # BisectingKMeans passes its raw tol to the inner Lloyd (sklearn/cluster/_bisect_k_means.py:333-341)
+MAX_ITER = 300
+
+
+@dataclass
+class RowSet:
+    """De-duplicated rows of one id matrix."""
+
+    n_rows: int
+    slot_of_row: torch.Tensor  # int32[n_rows] table slot of each row
+    slots: np.ndarray  # uint32[U] table slot of each point, ordered by first occurrence
+    count: np.ndarray  # int64[U]
+    count_plus: np.ndarray  # int64[U]
+    first_row: np.ndarray  # int64[U]
+    point_ids: np.ndarray  # uint16[U, n_cols] value ids of each point
+    point_of_slot: np.ndarray  # int32[capacity] slot -> point (-1 elsewhere)
+
+
+def dedup_rows(ids: torch.Tensor, strand: torch.Tensor, rows: torch.Tensor | None) -> RowSet:
+    dev = require_cuda()
+    n_rows, n_cols = int(ids.shape[0]), int(ids.shape[1])
+    capacity = max(1 << 12, _next_pow2(min(2 * n_rows, 1 << 22)))
+    while True:
+        table = torch.empty(_cabi.call("dj_row_table_bytes", capacity), dtype=torch.uint8, device=dev)
+        _cabi.call("dj_row_table_clear", _p(table), capacity, _stream())
+        slot_of_row = torch.empty(max(n_rows, 1), dtype=torch.int32, device=dev)
+        _cabi.call("dj_dedup_rows", _p(ids), n_rows, n_cols, _p(strand), _p(rows), _p(table), capacity,
+                   _p(slot_of_row), _stream())
+        recs = (_cabi.RowRecord * capacity)()
+        n_rec = ctypes.c_uint32(0)
+        try:
+            _cabi.call("dj_dedup_export", _p(table), capacity, ctypes.cast(recs, ctypes.c_void_p), capacity,
+                       ctypes.cast(ctypes.pointer(n_rec), ctypes.c_void_p), _stream())
+        except RuntimeError as exc:
+            if "overflow" in str(exc) and capacity < (1 << 27):
+                capacity <<= 2
+                continue
+            raise
+        if n_rec.value * 2 > capacity and capacity < (1 << 27):
+            capacity <<= 2
+            continue
+        break
+    rec = np.frombuffer(recs, dtype=np.dtype(_cabi.RowRecord), count=n_rec.value).copy()
+    rec = rec[np.argsort(rec["first_row"], kind="stable")]
+    first = rec["first_row"].astype(np.int64)
+    point_ids = ids[torch.as_tensor(first, device=dev)].cpu().numpy().view(np.uint16) if len(first) else \
+        np.zeros((0, n_cols), dtype=np.uint16)
+    point_of_slot = np.full(capacity, -1, dtype=np.int32)
+    point_of_slot[rec["slot"]] = np.arange(len(rec), dtype=np.int32)
+    return RowSet(n_rows, slot_of_row[:n_rows], rec["slot"], rec["count"].astype(np.int64),
+                  rec["count_plus"].astype(np.int64), first, point_ids, point_of_slot)
+
+
+def _bisect(X_d, w_d, leaf_host: np.ndarray, target: int, seed0: int, seed1: int):
+    dev = X_d.device
+    n_points, n_cols = int(X_d.shape[0]), int(X_d.shape[1])
+    leaf_d = torch.as_tensor(leaf_host.astype(np.int32), device=dev)
+    sub = torch.zeros(n_points, dtype=torch.int8, device=dev)
+    centers = torch.empty((2, n_cols), dtype=torch.float64, device=dev)
+    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    _cabi.call("dj_bisect", _p(X_d), _p(w_d), n_points, n_cols, _p(leaf_d), target, seed0, seed1, TOL, MAX_ITER,
+               _p(sub), _p(centers), _p(stats), _stream())
+    return sub.cpu().numpy(), stats.cpu().numpy()
+
+
+def _silhouette(X_d, w_d, labels: np.ndarray, n_clusters: int) -> float:
+    dev = X_d.device
+    lab_d = torch.as_tensor(labels.astype(np.int32), device=dev)
+    out = torch.zeros(1, dtype=torch.float64, device=dev)
+    _cabi.call("dj_silhouette", _p(X_d), _p(w_d), _p(lab_d), int(X_d.shape[0]), int(X_d.shape[1]), n_clusters, _p(out),
+               _stream())
+    return float(out.item())
+
+
+class _Tree:
+    """The bisecting tree of sklearn (``_bisect_k_means.py:28-80``): leaves in left-to-right order, next split =
+    leaf with the largest inertia (first one on ties)."""
+
+    def __init__(self):
+        self.nodes = {0: {"score": 0.0, "left": None, "right": None}}
+        self.next_id = 1
+
+    def leaves(self, node: int = 0):
+        n = self.nodes[node]
+        if n["left"] is None:
+            yield node
+        else:
+            yield from self.leaves(n["left"])
+            yield from self.leaves(n["right"])
+
+    def pick(self) -> int:
+        best, best_score = None, None
+        for leaf in self.leaves():
+            s = self.nodes[leaf]["score"]
+            if best_score is None or s > best_score:
+                best, best_score = leaf, s
+        return best
+
+    def split(self, node: int, scores) -> tuple[int, int]:
+        a, b = self.next_id, self.next_id + 1
+        self.next_id += 2
+        self.nodes[a] = {"score": float(scores[0]), "left": None, "right": None}
+        self.nodes[b] = {"score": float(scores[1]), "left": None, "right": None}
+        self.nodes[node]["left"], self.nodes[node]["right"] = a, b
+        return a, b
+
+
+class _MemberSelector:
+    """j-th member (in row order) of a leaf among the sample rows, then among the control-subset rows."""
+
+    def __init__(self, sample: RowSet, point_leaf_sample, control_rows_points: np.ndarray):
+        self.sample = sample
+        self.control_points = control_rows_points  # point id (in the control part) of each control-subset row
+
+    def sample_member(self, leaf_of_slot_d: torch.Tensor, target: int, rank: int) -> int:
+        dev = leaf_of_slot_d.device
+        n = self.sample.n_rows
+        n_blocks = (n + 1023) // 1024
+        counts = torch.empty(n_blocks, dtype=torch.int32, device=dev)
+        _cabi.call("dj_member_counts", _p(self.sample.slot_of_row), n, _p(leaf_of_slot_d), target, _p(counts), _stream())
+        cum = np.cumsum(counts.cpu().numpy().astype(np.int64))
+        block = int(np.searchsorted(cum, rank, side="right"))
+        before = int(cum[block - 1]) if block else 0
+        out = torch.full((1,), -1, dtype=torch.int32, device=dev)
+        _cabi.call("dj_member_locate", _p(self.sample.slot_of_row), n, _p(leaf_of_slot_d), target, block, rank - before,
+                   _p(out), _stream())
+        row = int(out.item())
+        if row < 0:
+            raise RuntimeError("member selection failed")
+        return row
+
+
+def _values_matrix(point_ids: np.ndarray, value_of_id: np.ndarray) -> np.ndarray:
+    return value_of_id[point_ids.astype(np.int64)] if point_ids.size else np.zeros(point_ids.shape, dtype=np.float64)
+
+
+def control_subset(ids_control: torch.Tensor, strand_control: torch.Tensor, model: KmerModel, limit: int = 1000):
+    """BisectingKMeans(2) on the control rows, then the first ``limit`` rows of the majority label
+    (reference ``clustering.py:63-72``, ``score_handler.py:10-12``).  Returns per-point weights of the subset."""
+    dev = ids_control.device
+    rs_c = dedup_rows(ids_control, strand_control, None)
+    n_c = rs_c.n_rows
+    Xc = _values_matrix(rs_c.point_ids, model.value_of_id)
+    slot_rows = rs_c.slot_of_row.cpu().numpy()
+    point_rows = rs_c.point_of_slot[slot_rows]  # point of every control row, file order
+    rng = np.random.RandomState(1)
+    seeds = rng.choice(n_c, size=2, replace=False, p=np.ones(n_c) / np.ones(n_c).sum())
+    X_d = torch.as_tensor(Xc, device=dev)
+    w_d = torch.as_tensor(rs_c.count.astype(np.float64), device=dev)
+    sub, _ = _bisect(X_d, w_d, np.zeros(len(Xc), dtype=np.int32), 0, int(point_rows[seeds[0]]), int(point_rows[seeds[1]]))
+    labels_rows = sub[point_rows].astype(np.int64)
+    major = Counter(labels_rows.tolist()).most_common()[0][0]
+    keep_rows = np.flatnonzero(labels_rows == major)[:limit]
+    weights = np.bincount(point_rows[keep_rows], minlength=len(Xc)).astype(np.int64)
+    keep_points = np.flatnonzero(weights)
+    # control-subset rows in X order, as point indices into the kept points
+    remap = -np.ones(len(Xc), dtype=np.int64)
+    remap[keep_points] = np.arange(len(keep_points))
+    return Xc[keep_points], weights[keep_points], remap[point_rows[keep_rows]]
+
+
+def optimize_labels_points(Xs: np.ndarray, ws: np.ndarray, Xc: np.ndarray, wc: np.ndarray, control_row_points: np.ndarray,
+                           sample: RowSet | None, sample_row_points: np.ndarray | None = None) -> np.ndarray:
+    """``optimize_labels`` (reference ``clustering.py:29-55``) on weighted points.  Returns the label of every
+    *sample point*.  Either ``sample`` (device row set) or ``sample_row_points`` (host array) gives the row order
+    needed to turn scikit-learn's random row draws into points."""
+    dev = require_cuda()
+    n_s_pts, n_c_pts = len(Xs), len(Xc)
+    coverage_sample, coverage_control = int(ws.sum()), int(wc.sum())
+    X = np.concatenate([Xs, Xc], axis=0) if n_c_pts else Xs.copy()
+    w = np.concatenate([ws, wc]).astype(np.float64)
+    X_d = torch.as_tensor(np.ascontiguousarray(X), device=dev)
+    w_d = torch.as_tensor(w, device=dev)
+    best = np.ones(n_s_pts, dtype=np.int64)
+    if X.shape[1] == 0:
+        return best
+    prev = -1.0
+    rng = np.random.RandomState(1)
+    tree = _Tree()
+    leaf = np.zeros(n_s_pts + n_c_pts, dtype=np.int32)
+    for n_clusters in range(2, coverage_sample):
+        target = tree.pick()
+        members = leaf == target
+        ns_leaf = int(ws[members[:n_s_pts]].sum())
+        nc_leaf = int(wc[members[n_s_pts:]].sum()) if n_c_pts else 0
+        n_sub = ns_leaf + nc_leaf
+        seeds = rng.choice(n_sub, size=2, replace=False, p=np.ones(n_sub) / np.ones(n_sub).sum())
+        seed_points = []
+        leaf_of_slot_d = None
+        for j in seeds.tolist():
+            if j < ns_leaf:
+                if sample_row_points is not None:
+                    rows_in = np.flatnonzero(members[:n_s_pts][sample_row_points])
+                    seed_points.append(int(sample_row_points[rows_in[j]]))
+                else:
+                    if leaf_of_slot_d is None:
+                        los = np.full(sample.point_of_slot.shape[0], -1, dtype=np.int32)
+                        los[sample.slots] = leaf[:n_s_pts]
+                        leaf_of_slot_d = torch.as_tensor(los, device=dev)
+                    row = _MemberSelector(sample, None, control_row_points).sample_member(leaf_of_slot_d, target, j)
+                    slot = int(sample.slot_of_row[row].item())
+                    seed_points.append(int(sample.point_of_slot[slot]))
+            else:
+                ctrl_members = np.flatnonzero(members[n_s_pts:][control_row_points])
+                seed_points.append(n_s_pts + int(control_row_points[ctrl_members[j - ns_leaf]]))
+        sub, stats = _bisect(X_d, w_d, leaf, target, seed_points[0], seed_points[1])
+        a, b = tree.split(target, stats[:2])
+        leaf = np.where(members, np.where(sub == 1, b, a), leaf).astype(np.int32)
+        order = {node: k for k, node in enumerate(tree.leaves())}
+        labels = np.array([order[n] for n in leaf.tolist()], dtype=np.int64)
+        lab_s, lab_c = labels[:n_s_pts], labels[n_s_pts:]
+        ctrl_clusters = 0
+        if n_c_pts:
+            per = np.bincount(lab_c, weights=wc, minlength=n_clusters)
+            ctrl_clusters = int((per / coverage_control > 0.01).sum())
+        if len(set(lab_s.tolist())) > 1:
+            cur = _silhouette(X_d, w_d, labels, n_clusters)
+        else:
+            cur = -1.0
+        if prev >= cur or ctrl_clusters > 1:
+            break
+        best, prev = lab_s.copy(), cur
+    return best
+
+
+def remove_biased_clusters(labels_pts: np.ndarray, rs: RowSet, X_pts_dense_fn, strand_all: dict[str, int]) -> np.ndarray:
+    """Strand-bias re-allocation (reference ``clustering/strand_bias_handler.py:56-134``) on weighted points."""
+    from scipy.stats import fisher_exact
+
+    labels = labels_pts.copy()
+
+    def biases(lab):
+        order = sorted(set(lab.tolist()), key=lambda v: rs.first_row[lab == v].min())
+        out = {}
+        for v in order:
+            m = lab == v
+            plus = int(rs.count_plus[m].sum())
+            minus = int(rs.count[m].sum()) - plus
+            ratio = plus / (plus + minus)
+            p = fisher_exact([[plus, minus], [strand_all["+"], strand_all["-"]]], alternative="two-sided").pvalue
+            out[v] = (not (0.2 < ratio < 0.8)) and p < 0.01
+        return out
+
+    biased = biases(labels)
+    it = 0
+    while len(set(biased.values())) > 1 and it < 1000:
+        from sklearn.tree import DecisionTreeClassifier
+
+        X = X_pts_dense_fn()
+        is_b = np.array([biased[v] for v in labels.tolist()])
+        # rows in first-occurrence order with their multiplicities == the reference's row-expanded training set
+        tree = DecisionTreeClassifier(random_state=1).fit(X[~is_b], labels[~is_b], sample_weight=rs.count[~is_b])
+        labels[is_b] = tree.predict(X[is_b])
+        biased = biases(labels)
+        it += 1
+    return labels
+
+
+def cluster_rows(ids_sample: torch.Tensor, strand_sample: torch.Tensor, rows_sample: torch.Tensor | None,
+                 ids_control: torch.Tensor, strand_control: torch.Tensor, model: KmerModel,
+                 strand_all: dict[str, int]) -> tuple[torch.Tensor, dict]:
+    """``return_labels`` + ``relabel_with_consective_order``: device labels (int32, 1-based, in first-occurrence
+    order) for every sample row plus a small summary dict."""
+    dev = require_cuda()
+    rs = dedup_rows(ids_sample, strand_sample, rows_sample)
+    Xs = _values_matrix(rs.point_ids, model.value_of_id)
+    Xc, wc, ctrl_rows = control_subset(ids_control, strand_control, model)
+    labels_pts = optimize_labels_points(Xs, rs.count, Xc, wc, ctrl_rows, rs)
+
+    def dense():
+        X = np.zeros((len(Xs), model.n_loci), dtype=np.float64)
+        X[:, model.col_locus] = Xs
+        return X
+
+    labels_pts = remove_biased_clusters(labels_pts, rs, dense, strand_all)
+    # relabel_with_consective_order (label_updator.py:4-26): labels numbered by first occurrence in row order
+    order = sorted(set(labels_pts.tolist()), key=lambda v: rs.first_row[labels_pts == v].min())
+    rank = {v: k + 1 for k, v in enumerate(order)}
+    final_pts = np.array([rank[v] for v in labels_pts.tolist()], dtype=np.int32)
+    label_of_slot = np.zeros(rs.point_of_slot.shape[0], dtype=np.int32)
+    label_of_slot[rs.slots] = final_pts
+    labels_d = torch.empty(max(rs.n_rows, 1), dtype=torch.int32, device=dev)
+    _cabi.call("dj_gather_labels", _p(rs.slot_of_row), rs.n_rows, _p(torch.as_tensor(label_of_slot, device=dev)),
+               _p(labels_d), _stream())
+    sizes = np.bincount(final_pts, weights=rs.count, minlength=len(order) + 1)[1:].astype(np.int64)
+    return labels_d[: rs.n_rows], {"n_points": len(Xs), "n_control_points": len(Xc), "cluster_sizes": sizes.tolist()}

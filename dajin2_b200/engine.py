@@ -1,0 +1,575 @@
+"""Device-side stages of the hot path: encode -> histogram -> loci selection -> 3-mer scores -> score rows.
+
+PyTorch is used for device memory, streams and host<->device copies only; every read-scale loop runs in the
+hand-written kernels of ``libdajin2_b200.so`` through the C ABI (``_cabi``).  There is no CPU fallback: without a
+CUDA device or without the built library these functions raise.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import re
+from dataclasses import dataclass, field
+from itertools import groupby
+
+import numpy as np
+import torch
+
+from . import _cabi, codes
+from .ingest import HostReads
+
+MUTS = ("+", "-", "*")
+_MASK_BIT = {"+": _cabi.MASK_INS, "-": _cabi.MASK_DEL, "*": _cabi.MASK_SUB}
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("dajin2_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    _cabi.load()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _p(t) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _to_device(arr: np.ndarray | torch.Tensor, device) -> torch.Tensor:
+    t = torch.from_numpy(arr) if isinstance(arr, np.ndarray) else arr
+    return t.to(device, non_blocking=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# encode
+# ---------------------------------------------------------------------------------------------------------
+
+
+class EncodedReads:
+    """One MIDSV file on the device: text, row index, read x locus code matrix and per-read scalars."""
+
+    def __init__(self, host: HostReads, n_loci: int, validate: bool = True, encode: bool = True):
+        dev = require_cuda()
+        self.n_reads = host.n_reads
+        self.n_loci = int(n_loci)
+        self.qnames = host.qnames
+        self.records = host.records
+        self.strand_host = host.strand
+        self.h2d_bytes = int(host.text.nbytes + host.row_off.nbytes + host.row_len.nbytes + host.strand.nbytes)
+        self.text = _to_device(host.text, dev)
+        self.row_off = _to_device(host.row_off, dev)
+        self.row_len = _to_device(host.row_len, dev)
+        self.strand = _to_device(host.strand, dev)
+        self.max_row_len = int(host.row_len.max()) if self.n_reads else 0
+        self.pitch = _cabi.call("dj_code_pitch", self.n_loci)
+        self.ckpt_pitch = _cabi.call("dj_ckpt_pitch", self.max_row_len)
+        n = max(self.n_reads, 1)
+        self.codes = torch.empty((n, self.pitch), dtype=torch.uint8, device=dev)
+        self.match_score = torch.empty(n, dtype=torch.int32, device=dev)
+        self.n_tokens = torch.empty(n, dtype=torch.int32, device=dev)
+        self.flags = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.ckpt = torch.empty((n, self.ckpt_pitch), dtype=torch.int32, device=dev)
+        if encode:
+            self.encode()
+            if validate:
+                self.validate()
+
+    def encode(self) -> None:
+        _cabi.call("dj_encode", _p(self.text), _p(self.row_off), _p(self.row_len), self.n_reads, self.n_loci,
+                   self.pitch, self.ckpt_pitch, _p(self.codes), _p(self.match_score), _p(self.n_tokens),
+                   _p(self.flags), _p(self.ckpt), _stream())
+
+    def validate(self) -> None:
+        if self.n_reads == 0:
+            return
+        worst = int(self.flags[: self.n_reads].max().item())
+        if worst == 0:
+            return
+        flags = self.flags[: self.n_reads].cpu().numpy()
+        bad = int(np.flatnonzero(flags)[0])
+        what = []
+        if flags[bad] & _cabi.FLAG_TOKEN_COUNT:
+            what.append(f"{int(self.n_tokens[bad].item())} tokens instead of {self.n_loci}")
+        if flags[bad] & _cabi.FLAG_BAD_TOKEN:
+            what.append("a token outside the supported MIDSV grammar")
+        raise ValueError(f"read {bad} ({self.qnames[bad].decode('ascii', 'replace')}): " + " and ".join(what))
+
+    def match_scores(self) -> np.ndarray:
+        """calc_match of every read (reference ``classification/classifier.py:11-24``)."""
+        return self.match_score[: self.n_reads].cpu().numpy()
+
+    def histogram(self, rows: torch.Tensor | None = None) -> np.ndarray:
+        """int32[10, L]: rows 0-3 = count_indels classes '=', '+', '-', '*' (skip rule applied); rows 4-9 =
+        startswith('+','-','*') counts on '+' then '-' strand reads (no skip rule)."""
+        out = torch.empty((_cabi.HIST_ROWS, self.n_loci), dtype=torch.int32, device=self.codes.device)
+        n = self.n_reads if rows is None else int(rows.shape[0])
+        _cabi.call("dj_hist", _p(self.codes), self.pitch, _p(self.strand), _p(rows), n, self.n_loci, _p(out), _stream())
+        return out.cpu().numpy()
+
+    def fetch_tokens(self, reads, loci) -> list[str]:
+        """Raw text of token ``loci[k]`` of read ``reads[k]`` (used to print raw insertion tokens)."""
+        n = len(reads)
+        if n == 0:
+            return []
+        dev = self.codes.device
+        max_len = 64
+        while True:
+            out = torch.zeros((n, max_len), dtype=torch.uint8, device=dev)
+            out_len = torch.zeros(n, dtype=torch.int32, device=dev)
+            _cabi.call("dj_fetch_tokens", _p(self.text), _p(self.row_off), _p(self.row_len), _p(self.ckpt),
+                       self.ckpt_pitch, _p(torch.as_tensor(np.asarray(reads, dtype=np.int32), device=dev)),
+                       _p(torch.as_tensor(np.asarray(loci, dtype=np.int32), device=dev)), n, _p(out), _p(out_len),
+                       max_len, _stream())
+            lens = out_len.cpu().numpy()
+            if (lens < 0).any():
+                raise RuntimeError("dj_fetch_tokens: token not found")
+            if lens.max() <= max_len:
+                raw = out.cpu().numpy()
+                return [raw[k, : lens[k]].tobytes().decode("ascii") for k in range(n)]
+            max_len = int(lens.max())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# histogram -> counts / normalisation (O(L) host arithmetic in float64, as the reference does it)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def counts_from_histogram(hist: np.ndarray) -> dict[str, list[int]]:
+    """The dict ``count_indels`` returns (reference ``mutation_processing/indel_counter.py:15-31``)."""
+    return {"=": hist[0].tolist(), "+": hist[1].tolist(), "-": hist[2].tolist(), "*": hist[3].tolist()}
+
+
+def normalize_indels(count: dict[str, list[int]]) -> dict[str, np.ndarray]:
+    """``count / (count + match) * 100`` per class (reference ``indel_counter.py:34-43``)."""
+    match = np.array(count["="], dtype=float)
+    out = {}
+    for op, values in count.items():
+        num = np.array(values, dtype=float)
+        den = num + match
+        out[op] = np.divide(num, den, out=np.zeros_like(den, dtype=float), where=den != 0) * 100
+    return out
+
+
+def strand_table(hist: np.ndarray, loci_t: list[set[str]]) -> dict[int, dict[str, dict[str, int]]]:
+    """The nested dict of ``count_strandless_of_indels`` (reference ``error_correction/strand_bias_handler.py:18-33``)
+    read off the startswith rows of the histogram: only (locus, op) pairs that occur at least once appear."""
+    out: dict = {}
+    for i, ops in enumerate(loci_t):
+        for op in ops:
+            j = MUTS.index(op)
+            plus, minus = int(hist[4 + j, i]), int(hist[7 + j, i])
+            if plus + minus:
+                out.setdefault(i, {})[op] = {"+": plus, "-": minus}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# loci selection (a-5 .. a-11): device histograms in, O(L) host logic around scikit-learn's MLP
+# ---------------------------------------------------------------------------------------------------------
+
+_HOMOPOLYMER = re.compile(r"A{4,}|C{4,}|G{4,}|T{4,}|N{4,}")
+
+
+def window_cosine(sample: np.ndarray, control: np.ndarray) -> tuple[np.ndarray, np.ndarray]:
+    dev = require_cuda()
+    n = int(sample.shape[0])
+    s = torch.as_tensor(np.ascontiguousarray(sample, dtype=np.float64), device=dev)
+    c = torch.as_tensor(np.ascontiguousarray(control, dtype=np.float64), device=dev)
+    d = torch.empty(n, dtype=torch.float64, device=dev)
+    dt = torch.empty(n, dtype=torch.float64, device=dev)
+    _cabi.call("dj_window_cosine", _p(s), _p(c), n, _p(d), _p(dt), _stream())
+    return d.cpu().numpy(), dt.cpu().numpy()
+
+
+def dissimilar_mask(sample: np.ndarray, control: np.ndarray, is_consensus: bool = False) -> np.ndarray:
+    """``is_dissimilar_loci`` for every locus (reference ``anomaly_detector.py:28-58``)."""
+    d, dt = window_cosine(sample, control)
+    big = (sample - control) > 20
+    big_ok = np.ones_like(big) if not is_consensus else sample > 50
+    den = d + dt
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio_ok = np.where(den != 0, d / np.where(den != 0, den, 1.0), 0.0) > 0.9
+    window_ok = (d > 0.05) & (den != 0) & ratio_ok
+    return np.where(big, big_ok, window_ok)
+
+
+def mlp_candidates(sample: np.ndarray, control: np.ndarray, threshold: float) -> np.ndarray:
+    """Candidate loci proposed by the reference's lbfgs MLP (``anomaly_detector.py:61-94``).  scikit-learn is the
+    reference's own dependency for this step; the training set is rebuilt exactly as the reference builds it."""
+    from sklearn.neural_network import MLPClassifier
+
+    rng = np.random.default_rng(seed=1)
+    n_rand, n_ctrl = 10_000, len(control)
+    base = rng.uniform(0, 100, n_rand)
+    base_err = np.clip(base + rng.uniform(0, threshold, n_rand), 0, 100)
+    base_mut = np.clip(base + rng.uniform(threshold, 100, n_rand), 0, 100)
+    ctrl_err = np.clip(control + rng.uniform(0, threshold, n_ctrl), 0, 100)
+    ctrl_mut = np.clip(control + rng.uniform(threshold, 100, n_ctrl), 0, 100)
+    err = np.concatenate([np.array([base, base_err]).T, np.array([control, ctrl_err]).T], axis=0)
+    mut = np.concatenate([np.array([base, base_mut]).T, np.array([control, ctrl_mut]).T], axis=0)
+    X = np.concatenate([err, mut], axis=0)
+    y = [0] * (n_rand + n_ctrl) + [1] * (n_rand + n_ctrl)
+    clf = MLPClassifier(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
+    clf.fit(X, y)
+    return clf.predict(np.array([control, sample]).T) == 1
+
+
+def extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False) -> dict[str, set[int]]:
+    out = {}
+    for op in MUTS:
+        s = np.asarray(norm_sample[op], dtype=float)
+        c = np.asarray(norm_control[op], dtype=float)
+        keep = mlp_candidates(s, c, thresholds[op]) & dissimilar_mask(s, c, is_consensus)
+        out[op] = set(np.flatnonzero(keep).tolist())
+    return out
+
+
+def homopolymer_errors(sequence: str, norm_sample, norm_control, loci: dict[str, set[int]]) -> dict[str, set[int]]:
+    """Reference ``error_correction/homopolymer_handler.py:9-68``."""
+    out = {}
+    for op in MUTS:
+        errors: set[int] = set()
+        for m in _HOMOPOLYMER.finditer(sequence):
+            start, end = m.span()
+            if (start - 1) in loci[op] and (end + 1) in loci[op]:
+                continue
+            x = np.array(norm_sample[op][start:end], dtype=float)
+            y = np.array(norm_control[op][start:end], dtype=float)
+            swap = y >= 3
+            y[swap] = x[swap]
+            den = np.linalg.norm(x) * np.linalg.norm(y)
+            sim = 0.0 if (x.size == 0 or den == 0 or np.isnan(den)) else float(np.dot(x, y) / den)
+            if sim > 0.8:
+                errors.update(range(start, end + 1))
+        out[op] = errors
+    return out
+
+
+def strand_biased_loci(hist_sample: np.ndarray, strand_host: np.ndarray, loci_t: list[set[str]]) -> dict[str, set[int]]:
+    """Reference ``error_correction/strand_bias_handler.py:36-61`` on the histogram's startswith rows."""
+    from scipy.stats import fisher_exact
+
+    n_plus = int((strand_host == ord("+")).sum())
+    n_minus = int(strand_host.shape[0]) - n_plus
+    biased = {op: set() for op in MUTS}
+    for i, per_op in strand_table(hist_sample, loci_t).items():
+        for op, c in per_op.items():
+            ratio = c["+"] / (c["+"] + c["-"])
+            off_balance = not (0.2 < ratio < 0.8)
+            if off_balance and fisher_exact([[c["+"], c["-"]], [n_plus, n_minus]], alternative="two-sided").pvalue < 0.01:
+                biased[op].add(i)
+    return biased
+
+
+def _count_between(sorted_idx, lo, hi) -> int:
+    import bisect
+
+    return bisect.bisect_right(sorted_idx, hi) - bisect.bisect_left(sorted_idx, lo)
+
+
+def merge_consecutive_indels(loci: dict[str, set[int]]) -> dict[str, set[int]]:
+    """Reference ``mutation_processing/indel_merger.py:22-68``."""
+    merged = {"*": loci["*"]}
+    for op in ("+", "-"):
+        idx = sorted(loci[op])
+        acc = set(idx)
+        for a, b in zip(idx, idx[1:]):
+            if _count_between(idx, a + 1, b - 1) == b - a + 1:
+                continue
+            if a + 10 > b:
+                acc.update(range(a + 1, b))
+        merged[op] = acc
+    for op in ("+", "-"):
+        idx = sorted(merged[op])
+        acc = set(idx)
+        for a, b in zip(idx, idx[1:]):
+            if _count_between(idx, a + 1, b - 1) == b - a + 1:
+                continue
+            if a + 20 < b:
+                continue
+            if _count_between(idx, a - 11, a - 1) >= 8 and _count_between(idx, b + 1, b + 11) >= 8:
+                acc.update(range(a + 1, b))
+        merged[op] = acc
+    return merged
+
+
+def transpose_loci(loci: dict[str, set[int]], n_loci: int) -> list[set[str]]:
+    out = [set() for _ in range(n_loci)]
+    for op, idx in loci.items():
+        for i in idx:
+            if 0 <= i < n_loci:
+                out[i].add(op)
+    return out
+
+
+def select_mutation_loci(hist_sample: np.ndarray, strand_host: np.ndarray, sequence: str, norm_sample, norm_control_raw,
+                         knockin: set[int] | None = None, thresholds=None, is_consensus: bool = False,
+                         insample_filter=None) -> list[set[str]]:
+    """``extract_mutation_loci`` (reference ``mutation_processing/mutation_extractor.py:28-87``) fed by the device
+    histogram of the sample file instead of two more passes over its JSONL."""
+    thresholds = thresholds or {"*": 0.1, "-": 0.1, "+": 0.1}
+    norm_control = {op: np.minimum(norm_control_raw[op], norm_sample[op]) for op in MUTS}
+    loci = extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus)
+    if knockin is not None:
+        loci = {op: loci[op] | set(knockin) for op in MUTS}
+    homo = homopolymer_errors(sequence, norm_sample, norm_control, loci)
+    bias = strand_biased_loci(hist_sample, strand_host, transpose_loci(loci, len(sequence)))
+    loci = {op: loci[op] - homo[op] for op in MUTS}
+    loci = {op: loci[op] - bias[op] for op in MUTS}
+    if is_consensus and insample_filter is not None:
+        extra = insample_filter(norm_sample)
+        loci = {op: loci[op] - extra[op] for op in MUTS}
+    return transpose_loci(merge_consecutive_indels(loci), len(sequence))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 3-mer scores (a-14 .. a-16)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _next_pow2(n: int) -> int:
+    p = 1
+    while p < n:
+        p <<= 1
+    return p
+
+
+@dataclass
+class KmerModel:
+    """Everything ``make_score`` produces, in device form (table + id maps) and host form (score dicts)."""
+
+    n_loci: int
+    loci_mask: torch.Tensor  # uint8[L]
+    sel: np.ndarray  # selected loci (ascending) handed to the count kernel
+    table: torch.Tensor
+    capacity: int
+    col_locus: np.ndarray  # loci with a non-empty score dict, ascending
+    col_locus_d: torch.Tensor = None
+    col_sel_d: torch.Tensor = None
+    col_at_id_d: torch.Tensor = None
+    slot_value_id: torch.Tensor = None
+    value_of_id: np.ndarray = None  # float64, id 0 = 0.0
+    score: list = field(default_factory=list)  # list[dict[str, float]] of length L (make_score's return value)
+
+    @property
+    def n_cols(self) -> int:
+        return int(self.col_locus.shape[0])
+
+
+def loci_to_mask(loci_t: list[set[str]]) -> np.ndarray:
+    return np.array([sum(_MASK_BIT[m] for m in s) for s in loci_t], dtype=np.uint8)
+
+
+def _count_kmers(enc: EncodedReads, rows, n_rows, mask_d, sel_d, n_sel, which, table, capacity):
+    _cabi.call("dj_kmer_count", _p(enc.codes), enc.pitch, _p(rows), n_rows, _p(enc.text), _p(enc.row_off),
+               _p(enc.row_len), _p(enc.ckpt), enc.ckpt_pitch, _p(mask_d), enc.n_loci, _p(sel_d), n_sel, which,
+               _p(table), capacity, _stream())
+
+
+@dataclass
+class KmerCounts:
+    """Distinct 3-mers at the selected loci of up to two files, as exported from the device table."""
+
+    n_loci: int
+    mask_d: torch.Tensor
+    sel: np.ndarray
+    table: torch.Tensor
+    capacity: int
+    records: np.ndarray  # structured array of DjKmerRecord
+    names: list  # "prev,cur,next" string of every record
+    per_locus: dict  # locus -> record indices
+
+
+def count_kmers(sample: EncodedReads, rows_sample: torch.Tensor | None, control: EncodedReads | None,
+                loci_t: list[set[str]], capacity: int = 1 << 18) -> KmerCounts:
+    """generate_mutation_kmers + call_count (reference ``kmer_generator.py:35-56``, ``score_handler.py:15-16``) for
+    the sample file (file 0) and optionally the control file (file 1); "@,@,@" is implicit."""
+    dev = require_cuda()
+    L = sample.n_loci
+    mask = loci_to_mask(loci_t)
+    sel = np.array([i for i in range(1, L - 1) if mask[i]], dtype=np.int32)
+    mask_d = torch.as_tensor(mask, device=dev)
+    sel_d = torch.as_tensor(sel, device=dev)
+    n_s = sample.n_reads if rows_sample is None else int(rows_sample.shape[0])
+    while True:
+        table = torch.empty(_cabi.call("dj_kmer_table_bytes", capacity), dtype=torch.uint8, device=dev)
+        _cabi.call("dj_kmer_table_clear", _p(table), capacity, _stream())
+        _count_kmers(sample, rows_sample, n_s, mask_d, sel_d, len(sel), 0, table, capacity)
+        if control is not None:
+            _count_kmers(control, None, control.n_reads, mask_d, sel_d, len(sel), 1, table, capacity)
+        recs = (_cabi.KmerRecord * capacity)()
+        n_rec = ctypes.c_uint32(0)
+        try:
+            _cabi.call("dj_kmer_export", _p(table), capacity, ctypes.cast(recs, ctypes.c_void_p), capacity,
+                       ctypes.cast(ctypes.pointer(n_rec), ctypes.c_void_p), _stream())
+        except RuntimeError as exc:
+            if "overflow" in str(exc) and capacity < (1 << 26):
+                capacity <<= 2
+                continue
+            raise
+        if n_rec.value * 2 > capacity and capacity < (1 << 26):  # keep probe sequences short
+            capacity <<= 2
+            continue
+        break
+    records = np.frombuffer(recs, dtype=np.dtype(_cabi.KmerRecord), count=n_rec.value).copy()
+
+    # raw insertion tokens have to be printed from the text: fetch one example per record that needs it
+    raw_text: dict[tuple[int, str], str] = {}
+    need = [(k, side) for k in range(len(records)) for side in ("prev", "next") if records[side][k] == codes.KMER_RAW]
+    by_file: dict[int, list] = {0: [], 1: []}
+    for k, side in need:
+        ex = int(records["example"][k])
+        locus = int(sel[records["sel_index"][k]]) + (-1 if side == "prev" else 1)
+        by_file[ex >> 31].append((k, side, ex & 0x7FFFFFFF, locus))
+    for which, items in by_file.items():
+        if items:
+            enc = sample if which == 0 else control
+            toks = enc.fetch_tokens([it[2] for it in items], [it[3] for it in items])
+            for (k, side, _, _), tok in zip(items, toks):
+                raw_text[(k, side)] = tok
+
+    def side_str(k: int, side: str) -> str:
+        v = int(records[side][k])
+        if v == codes.KMER_AT:
+            return "@"
+        if v == codes.KMER_RAW:
+            return raw_text[(k, side)]
+        return codes.token_str(v)
+
+    names = [",".join((side_str(k, "prev"), codes.token_str(int(records["cur"][k])), side_str(k, "next")))
+             for k in range(len(records))]
+    per_locus: dict[int, list[int]] = {}
+    for k in range(len(records)):
+        per_locus.setdefault(int(sel[records["sel_index"][k]]), []).append(k)
+    return KmerCounts(L, mask_d, sel, table, capacity, records, names, per_locus)
+
+
+def score_from_counts(kc: KmerCounts, n_s: int, n_c: int, loci_t: list[set[str]], knockin: set[int]) -> list[dict]:
+    """call_percent .. discard_matches_and_ns (reference ``score_handler.py:19-127``) in Python floats."""
+    L = kc.n_loci
+    records, names = kc.records, kc.names
+
+    def percent(count: int, total: int) -> float:
+        return round(count / total * 100, 3)  # call_percent, score_handler.py:19-21
+
+    score: list[dict[str, float]] = [dict() for _ in range(L)]
+    for i in sorted(set(kc.per_locus) | {j for j in knockin if 0 <= j < L}):
+        ps: dict[str, float] = {}
+        pc: dict[str, float] = {}
+        cs_total = cc_total = 0
+        for k in kc.per_locus.get(i, []):
+            s_cnt, c_cnt = int(records["count_sample"][k]), int(records["count_control"][k])
+            cs_total += s_cnt
+            cc_total += c_cnt
+            if s_cnt:
+                ps[names[k]] = ps.get(names[k], 0) + s_cnt
+            if c_cnt:
+                pc[names[k]] = pc.get(names[k], 0) + c_cnt
+        if n_s - cs_total > 0:
+            ps["@,@,@"] = n_s - cs_total
+        if n_c - cc_total > 0:
+            pc["@,@,@"] = n_c - cc_total
+        ps = {k: percent(v, n_s) for k, v in ps.items()}
+        pc = {k: percent(v, n_c) for k, v in pc.items()}
+        if i in knockin:
+            diff = dict(ps)  # subtract_percentage keeps the sample dict at knock-in loci (score_handler.py:24-31)
+        else:
+            diff = {}
+            for k, v in ps.items():  # Counter subtraction: strictly positive differences only
+                d = v - pc.get(k, 0)
+                if d > 0:
+                    diff[k] = d
+        score[i] = {k: v for k, v in diff.items() if v > 0.5}  # discard_common_error, :34-35
+    # update_insertion_score (:60-107): '+'-centred k-mers inside a run of consecutive '+' loci take the run's max
+    plus_idx = sorted(i for i, m in enumerate(loci_t) if "+" in m)
+    for _, grp in groupby(enumerate(plus_idx), lambda t: t[0] - t[1]):
+        run = [i for _, i in grp]
+        top = 0
+        for i in run:
+            for k, v in score[i].items():
+                if k.split(",")[1].startswith("+"):
+                    top = max(top, v)
+        for i in run:
+            for k in score[i]:
+                if k.split(",")[1].startswith("+"):
+                    score[i][k] = top
+    # discard_matches_and_ns (:38-52)
+    return [{k: v for k, v in d.items() if not k.split(",")[1].startswith("=")} for d in score]
+
+
+def model_from_score(kc: KmerCounts, score: list[dict]) -> KmerModel:
+    """Device form of a score table: one uint16 id per distinct (column, value); id 0 is the score 0."""
+    dev = kc.mask_d.device
+    col_locus = np.array([i for i, d in enumerate(score) if d], dtype=np.int32)
+    sel_pos = {int(loc): j for j, loc in enumerate(kc.sel)}
+    name_records: dict[tuple[int, str], list[int]] = {}
+    for i, ks in kc.per_locus.items():
+        for k in ks:
+            name_records.setdefault((i, kc.names[k]), []).append(k)
+    values = [0.0]
+    value_id: dict[tuple[int, float], int] = {}
+    slot_value = np.zeros(kc.capacity, dtype=np.uint16)
+    col_at = np.zeros(len(col_locus), dtype=np.uint16)
+    for c, i in enumerate(col_locus.tolist()):
+        for name, v in score[i].items():
+            vid = value_id.get((c, float(v)))
+            if vid is None:
+                vid = len(values)
+                if vid > 0xFFFF:
+                    raise RuntimeError("more than 65535 distinct (locus, score) pairs: uint16 score ids overflow")
+                values.append(float(v))
+                value_id[(c, float(v))] = vid
+            if name == "@,@,@":
+                col_at[c] = vid
+            else:
+                for k in name_records.get((i, name), []):
+                    slot_value[int(kc.records["slot"][k])] = vid
+    col_sel = np.array([sel_pos.get(int(i), -1) for i in col_locus], dtype=np.int32)
+    return KmerModel(
+        n_loci=kc.n_loci, loci_mask=kc.mask_d, sel=kc.sel, table=kc.table, capacity=kc.capacity, col_locus=col_locus,
+        col_locus_d=torch.as_tensor(col_locus, device=dev), col_sel_d=torch.as_tensor(col_sel, device=dev),
+        col_at_id_d=torch.as_tensor(col_at.view(np.int16), device=dev),
+        slot_value_id=torch.as_tensor(slot_value.view(np.int16), device=dev),
+        value_of_id=np.array(values, dtype=np.float64), score=score,
+    )
+
+
+def build_kmer_model(sample: EncodedReads, rows_sample: torch.Tensor | None, control: EncodedReads,
+                     loci_t: list[set[str]], knockin: set[int] | None) -> KmerModel:
+    """``make_score`` (reference ``clustering/score_handler.py:115-127``): the per-locus 3-mer counts come from the
+    device, the O(K x vocabulary) percentage arithmetic is done in Python floats exactly as the reference does."""
+    kc = count_kmers(sample, rows_sample, control, loci_t)
+    n_s = sample.n_reads if rows_sample is None else int(rows_sample.shape[0])
+    score = score_from_counts(kc, n_s, control.n_reads, loci_t, set(knockin or ()))
+    return model_from_score(kc, score)
+
+
+def annotate_ids(enc: EncodedReads, rows: torch.Tensor | None, model: KmerModel, is_control: bool) -> torch.Tensor:
+    """Score rows as uint16 value ids [n_rows, n_cols] (``annotate_score``, reference ``score_handler.py:136-148``)."""
+    dev = enc.codes.device
+    n = enc.n_reads if rows is None else int(rows.shape[0])
+    ids = torch.zeros((max(n, 1), max(model.n_cols, 1)), dtype=torch.int16, device=dev)
+    if n and model.n_cols:
+        _cabi.call("dj_annotate", _p(enc.codes), enc.pitch, _p(rows), n, _p(enc.text), _p(enc.row_off), _p(enc.row_len),
+                   _p(enc.ckpt), enc.ckpt_pitch, _p(model.loci_mask), enc.n_loci, _p(model.col_locus_d),
+                   _p(model.col_sel_d), _p(model.col_at_id_d), model.n_cols, 1 if is_control else 0, _p(model.table),
+                   model.capacity, _p(model.slot_value_id), _p(ids), _stream())
+    return ids[:n] if n else ids[:0]
+
+
+def dense_score_rows(ids: torch.Tensor, model: KmerModel) -> list[list]:
+    """Materialise the reference's dense rows (length L, ints 0 where nothing scored) from the id matrix."""
+    arr = ids.cpu().numpy().view(np.uint16)
+    out = []
+    cols = model.col_locus.tolist()
+    vals = model.value_of_id
+    for r in range(arr.shape[0]):
+        row = [0] * model.n_loci
+        for c, i in enumerate(cols):
+            v = arr[r, c]
+            if v:
+                row[i] = float(vals[v])
+        out.append(row)
+    return out

@@ -1,0 +1,143 @@
+"""The fused hot path on packed host buffers — what the path-based drop-in functions do underneath, without
+the JSONL / pickle round trips: encode -> histogram -> loci selection -> 3-mer scores -> score rows -> clustering
+-> labels and allele percentages (single FASTA allele; multi-allele samples go through ``classification`` first).
+This is the entry point ``bench.py`` times (``e2e`` includes the host->device copies and the label read-back).
+"""
+
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import clusterer, engine
+from .ingest import HostReads
+
+
+@dataclass
+class HotPathResult:
+    labels: np.ndarray | None  # int32[N] in QNAME order (None when fetch_labels=False)
+    order: np.ndarray  # QNAME-sorted row order the labels refer to
+    cluster_sizes: list[int]
+    percentages: list[float]  # round(size / N * 100, 3) per label (reference appender.py:34-45)
+    mutation_loci: list[set[str]]
+    model: engine.KmerModel
+    timings: dict = field(default_factory=dict)
+
+
+def qname_order(qnames: np.ndarray) -> np.ndarray:
+    """Stable sort by QNAME as ``extract_alleles_with_max_score`` does (reference classifier.py:38-46); bytewise
+    order of the ASCII names equals Python's ``str`` order."""
+    return np.argsort(qnames, kind="stable").astype(np.int32)
+
+
+class _Timer:
+    def __init__(self, timings: dict):
+        self.timings = timings
+
+    def device(self, name):
+        return _DeviceSpan(self.timings, name)
+
+    def host(self, name):
+        return _HostSpan(self.timings, name)
+
+
+class _DeviceSpan:
+    def __init__(self, timings, name):
+        self.t, self.name = timings, name
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+
+    def __exit__(self, *exc):
+        self.b.record()
+        self.t.setdefault("_events", []).append((self.name, self.a, self.b))
+
+
+class _HostSpan:
+    def __init__(self, timings, name):
+        self.t, self.name = timings, name
+
+    def __enter__(self):
+        self.t0 = time.perf_counter()
+
+    def __exit__(self, *exc):
+        self.t[self.name] = self.t.get(self.name, 0.0) + (time.perf_counter() - self.t0) * 1e3
+
+
+def _finish(timings: dict) -> None:
+    torch.cuda.synchronize()
+    for name, a, b in timings.pop("_events", []):
+        timings[name] = timings.get(name, 0.0) + a.elapsed_time(b)
+
+
+def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequence: str, knockin: set[int] | None = None,
+               order: np.ndarray | None = None, fetch_labels: bool = True, reencode: bool = True,
+               comm=None) -> HotPathResult:
+    """Hot path on reads whose text already sits in HBM."""
+    dev = engine.require_cuda()
+    if comm is not None:
+        from . import distributed
+
+        return distributed.run_device_sharded(sample, control, sequence, knockin, comm, fetch_labels, reencode)
+    timings: dict = {}
+    tm = _Timer(timings)
+    if reencode:
+        with tm.device("encode_ms"):
+            sample.encode()
+            control.encode()
+        sample.validate()
+        control.validate()
+    with tm.device("hist_ms"):
+        hist_s = sample.histogram()
+        hist_c = control.histogram()
+    with tm.host("loci_host_ms"):
+        count_s = engine.counts_from_histogram(hist_s)
+        count_c = engine.counts_from_histogram(hist_c)
+        norm_s = engine.normalize_indels(count_s)
+        norm_c = engine.normalize_indels(count_c)
+        loci = engine.select_mutation_loci(hist_s, sample.strand_host, sequence, norm_s, norm_c, knockin)
+    with tm.host("order_host_ms"):
+        if order is None:
+            order = qname_order(sample.qnames)
+        rows = torch.as_tensor(order, device=dev)
+    n = sample.n_reads
+    if all(not m for m in loci) or n < 5:
+        labels = np.ones(n, dtype=np.int32) if fetch_labels else None
+        _finish(timings)
+        return HotPathResult(labels, order, [n], [100.0], loci, None, timings)
+    with tm.host("score_ms"):
+        model = engine.build_kmer_model(sample, rows, control, loci, knockin)
+    with tm.device("annotate_ms"):
+        ids_s = engine.annotate_ids(sample, rows, model, False)
+        ids_c = engine.annotate_ids(control, None, model, True)
+    plus = int((sample.strand_host == ord("+")).sum())
+    with tm.host("cluster_ms"):
+        labels_d, info = clusterer.cluster_rows(ids_s, sample.strand, rows, ids_c, control.strand, model,
+                                                {"+": plus, "-": n - plus})
+    with tm.host("labels_d2h_ms"):
+        labels = labels_d.cpu().numpy() if fetch_labels else None
+    sizes = info["cluster_sizes"]
+    pct = [round(s / n * 100, 3) for s in sizes]
+    _finish(timings)
+    timings.update({"n_points": info["n_points"], "n_cols": model.n_cols})
+    return HotPathResult(labels, order, sizes, pct, loci, model, timings)
+
+
+def run_host(sample: HostReads, control: HostReads, sequence: str, knockin: set[int] | None = None,
+             order: np.ndarray | None = None, comm=None) -> HotPathResult:
+    """Hot path from packed HOST buffers: host->device copies, the device path, label read-back."""
+    t0 = time.perf_counter()
+    enc_s = engine.EncodedReads(sample, len(sequence), validate=False, encode=False)
+    enc_c = engine.EncodedReads(control, len(sequence), validate=False, encode=False)
+    torch.cuda.synchronize()
+    h2d_ms = (time.perf_counter() - t0) * 1e3
+    res = run_device(enc_s, enc_c, sequence, knockin, order, comm=comm)
+    res.timings["h2d_ms"] = h2d_ms
+    res.timings["h2d_bytes"] = enc_s.h2d_bytes + enc_c.h2d_bytes
+    res.timings["d2h_bytes"] = int(res.labels.nbytes) if res.labels is not None else 0
+    return res

@@ -1,0 +1,75 @@
+"""``install()`` rebinds the reference's hot-path functions to the dajin2_b200 implementations.
+
+The reference has no plugin interface: the seams are plain module attributes, several of them imported by
+value (``from x import f``), so every importer listed in SURVEY.md §8b is patched as well as the defining module.
+Call ``install()`` before ``DAJIN2.core.core.execute_sample`` runs (or at any time: the lazily cached package
+attributes are overwritten too).  ``uninstall()`` restores the originals.
+"""
+
+from __future__ import annotations
+
+import importlib
+
+from . import classification, clustering, preprocess
+
+_PATCHES = [
+    # (module, attribute, replacement)
+    ("DAJIN2.core.preprocess.mutation_processing.indel_counter", "count_indels", preprocess.count_indels),
+    ("DAJIN2.core.preprocess.mutation_processing.indel_counter", "summarize_indels", preprocess.summarize_indels),
+    ("DAJIN2.core.preprocess.mutation_processing.mutation_extractor", "summarize_indels", preprocess.summarize_indels),
+    ("DAJIN2.core.preprocess.mutation_processing.mutation_extractor", "extract_mutation_loci",
+     preprocess.extract_mutation_loci),
+    ("DAJIN2.core.preprocess.mutation_processing.mutation_extractor", "cache_indels_count", preprocess.cache_indels_count),
+    ("DAJIN2.core.preprocess.mutation_processing.mutation_extractor", "cache_mutation_loci",
+     preprocess.cache_mutation_loci),
+    ("DAJIN2.core.preprocess.mutation_processing.mutation_extractor", "extract_sequence_errors_in_strand_biased_loci",
+     preprocess.extract_sequence_errors_in_strand_biased_loci),
+    ("DAJIN2.core.preprocess.error_correction.strand_bias_handler", "count_strandless_of_indels",
+     preprocess.count_strandless_of_indels),
+    ("DAJIN2.core.preprocess.error_correction.strand_bias_handler", "extract_sequence_errors_in_strand_biased_loci",
+     preprocess.extract_sequence_errors_in_strand_biased_loci),
+    ("DAJIN2.core.preprocess", "cache_mutation_loci", preprocess.cache_mutation_loci),
+    ("DAJIN2.core.classification.classifier", "calc_match", classification.calc_match),
+    ("DAJIN2.core.classification.classifier", "score_allele", classification.score_allele),
+    ("DAJIN2.core.classification.classifier", "classify_alleles", classification.classify_alleles),
+    ("DAJIN2.core.classification", "classify_alleles", classification.classify_alleles),
+    ("DAJIN2.core.clustering.score_handler", "make_score", clustering.make_score),
+    ("DAJIN2.core.clustering.score_handler", "annotate_score", clustering.annotate_score),
+    ("DAJIN2.core.clustering.clustering", "optimize_labels", clustering.optimize_labels),
+    ("DAJIN2.core.clustering.clustering", "return_labels", clustering.return_labels),
+    ("DAJIN2.core.clustering.label_extractor", "make_score", clustering.make_score),
+    ("DAJIN2.core.clustering.label_extractor", "annotate_score", clustering.annotate_score),
+    ("DAJIN2.core.clustering.label_extractor", "return_labels", clustering.return_labels),
+    ("DAJIN2.core.clustering.label_extractor", "extract_labels", clustering.extract_labels),
+    ("DAJIN2.core.clustering", "extract_labels", clustering.extract_labels),
+    ("DAJIN2.core.preprocess.structural_variants.sv_detector", "optimize_labels", clustering.optimize_labels),
+]
+
+_saved: list[tuple] = []
+
+
+def install(strict: bool = False) -> list[str]:
+    """Patch the reference in place; returns the list of ``module.attribute`` names that were rebound."""
+    done = []
+    for mod_name, attr, repl in _PATCHES:
+        try:
+            mod = importlib.import_module(mod_name)
+        except Exception:
+            if strict:
+                raise
+            continue
+        missing = object()
+        old = mod.__dict__.get(attr, missing)
+        _saved.append((mod, attr, old, missing))
+        setattr(mod, attr, repl)
+        done.append(f"{mod_name}.{attr}")
+    return done
+
+
+def uninstall() -> None:
+    while _saved:
+        mod, attr, old, missing = _saved.pop()
+        if old is missing:
+            mod.__dict__.pop(attr, None)
+        else:
+            setattr(mod, attr, old)

@@ -147,7 +147,9 @@ class MidsvBatch:
         return path
 
 
-def generate(pop: Population, n_reads: int, seed: int = SEED, first_read: int = 0, stride: int = 1) -> MidsvBatch:
+def generate(pop: Population, n_reads: int, seed: int = SEED, first_read: int = 0, stride: int = 1,
+             text_alloc=None) -> MidsvBatch:
+    """``text_alloc(nbytes)`` may supply the uint8 buffer for the text (e.g. a view of pinned host memory)."""
     lib = _load()
     sub, dele, ins = PROFILES[pop.profile]
     params = _Params(sub, dele, ins, 0.6, 3.0, pop.trunc_prob, 0.05, 0.30, 0.5)
@@ -167,7 +169,8 @@ def generate(pop: Population, n_reads: int, seed: int = SEED, first_read: int = 
             cdf.ctypes.data, len(pop.alleles))
     total = lib.dj_synth_generate(*args, None, 0, row_off.ctypes.data, row_len.ctypes.data,
                                   strand.ctypes.data, allele.ctypes.data)
-    text = np.zeros(total + 64, dtype=np.uint8)
+    text = np.zeros(total + 64, dtype=np.uint8) if text_alloc is None else text_alloc(total + 64)
+    text[total:] = 10
     got = lib.dj_synth_generate(*args, text.ctypes.data, total, row_off.ctypes.data, row_len.ctypes.data,
                                 strand.ctypes.data, allele.ctypes.data)
     if got != total:

@@ -1,0 +1,261 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors of the real reference and
+against the oracle on the same inputs.  Bit-exact for codes, counts, loci, score dicts and score rows;
+ARI >= 0.99 and allele percentages within 0.5 percentage points for clustering (BASELINE.json north_star)."""
+from __future__ import annotations
+
+import json
+import pickle
+from collections import Counter
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from tests.helpers import (SINGLE_CASES, encode_rows, golden_loci, golden_score, load_case, sparse_rows)
+
+pytestmark = pytest.mark.gpu
+
+
+def _enc(part, n_loci):
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+
+    return engine.EncodedReads(pack_rows(part["rows"], part["strands"], part["qnames"]), n_loci)
+
+
+def _ari(a, b):
+    from sklearn.metrics import adjusted_rand_score
+
+    return adjusted_rand_score(a, b)
+
+
+def _percent_gap(ref_labels, got_labels):
+    """Largest |percent difference| between matched clusters (matched by descending size)."""
+    n = len(ref_labels)
+    pr = sorted((c / n * 100 for c in Counter(ref_labels).values()), reverse=True)
+    pg = sorted((c / n * 100 for c in Counter(got_labels).values()), reverse=True)
+    m = max(len(pr), len(pg))
+    pr += [0.0] * (m - len(pr))
+    pg += [0.0] * (m - len(pg))
+    return max(abs(x - y) for x, y in zip(pr, pg))
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like"])
+def test_encode_codes_and_scalars(name):
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        L = len(a["sequence"])
+        for part in ("sample", "control"):
+            enc = _enc(a[part], L)
+            want = encode_rows(a[part]["rows"])
+            got = enc.codes[: enc.n_reads, :L].cpu().numpy()
+            assert np.array_equal(got, want), f"{name}/{aname}/{part}: code matrix differs"
+            assert (enc.n_tokens[: enc.n_reads].cpu().numpy() == L).all()
+        enc = _enc(a["sample"], L)
+        assert enc.match_scores().tolist() == golden["alleles"][aname]["calc_match"]
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like"])
+def test_histogram_counts(name):
+    from dajin2_b200 import engine
+
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        g = golden["alleles"][aname]
+        L = len(a["sequence"])
+        enc = _enc(a["sample"], L)
+        hist = enc.histogram()
+        if "count_sample" in g:
+            count = engine.counts_from_histogram(hist)
+            assert count == g["count_sample"]
+            norm = engine.normalize_indels(count)
+            for op, vals in g["norm_sample"].items():
+                assert [float(x).hex() for x in norm[op]] == vals
+            assert engine.counts_from_histogram(_enc(a["control"], L).histogram()) == g["count_control"]
+        got = engine.strand_table(hist, golden_loci(g))
+        assert {str(i): v for i, v in got.items()} == g["strand_counts"]
+
+
+@pytest.mark.parametrize("name", [n for n in SINGLE_CASES if n != "kat"] + ["flox_like"])
+def test_mutation_loci(name):
+    from dajin2_b200 import engine
+
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        g = golden["alleles"][aname]
+        L = len(a["sequence"])
+        es, ec = _enc(a["sample"], L), _enc(a["control"], L)
+        hs = es.histogram()
+        ns = engine.normalize_indels(engine.counts_from_histogram(hs))
+        nc = engine.normalize_indels(engine.counts_from_histogram(ec.histogram()))
+        loci = engine.select_mutation_loci(hs, es.strand_host, a["sequence"], ns, nc, a.get("knockin"))
+        assert ["".join(sorted(s)) for s in loci] == g["mutation_loci"]
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like"])
+def test_scores_and_rows(name):
+    from dajin2_b200 import engine
+
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        g = golden["alleles"][aname]
+        L = len(a["sequence"])
+        loci = golden_loci(g)
+        es, ec = _enc(a["sample"], L), _enc(a["control"], L)
+        model = engine.build_kmer_model(es, None, ec, loci, a.get("knockin") or set())
+        assert model.score == golden_score(g, L)
+        rows_s = engine.dense_score_rows(engine.annotate_ids(es, None, model, False), model)
+        rows_c = engine.dense_score_rows(engine.annotate_ids(ec, None, model, True), model)
+        assert sparse_rows(rows_s) == g["rows_sample"]
+        assert sparse_rows(rows_c) == g["rows_control"]
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES)
+def test_return_labels(name):
+    from dajin2_b200 import clusterer, engine
+
+    alleles, golden = load_case(name)
+    a, g = alleles["control"], golden["alleles"]["control"]
+    if "return_labels" not in g:
+        pytest.skip("no clustering in this case")
+    L = len(a["sequence"])
+    loci = golden_loci(g)
+    es, ec = _enc(a["sample"], L), _enc(a["control"], L)
+    model = engine.build_kmer_model(es, None, ec, loci, a.get("knockin") or set())
+    ids_s = engine.annotate_ids(es, None, model, False)
+    ids_c = engine.annotate_ids(ec, None, model, True)
+    strands = a["sample"]["strands"]
+    labels_d, info = clusterer.cluster_rows(ids_s, es.strand, None, ids_c, ec.strand, model,
+                                            {"+": strands.count("+"), "-": strands.count("-")})
+    got = labels_d.cpu().numpy().tolist()
+    ref = g["return_labels"]
+    assert _ari(ref, got) >= 0.99, (Counter(ref), Counter(got))
+    assert _percent_gap(ref, got) <= 0.5
+    assert sorted(info["cluster_sizes"], reverse=True) == sorted(Counter(got).values(), reverse=True)
+
+
+def _write_tree(tmp_path, alleles, sname="sample", cname="ctrl"):
+    from dajin2_b200.preprocess import _allele_key
+
+    for name, a in alleles.items():
+        key = _allele_key(name)
+        for who, part in ((sname, "sample"), (cname, "control")):
+            p = tmp_path / who / "midsv" / key / f"{who}_midsv.jsonl"
+            p.parent.mkdir(parents=True, exist_ok=True)
+            with open(p, "w") as f:
+                for q, row, s in zip(a[part]["qnames"], a[part]["rows"], a[part]["strands"]):
+                    f.write(json.dumps({"QNAME": q, "RNAME": name, "MIDSV": row, "STRAND": s, "PRESET": "map-ont"}) + "\n")
+        if a.get("knockin") is not None:
+            p = tmp_path / sname / "knockin_loci" / key / "knockin.pickle"
+            p.parent.mkdir(parents=True, exist_ok=True)
+            p.write_bytes(pickle.dumps(set(a["knockin"])))
+    (tmp_path / sname / "clustering").mkdir(parents=True, exist_ok=True)
+    return SimpleNamespace(tempdir=tmp_path, sample_name=sname, control_name=cname,
+                           fasta_alleles={n: a["sequence"] for n, a in alleles.items()})
+
+
+@pytest.mark.parametrize("name", ["flox_like", "tp_L1000_N2000_r10", "tp_L1000_N1200_r9", "point_L900_N1500",
+                                  "fixture_flox100", "inv_L2724_N300"])
+def test_dropin_entry_points_on_files(name, tmp_path):
+    """The reference's own call sequence (core.py:95,161,217-233) through the drop-in functions, on JSONL files."""
+    from dajin2_b200 import cache, classification, clustering, preprocess
+    from dajin2_b200.preprocess import _allele_key
+
+    cache.clear()
+    alleles, golden = load_case(name)
+    args = _write_tree(tmp_path, alleles)
+    preprocess.cache_mutation_loci(args, is_control=True)
+    preprocess.cache_mutation_loci(args, is_control=False)
+    for aname in alleles:
+        g = golden["alleles"][aname]
+        d = tmp_path / "sample" / "mutation_loci" / _allele_key(aname)
+        assert pickle.loads((d / "sample_count.pickle").read_bytes()) == g["count_sample"]
+        loci = pickle.loads((d / "mutation_loci.pickle").read_bytes())
+        assert ["".join(sorted(s)) for s in loci] == g["mutation_loci"]
+    classif = classification.classify_alleles(tmp_path, args.fasta_alleles, "sample")
+    assert [[c["QNAME"], c["ALLELE"]] for c in classif] == golden["classify"]
+    labels = clustering.extract_labels(classif, tmp_path, "sample", "ctrl")
+    assert [c["QNAME"] for c in classif] == golden["extract_labels_order"]
+    assert _ari(golden["extract_labels"], labels) >= 0.99
+    clust = clustering.update_labels(clustering.add_percent(clustering.add_readnum(clustering.add_labels(classif, labels))))
+    ref_pct = sorted({(f[2], f[4]) for f in golden["final"]})
+    got_pct = sorted({(c["LABEL"], c["PERCENT"]) for c in clust})
+    assert len(ref_pct) == len(got_pct)
+    for (_, pr), (_, pg) in zip(ref_pct, got_pct):
+        assert abs(pr - pg) <= 0.5
+
+
+def test_window_cosine_matches_oracle():
+    from dajin2_b200 import engine
+    from oracle import dajin2_oracle as orc
+
+    rng = np.random.default_rng(3)
+    s = rng.uniform(0, 5, 257)
+    c = rng.uniform(0, 5, 257)
+    s[40] = 60.0
+    s[100:104] = 0.0
+    c[100:112] = 0.0
+    s[100:112] = 0.0
+    d, dt = engine.window_cosine(s, c)
+    for i in range(257):
+        x, y = s[i : i + 10], c[i : i + 10]
+        assert d[i] == pytest.approx(orc.cosine_distance(x, y), abs=1e-12)
+        assert dt[i] == pytest.approx(orc.cosine_distance(x[1:], y[1:]), abs=1e-12)
+    mask = engine.dissimilar_mask(s, c)
+    assert mask.tolist() == [orc.is_dissimilar_loci(s, c, i) for i in range(257)]
+
+
+def test_encoder_edge_cases():
+    from dajin2_b200 import classification, engine
+    from dajin2_b200.ingest import pack_rows
+    from oracle import dajin2_oracle as orc
+
+    # long insertions, every row alignment, rows longer than one 512-byte iteration, lowercase blocks
+    long_ins = "+" + "|+".join("ACGT"[i % 4] for i in range(300)) + "|=A"
+    rows = []
+    for k in range(40):
+        toks = ["=A", "*AG", "-c", "=n", "+a|+c|=g", "=N", "+T|*CA", "+G|-T"] * (20 + k)
+        toks[k] = long_ins
+        rows.append(",".join(toks))
+    rows.append("=A")
+    rows.append(long_ins)
+    for r in rows:
+        L = r.count(",") + 1
+        enc = engine.EncodedReads(pack_rows([r]), L)
+        assert np.array_equal(enc.codes[0, :L].cpu().numpy(), encode_rows([r])[0])
+        assert int(enc.match_scores()[0]) == orc.calc_match(r)
+        assert engine.counts_from_histogram(enc.histogram()) == orc.count_indels([r], L)
+    same_len = [r for r in rows if r.count(",") + 1 == 160][:1] * 3 + [",".join(["=A"] * 160)]
+    enc = engine.EncodedReads(pack_rows(same_len), 160)
+    assert np.array_equal(enc.codes[:4, :160].cpu().numpy(), encode_rows(same_len))
+    # raw tokens are recoverable through the checkpoints
+    assert enc.fetch_tokens([0, 3, 0], [0, 159, 4]) == [same_len[0].split(",")[0], "=A", same_len[0].split(",")[4]]
+    # ragged input and unsupported tokens fail loudly
+    with pytest.raises(ValueError, match="tokens instead of"):
+        engine.EncodedReads(pack_rows(["=A,=C,=G", "=A,=C"]), 3)
+    with pytest.raises(ValueError, match="grammar"):
+        engine.EncodedReads(pack_rows(["=A,=R,=G"]), 3)
+    with pytest.raises(ValueError, match="grammar"):
+        engine.EncodedReads(pack_rows(["=A,+A|=g,=G"]), 3)
+    assert classification.calc_match("=A,+T|+T|=C,=g,*ag") == orc.calc_match("=A,+T|+T|=C,=g,*ag")
+    # empty input
+    empty = engine.EncodedReads(pack_rows([]), 5)
+    assert empty.histogram().sum() == 0
+
+
+def test_first_token_raw_insertion_quirk():
+    """Token 0 is never a k-mer centre, so as 'prev' of locus 1 it stays uncompressed (kmer_generator.py:40-52)."""
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+    from oracle import dajin2_oracle as orc
+
+    sample = ["+A|+C|=G,-T,+G|=A,=C,=A"] * 6 + ["+A|=G,-T,=A,=C,=A"] * 3 + ["=G,=T,=A,=C,=A"] * 3
+    control = ["=G,=T,=A,=C,=A"] * 10
+    loci = [{"+"}, {"-"}, {"+"}, set(), set()]
+    es = engine.EncodedReads(pack_rows(sample), 5)
+    ec = engine.EncodedReads(pack_rows(control), 5)
+    model = engine.build_kmer_model(es, None, ec, loci, set())
+    want = orc.make_score(sample, control, loci, set())
+    assert model.score == want
+    rows = engine.dense_score_rows(engine.annotate_ids(es, None, model, False), model)
+    assert rows == list(orc.annotate_score(sample, want, loci))

@@ -1,0 +1,75 @@
+"""CPU tests of the host-side logic that surrounds the kernels (no CUDA needed)."""
+from __future__ import annotations
+
+import json
+
+import numpy as np
+
+from dajin2_b200 import codes, engine, synth
+from dajin2_b200.ingest import pack_rows, read_midsv_jsonl
+from dajin2_b200.pipeline import qname_order
+from oracle import dajin2_oracle as orc
+from tests.helpers import encode_token, load_case
+
+
+def test_code_roundtrip():
+    toks = ["=A", "=n", "-G", "-t", "*AG", "*ag", "=N", "*NT"]
+    for t in toks:
+        assert codes.token_str(encode_token(t)) == t
+    assert codes.token_str(encode_token("+A|+C|=G")) == "+I=G"
+    assert codes.token_str(encode_token("+a|*ag")) == "+I*ag"
+    assert encode_token("*Ag") == 0x7F and encode_token("=R") == 0x7F
+    assert codes.op_char(encode_token("+A|=G")) == "+" and codes.op_char(encode_token("*AG")) == "*"
+
+
+def test_ingest_jsonl_spans(tmp_path):
+    rows = ["=A,=C,+T|+T|=G", "=A,-C,=G", "*AG,=C,=G"]
+    p = tmp_path / "x.jsonl"
+    with open(p, "w") as f:
+        for i, r in enumerate(rows):
+            f.write(json.dumps({"QNAME": f"q{i}", "RNAME": "control", "MIDSV": r, "STRAND": "+-"[i % 2]}) + "\n")
+    host = read_midsv_jsonl(p)
+    assert host.n_reads == 3
+    got = [host.text[o : o + n].tobytes().decode() for o, n in zip(host.row_off, host.row_len)]
+    assert got == rows
+    assert host.strand.tobytes() == b"+-+" and host.qnames.tolist() == [b"q0", b"q1", b"q2"]
+    assert host.text.shape[0] >= int(host.row_off[-1] + host.row_len[-1]) + 16
+    packed = pack_rows(rows, ["+", "-", "+"], ["q0", "q1", "q2"])
+    got = [packed.text[o : o + n].tobytes().decode() for o, n in zip(packed.row_off, packed.row_len)]
+    assert got == rows
+
+
+def test_qname_order_is_python_sort():
+    b = synth.generate(synth.throughput_population(50), 500)
+    q = b.qnames()
+    names = [x.decode() for x in q]
+    assert qname_order(q).tolist() == sorted(range(len(names)), key=lambda i: names[i])
+
+
+def test_generator_is_shard_invariant():
+    pop = synth.throughput_population(200)
+    whole = synth.generate(pop, 64)
+    even = synth.generate(pop, 32, first_read=0, stride=2)
+    odd = synth.generate(pop, 32, first_read=1, stride=2)
+    for k in range(32):
+        assert whole.midsv(2 * k) == even.midsv(k) and whole.midsv(2 * k + 1) == odd.midsv(k)
+    assert whole.qnames()[1::2].tolist() == odd.qnames().tolist()
+
+
+def test_loci_set_algebra_matches_oracle():
+    loci = {"+": {3, 9, 40, 41, 42, 43, 44, 45, 46, 47, 49, 60, 61, 62, 63, 64, 65, 66, 67, 68}, "-": {1, 5, 30}, "*": {7}}
+    assert engine.merge_consecutive_indels(loci) == orc.merge_consecutive_indels(loci)
+    assert engine.transpose_loci(loci, 70) == orc.transpose_loci(loci, 70)
+
+
+def test_strand_table_from_histogram_rows():
+    alleles, golden = load_case("kat")
+    a, g = alleles["control"], golden["alleles"]["control"]
+    loci = [set(s) for s in g["mutation_loci"]]
+    hist = np.zeros((10, 6), dtype=np.int32)
+    for row, s in zip(a["sample"]["rows"], a["sample"]["strands"]):
+        for i, tok in enumerate(row.split(",")):
+            for j, op in enumerate("+-*"):
+                if tok.startswith(op):
+                    hist[4 + j + (0 if s == "+" else 3), i] += 1
+    assert {str(i): v for i, v in engine.strand_table(hist, loci).items()} == g["strand_counts"]

@@ -1,0 +1,147 @@
+"""Pin the oracle (oracle/dajin2_oracle.py) to the outputs of the real reference stored under tests/golden/
+and to the known-answer tests the reference's own test-suite holds for this path."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import dajin2_oracle as orc
+from tests.helpers import SINGLE_CASES, golden_loci, golden_score, load_case, sparse_rows
+
+FAST = ["kat", "fixture_flox100", "tp_L1000_N1200_r9", "inv_L2724_N300"]
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES)
+def test_histogram_and_match_score(name):
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        g = golden["alleles"][aname]
+        L = len(a["sequence"])
+        if "count_sample" in g:
+            hist = orc.count_indels(a["sample"]["rows"], L)
+            assert hist == g["count_sample"]
+            norm = orc.normalize_indels(hist)
+            for op, vals in g["norm_sample"].items():
+                assert [float(x).hex() for x in norm[op]] == vals
+            assert orc.count_indels(a["control"]["rows"], L) == g["count_control"]
+        assert [orc.calc_match(r) for r in a["sample"]["rows"]] == g["calc_match"]
+        got = orc.count_strand_of_indels(a["sample"]["rows"], a["sample"]["strands"], golden_loci(g))
+        assert {str(i): v for i, v in got.items()} == g["strand_counts"]
+
+
+@pytest.mark.parametrize("name", [n for n in FAST if n != "kat"])
+def test_mutation_loci(name):
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        g = golden["alleles"][aname]
+        L = len(a["sequence"])
+        ns = orc.normalize_indels(orc.count_indels(a["sample"]["rows"], L))
+        nc = orc.normalize_indels(orc.count_indels(a["control"]["rows"], L))
+        loci = orc.extract_mutation_loci(a["sample"]["rows"], a["sample"]["strands"], a["sequence"], ns, nc,
+                                         a.get("knockin"))
+        assert ["".join(sorted(s)) for s in loci] == g["mutation_loci"]
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES)
+def test_scores_and_rows(name):
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        g = golden["alleles"][aname]
+        loci = golden_loci(g)
+        score = orc.make_score(a["sample"]["rows"], a["control"]["rows"], loci, a.get("knockin") or set())
+        assert {str(i): {k: float(v).hex() for k, v in d.items()} for i, d in enumerate(score) if d} == g["make_score"]
+        assert score == golden_score(g, len(loci))
+        assert sparse_rows(orc.annotate_score(a["sample"]["rows"], score, loci)) == g["rows_sample"]
+        assert sparse_rows(orc.annotate_score(a["control"]["rows"], score, loci, True)) == g["rows_control"]
+
+
+@pytest.mark.parametrize("name", FAST)
+def test_return_labels(name):
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        g = golden["alleles"][aname]
+        if "return_labels" not in g:
+            continue
+        loci = golden_loci(g)
+        score = golden_score(g, len(loci))
+        xs = list(orc.annotate_score(a["sample"]["rows"], score, loci))
+        xc = list(orc.annotate_score(a["control"]["rows"], score, loci, True))
+        strands = a["sample"]["strands"]
+        strand_all = {"+": strands.count("+"), "-": strands.count("-")}
+        assert orc.return_labels(xs, xc, strands, strand_all) == g["return_labels"]
+
+
+def test_flox_like_multi_allele():
+    alleles, golden = load_case("flox_like")
+    for aname, a in alleles.items():
+        g = golden["alleles"][aname]
+        L = len(a["sequence"])
+        assert orc.count_indels(a["sample"]["rows"], L) == g["count_sample"]
+        ns = orc.normalize_indels(orc.count_indels(a["sample"]["rows"], L))
+        nc = orc.normalize_indels(orc.count_indels(a["control"]["rows"], L))
+        loci = orc.extract_mutation_loci(a["sample"]["rows"], a["sample"]["strands"], a["sequence"], ns, nc,
+                                         a.get("knockin"))
+        assert ["".join(sorted(s)) for s in loci] == g["mutation_loci"]
+        score = orc.make_score(a["sample"]["rows"], a["control"]["rows"], loci, a.get("knockin") or set())
+        assert score == golden_score(g, L)
+        assert sparse_rows(orc.annotate_score(a["sample"]["rows"], score, loci)) == g["rows_sample"]
+    records = {
+        aname: [{"QNAME": q, "MIDSV": r, "STRAND": s} for q, r, s in
+                zip(a["sample"]["qnames"], a["sample"]["rows"], a["sample"]["strands"])]
+        for aname, a in alleles.items()
+    }
+    classif = orc.classify_alleles(records)
+    assert [[c["QNAME"], c["ALLELE"]] for c in classif] == golden["classify"]
+
+
+# --- known-answer tests restated from the reference's own test-suite ---------------------------------------
+
+
+def test_kat_is_n_token():  # tests/src/utils/test_midsv_handler.py:12-27
+    assert orc.is_n_token("=N") and orc.is_n_token("=n") and orc.is_n_token("+A|+C|=N") and orc.is_n_token("+a|=n")
+    assert not orc.is_n_token("N") and not orc.is_n_token("-N") and not orc.is_n_token("=A") and not orc.is_n_token("+N|=A")
+
+
+def test_kat_calc_match():  # tests/src/classification/test_classification.py:6-18
+    assert orc.calc_match("=A,=C,=G,=T") == 0
+    assert orc.calc_match("=A,+T|=C,=G") == -1
+    assert orc.calc_match("=A,+T|+T|=C,=G") == -2
+    assert orc.calc_match("=A,-C,=G") == -1
+    assert orc.calc_match("=A,*CT,=G") == -1
+    assert orc.calc_match("=A,=c,=g,=T") == -2
+
+
+def test_kat_count_indels_skips_n_and_lowercase():  # tests/.../test_indel_counter.py:22-65
+    rows = ["=A,+C|=N,-G,*TA,=n", "=a,=C,-G,=T,=A"]
+    hist = orc.count_indels(rows, 5)
+    assert hist == {"=": [1, 1, 0, 1, 1], "+": [0, 0, 0, 0, 0], "-": [0, 0, 2, 0, 0], "*": [0, 0, 0, 1, 0]}
+    norm = orc.normalize_indels({"=": [0, 10], "+": [0, 10], "-": [0, 0], "*": [0, 30]})
+    assert norm["+"].tolist() == [0.0, 50.0] and norm["*"].tolist() == [0.0, 75.0] and norm["-"].tolist() == [0.0, 0.0]
+
+
+def test_kat_kmers():  # tests/src/clustering/test_kmer_generator.py:25-39
+    loci = [set(), {"-"}, {"+"}, set()]
+    got = list(orc.mutation_kmers(["=A,-g,+t|t|t|=A,=C"], loci))
+    assert got == [["@,@,@", "@,-g,+t|t|t|=A", "-g,+I=A,@", "@,@,@"]]
+
+
+def test_kat_merge_consecutive_indels():  # tests/.../test_indel_merger.py
+    loci = {"+": set(), "-": {1, 5, 30}, "*": {7}}
+    merged = orc.merge_consecutive_indels(loci)
+    assert merged["-"] == {1, 2, 3, 4, 5, 30} and merged["*"] == {7}
+
+
+def test_kat_labels():  # tests/src/clustering/test_label_updator.py, test_appender.py
+    assert orc.relabel_consecutive([5, 5, 2, 9, 2], start=3) == [3, 3, 4, 5, 4]
+    assert orc.label_percentages([1, 1, 2, 3]) == {1: 50.0, 2: 25.0, 3: 25.0}
+    assert orc.rank_labels_by_percent([7, 3, 3, 3, 9, 9]) == [3, 1, 1, 1, 2, 2]
+
+
+def test_kat_cosine_and_dissimilar():  # tests/.../test_anomaly_detector.py
+    assert orc.cosine_distance([1, 0], [1, 0]) == pytest.approx(0.0, abs=1e-12)
+    assert orc.cosine_distance([0, 0], [1, 1]) == 1.0
+    assert orc.cosine_distance([], []) == 0.0
+    s = np.array([30.0] + [0.0] * 12)
+    c = np.zeros(13)
+    assert orc.is_dissimilar_loci(s, c, 0)
+    assert not orc.is_dissimilar_loci(c, c, 3)
