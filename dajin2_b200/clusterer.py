@@ -303,7 +303,7 @@ def cluster_rows(ids_sample: torch.Tensor, strand_sample: torch.Tensor, rows_sam
     label_of_slot = np.zeros(rs.point_of_slot.shape[0], dtype=np.int32)
     label_of_slot[rs.slots] = final_pts
     labels_d = torch.empty(max(rs.n_rows, 1), dtype=torch.int32, device=dev)
-    _cabi.call("dj_gather_labels", _p(rs.slot_of_row), rs.n_rows, _p(torch.as_tensor(label_of_slot, device=dev)),
-               _p(labels_d), _stream())
+    label_of_slot_d = torch.as_tensor(label_of_slot, device=dev)
+    _cabi.call("dj_gather_labels", _p(rs.slot_of_row), rs.n_rows, _p(label_of_slot_d), _p(labels_d), _stream())
     sizes = np.bincount(final_pts, weights=rs.count, minlength=len(order) + 1)[1:].astype(np.int64)
     return labels_d[: rs.n_rows], {"n_points": len(Xs), "n_control_points": len(Xc), "cluster_sizes": sizes.tolist()}

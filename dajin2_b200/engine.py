@@ -115,13 +115,14 @@ class EncodedReads:
             return []
         dev = self.codes.device
         max_len = 64
+        # keep the argument tensors alive in locals: temporaries would be freed (and aliased) before the launch
+        reads_d = torch.as_tensor(np.asarray(reads, dtype=np.int32), device=dev)
+        loci_d = torch.as_tensor(np.asarray(loci, dtype=np.int32), device=dev)
         while True:
             out = torch.zeros((n, max_len), dtype=torch.uint8, device=dev)
             out_len = torch.zeros(n, dtype=torch.int32, device=dev)
             _cabi.call("dj_fetch_tokens", _p(self.text), _p(self.row_off), _p(self.row_len), _p(self.ckpt),
-                       self.ckpt_pitch, _p(torch.as_tensor(np.asarray(reads, dtype=np.int32), device=dev)),
-                       _p(torch.as_tensor(np.asarray(loci, dtype=np.int32), device=dev)), n, _p(out), _p(out_len),
-                       max_len, _stream())
+                       self.ckpt_pitch, _p(reads_d), _p(loci_d), n, _p(out), _p(out_len), max_len, _stream())
             lens = out_len.cpu().numpy()
             if (lens < 0).any():
                 raise RuntimeError("dj_fetch_tokens: token not found")
