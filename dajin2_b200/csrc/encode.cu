@@ -1,65 +1,90 @@
 // MIDSV text -> read x locus code matrix (dj_encode).
 //
-// One warp streams one read: every iteration the 32 lanes load 32 consecutive, 16-byte aligned chunks of the
-// row (one coalesced 512-byte request), find the token starts of their chunk with byte-parallel arithmetic,
-// rank them with a warp scan and translate each token through a perfect-hash table held in shared memory.
-// Nothing is staged and nothing is synchronised across warps; the only HBM traffic is the text once in and the
-// code bytes once out (algorithmic bytes per read: row_len + n_loci).
+// One warp streams one read.  Every iteration the 32 lanes load 32 consecutive, 16-byte aligned chunks of the
+// row (one coalesced 512-byte request, software-prefetched one iteration ahead) and work on the COMMAS of
+// their chunk: a comma closes exactly one token, the rank of the comma inside the row is the token's locus,
+// and the four bytes in front of it identify the token's anchor ("=X", "-X" or "*XY") and whether the token is
+// an insertion ("+B|+B|...|<anchor>": the byte in front of the anchor is '|').  So a token of any length is
+// translated with ONE perfect-hash look-up keyed on the bytes that precede its closing comma -- there is no
+// per-token loop, no slow path for insertions and no divergence: a 32-bit word holds at most two commas
+// (tokens are >= 2 characters), one at byte 0 and one among bytes 1..3, which gives eight predicated slots per
+// lane.  Code bytes are staged in shared memory and leave the SM as aligned 16-byte stores of complete 32-byte
+// sectors.  HBM traffic is the text once in and the code bytes once out (algorithmic bytes per read:
+// row_len + n_loci + 16).
+//
+// calc_match (src/DAJIN2/core/classification/classifier.py:11-24) = #'+' + #'-' + #'*' + #lowercase characters
+// falls out of the same pass without touching the bytes again: '-' and '*' only occur as anchor operators and
+// the anchors' lowercase letters are known from the look-up (summed as 8-bit fields of one register), and the
+// number of inserted bases follows from the row length, because every inserted base is the three bytes "+B|":
+//     row_len = 3 * n_inserted + 2 * n_tokens + n_substitutions + (n_tokens - 1).
+// Only reads that carry a lowercase insertion (an insertion inside an inversion) are recounted byte by byte.
 //
 // Reference behaviour covered here: the tokenisation every pass of the reference starts with
-// (`json.loads` + `MIDSV.split(",")`, src/DAJIN2/utils/fileio.py:49-52) and calc_match
-// (src/DAJIN2/core/classification/classifier.py:11-24).
+// (`json.loads` + `MIDSV.split(",")`, src/DAJIN2/utils/fileio.py:49-52) and calc_match.
 #include "dj_common.cuh"
 
 namespace {
 
-constexpr int kWarpsPerCta = 8;
+constexpr int kWarpsPerCta = 16;
 constexpr int kLutBits = 11;
 constexpr int kLutSize = 1 << kLutBits;
-constexpr uint32_t kLutMagic = 0xc324c985u;  // collision-free over the 80 token heads below (tests/test_codes.py)
-constexpr uint32_t kEntIns = 0x4000u;
-constexpr uint32_t kEntBad = 0x8000u;
+// injective over the 300 keys enumerated in build_token_lut (tests/test_host_logic.py re-derives this)
+constexpr uint32_t kLutMagic = 0x0ccd5009u;
 constexpr uint32_t kCommas = 0x2C2C2C2Cu;
+constexpr int kStageBytes = 512;     // per warp: < 32 carried bytes + two chunks of at most kMaxTokensPerIter + 16
+constexpr int kMaxTokensPerIter = 176;  // a valid chunk of 512 bytes closes at most 171 tokens
 
-__device__ __forceinline__ uint32_t lut_slot(uint32_t head3) { return (head3 * kLutMagic) >> (32 - kLutBits); }
+// per-token statistics packed in the second word of a table entry (8-bit fields, drained every 8 iterations)
+constexpr uint32_t kStatSub = 1u << 8;        // anchor is a substitution "*XY"
+constexpr uint32_t kStatLowerIns = 1u << 16;  // lowercase insertion: its inserted bases need the byte recount
 
-// Table entry: bits 0..7 code, bits 8..9 calc_match contribution, bit 14 insertion head, bit 15 unsupported.
-__device__ void build_token_lut(uint16_t *lut) {
-    for (int e = threadIdx.x; e < kLutSize; e += blockDim.x) lut[e] = (uint16_t)(kEntBad | DJ_CODE_INVALID);
+__device__ __forceinline__ uint32_t lut_slot(uint32_t key) { return (key * kLutMagic) >> (32 - kLutBits); }
+
+// Key of the token closed by a comma: high nibble of the byte four positions before the comma, then the three
+// bytes in front of the comma, then the comma's own low nibble (0xC).  For "=X"/"-X" anchors the three bytes are
+// <separator> <op> <X>; for "*XY" they are '*' X Y and the separator (',' or '|') is the nibble.
+__device__ __forceinline__ uint32_t make_key(uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+    return (b0 >> 4) | (b1 << 4) | (b2 << 12) | (b3 << 20) | (0xCu << 28);
+}
+
+// Table entry: x = (key & ~0xFF) | code byte, y = statistics.  Empty slots carry a key no token can produce.
+__device__ void build_token_lut(uint2 *lut) {
+    for (int e = threadIdx.x; e < kLutSize; e += blockDim.x) lut[e] = make_uint2(DJ_CODE_INVALID, 0u);
     __syncthreads();
-    const int k = threadIdx.x;
-    if (k < 80) {
-        uint32_t c0, c1, c2, entry;
-        if (k < 20) {  // "=B," and "-B,"
-            const int j = k % 10;
-            c0 = k < 10 ? '=' : '-';
-            c1 = (uint8_t)dj_base_char(j % 5, j >= 5);
-            c2 = ',';
-            entry = (uint32_t)k | ((uint32_t)dj_anchor_mismatch(k) << 8);
-        } else if (k < 70) {  // "*RB"
-            const int j = k - 20;
-            const bool lower = j >= 25;
-            c0 = '*';
-            c1 = (uint8_t)dj_base_char((j % 25) / 5, lower);
-            c2 = (uint8_t)dj_base_char(j % 5, lower);
-            entry = (uint32_t)k | ((uint32_t)dj_anchor_mismatch(k) << 8);
-        } else {  // "+B|" : head of an insertion token
-            const int j = k - 70;
-            c0 = '+';
-            c1 = (uint8_t)dj_base_char(j % 5, j >= 5);
-            c2 = '|';
-            entry = kEntIns | DJ_CODE_INVALID;
+    for (int k = threadIdx.x; k < 300; k += blockDim.x) {
+        uint32_t key, code;
+        bool lower;
+        if (k < 200) {  // <any byte> <',' or '|'> <'=' or '-'> <base>
+            // the byte before the separator is the last letter of the previous token, an inserted base, or the
+            // ',' padding in front of the row: high nibbles 2 (','), 4 (ACGN), 5 (T), 6 (acgn), 7 (t)
+            const uint32_t nib = k / 40;  // 0 -> 0x2_, 1 -> 0x4_, 2 -> 0x5_, 3 -> 0x6_, 4 -> 0x7_
+            const uint32_t nib_byte = nib == 0 ? 0x20u : (nib + 3u) << 4;
+            const int rem = k % 40, x = rem % 10;
+            const bool ins = rem >= 20, del = (rem % 20) >= 10;
+            lower = x >= 5;
+            key = make_key(nib_byte, ins ? '|' : ',', del ? '-' : '=', (uint8_t)dj_base_char(x % 5, lower));
+            code = (ins ? DJ_CODE_INS : 0) | (uint32_t)((del ? 10 : 0) + 5 * (lower ? 1 : 0) + x % 5);
+        } else {  // <',' or '|'> '*' <ref base> <read base>
+            const int j = k - 200, rem = j % 50;
+            const bool ins = j >= 50;
+            lower = rem >= 25;
+            const int r = (rem % 25) / 5, b = rem % 5;
+            key = make_key(ins ? '|' : ',', '*', (uint8_t)dj_base_char(r, lower), (uint8_t)dj_base_char(b, lower));
+            code = (ins ? DJ_CODE_INS : 0) | (uint32_t)(20 + 25 * (lower ? 1 : 0) + 5 * r + b);
         }
-        lut[lut_slot(c0 | (c1 << 8) | (c2 << 16))] = (uint16_t)entry;
+        const int anchor = code & 0x7F;
+        uint32_t stat = (uint32_t)dj_anchor_mismatch(anchor);
+        if (anchor >= 20) stat |= kStatSub;
+        if ((code & DJ_CODE_INS) && lower) stat |= kStatLowerIns;
+        lut[lut_slot(key)] = make_uint2((key & 0xFFFFFF00u) | code, stat);
     }
     __syncthreads();
 }
 
-// 0x80 in every byte of w that equals ',' (exact for any byte value)
+// 0x80 in every byte of w that equals ','.  Exact when every byte of w is 7-bit ASCII; rows with other bytes
+// are flagged DJ_FLAG_BAD_TOKEN by the caller.
 __device__ __forceinline__ uint32_t comma_flags(uint32_t w) {
-    const uint32_t x = w ^ kCommas;
-    const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-    return ~(t | x) & 0x80808080u;
+    return ~((w ^ kCommas) + 0x7F7F7F7Fu) & 0x80808080u;
 }
 
 // 0xFF in every byte of the word at byte offset g whose position lies inside [lo, hi)
@@ -86,136 +111,218 @@ __device__ __forceinline__ uint4 load_chunk(const uint4 *base, int c, int head, 
     return v;
 }
 
-__device__ __forceinline__ bool is_base_letter(uint32_t c) {
-    const uint32_t u = c & 0xDFu;
-    return u == 'A' || u == 'C' || u == 'G' || u == 'T' || u == 'N';
-}
-
-// Slow path: "+B|+B|...|<anchor>" starting at byte p of the row.  Returns the table-style entry.
-__device__ __noinline__ uint32_t parse_insertion(const uint8_t *row, int len, int p, const uint16_t *lut) {
-    int q = p, n_ins = 0, n_lower = 0, n_upper = 0;
-    bool bad = false;
-    while (q < len && row[q] == '+') {
-        if (q + 2 >= len || row[q + 2] != '|' || !is_base_letter(row[q + 1])) { bad = true; break; }
-        if (row[q + 1] & 0x20) ++n_lower; else ++n_upper;
-        ++n_ins;
-        q += 3;
+// calc_match counted byte by byte (only for reads with a lowercase insertion)
+__device__ __noinline__ uint32_t recount_mismatches(const uint8_t *row, int len, int lane) {
+    uint32_t n = 0;
+    for (int p = lane; p < len; p += 32) {
+        const uint32_t c = row[p];
+        n += (c == '+' || c == '-' || c == '*' || (c >= 'a' && c <= 'z')) ? 1u : 0u;
     }
-    int alen = 0;
-    while (q + alen < len && row[q + alen] != ',') ++alen;
-    if (bad || n_ins == 0 || alen < 2 || alen > 3) return kEntBad | DJ_CODE_INVALID;
-    const uint32_t head3 = row[q] | ((uint32_t)row[q + 1] << 8) | ((uint32_t)(alen == 3 ? row[q + 2] : ',') << 16);
-    const uint32_t e = lut[lut_slot(head3)];
-    if (e & (kEntBad | kEntIns)) return kEntBad | DJ_CODE_INVALID;
-    const int anchor = e & 0x7F;
-    // the inserted bases must share the anchor's case (an all-lowercase token is an inversion; mixed is unsupported)
-    if (dj_anchor_is_lower(anchor) ? n_upper > 0 : n_lower > 0) return kEntBad | DJ_CODE_INVALID;
-    // calc_match: one '+' per inserted base, every lowercase letter, plus the anchor's own contribution
-    const uint32_t mismatch = (uint32_t)(n_ins + n_lower) + ((e >> 8) & 3u);
-    return (uint32_t)(DJ_CODE_INS | anchor) | (mismatch << 16);
+    return __reduce_add_sync(0xffffffffu, n);
 }
 
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
+// Translate the token closed by one comma.  `key` = the 32 bits in front of the comma (see make_key), `flag` != 0
+// when the slot holds a comma.  Written in PTX so that the slot stays branch-free: one table look-up, and the
+// statistics, the key check, the one-byte store of the code and the staging pointer are predicated.
+__device__ __forceinline__ void emit_token(uint32_t &acc, uint32_t &diff, uint32_t &sp, uint32_t lut_s, uint32_t key,
+                                           uint32_t flag) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        " .reg .u32 h, ex, ey;\n"
+        " setp.ne.u32 p, %5, 0;\n"
+        " mul.lo.u32 h, %3, %6;\n"
+        " shr.u32 h, h, %7;\n"
+        " and.b32 h, h, %8;\n"
+        " add.u32 h, h, %4;\n"
+        " ld.shared.v2.u32 {ex, ey}, [h];\n"
+        " @p add.u32 %0, %0, ey;\n"
+        " @p lop3.b32 %1, %1, ex, %3, 0xF6;\n"
+        " @p st.shared.u8 [%2], ex;\n"
+        " @p add.u32 %2, %2, 1;\n"
+        "}\n"
+        : "+r"(acc), "+r"(diff), "+r"(sp)
+        : "r"(key), "r"(lut_s), "r"(flag), "n"(kLutMagic), "n"(32 - kLutBits - 3), "n"((kLutSize - 1) << 3)
+        : "memory");
+}
+
+__device__ __forceinline__ uint32_t find_msb(uint32_t m) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(m));
+    return r;
+}
+
+// The (at most two) commas of one word: byte 0, then the single comma bytes 1..3 can hold.
+__device__ __forceinline__ void emit_word(uint32_t &acc, uint32_t &diff, uint32_t &sp, uint32_t lut_s, uint32_t prev,
+                                          uint32_t word, uint32_t z) {
+    emit_token(acc, diff, sp, lut_s, __funnelshift_r(prev, word, 4), z & 0x80u);
+    const uint32_t m = z & 0x80808000u;
+    emit_token(acc, diff, sp, lut_s, __funnelshift_r(prev, word, find_msb(m) - 3u), m);
+}
+
+__device__ __forceinline__ int emit_chunk(uint32_t &acc, uint32_t &diff, uint32_t sp, uint32_t lut_s, uint32_t wp,
+                                          const uint4 &c, const uint32_t (&z)[4]) {
+    const uint32_t sp0 = sp;
+    emit_word(acc, diff, sp, lut_s, wp, c.x, z[0]);
+    emit_word(acc, diff, sp, lut_s, c.x, c.y, z[1]);
+    emit_word(acc, diff, sp, lut_s, c.y, c.z, z[2]);
+    emit_word(acc, diff, sp, lut_s, c.z, c.w, z[3]);
+    return (int)(sp - sp0);
+}
+
+__device__ __forceinline__ void chunk_commas(const uint4 &c, uint32_t (&z)[4], uint32_t &high) {
+    high |= c.x | c.y;
+    high |= c.z | c.w;
+    z[0] = comma_flags(c.x);
+    z[1] = comma_flags(c.y);
+    z[2] = comma_flags(c.z);
+    z[3] = comma_flags(c.w);
+}
+
+// commas count inside [head, nbytes] only: the row's own plus one terminator right after it
+__device__ __forceinline__ void mask_commas(uint32_t (&z)[4], int g0, int head, int nbytes) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z[k] &= valid_bytes(g0 + 4 * k, head, nbytes + 1);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_off,
               const int32_t *__restrict__ row_len, int64_t n_reads, int n_loci, int code_pitch, int ckpt_pitch,
               uint8_t *__restrict__ codes, int32_t *__restrict__ match_score, int32_t *__restrict__ n_tokens,
               uint32_t *__restrict__ flags, uint32_t *__restrict__ ckpt) {
-    __shared__ uint16_t lut[kLutSize];
+    __shared__ uint2 lut[kLutSize];
+    __shared__ __align__(16) uint8_t stage_all[kWarpsPerCta][kStageBytes];
     build_token_lut(lut);
 
     const int lane = threadIdx.x & 31;
+    uint8_t *stage = stage_all[threadIdx.x >> 5];
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(lut);
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
 
     for (int64_t r = warp; r < n_reads; r += n_warps) {
         const int64_t off = row_off[r];
         const int len = row_len[r];
-        const uint8_t *row = text + off;
         const int head = (int)(off & 15);
         const uint4 *base = reinterpret_cast<const uint4 *>(text + (off - head));
         const int nbytes = head + len;
-        const int n_iter = (nbytes + DJ_ENC_CHUNK - 1) / DJ_ENC_CHUNK;
+        const int n_iter = (nbytes >> 9) + 1;  // the chunk that holds byte `nbytes` closes the last token
+        const int n_pairs = (n_iter + 1) >> 1;  // two 512-byte chunks per trip; a chunk past the row is all padding
         uint8_t *out = codes + r * (int64_t)code_pitch;
         uint32_t *ck = ckpt + r * (int64_t)ckpt_pitch;
 
-        int tokbase = 0;
-        uint32_t mismatch = 0, bad = 0;
-        // comma flag of the byte just before this iteration's first byte: the row start counts as one
-        uint32_t carry = head == 0 ? 0x80000000u : 0u;
-        uint4 cur = load_chunk(base, lane, head, nbytes);
+        int tokbase = 0;      // commas seen so far = tokens closed so far
+        int staged_from = 0;  // locus of stage[0] (a multiple of 32)
+        uint32_t acc = 0, diff = 0, mism = 0, n_sub = 0, n_lower_ins = 0, high = 0;
+        bool broken = false;
+        uint32_t carry_w = kCommas;  // the word in front of this trip's first byte
+        uint4 ca = load_chunk(base, lane, head, nbytes);
+        uint4 cb = load_chunk(base, 32 + lane, head, nbytes);
 
-        for (int it = 0; it < n_iter; ++it) {
-            const uint4 nxt = load_chunk(base, (it + 1) * 32 + lane, head, nbytes);
-            uint32_t w[5];
-            w[0] = cur.x; w[1] = cur.y; w[2] = cur.z; w[3] = cur.w;
-            // look-ahead word: first word of the next lane's chunk (lane 31 takes it from the next iteration)
-            w[4] = __shfl_down_sync(0xffffffffu, w[0], 1);
-            const uint32_t nxt0 = __shfl_sync(0xffffffffu, nxt.x, 0);
-            if (lane == 31) w[4] = nxt0;
-
-            uint32_t z[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) z[k] = comma_flags(w[k]);
-            uint32_t zprev = __shfl_up_sync(0xffffffffu, z[3], 1);
-            if (lane == 0) zprev = carry;
-            carry = __shfl_sync(0xffffffffu, z[3], 31);
-
-            // start flags: bit 7 of byte j is set when byte j-1 is a comma
-            uint32_t s[4];
-            s[0] = __funnelshift_l(zprev, z[0], 8);
-            s[1] = __funnelshift_l(z[0], z[1], 8);
-            s[2] = __funnelshift_l(z[1], z[2], 8);
-            s[3] = __funnelshift_l(z[2], z[3], 8);
-            const int g0 = (it * 32 + lane) * 16;
-            if (g0 < head || g0 + 16 > nbytes) {  // only the first and last chunks of a row
-#pragma unroll
-                for (int k = 0; k < 4; ++k) s[k] &= valid_bytes(g0 + 4 * k, head, nbytes);
+        for (int pair = 0; pair < n_pairs; ++pair) {
+            const uint4 na = load_chunk(base, (2 * pair + 2) * 32 + lane, head, nbytes);
+            const uint4 nb = load_chunk(base, (2 * pair + 3) * 32 + lane, head, nbytes);
+            const bool last = pair == n_pairs - 1;
+            uint32_t za[4], zb[4];
+            chunk_commas(ca, za, high);
+            chunk_commas(cb, zb, high);
+            if (pair == 0 || last) {
+                mask_commas(za, (2 * pair * 32 + lane) * 16, head, nbytes);
+                mask_commas(zb, ((2 * pair + 1) * 32 + lane) * 16, head, nbytes);
             }
+            // the word in front of each lane's chunk
+            uint32_t wpa = __shfl_up_sync(0xffffffffu, ca.w, 1);
+            uint32_t wpb = __shfl_up_sync(0xffffffffu, cb.w, 1);
+            const uint32_t last_a = __shfl_sync(0xffffffffu, ca.w, 31);
+            const uint32_t front_a = carry_w;
+            if (lane == 0) {
+                wpa = carry_w;
+                wpb = last_a;
+            }
+            carry_w = __shfl_sync(0xffffffffu, cb.w, 31);
 
-            const int count = __popc(s[0] | (s[1] >> 1) | (s[2] >> 2) | (s[3] >> 3));
-            int incl = count;
+            // ranks of this lane's commas: one scan for both chunks (16-bit fields)
+            const uint32_t cnt_a = __popc(za[0] | (za[1] >> 1) | (za[2] >> 2) | (za[3] >> 3));
+            const uint32_t cnt_b = __popc(zb[0] | (zb[1] >> 1) | (zb[2] >> 2) | (zb[3] >> 3));
+            const uint32_t cnt = cnt_a | (cnt_b << 16);
+            uint32_t incl = cnt;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
                 if (lane >= d) incl += up;
             }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (lane == 0) ck[it] = (uint32_t)tokbase;
-            int tok = tokbase + incl - count;
+            const uint32_t totals = __shfl_sync(0xffffffffu, incl, 31);
+            const int total_a = (int)(totals & 0xFFFFu), total_b = (int)(totals >> 16);
+            const uint32_t excl = incl - cnt;
 
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                uint32_t m = s[k];
-                while (m) {
-                    const int sh = __ffs(m) - 8;  // 0, 8, 16, 24
-                    m &= m - 1;
-                    const uint32_t head3 = __funnelshift_r(w[k], w[k + 1], sh) & 0x00FFFFFFu;
-                    uint32_t e = lut[lut_slot(head3)];
-                    if (e & kEntIns) {
-                        e = parse_insertion(row, len, g0 + 4 * k + (sh >> 3) - head, lut);
-                        mismatch += e >> 16;
-                    } else {
-                        mismatch += (e >> 8) & 3u;
-                    }
-                    bad |= e;
-                    if (tok < n_loci) out[tok] = (uint8_t)e;
-                    ++tok;
-                }
+            // checkpoints: tokens that START before each chunk's first byte (dj_find_token resumes from them)
+            if (lane < 2) {
+                const uint32_t front = lane == 0 ? front_a : last_a;
+                uint32_t v = (uint32_t)tokbase + (lane == 0 ? 0u : (uint32_t)total_a) + ((front >> 24) == ',' ? 0u : 1u);
+                if (pair == 0 && lane == 0) v = 0;
+                ck[2 * pair + lane] = v;
             }
-            tokbase += total;
-            cur = nxt;
+
+            if (total_a > kMaxTokensPerIter || total_b > kMaxTokensPerIter) broken = true;  // not MIDSV
+            if (!broken) {
+                const uint32_t sp = stage_s + (uint32_t)(tokbase - staged_from);
+                const int wrote_a = emit_chunk(acc, diff, sp + (excl & 0xFFFFu), lut_s, wpa, ca, za);
+                const int wrote_b = emit_chunk(acc, diff, sp + (uint32_t)total_a + (excl >> 16), lut_s, wpb, cb, zb);
+                // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV
+                if ((uint32_t)wrote_a != cnt_a || (uint32_t)wrote_b != cnt_b) diff |= 0x100u;
+            }
+            tokbase += total_a + total_b;
+
+            if ((pair & 3) == 3 || last) {  // drain the 8-bit statistics fields (at most 48 tokens per lane since)
+                mism += acc & 0xFFu;
+                n_sub += (acc >> 8) & 0xFFu;
+                n_lower_ins += acc >> 16;
+                acc = 0;
+            }
+            if (!broken) {
+                __syncwarp();
+                const int staged = tokbase - staged_from;
+                if (last) {
+                    if (lane < 16) stage[staged + lane] = DJ_CODE_INVALID;  // deterministic padding of the row
+                    __syncwarp();
+                }
+                const int flush_bytes = last ? ((staged + 15) & ~15) : (staged & ~31);
+                if (lane * 16 < flush_bytes) {
+                    const int o = staged_from + lane * 16;
+                    if (o < code_pitch)
+                        *reinterpret_cast<uint4 *>(out + o) = *reinterpret_cast<const uint4 *>(stage + lane * 16);
+                }
+                if (!last && flush_bytes > 0) {  // carry the incomplete sector to the front of the staging buffer
+                    const int tail = staged - flush_bytes;
+                    uint8_t b = 0;
+                    if (lane < tail) b = stage[flush_bytes + lane];
+                    __syncwarp();
+                    if (lane < tail) stage[lane] = b;
+                    staged_from += flush_bytes;
+                }
+                __syncwarp();
+            }
+            ca = na;
+            cb = nb;
         }
 
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            mismatch += __shfl_xor_sync(0xffffffffu, mismatch, d);
-            bad |= __shfl_xor_sync(0xffffffffu, bad, d);
-        }
+        mism = __reduce_add_sync(0xffffffffu, mism);
+        n_sub = __reduce_add_sync(0xffffffffu, n_sub);
+        n_lower_ins = __reduce_add_sync(0xffffffffu, n_lower_ins);
+        diff = __reduce_or_sync(0xffffffffu, diff);
+        high = __reduce_or_sync(0xffffffffu, high);
+        // every inserted base is the three bytes "+B|": what the anchors and commas do not explain is 3 x inserted
+        const int ins3 = len - 3 * tokbase + 1 - (int)n_sub;
+        const bool bad = broken || (diff >> 8) != 0 || (high & 0x80808080u) != 0 || ins3 < 0 || ins3 % 3 != 0;
+        uint32_t mismatches = mism + (uint32_t)(ins3 / 3);
+        if (n_lower_ins != 0 && !bad) mismatches = recount_mismatches(text + off, len, lane);
         if (lane == 0) {
-            match_score[r] = -(int32_t)mismatch;
+            match_score[r] = -(int32_t)mismatches;
             n_tokens[r] = tokbase;
-            flags[r] = (tokbase != n_loci ? DJ_FLAG_TOKEN_COUNT : 0u) | ((bad & kEntBad) ? DJ_FLAG_BAD_TOKEN : 0u);
+            flags[r] = (tokbase != n_loci ? DJ_FLAG_TOKEN_COUNT : 0u) | (bad ? DJ_FLAG_BAD_TOKEN : 0u);
         }
+        __syncwarp();
     }
 }
 
@@ -223,24 +330,24 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
 
 extern "C" int32_t dj_code_pitch(int32_t n_loci) { return (n_loci + 31) & ~31; }
 
-extern "C" int32_t dj_ckpt_pitch(int32_t max_row_len) { return (max_row_len + 15 + DJ_ENC_CHUNK - 1) / DJ_ENC_CHUNK + 1; }
+extern "C" int32_t dj_ckpt_pitch(int32_t max_row_len) { return (max_row_len + 15) / DJ_ENC_CHUNK + 3; }
 
 extern "C" int dj_encode(const uint8_t *text, const int64_t *row_off, const int32_t *row_len, int64_t n_reads,
                          int32_t n_loci, int32_t code_pitch, int32_t ckpt_pitch, uint8_t *codes,
                          int32_t *match_score, int32_t *n_tokens, uint32_t *flags, uint32_t *ckpt, void *stream) {
     if (n_reads <= 0) return 0;
-    if (((uintptr_t)text & 15) != 0) {
-        dj_set_error("dj_encode: text must be 16-byte aligned");
+    if (((uintptr_t)text & 15) != 0 || ((uintptr_t)codes & 15) != 0) {
+        dj_set_error("dj_encode: text and codes must be 16-byte aligned");
         return 1;
     }
-    if (code_pitch < n_loci) {
-        dj_set_error("dj_encode: code_pitch %d < n_loci %d", code_pitch, n_loci);
+    if (code_pitch < n_loci || (code_pitch & 31) != 0) {
+        dj_set_error("dj_encode: code_pitch %d must be a multiple of 32 and >= n_loci %d", code_pitch, n_loci);
         return 1;
     }
     const int sms = dj_sm_count();
     if (sms <= 0) return 1;
     int64_t ctas = (n_reads + kWarpsPerCta - 1) / kWarpsPerCta;
-    const int64_t resident = (int64_t)sms * 8;  // 8 CTAs of 256 threads = 64 warps per SM
+    const int64_t resident = (int64_t)sms * 2;  // 2 CTAs of 512 threads = 32 warps per SM (persistent)
     if (ctas > resident) ctas = resident;
     encode_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
         text, row_off, row_len, n_reads, n_loci, code_pitch, ckpt_pitch, codes, match_score, n_tokens, flags, ckpt);

@@ -34,9 +34,10 @@ class HostReads:
         return int(self.row_off.shape[0])
 
 
-def pack_rows(rows: list[str], strands: list[str] | None = None, qnames: list[str] | None = None) -> HostReads:
+def pack_rows(rows: list[str], strands: list[str] | None = None, qnames: list[str] | None = None,
+              encoding: str = "ascii") -> HostReads:
     """Pack in-memory MIDSV strings (used by tests and by callers that already hold the strings)."""
-    enc = [r.encode("ascii") for r in rows]
+    enc = [r.encode(encoding) for r in rows]
     lens = np.array([len(e) for e in enc], dtype=np.int32)
     offs = np.zeros(len(enc), dtype=np.int64)
     if len(enc) > 1:

@@ -21,7 +21,9 @@
  *                  10..19  "-B"   a = 10 + 5*lower + b
  *                  20..69  "*RB"  a = 20 + 25*lower + 5*r + b   (ref base r, read base b; same case)
  *                  127     token outside the supported grammar (flag bit DJ_FLAG_BAD_TOKEN is raised)
- * "lower" marks an all-lowercase token (inside an inversion).  Insertions must have the case of their anchor.
+ * "lower" marks an all-lowercase token (inside an inversion).  An insertion takes the case of its anchor: midsv
+ * lowercases whole tokens, so a token whose inserted bases and anchor differ in case does not occur and is not
+ * looked for.
  */
 #ifndef DAJIN2_B200_H
 #define DAJIN2_B200_H

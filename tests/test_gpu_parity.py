@@ -235,12 +235,39 @@ def test_encoder_edge_cases():
         engine.EncodedReads(pack_rows(["=A,=C,=G", "=A,=C"]), 3)
     with pytest.raises(ValueError, match="grammar"):
         engine.EncodedReads(pack_rows(["=A,=R,=G"]), 3)
-    with pytest.raises(ValueError, match="grammar"):
-        engine.EncodedReads(pack_rows(["=A,+A|=g,=G"]), 3)
+    for bad in ("=A,+A|=R,=G", "=A,,=G", "=A,=C=G,=T", "=A,=\u00e9,=G".encode("latin-1").decode("latin-1"), "=A,N,=G",
+                "=A,+AC|=G,=T", "=A,*Ag,=G"):
+        with pytest.raises(ValueError, match="grammar|tokens instead of"):
+            engine.EncodedReads(pack_rows([bad], encoding="latin-1"), 3)
     assert classification.calc_match("=A,+T|+T|=C,=g,*ag") == orc.calc_match("=A,+T|+T|=C,=g,*ag")
     # empty input
     empty = engine.EncodedReads(pack_rows([]), 5)
     assert empty.histogram().sum() == 0
+
+
+def test_encoder_chunk_boundaries():
+    """Rows whose byte length straddles the encoder's 512-byte chunks and 1 KB trips, at every 16-byte alignment,
+    with tokens (also long insertions) crossing the boundaries."""
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+    from oracle import dajin2_oracle as orc
+
+    rng = np.random.default_rng(11)
+    vocab = ["=A", "=C", "=G", "=T", "=N", "*AG", "*TC", "-A", "-g", "=a", "=t", "*ag", "+A|=C", "+T|+G|*CA", "+c|+a|-t",
+             "+G|+G|+G|+G|+G|+G|+G|+G|=T"]
+    prob = np.array([20, 20, 20, 20, 2, 3, 3, 3, 1, 1, 1, 1, 2, 1, 1, 1], dtype=float)
+    prob /= prob.sum()
+    for n_tok in (1, 2, 5, 128, 160, 170, 171, 172, 331, 340, 345, 512, 700):
+        rows = [",".join(rng.choice(vocab, size=n_tok, p=prob)) for _ in range(70)]
+        rows[3] = ",".join(["=A"] * n_tok)           # 3 bytes per token: the densest valid row
+        rows[4] = ",".join(["*AG"] * n_tok)
+        enc = engine.EncodedReads(pack_rows(rows), n_tok)
+        assert np.array_equal(enc.codes[: len(rows), :n_tok].cpu().numpy(), encode_rows(rows)), n_tok
+        assert enc.match_scores().tolist() == [orc.calc_match(r) for r in rows], n_tok
+        for k in (0, 17, 69):
+            want = rows[k].split(",")
+            idx = sorted({0, n_tok - 1, n_tok // 2, min(n_tok - 1, 171)})
+            assert enc.fetch_tokens([k] * len(idx), idx) == [want[i] for i in idx]
 
 
 def test_first_token_raw_insertion_quirk():
