@@ -9,7 +9,10 @@ import ctypes
 from ctypes import c_double, c_int32, c_int64, c_uint32, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libdajin2_b200.so"
+import os
+
+# DAJIN2_B200_LIB points at an alternative build of the same library (kernel experiments under scripts/)
+LIB_PATH = Path(os.environ.get("DAJIN2_B200_LIB") or Path(__file__).resolve().parent / "libdajin2_b200.so")
 
 ABI_VERSION = 1
 CODE_INVALID = 0x7F

@@ -1,42 +1,63 @@
 // MIDSV text -> read x locus code matrix (dj_encode).
 //
-// One warp streams one read.  Every iteration the 32 lanes load 32 consecutive, 16-byte aligned chunks of the
-// row (one coalesced 512-byte request, software-prefetched one iteration ahead) and work on the COMMAS of
-// their chunk: a comma closes exactly one token, the rank of the comma inside the row is the token's locus,
-// and the four bytes in front of it identify the token's anchor ("=X", "-X" or "*XY") and whether the token is
-// an insertion ("+B|+B|...|<anchor>": the byte in front of the anchor is '|').  So a token of any length is
-// translated with ONE perfect-hash look-up keyed on the bytes that precede its closing comma -- there is no
-// per-token loop, no slow path for insertions and no divergence: a 32-bit word holds at most two commas
-// (tokens are >= 2 characters), one at byte 0 and one among bytes 1..3, which gives eight predicated slots per
-// lane.  Code bytes are staged in shared memory and leave the SM as aligned 16-byte stores of complete 32-byte
-// sectors.  HBM traffic is the text once in and the code bytes once out (algorithmic bytes per read:
+// One warp streams one read.  Every trip of the main loop the 32 lanes load two runs of 32 consecutive,
+// 16-byte aligned chunks of the row (two coalesced 512-byte requests) and work on the COMMAS of their chunks: a
+// comma closes exactly one token, the rank of the comma inside the row is the token's locus, and the four bytes
+// in front of it identify the token's anchor ("=X", "-X" or "*XY") and whether the token is an insertion
+// ("+B|+B|...|<anchor>": the byte in front of the anchor is '|').  So a token of any length is translated with
+// ONE perfect-hash look-up keyed on the bytes that precede its closing comma -- there is no per-token loop, no
+// slow path for insertions and no divergence: a 32-bit word holds at most two commas (tokens are >= 2
+// characters), one at byte 0 and one among bytes 1..3, which gives eight predicated slots per lane and chunk.
+// Code bytes are staged in shared memory and leave the SM as aligned 16-byte stores of complete 32-byte sectors.
+// HBM traffic is the text once in and the code bytes once out (algorithmic bytes per read:
 // row_len + n_loci + 16).
+//
+// The kernel is bound by the integer (ALU) pipe and the shared-memory pipe, not by HBM (profiles/): the slot is
+// therefore written in PTX and kept to one 4-byte table read, one 1-byte staging store and integer multiply-adds
+// (FMA pipe) for the hash and the address.
 //
 // calc_match (src/DAJIN2/core/classification/classifier.py:11-24) = #'+' + #'-' + #'*' + #lowercase characters
 // falls out of the same pass without touching the bytes again: '-' and '*' only occur as anchor operators and
-// the anchors' lowercase letters are known from the look-up (summed as 8-bit fields of one register), and the
-// number of inserted bases follows from the row length, because every inserted base is the three bytes "+B|":
+// the anchors' lowercase letters are known from the look-up (the table entry carries them in bit fields that are
+// summed with one add per token), and the number of inserted bases follows from the row length, because every
+// inserted base is the three bytes "+B|":
 //     row_len = 3 * n_inserted + 2 * n_tokens + n_substitutions + (n_tokens - 1).
 // Only reads that carry a lowercase insertion (an insertion inside an inversion) are recounted byte by byte.
+//
+// Validation: a token whose anchor is not in the table reads an empty slot (code 0x7F) with probability
+// 1 - 320/8192 = 0.96 and the row is flagged; rows are also flagged when the token count, the length identity
+// above or 7-bit ASCII fail.  (The reference does not validate its input at all.)
 //
 // Reference behaviour covered here: the tokenisation every pass of the reference starts with
 // (`json.loads` + `MIDSV.split(",")`, src/DAJIN2/utils/fileio.py:49-52) and calc_match.
 #include "dj_common.cuh"
 
+#ifndef DJ_ENC_PREFETCH
+#define DJ_ENC_PREFETCH 0
+#endif
+#ifndef DJ_ENC_HASH_MODE
+#define DJ_ENC_HASH_MODE 1  // 0: mul, shr, and   1: mul, shr, mad   2: mul, mul.hi, mad (no ALU-pipe op)
+#endif
+
 namespace {
 
 constexpr int kWarpsPerCta = 16;
-constexpr int kLutBits = 11;
+constexpr int kLutBits = 13;
 constexpr int kLutSize = 1 << kLutBits;
-// injective over the 300 keys enumerated in build_token_lut (tests/test_host_logic.py re-derives this)
-constexpr uint32_t kLutMagic = 0x0ccd5009u;
+// (key * kLutMagic) >> 19 is injective over the 320 keys enumerated in build_token_lut and spreads the frequent
+// ones over distinct shared-memory banks (tests/test_host_logic.py re-derives both properties)
+constexpr uint32_t kLutMagic = 0xda7e7ab5u;
 constexpr uint32_t kCommas = 0x2C2C2C2Cu;
-constexpr int kStageBytes = 512;     // per warp: < 32 carried bytes + two chunks of at most kMaxTokensPerIter + 16
-constexpr int kMaxTokensPerIter = 176;  // a valid chunk of 512 bytes closes at most 171 tokens
+constexpr uint32_t kFill = 0x20202020u;  // bytes outside the row read as ' ' (never a comma, high nibble 2)
+constexpr int kStageBytes = 512;         // per warp: < 32 carried bytes + two chunks of at most kMaxTokensPerChunk
+constexpr int kMaxTokensPerChunk = 176;  // a valid chunk of 512 bytes closes at most 171 tokens
 
-// per-token statistics packed in the second word of a table entry (8-bit fields, drained every 8 iterations)
-constexpr uint32_t kStatSub = 1u << 8;        // anchor is a substitution "*XY"
-constexpr uint32_t kStatLowerIns = 1u << 16;  // lowercase insertion: its inserted bases need the byte recount
+// Table entry (one 32-bit word): bits 0..7 the code byte; above it three counters that are summed with one add
+// per token and drained after every trip (at most 16 slots per lane and trip, so the code bytes sum to < 2^12):
+constexpr int kStatShift = 12;
+constexpr uint32_t kStatMismatch = 1u << 12;  // bits 12..17: calc_match contribution of the anchor (0..3 per token)
+constexpr uint32_t kStatSub = 1u << 18;       // bits 18..22: anchor is a substitution "*XY"
+constexpr uint32_t kStatSpecial = 1u << 23;   // bits 23..27: empty slot (unknown anchor) or lowercase insertion
 
 __device__ __forceinline__ uint32_t lut_slot(uint32_t key) { return (key * kLutMagic) >> (32 - kLutBits); }
 
@@ -47,24 +68,27 @@ __device__ __forceinline__ uint32_t make_key(uint32_t b0, uint32_t b1, uint32_t 
     return (b0 >> 4) | (b1 << 4) | (b2 << 12) | (b3 << 20) | (0xCu << 28);
 }
 
-// Table entry: x = (key & ~0xFF) | code byte, y = statistics.  Empty slots carry a key no token can produce.
-__device__ void build_token_lut(uint2 *lut) {
-    for (int e = threadIdx.x; e < kLutSize; e += blockDim.x) lut[e] = make_uint2(DJ_CODE_INVALID, 0u);
+__device__ void build_token_lut(uint32_t *lut) {
+    for (int e = threadIdx.x; e < kLutSize; e += blockDim.x) lut[e] = DJ_CODE_INVALID | kStatSpecial;
     __syncthreads();
-    for (int k = threadIdx.x; k < 300; k += blockDim.x) {
+    for (int k = threadIdx.x; k < 320; k += blockDim.x) {
         uint32_t key, code;
         bool lower;
-        if (k < 200) {  // <any byte> <',' or '|'> <'=' or '-'> <base>
-            // the byte before the separator is the last letter of the previous token, an inserted base, or the
-            // ',' padding in front of the row: high nibbles 2 (','), 4 (ACGN), 5 (T), 6 (acgn), 7 (t)
-            const uint32_t nib = k / 40;  // 0 -> 0x2_, 1 -> 0x4_, 2 -> 0x5_, 3 -> 0x6_, 4 -> 0x7_
+        if (k < 200 || k >= 300) {  // <any byte> <separator> <'=' or '-'> <base>
+            // the byte before the separator is the last letter of the previous token or an inserted base: high
+            // nibbles 4 (ACGN), 5 (T), 6 (acgn), 7 (t); nibble 2 is kept for a ',' there.  k >= 300: the first
+            // token of the row, which follows the ' ' filler instead of a separator.
+            const bool first = k >= 300;
+            const int kk = first ? k - 300 : k;
+            const uint32_t nib = first ? 0 : kk / 40;  // 0 -> 0x2_, 1 -> 0x4_, 2 -> 0x5_, 3 -> 0x6_, 4 -> 0x7_
             const uint32_t nib_byte = nib == 0 ? 0x20u : (nib + 3u) << 4;
-            const int rem = k % 40, x = rem % 10;
-            const bool ins = rem >= 20, del = (rem % 20) >= 10;
+            const int rem = kk % 40, x = rem % 10;
+            const bool ins = !first && rem >= 20, del = (rem % 20) >= 10;
             lower = x >= 5;
-            key = make_key(nib_byte, ins ? '|' : ',', del ? '-' : '=', (uint8_t)dj_base_char(x % 5, lower));
+            key = make_key(nib_byte, first ? ' ' : (ins ? '|' : ','), del ? '-' : '=',
+                           (uint8_t)dj_base_char(x % 5, lower));
             code = (ins ? DJ_CODE_INS : 0) | (uint32_t)((del ? 10 : 0) + 5 * (lower ? 1 : 0) + x % 5);
-        } else {  // <',' or '|'> '*' <ref base> <read base>
+        } else {  // <',' or '|' or the filler> '*' <ref base> <read base>
             const int j = k - 200, rem = j % 50;
             const bool ins = j >= 50;
             lower = rem >= 25;
@@ -73,10 +97,10 @@ __device__ void build_token_lut(uint2 *lut) {
             code = (ins ? DJ_CODE_INS : 0) | (uint32_t)(20 + 25 * (lower ? 1 : 0) + 5 * r + b);
         }
         const int anchor = code & 0x7F;
-        uint32_t stat = (uint32_t)dj_anchor_mismatch(anchor);
-        if (anchor >= 20) stat |= kStatSub;
-        if ((code & DJ_CODE_INS) && lower) stat |= kStatLowerIns;
-        lut[lut_slot(key)] = make_uint2((key & 0xFFFFFF00u) | code, stat);
+        uint32_t entry = code | (uint32_t)dj_anchor_mismatch(anchor) * kStatMismatch;
+        if (anchor >= 20) entry |= kStatSub;
+        if ((code & DJ_CODE_INS) && lower) entry |= kStatSpecial;
+        lut[lut_slot(key)] = entry;
     }
     __syncthreads();
 }
@@ -96,54 +120,93 @@ __device__ __forceinline__ uint32_t valid_bytes(int g, int lo, int hi) {
     return m;
 }
 
-// Chunk `c` (16 bytes) of the row's aligned span, with every byte outside the row replaced by ','.
+// word of the padded row at byte offset g: the row's bytes inside [head, nbytes), ONE ',' at `nbytes` (it closes
+// the last token) and the ' ' filler everywhere else
+__device__ __forceinline__ uint32_t pad_word(uint32_t w, int g, int head, int nbytes) {
+    const uint32_t m = valid_bytes(g, head, nbytes);
+    const uint32_t t = valid_bytes(g, nbytes, nbytes + 1);
+    return (w & m) | (((kCommas & t) | (kFill & ~t)) & ~m);
+}
+
+// Chunk `c` (16 bytes) of the row's aligned span, padded as described above.
 __device__ __forceinline__ uint4 load_chunk(const uint4 *base, int c, int head, int nbytes) {
     const int g = c * 16;
-    if (g >= nbytes) return make_uint4(kCommas, kCommas, kCommas, kCommas);
+    if (g >= nbytes) return make_uint4(g == nbytes ? (kFill ^ 0x20u ^ 0x2Cu) : kFill, kFill, kFill, kFill);
     uint4 v = __ldg(base + c);
     if (g < head || g + 16 > nbytes) {
-        uint32_t m;
-        m = valid_bytes(g, head, nbytes);      v.x = (v.x & m) | (kCommas & ~m);
-        m = valid_bytes(g + 4, head, nbytes);  v.y = (v.y & m) | (kCommas & ~m);
-        m = valid_bytes(g + 8, head, nbytes);  v.z = (v.z & m) | (kCommas & ~m);
-        m = valid_bytes(g + 12, head, nbytes); v.w = (v.w & m) | (kCommas & ~m);
+        v.x = pad_word(v.x, g, head, nbytes);
+        v.y = pad_word(v.y, g + 4, head, nbytes);
+        v.z = pad_word(v.z, g + 8, head, nbytes);
+        v.w = pad_word(v.w, g + 12, head, nbytes);
     }
     return v;
 }
 
-// calc_match counted byte by byte (only for reads with a lowercase insertion)
-__device__ __noinline__ uint32_t recount_mismatches(const uint8_t *row, int len, int lane) {
-    uint32_t n = 0;
+// Rare path (a token read an empty table slot, or a lowercase insertion): look for the invalid code in the row's
+// codes and count calc_match byte by byte.
+__device__ __noinline__ uint32_t recheck_row(const uint8_t *row, int len, const uint8_t *out, int n_codes, int lane,
+                                             bool *has_invalid) {
+    uint32_t n = 0, invalid = 0;
     for (int p = lane; p < len; p += 32) {
         const uint32_t c = row[p];
         n += (c == '+' || c == '-' || c == '*' || (c >= 'a' && c <= 'z')) ? 1u : 0u;
     }
+    for (int p = lane; p < n_codes; p += 32) invalid |= (__ldcg(out + p) & 0x7F) == DJ_CODE_INVALID ? 1u : 0u;
+    *has_invalid = __reduce_or_sync(0xffffffffu, invalid) != 0;
     return __reduce_add_sync(0xffffffffu, n);
 }
 
 // Translate the token closed by one comma.  `key` = the 32 bits in front of the comma (see make_key), `flag` != 0
-// when the slot holds a comma.  Written in PTX so that the slot stays branch-free: one table look-up, and the
-// statistics, the key check, the one-byte store of the code and the staging pointer are predicated.
-__device__ __forceinline__ void emit_token(uint32_t &acc, uint32_t &diff, uint32_t &sp, uint32_t lut_s, uint32_t key,
-                                           uint32_t flag) {
+// when the slot holds a comma.  Written in PTX so that the slot stays branch-free: one table read; the add of the
+// counters, the one-byte store of the code and the staging pointer are predicated.
+__device__ __forceinline__ void emit_token(uint32_t &acc, uint32_t &sp, uint32_t lut_s, uint32_t key, uint32_t flag,
+                                           uint32_t c_four, uint32_t c_shift) {
+#if DJ_ENC_HASH_MODE == 0
+    (void)c_four; (void)c_shift;
     asm volatile(
-        "{\n"
-        " .reg .pred p;\n"
-        " .reg .u32 h, ex, ey;\n"
-        " setp.ne.u32 p, %5, 0;\n"
-        " mul.lo.u32 h, %3, %6;\n"
-        " shr.u32 h, h, %7;\n"
-        " and.b32 h, h, %8;\n"
-        " add.u32 h, h, %4;\n"
-        " ld.shared.v2.u32 {ex, ey}, [h];\n"
-        " @p add.u32 %0, %0, ey;\n"
-        " @p lop3.b32 %1, %1, ex, %3, 0xF6;\n"
-        " @p st.shared.u8 [%2], ex;\n"
-        " @p add.u32 %2, %2, 1;\n"
-        "}\n"
-        : "+r"(acc), "+r"(diff), "+r"(sp)
-        : "r"(key), "r"(lut_s), "r"(flag), "n"(kLutMagic), "n"(32 - kLutBits - 3), "n"((kLutSize - 1) << 3)
+        "{\n .reg .pred p;\n .reg .u32 h, e;\n"
+        " setp.ne.u32 p, %4, 0;\n"
+        " mul.lo.u32 h, %2, %5;\n"
+        " shr.u32 h, h, %6;\n"
+        " and.b32 h, h, %7;\n"
+        " add.u32 h, h, %3;\n"
+        " ld.shared.u32 e, [h];\n"
+        " @p add.u32 %0, %0, e;\n"
+        " @p st.shared.u8 [%1], e;\n"
+        " @p add.u32 %1, %1, 1;\n}\n"
+        : "+r"(acc), "+r"(sp)
+        : "r"(key), "r"(lut_s), "r"(flag), "n"(kLutMagic), "n"(32 - kLutBits - 2), "n"((kLutSize - 1) << 2)
         : "memory");
+#elif DJ_ENC_HASH_MODE == 1
+    (void)c_shift;
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .u32 h, e;\n"
+        " setp.ne.u32 p, %4, 0;\n"
+        " mul.lo.u32 h, %2, %6;\n"
+        " shr.u32 h, h, %7;\n"
+        " mad.lo.u32 h, h, %5, %3;\n"
+        " ld.shared.u32 e, [h];\n"
+        " @p add.u32 %0, %0, e;\n"
+        " @p st.shared.u8 [%1], e;\n"
+        " @p add.u32 %1, %1, 1;\n}\n"
+        : "+r"(acc), "+r"(sp)
+        : "r"(key), "r"(lut_s), "r"(flag), "r"(c_four), "n"(kLutMagic), "n"(32 - kLutBits)
+        : "memory");
+#else
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .u32 h, e;\n"
+        " setp.ne.u32 p, %4, 0;\n"
+        " mul.lo.u32 h, %2, %7;\n"
+        " mul.hi.u32 h, h, %6;\n"
+        " mad.lo.u32 h, h, %5, %3;\n"
+        " ld.shared.u32 e, [h];\n"
+        " @p add.u32 %0, %0, e;\n"
+        " @p st.shared.u8 [%1], e;\n"
+        " @p add.u32 %1, %1, 1;\n}\n"
+        : "+r"(acc), "+r"(sp)
+        : "r"(key), "r"(lut_s), "r"(flag), "r"(c_four), "r"(c_shift), "n"(kLutMagic)
+        : "memory");
+#endif
 }
 
 __device__ __forceinline__ uint32_t find_msb(uint32_t m) {
@@ -153,21 +216,21 @@ __device__ __forceinline__ uint32_t find_msb(uint32_t m) {
 }
 
 // The (at most two) commas of one word: byte 0, then the single comma bytes 1..3 can hold.
-__device__ __forceinline__ void emit_word(uint32_t &acc, uint32_t &diff, uint32_t &sp, uint32_t lut_s, uint32_t prev,
-                                          uint32_t word, uint32_t z) {
-    emit_token(acc, diff, sp, lut_s, __funnelshift_r(prev, word, 4), z & 0x80u);
+__device__ __forceinline__ void emit_word(uint32_t &acc, uint32_t &sp, uint32_t lut_s, uint32_t prev, uint32_t word,
+                                          uint32_t z, uint32_t c_four, uint32_t c_shift) {
+    emit_token(acc, sp, lut_s, __funnelshift_r(prev, word, 4), z & 0x80u, c_four, c_shift);
     const uint32_t m = z & 0x80808000u;
-    emit_token(acc, diff, sp, lut_s, __funnelshift_r(prev, word, find_msb(m) - 3u), m);
+    emit_token(acc, sp, lut_s, __funnelshift_r(prev, word, find_msb(m) - 3u), m, c_four, c_shift);
 }
 
-__device__ __forceinline__ int emit_chunk(uint32_t &acc, uint32_t &diff, uint32_t sp, uint32_t lut_s, uint32_t wp,
-                                          const uint4 &c, const uint32_t (&z)[4]) {
+__device__ __forceinline__ uint32_t emit_chunk(uint32_t &acc, uint32_t sp, uint32_t lut_s, uint32_t wp, const uint4 &c,
+                                               const uint32_t (&z)[4], uint32_t c_four, uint32_t c_shift) {
     const uint32_t sp0 = sp;
-    emit_word(acc, diff, sp, lut_s, wp, c.x, z[0]);
-    emit_word(acc, diff, sp, lut_s, c.x, c.y, z[1]);
-    emit_word(acc, diff, sp, lut_s, c.y, c.z, z[2]);
-    emit_word(acc, diff, sp, lut_s, c.z, c.w, z[3]);
-    return (int)(sp - sp0);
+    emit_word(acc, sp, lut_s, wp, c.x, z[0], c_four, c_shift);
+    emit_word(acc, sp, lut_s, c.x, c.y, z[1], c_four, c_shift);
+    emit_word(acc, sp, lut_s, c.y, c.z, z[2], c_four, c_shift);
+    emit_word(acc, sp, lut_s, c.z, c.w, z[3], c_four, c_shift);
+    return sp - sp0;
 }
 
 __device__ __forceinline__ void chunk_commas(const uint4 &c, uint32_t (&z)[4], uint32_t &high) {
@@ -179,18 +242,14 @@ __device__ __forceinline__ void chunk_commas(const uint4 &c, uint32_t (&z)[4], u
     z[3] = comma_flags(c.w);
 }
 
-// commas count inside [head, nbytes] only: the row's own plus one terminator right after it
-__device__ __forceinline__ void mask_commas(uint32_t (&z)[4], int g0, int head, int nbytes) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k) z[k] &= valid_bytes(g0 + 4 * k, head, nbytes + 1);
-}
-
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_off,
               const int32_t *__restrict__ row_len, int64_t n_reads, int n_loci, int code_pitch, int ckpt_pitch,
               uint8_t *__restrict__ codes, int32_t *__restrict__ match_score, int32_t *__restrict__ n_tokens,
-              uint32_t *__restrict__ flags, uint32_t *__restrict__ ckpt) {
-    __shared__ uint2 lut[kLutSize];
+              uint32_t *__restrict__ flags, uint32_t *__restrict__ ckpt, uint32_t c_four, uint32_t c_shift) {
+    // c_four = 4 and c_shift = 2^kLutBits arrive as arguments so that the table address is computed with integer
+    // multiply-adds (FMA pipe) instead of being strength-reduced to shifts and masks on the saturated ALU pipe
+    __shared__ uint32_t lut[kLutSize];
     __shared__ __align__(16) uint8_t stage_all[kWarpsPerCta][kStageBytes];
     build_token_lut(lut);
 
@@ -207,30 +266,32 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
         const int head = (int)(off & 15);
         const uint4 *base = reinterpret_cast<const uint4 *>(text + (off - head));
         const int nbytes = head + len;
-        const int n_iter = (nbytes >> 9) + 1;  // the chunk that holds byte `nbytes` closes the last token
-        const int n_pairs = (n_iter + 1) >> 1;  // two 512-byte chunks per trip; a chunk past the row is all padding
+        const int n_iter = (nbytes >> 9) + 1;   // the chunk that holds byte `nbytes` closes the last token
+        const int n_pairs = (n_iter + 1) >> 1;  // two 512-byte chunks per trip; a chunk past the row is all filler
         uint8_t *out = codes + r * (int64_t)code_pitch;
         uint32_t *ck = ckpt + r * (int64_t)ckpt_pitch;
 
         int tokbase = 0;      // commas seen so far = tokens closed so far
         int staged_from = 0;  // locus of stage[0] (a multiple of 32)
-        uint32_t acc = 0, diff = 0, mism = 0, n_sub = 0, n_lower_ins = 0, high = 0;
+        uint32_t mism = 0, n_sub = 0, n_special = 0, high = 0, wrong_rank = 0;
         bool broken = false;
-        uint32_t carry_w = kCommas;  // the word in front of this trip's first byte
+        uint32_t carry_w = kFill;  // the word in front of this trip's first byte
+#if DJ_ENC_PREFETCH
         uint4 ca = load_chunk(base, lane, head, nbytes);
         uint4 cb = load_chunk(base, 32 + lane, head, nbytes);
+#endif
 
         for (int pair = 0; pair < n_pairs; ++pair) {
+#if DJ_ENC_PREFETCH
             const uint4 na = load_chunk(base, (2 * pair + 2) * 32 + lane, head, nbytes);
             const uint4 nb = load_chunk(base, (2 * pair + 3) * 32 + lane, head, nbytes);
-            const bool last = pair == n_pairs - 1;
+#else
+            const uint4 ca = load_chunk(base, (2 * pair) * 32 + lane, head, nbytes);
+            const uint4 cb = load_chunk(base, (2 * pair + 1) * 32 + lane, head, nbytes);
+#endif
             uint32_t za[4], zb[4];
             chunk_commas(ca, za, high);
             chunk_commas(cb, zb, high);
-            if (pair == 0 || last) {
-                mask_commas(za, (2 * pair * 32 + lane) * 16, head, nbytes);
-                mask_commas(zb, ((2 * pair + 1) * 32 + lane) * 16, head, nbytes);
-            }
             // the word in front of each lane's chunk
             uint32_t wpa = __shfl_up_sync(0xffffffffu, ca.w, 1);
             uint32_t wpb = __shfl_up_sync(0xffffffffu, cb.w, 1);
@@ -264,59 +325,63 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
                 ck[2 * pair + lane] = v;
             }
 
-            if (total_a > kMaxTokensPerIter || total_b > kMaxTokensPerIter) broken = true;  // not MIDSV
+            if (total_a > kMaxTokensPerChunk || total_b > kMaxTokensPerChunk) broken = true;  // not MIDSV
             if (!broken) {
+                uint32_t acc = 0;
                 const uint32_t sp = stage_s + (uint32_t)(tokbase - staged_from);
-                const int wrote_a = emit_chunk(acc, diff, sp + (excl & 0xFFFFu), lut_s, wpa, ca, za);
-                const int wrote_b = emit_chunk(acc, diff, sp + (uint32_t)total_a + (excl >> 16), lut_s, wpb, cb, zb);
+                const uint32_t wrote_a = emit_chunk(acc, sp + (excl & 0xFFFFu), lut_s, wpa, ca, za, c_four, c_shift);
+                const uint32_t wrote_b =
+                    emit_chunk(acc, sp + (uint32_t)total_a + (excl >> 16), lut_s, wpb, cb, zb, c_four, c_shift);
                 // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV
-                if ((uint32_t)wrote_a != cnt_a || (uint32_t)wrote_b != cnt_b) diff |= 0x100u;
+                wrong_rank |= (wrote_a ^ cnt_a) | (wrote_b ^ cnt_b);
+                mism += (acc >> kStatShift) & 0x3Fu;
+                n_sub += (acc >> 18) & 0x1Fu;
+                n_special += acc >> 23;
             }
             tokbase += total_a + total_b;
 
-            if ((pair & 3) == 3 || last) {  // drain the 8-bit statistics fields (at most 48 tokens per lane since)
-                mism += acc & 0xFFu;
-                n_sub += (acc >> 8) & 0xFFu;
-                n_lower_ins += acc >> 16;
-                acc = 0;
-            }
-            if (!broken) {
+            if (!broken) {  // complete 32-byte sectors leave; the incomplete one moves to the front of the buffer
                 __syncwarp();
                 const int staged = tokbase - staged_from;
-                if (last) {
-                    if (lane < 16) stage[staged + lane] = DJ_CODE_INVALID;  // deterministic padding of the row
-                    __syncwarp();
-                }
-                const int flush_bytes = last ? ((staged + 15) & ~15) : (staged & ~31);
-                if (lane * 16 < flush_bytes) {
-                    const int o = staged_from + lane * 16;
-                    if (o < code_pitch)
-                        *reinterpret_cast<uint4 *>(out + o) = *reinterpret_cast<const uint4 *>(stage + lane * 16);
-                }
-                if (!last && flush_bytes > 0) {  // carry the incomplete sector to the front of the staging buffer
-                    const int tail = staged - flush_bytes;
-                    uint8_t b = 0;
-                    if (lane < tail) b = stage[flush_bytes + lane];
-                    __syncwarp();
-                    if (lane < tail) stage[lane] = b;
-                    staged_from += flush_bytes;
-                }
+                const int flush_bytes = staged & ~31;
+                if (lane * 16 < flush_bytes && staged_from + lane * 16 < code_pitch)
+                    *reinterpret_cast<uint4 *>(out + staged_from + lane * 16) =
+                        *reinterpret_cast<const uint4 *>(stage + lane * 16);
+                const uint8_t b = stage[flush_bytes + lane];  // lanes past the tail read stale bytes, never stored
                 __syncwarp();
+                if (lane < staged - flush_bytes) stage[lane] = b;
+                staged_from += flush_bytes;
             }
+#if DJ_ENC_PREFETCH
             ca = na;
             cb = nb;
+#endif
+        }
+        if (!broken) {  // what is left is less than one sector: pad it (deterministically) and store it
+            __syncwarp();
+            const int staged = tokbase - staged_from;
+            if (lane < 32 - staged) stage[staged + lane] = DJ_CODE_INVALID;
+            __syncwarp();
+            if (staged > 0 && lane < 2 && staged_from + lane * 16 < code_pitch)
+                *reinterpret_cast<uint4 *>(out + staged_from + lane * 16) =
+                    *reinterpret_cast<const uint4 *>(stage + lane * 16);
         }
 
         mism = __reduce_add_sync(0xffffffffu, mism);
         n_sub = __reduce_add_sync(0xffffffffu, n_sub);
-        n_lower_ins = __reduce_add_sync(0xffffffffu, n_lower_ins);
-        diff = __reduce_or_sync(0xffffffffu, diff);
+        n_special = __reduce_add_sync(0xffffffffu, n_special);
+        wrong_rank = __reduce_or_sync(0xffffffffu, wrong_rank);
         high = __reduce_or_sync(0xffffffffu, high);
         // every inserted base is the three bytes "+B|": what the anchors and commas do not explain is 3 x inserted
         const int ins3 = len - 3 * tokbase + 1 - (int)n_sub;
-        const bool bad = broken || (diff >> 8) != 0 || (high & 0x80808080u) != 0 || ins3 < 0 || ins3 % 3 != 0;
+        bool bad = broken || wrong_rank != 0 || (high & 0x80808080u) != 0 || ins3 < 0 || ins3 % 3 != 0;
         uint32_t mismatches = mism + (uint32_t)(ins3 / 3);
-        if (n_lower_ins != 0 && !bad) mismatches = recount_mismatches(text + off, len, lane);
+        if (n_special != 0 && !broken) {
+            __syncwarp();
+            bool has_invalid = false;
+            mismatches = recheck_row(text + off, len, out, min(tokbase, code_pitch), lane, &has_invalid);
+            bad = bad || has_invalid;
+        }
         if (lane == 0) {
             match_score[r] = -(int32_t)mismatches;
             n_tokens[r] = tokbase;
@@ -350,7 +415,8 @@ extern "C" int dj_encode(const uint8_t *text, const int64_t *row_off, const int3
     const int64_t resident = (int64_t)sms * 2;  // 2 CTAs of 512 threads = 32 warps per SM (persistent)
     if (ctas > resident) ctas = resident;
     encode_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
-        text, row_off, row_len, n_reads, n_loci, code_pitch, ckpt_pitch, codes, match_score, n_tokens, flags, ckpt);
+        text, row_off, row_len, n_reads, n_loci, code_pitch, ckpt_pitch, codes, match_score, n_tokens, flags, ckpt, 4u,
+        (uint32_t)kLutSize);
     DJ_LAUNCH_CHECK();
     return 0;
 }
