@@ -19,7 +19,7 @@ CODE_INVALID = 0x7F
 CODE_INS = 0x80
 FLAG_TOKEN_COUNT = 1
 FLAG_BAD_TOKEN = 2
-ENC_CHUNK = 512
+ENC_CHUNK = 1024
 HIST_ROWS = 10
 MASK_INS, MASK_DEL, MASK_SUB = 1, 2, 4
 KMER_AT, KMER_RAW = 256, 257

@@ -32,8 +32,13 @@
 // (`json.loads` + `MIDSV.split(",")`, src/DAJIN2/utils/fileio.py:49-52) and calc_match.
 #include "dj_common.cuh"
 
-#ifndef DJ_ENC_PREFETCH
-#define DJ_ENC_PREFETCH 0
+#ifndef DJ_ENC_PRED_LDS
+#define DJ_ENC_PRED_LDS 0  // 1: slots without a comma do not read the table (fewer bank conflicts, one more move)
+#endif
+#if DJ_ENC_PRED_LDS
+#define DJ_ENC_LDS " mov.u32 e, 0;\n @p ld.shared.u32 e, [h];\n"
+#else
+#define DJ_ENC_LDS " ld.shared.u32 e, [h];\n"
 #endif
 #ifndef DJ_ENC_HASH_MODE
 #define DJ_ENC_HASH_MODE 1  // 0: mul, shr, and   1: mul, shr, mad   2: mul, mul.hi, mad (no ALU-pipe op)
@@ -58,6 +63,7 @@ constexpr int kStatShift = 12;
 constexpr uint32_t kStatMismatch = 1u << 12;  // bits 12..17: calc_match contribution of the anchor (0..3 per token)
 constexpr uint32_t kStatSub = 1u << 18;       // bits 18..22: anchor is a substitution "*XY"
 constexpr uint32_t kStatSpecial = 1u << 23;   // bits 23..27: empty slot (unknown anchor) or lowercase insertion
+constexpr uint32_t kStickyBroken = 1u << 16;  // per-row flag word: see the main loop
 
 __device__ __forceinline__ uint32_t lut_slot(uint32_t key) { return (key * kLutMagic) >> (32 - kLutBits); }
 
@@ -170,7 +176,7 @@ __device__ __forceinline__ void emit_token(uint32_t &acc, uint32_t &sp, uint32_t
         " shr.u32 h, h, %6;\n"
         " and.b32 h, h, %7;\n"
         " add.u32 h, h, %3;\n"
-        " ld.shared.u32 e, [h];\n"
+        DJ_ENC_LDS
         " @p add.u32 %0, %0, e;\n"
         " @p st.shared.u8 [%1], e;\n"
         " @p add.u32 %1, %1, 1;\n}\n"
@@ -185,7 +191,7 @@ __device__ __forceinline__ void emit_token(uint32_t &acc, uint32_t &sp, uint32_t
         " mul.lo.u32 h, %2, %6;\n"
         " shr.u32 h, h, %7;\n"
         " mad.lo.u32 h, h, %5, %3;\n"
-        " ld.shared.u32 e, [h];\n"
+        DJ_ENC_LDS
         " @p add.u32 %0, %0, e;\n"
         " @p st.shared.u8 [%1], e;\n"
         " @p add.u32 %1, %1, 1;\n}\n"
@@ -199,7 +205,7 @@ __device__ __forceinline__ void emit_token(uint32_t &acc, uint32_t &sp, uint32_t
         " mul.lo.u32 h, %2, %7;\n"
         " mul.hi.u32 h, h, %6;\n"
         " mad.lo.u32 h, h, %5, %3;\n"
-        " ld.shared.u32 e, [h];\n"
+        DJ_ENC_LDS
         " @p add.u32 %0, %0, e;\n"
         " @p st.shared.u8 [%1], e;\n"
         " @p add.u32 %1, %1, 1;\n}\n"
@@ -215,31 +221,30 @@ __device__ __forceinline__ uint32_t find_msb(uint32_t m) {
     return r;
 }
 
-// The (at most two) commas of one word: byte 0, then the single comma bytes 1..3 can hold.
+// Comma flags of one 16-byte chunk in one word: bit 7-k of byte j is set when byte j of word k is a comma.
+__device__ __forceinline__ uint32_t chunk_commas(const uint4 &c, uint32_t &high) {
+    high |= c.x | c.y;
+    high |= c.z | c.w;
+    return comma_flags(c.x) | (comma_flags(c.y) >> 1) | (comma_flags(c.z) >> 2) | (comma_flags(c.w) >> 3);
+}
+
+// The (at most two) commas of word k: byte 0, then the single comma bytes 1..3 can hold.
+template <int k>
 __device__ __forceinline__ void emit_word(uint32_t &acc, uint32_t &sp, uint32_t lut_s, uint32_t prev, uint32_t word,
-                                          uint32_t z, uint32_t c_four, uint32_t c_shift) {
-    emit_token(acc, sp, lut_s, __funnelshift_r(prev, word, 4), z & 0x80u, c_four, c_shift);
-    const uint32_t m = z & 0x80808000u;
-    emit_token(acc, sp, lut_s, __funnelshift_r(prev, word, find_msb(m) - 3u), m, c_four, c_shift);
+                                          uint32_t zz, uint32_t c_four, uint32_t c_shift) {
+    emit_token(acc, sp, lut_s, __funnelshift_r(prev, word, 4), zz & (0x80u >> k), c_four, c_shift);
+    const uint32_t m = zz & (0x80808000u >> k);
+    emit_token(acc, sp, lut_s, __funnelshift_r(prev, word, find_msb(m) + (uint32_t)(k - 3)), m, c_four, c_shift);
 }
 
 __device__ __forceinline__ uint32_t emit_chunk(uint32_t &acc, uint32_t sp, uint32_t lut_s, uint32_t wp, const uint4 &c,
-                                               const uint32_t (&z)[4], uint32_t c_four, uint32_t c_shift) {
+                                               uint32_t zz, uint32_t c_four, uint32_t c_shift) {
     const uint32_t sp0 = sp;
-    emit_word(acc, sp, lut_s, wp, c.x, z[0], c_four, c_shift);
-    emit_word(acc, sp, lut_s, c.x, c.y, z[1], c_four, c_shift);
-    emit_word(acc, sp, lut_s, c.y, c.z, z[2], c_four, c_shift);
-    emit_word(acc, sp, lut_s, c.z, c.w, z[3], c_four, c_shift);
+    emit_word<0>(acc, sp, lut_s, wp, c.x, zz, c_four, c_shift);
+    emit_word<1>(acc, sp, lut_s, c.x, c.y, zz, c_four, c_shift);
+    emit_word<2>(acc, sp, lut_s, c.y, c.z, zz, c_four, c_shift);
+    emit_word<3>(acc, sp, lut_s, c.z, c.w, zz, c_four, c_shift);
     return sp - sp0;
-}
-
-__device__ __forceinline__ void chunk_commas(const uint4 &c, uint32_t (&z)[4], uint32_t &high) {
-    high |= c.x | c.y;
-    high |= c.z | c.w;
-    z[0] = comma_flags(c.x);
-    z[1] = comma_flags(c.y);
-    z[2] = comma_flags(c.z);
-    z[3] = comma_flags(c.w);
 }
 
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
@@ -271,41 +276,31 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
         uint8_t *out = codes + r * (int64_t)code_pitch;
         uint32_t *ck = ckpt + r * (int64_t)ckpt_pitch;
 
-        int tokbase = 0;      // commas seen so far = tokens closed so far
-        int staged_from = 0;  // locus of stage[0] (a multiple of 32)
-        uint32_t mism = 0, n_sub = 0, n_special = 0, high = 0, wrong_rank = 0;
-        bool broken = false;
-        uint32_t carry_w = kFill;  // the word in front of this trip's first byte
-#if DJ_ENC_PREFETCH
-        uint4 ca = load_chunk(base, lane, head, nbytes);
-        uint4 cb = load_chunk(base, 32 + lane, head, nbytes);
-#endif
+        int tokbase = 0;                  // commas seen so far = tokens closed so far
+        uint32_t counts = 0;              // anchors' calc_match contributions (low half) | substitutions (high half)
+        uint32_t sticky = 0;              // OR of the kSticky* bits, of rank errors (bits 0..3) and of specials (8..12)
+        uint32_t high = 0;                // OR of every text word: bit 7 of a byte set <=> the row is not 7-bit ASCII
+        uint32_t carry_w = kFill;         // the word in front of this trip's first byte
+        uint8_t *outp = out + lane * 16;  // where this lane's 16 bytes of the next flush go
+        int pair = 0;
 
-        for (int pair = 0; pair < n_pairs; ++pair) {
-#if DJ_ENC_PREFETCH
-            const uint4 na = load_chunk(base, (2 * pair + 2) * 32 + lane, head, nbytes);
-            const uint4 nb = load_chunk(base, (2 * pair + 3) * 32 + lane, head, nbytes);
-#else
-            const uint4 ca = load_chunk(base, (2 * pair) * 32 + lane, head, nbytes);
-            const uint4 cb = load_chunk(base, (2 * pair + 1) * 32 + lane, head, nbytes);
-#endif
-            uint32_t za[4], zb[4];
-            chunk_commas(ca, za, high);
-            chunk_commas(cb, zb, high);
+        // One trip = two chunks of 512 bytes.  stage[0] always holds locus (tokbase & ~31) of the row.
+        auto trip = [&](const uint4 &ca, const uint4 &cb) {
+            const uint32_t zza = chunk_commas(ca, high), zzb = chunk_commas(cb, high);
             // the word in front of each lane's chunk
             uint32_t wpa = __shfl_up_sync(0xffffffffu, ca.w, 1);
             uint32_t wpb = __shfl_up_sync(0xffffffffu, cb.w, 1);
             const uint32_t last_a = __shfl_sync(0xffffffffu, ca.w, 31);
-            const uint32_t front_a = carry_w;
+            // checkpoint: tokens that START before this trip's first byte (dj_find_token resumes from it)
             if (lane == 0) {
+                ck[pair] = pair == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
                 wpa = carry_w;
                 wpb = last_a;
             }
             carry_w = __shfl_sync(0xffffffffu, cb.w, 31);
 
             // ranks of this lane's commas: one scan for both chunks (16-bit fields)
-            const uint32_t cnt_a = __popc(za[0] | (za[1] >> 1) | (za[2] >> 2) | (za[3] >> 3));
-            const uint32_t cnt_b = __popc(zb[0] | (zb[1] >> 1) | (zb[2] >> 2) | (zb[3] >> 3));
+            const uint32_t cnt_a = __popc(zza), cnt_b = __popc(zzb);
             const uint32_t cnt = cnt_a | (cnt_b << 16);
             uint32_t incl = cnt;
 #pragma unroll
@@ -317,66 +312,60 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
             const int total_a = (int)(totals & 0xFFFFu), total_b = (int)(totals >> 16);
             const uint32_t excl = incl - cnt;
 
-            // checkpoints: tokens that START before each chunk's first byte (dj_find_token resumes from them)
-            if (lane < 2) {
-                const uint32_t front = lane == 0 ? front_a : last_a;
-                uint32_t v = (uint32_t)tokbase + (lane == 0 ? 0u : (uint32_t)total_a) + ((front >> 24) == ',' ? 0u : 1u);
-                if (pair == 0 && lane == 0) v = 0;
-                ck[2 * pair + lane] = v;
+            // not MIDSV: more commas than a chunk of tokens can hold, or more tokens than the row has room for
+            if (total_a > kMaxTokensPerChunk || total_b > kMaxTokensPerChunk || tokbase >= code_pitch) {
+                sticky |= kStickyBroken;
+                pair = 0x3FFFFFFF;  // leave the row: it is flagged, its codes are not defined
+                return;
             }
-
-            if (total_a > kMaxTokensPerChunk || total_b > kMaxTokensPerChunk) broken = true;  // not MIDSV
-            if (!broken) {
-                uint32_t acc = 0;
-                const uint32_t sp = stage_s + (uint32_t)(tokbase - staged_from);
-                const uint32_t wrote_a = emit_chunk(acc, sp + (excl & 0xFFFFu), lut_s, wpa, ca, za, c_four, c_shift);
-                const uint32_t wrote_b =
-                    emit_chunk(acc, sp + (uint32_t)total_a + (excl >> 16), lut_s, wpb, cb, zb, c_four, c_shift);
-                // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV
-                wrong_rank |= (wrote_a ^ cnt_a) | (wrote_b ^ cnt_b);
-                mism += (acc >> kStatShift) & 0x3Fu;
-                n_sub += (acc >> 18) & 0x1Fu;
-                n_special += acc >> 23;
-            }
+            uint32_t acc = 0;
+            const uint32_t sp = stage_s + (uint32_t)(tokbase & 31);
+            const uint32_t wrote_a = emit_chunk(acc, sp + (excl & 0xFFFFu), lut_s, wpa, ca, zza, c_four, c_shift);
+            const uint32_t wrote_b =
+                emit_chunk(acc, sp + (uint32_t)total_a + (excl >> 16), lut_s, wpb, cb, zzb, c_four, c_shift);
+            // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV: bits 0..3;
+            // the table's "special" counter: bits 8..12
+            sticky |= (wrote_a ^ cnt_a) | (wrote_b ^ cnt_b) | ((acc >> 15) & 0x1F00u);
+            counts += ((acc >> kStatShift) & 0x3Fu) | ((acc >> 2) & 0x1F0000u);
+            // complete 32-byte sectors leave; the incomplete one moves to the front of the staging buffer
+            __syncwarp();
+            const int staged = (tokbase & 31) + total_a + total_b;
+            const int flush_bytes = staged & ~31;
+            if (lane * 16 < flush_bytes) *reinterpret_cast<uint4 *>(outp) = *reinterpret_cast<const uint4 *>(stage + lane * 16);
+            const uint8_t b = stage[flush_bytes + lane];  // lanes past the tail read stale bytes, never stored
+            __syncwarp();
+            if (lane < staged - flush_bytes) stage[lane] = b;
             tokbase += total_a + total_b;
+            outp += flush_bytes;
+        };
 
-            if (!broken) {  // complete 32-byte sectors leave; the incomplete one moves to the front of the buffer
-                __syncwarp();
-                const int staged = tokbase - staged_from;
-                const int flush_bytes = staged & ~31;
-                if (lane * 16 < flush_bytes && staged_from + lane * 16 < code_pitch)
-                    *reinterpret_cast<uint4 *>(out + staged_from + lane * 16) =
-                        *reinterpret_cast<const uint4 *>(stage + lane * 16);
-                const uint8_t b = stage[flush_bytes + lane];  // lanes past the tail read stale bytes, never stored
-                __syncwarp();
-                if (lane < staged - flush_bytes) stage[lane] = b;
-                staged_from += flush_bytes;
-            }
-#if DJ_ENC_PREFETCH
-            ca = na;
-            cb = nb;
-#endif
-        }
+        // first trip (the row may start inside its first chunk), trips that lie entirely inside the row, last trips
+        trip(load_chunk(base, lane, head, nbytes), load_chunk(base, 32 + lane, head, nbytes));
+        const int n_inside = nbytes >> 10;
+#pragma unroll 1
+        for (++pair; pair < n_inside; ++pair) trip(__ldg(base + pair * 64 + lane), __ldg(base + pair * 64 + 32 + lane));
+#pragma unroll 1
+        for (; pair < n_pairs; ++pair)
+            trip(load_chunk(base, pair * 64 + lane, head, nbytes), load_chunk(base, pair * 64 + 32 + lane, head, nbytes));
+
+        const bool broken = (sticky & kStickyBroken) != 0;
         if (!broken) {  // what is left is less than one sector: pad it (deterministically) and store it
             __syncwarp();
-            const int staged = tokbase - staged_from;
+            const int staged = tokbase & 31;
             if (lane < 32 - staged) stage[staged + lane] = DJ_CODE_INVALID;
             __syncwarp();
-            if (staged > 0 && lane < 2 && staged_from + lane * 16 < code_pitch)
-                *reinterpret_cast<uint4 *>(out + staged_from + lane * 16) =
-                    *reinterpret_cast<const uint4 *>(stage + lane * 16);
+            if (staged > 0 && lane < 2 && (tokbase & ~31) < code_pitch)
+                *reinterpret_cast<uint4 *>(outp) = *reinterpret_cast<const uint4 *>(stage + lane * 16);
         }
 
-        mism = __reduce_add_sync(0xffffffffu, mism);
-        n_sub = __reduce_add_sync(0xffffffffu, n_sub);
-        n_special = __reduce_add_sync(0xffffffffu, n_special);
-        wrong_rank = __reduce_or_sync(0xffffffffu, wrong_rank);
-        high = __reduce_or_sync(0xffffffffu, high);
+        counts = __reduce_add_sync(0xffffffffu, counts);  // 16-bit fields: dj_encode limits n_loci accordingly
+        sticky = __reduce_or_sync(0xffffffffu, sticky | (high & 0x80808080u));
+        const uint32_t mism = counts & 0xFFFFu, n_sub = counts >> 16;
         // every inserted base is the three bytes "+B|": what the anchors and commas do not explain is 3 x inserted
         const int ins3 = len - 3 * tokbase + 1 - (int)n_sub;
-        bool bad = broken || wrong_rank != 0 || (high & 0x80808080u) != 0 || ins3 < 0 || ins3 % 3 != 0;
+        bool bad = (sticky & (kStickyBroken | 0x8080808Fu)) != 0 || ins3 < 0 || ins3 % 3 != 0;
         uint32_t mismatches = mism + (uint32_t)(ins3 / 3);
-        if (n_special != 0 && !broken) {
+        if ((sticky & 0x1F00u) != 0 && !broken) {
             __syncwarp();
             bool has_invalid = false;
             mismatches = recheck_row(text + off, len, out, min(tokbase, code_pitch), lane, &has_invalid);
@@ -395,7 +384,7 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
 
 extern "C" int32_t dj_code_pitch(int32_t n_loci) { return (n_loci + 31) & ~31; }
 
-extern "C" int32_t dj_ckpt_pitch(int32_t max_row_len) { return (max_row_len + 15) / DJ_ENC_CHUNK + 3; }
+extern "C" int32_t dj_ckpt_pitch(int32_t max_row_len) { return (max_row_len + 15) / DJ_ENC_CHUNK + 2; }
 
 extern "C" int dj_encode(const uint8_t *text, const int64_t *row_off, const int32_t *row_len, int64_t n_reads,
                          int32_t n_loci, int32_t code_pitch, int32_t ckpt_pitch, uint8_t *codes,
@@ -403,6 +392,10 @@ extern "C" int dj_encode(const uint8_t *text, const int64_t *row_off, const int3
     if (n_reads <= 0) return 0;
     if (((uintptr_t)text & 15) != 0 || ((uintptr_t)codes & 15) != 0) {
         dj_set_error("dj_encode: text and codes must be 16-byte aligned");
+        return 1;
+    }
+    if (n_loci > 400000) {  // the per-row counters are reduced as 16-bit fields: 3 * n_loci / 32 must fit
+        dj_set_error("dj_encode: n_loci %d is beyond the supported 400000", n_loci);
         return 1;
     }
     if (code_pitch < n_loci || (code_pitch & 31) != 0) {

@@ -43,8 +43,8 @@ extern "C" {
 #define DJ_FLAG_TOKEN_COUNT 1u /* number of tokens != n_loci */
 #define DJ_FLAG_BAD_TOKEN 2u   /* a token outside the supported grammar */
 
-/* bytes of text one warp iteration of the encoder covers; checkpoint granularity of the token index */
-#define DJ_ENC_CHUNK 512
+/* bytes of text one trip of the encoder's main loop covers; checkpoint granularity of the token index */
+#define DJ_ENC_CHUNK 1024
 
 /* rows of dj_hist output: counts[DJ_HIST_ROWS][n_loci] (int32) */
 #define DJ_HIST_MATCH 0   /* '=' with the N / lowercase skip rule   (indel_counter.py:15-31)            */
