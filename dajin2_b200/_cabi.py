@@ -89,7 +89,7 @@ _NO_STATUS = {"dj_abi_version", "dj_last_error", "dj_code_pitch", "dj_ckpt_pitch
 
 # kernels launched per call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    "dj_encode": 1, "dj_hist": 1, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
+    "dj_encode": 1, "dj_hist": 2, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
     "dj_fetch_tokens": 1, "dj_dedup_rows": 1, "dj_dedup_export": 1, "dj_bisect": 1, "dj_assign_rows": 1,
     "dj_silhouette": 2, "dj_member_counts": 1, "dj_member_locate": 1, "dj_gather_labels": 1,
 }

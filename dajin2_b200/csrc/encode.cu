@@ -32,6 +32,12 @@
 // (`json.loads` + `MIDSV.split(",")`, src/DAJIN2/utils/fileio.py:49-52) and calc_match.
 #include "dj_common.cuh"
 
+#ifndef DJ_ENC_PREFETCH_DIST
+#define DJ_ENC_PREFETCH_DIST 1  // trips (of 1 KB per warp) the text is prefetched ahead of its use; 0 = off
+#endif
+#ifndef DJ_ENC_PREFETCH_LEVEL
+#define DJ_ENC_PREFETCH_LEVEL "L1"
+#endif
 #ifndef DJ_ENC_PRED_LDS
 #define DJ_ENC_PRED_LDS 0  // 1: slots without a comma do not read the table (fewer bank conflicts, one more move)
 #endif
@@ -343,7 +349,17 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
         trip(load_chunk(base, lane, head, nbytes), load_chunk(base, 32 + lane, head, nbytes));
         const int n_inside = nbytes >> 10;
 #pragma unroll 1
-        for (++pair; pair < n_inside; ++pair) trip(__ldg(base + pair * 64 + lane), __ldg(base + pair * 64 + 32 + lane));
+        for (++pair; pair < n_inside; ++pair) {
+            const uint4 *p = base + pair * 64 + lane;
+#if DJ_ENC_PREFETCH_DIST > 0
+            // the loads of the trip after next (never past the row: its last trips are not "inside")
+            if (pair + DJ_ENC_PREFETCH_DIST < n_inside) {
+                asm volatile("prefetch.global." DJ_ENC_PREFETCH_LEVEL " [%0];" ::"l"(p + 64 * DJ_ENC_PREFETCH_DIST));
+                asm volatile("prefetch.global." DJ_ENC_PREFETCH_LEVEL " [%0];" ::"l"(p + 64 * DJ_ENC_PREFETCH_DIST + 32));
+            }
+#endif
+            trip(__ldg(p), __ldg(p + 32));
+        }
 #pragma unroll 1
         for (; pair < n_pairs; ++pair)
             trip(load_chunk(base, pair * 64 + lane, head, nbytes), load_chunk(base, pair * 64 + 32 + lane, head, nbytes));
