@@ -73,3 +73,42 @@ def test_strand_table_from_histogram_rows():
                 if tok.startswith(op):
                     hist[4 + j + (0 if s == "+" else 3), i] += 1
     assert {str(i): v for i, v in engine.strand_table(hist, loci).items()} == g["strand_counts"]
+
+
+def test_encoder_token_table_is_collision_free():
+    """The encoder's perfect hash (dajin2_b200/csrc/encode.cu: make_key, kLutMagic, kLutBits) maps the 320 keys of
+    valid token endings to distinct table slots, and the frequent ones to distinct shared-memory banks."""
+    import re
+    from pathlib import Path
+
+    src = (Path(__file__).resolve().parent.parent / "dajin2_b200" / "csrc" / "encode.cu").read_text()
+    magic = int(re.search(r"kLutMagic = (0x[0-9a-fA-F]+)u", src).group(1), 16)
+    bits = int(re.search(r"kLutBits = (\d+);", src).group(1))
+
+    def key(b0, b1, b2, b3):
+        return (b0 >> 4) | (b1 << 4) | (b2 << 12) | (b3 << 20) | (0xC << 28)
+
+    def slot(k):
+        return ((k * magic) & 0xFFFFFFFF) >> (32 - bits)
+
+    keys = {}
+    up, lo = "ACGTN", "acgtn"
+    for b0 in (0x20, 0x40, 0x50, 0x60, 0x70):  # high nibbles of ',' / ' ', ACGN, T, acgn, t
+        for sep, ins in ((",", 0), ("|", 0x80)):
+            for lower, letters in ((0, up), (1, lo)):
+                for b, ch in enumerate(letters):
+                    keys[key(b0, ord(sep), ord("="), ord(ch))] = ins | (5 * lower + b)
+                    keys[key(b0, ord(sep), ord("-"), ord(ch))] = ins | (10 + 5 * lower + b)
+    for sep, ins in ((",", 0), ("|", 0x80)):
+        for lower, letters in ((0, up), (1, lo)):
+            for r, cr in enumerate(letters):
+                for b, cb in enumerate(letters):
+                    keys[key(ord(sep), ord("*"), ord(cr), ord(cb))] = ins | (20 + 25 * lower + 5 * r + b)
+    for lower, letters in ((0, up), (1, lo)):  # first token of a row: preceded by the ' ' filler
+        for b, ch in enumerate(letters):
+            keys[key(0x20, 0x20, ord("="), ord(ch))] = 5 * lower + b
+            keys[key(0x20, 0x20, ord("-"), ord(ch))] = 10 + 5 * lower + b
+    assert len(keys) == 320
+    assert len({slot(k) for k in keys}) == 320
+    hot = [key(ord(p), ord(","), ord("="), ord(x)) for p in "AT" for x in "ACGT"]
+    assert len({slot(k) & 31 for k in hot}) == len(hot)
