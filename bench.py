@@ -350,8 +350,10 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
 
-    from dajin2_b200 import _cabi, engine, pipeline
+    from dajin2_b200 import _cabi, engine, mlp_pool, pipeline
     from dajin2_b200 import distributed as djdist
+
+    mlp_pool.warm_up()  # the interpreter start-up of the MLP workers is not part of a step
 
     pop, hs, hc, keep = make_workload(args, rank, world, pinned=True)
     sequence = pop.reference

@@ -198,32 +198,26 @@ def dissimilar_mask(sample: np.ndarray, control: np.ndarray, is_consensus: bool 
 
 def mlp_candidates(sample: np.ndarray, control: np.ndarray, threshold: float) -> np.ndarray:
     """Candidate loci proposed by the reference's lbfgs MLP (``anomaly_detector.py:61-94``).  scikit-learn is the
-    reference's own dependency for this step; the training set is rebuilt exactly as the reference builds it."""
-    from sklearn.neural_network import MLPClassifier
+    reference's own dependency for this step (see ``mlp_pool`` for why it stays there)."""
+    from . import mlp_pool
 
-    rng = np.random.default_rng(seed=1)
-    n_rand, n_ctrl = 10_000, len(control)
-    base = rng.uniform(0, 100, n_rand)
-    base_err = np.clip(base + rng.uniform(0, threshold, n_rand), 0, 100)
-    base_mut = np.clip(base + rng.uniform(threshold, 100, n_rand), 0, 100)
-    ctrl_err = np.clip(control + rng.uniform(0, threshold, n_ctrl), 0, 100)
-    ctrl_mut = np.clip(control + rng.uniform(threshold, 100, n_ctrl), 0, 100)
-    err = np.concatenate([np.array([base, base_err]).T, np.array([control, ctrl_err]).T], axis=0)
-    mut = np.concatenate([np.array([base, base_mut]).T, np.array([control, ctrl_mut]).T], axis=0)
-    X = np.concatenate([err, mut], axis=0)
-    y = [0] * (n_rand + n_ctrl) + [1] * (n_rand + n_ctrl)
-    clf = MLPClassifier(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
-    clf.fit(X, y)
-    return clf.predict(np.array([control, sample]).T) == 1
+    return mlp_pool.submit(sample, control, threshold).result()
 
 
 def extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False) -> dict[str, set[int]]:
-    out = {}
+    """``extract_anomal_loci`` (reference ``anomaly_detector.py:99-109``): the three MLP fits run concurrently in the
+    worker pool while the window distances are computed on the device."""
+    from . import mlp_pool
+
+    pending = {}
     for op in MUTS:
         s = np.asarray(norm_sample[op], dtype=float)
         c = np.asarray(norm_control[op], dtype=float)
-        keep = mlp_candidates(s, c, thresholds[op]) & dissimilar_mask(s, c, is_consensus)
-        out[op] = set(np.flatnonzero(keep).tolist())
+        pending[op] = (s, c, mlp_pool.submit(s, c, thresholds[op]))
+    out = {}
+    masks = {op: dissimilar_mask(s, c, is_consensus) for op, (s, c, _) in pending.items()}
+    for op, (_, _, fut) in pending.items():
+        out[op] = set(np.flatnonzero(fut.result() & masks[op]).tolist())
     return out
 
 

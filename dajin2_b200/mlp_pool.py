@@ -1,0 +1,198 @@
+"""Worker processes for the reference's lbfgs MLP (``mutation_processing/anomaly_detector.py:61-94``).
+
+Loci selection trains one scikit-learn ``MLPClassifier`` per mutation type on 2 x (10 000 + L) synthetic points — a
+fixed ~0.3-1.2 s of single-threaded host arithmetic per fit that does not depend on the number of reads.  The fit is
+chaotic in its floating-point summation order (profiles/r01_mlp_stability.log: shuffling the training rows or a 1e-13
+perturbation of the inputs changes the predicted candidate loci), so it cannot be re-implemented on the device and
+stay bit-exact with the reference; it is therefore kept on scikit-learn, the reference's own dependency, with the
+BLAS thread count pinned to 1 exactly as the reference pins it (``main.py:5-9``).  What this module adds is
+concurrency: the three fits of an allele (and the fits of further alleles / samples) run side by side in a small pool
+of spawned workers while the GPU and the calling thread carry on.
+
+``DAJIN2_B200_MLP_WORKERS=0`` keeps the fits in the calling process.
+"""
+
+from __future__ import annotations
+
+import atexit
+import os
+import pickle
+import queue
+import struct
+import subprocess
+import sys
+import threading
+from concurrent.futures import Future, ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+def fit_predict(sample: np.ndarray, control: np.ndarray, threshold: float) -> np.ndarray:
+    """Candidate loci proposed by the reference's MLP; the training set is rebuilt exactly as the reference does."""
+    import warnings
+
+    from sklearn.neural_network import MLPClassifier
+
+    rng = np.random.default_rng(seed=1)
+    n_rand, n_ctrl = 10_000, len(control)
+    base = rng.uniform(0, 100, n_rand)
+    base_err = np.clip(base + rng.uniform(0, threshold, n_rand), 0, 100)
+    base_mut = np.clip(base + rng.uniform(threshold, 100, n_rand), 0, 100)
+    ctrl_err = np.clip(control + rng.uniform(0, threshold, n_ctrl), 0, 100)
+    ctrl_mut = np.clip(control + rng.uniform(threshold, 100, n_ctrl), 0, 100)
+    err = np.concatenate([np.array([base, base_err]).T, np.array([control, ctrl_err]).T], axis=0)
+    mut = np.concatenate([np.array([base, base_mut]).T, np.array([control, ctrl_mut]).T], axis=0)
+    X = np.concatenate([err, mut], axis=0)
+    y = [0] * (n_rand + n_ctrl) + [1] * (n_rand + n_ctrl)
+    clf = MLPClassifier(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # ConvergenceWarning, as the reference silences it (utils/config.py:79-83)
+        clf.fit(X, y)
+    return clf.predict(np.array([control, sample]).T) == 1
+
+
+def workers() -> int:
+    raw = os.environ.get("DAJIN2_B200_MLP_WORKERS")
+    if raw is not None:
+        return max(0, int(raw))
+    return max(3, min(12, (os.cpu_count() or 3) - 1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the pool: N interpreter subprocesses running this file's worker loop, fed through pipes with pickled requests.
+# (Not multiprocessing: its spawn / forkserver start methods re-import the parent's __main__ — bench.py, pytest —
+# in every worker, and fork()ing a process that holds a CUDA context is not an option.)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _send(stream, obj) -> None:
+    blob = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+    stream.write(struct.pack("<Q", len(blob)))
+    stream.write(blob)
+    stream.flush()
+
+
+def _recv(stream):
+    head = stream.read(8)
+    if len(head) < 8:
+        raise EOFError("MLP worker closed its pipe")
+    (n,) = struct.unpack("<Q", head)
+    return pickle.loads(stream.read(n))
+
+
+def _worker_main() -> None:
+    stdin, stdout = sys.stdin.buffer, sys.stdout.buffer
+    sys.stdout = sys.stderr  # stray prints must not corrupt the reply stream
+    import sklearn.neural_network  # noqa: F401  (pay the import once, at start-up)
+
+    _send(stdout, "ready")
+    while True:
+        try:
+            req = _recv(stdin)
+        except EOFError:
+            return
+        try:
+            _send(stdout, ("ok", fit_predict(*req)))
+        except BaseException as exc:  # noqa: BLE001 - reported to the parent
+            _send(stdout, ("error", repr(exc)))
+
+
+class _Worker:
+    def __init__(self):
+        env = dict(os.environ)
+        for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+            env[v] = "1"  # as the reference runs a sample (main.py:5-9): the fit is sensitive to the summation order
+        env["CUDA_VISIBLE_DEVICES"] = ""
+        root = str(Path(__file__).resolve().parent.parent)
+        env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+        self.proc = subprocess.Popen([sys.executable, "-m", "dajin2_b200.mlp_pool", "--worker"], stdin=subprocess.PIPE,
+                                     stdout=subprocess.PIPE, env=env, cwd=root)
+        self.ready = False
+
+    def call(self, args):
+        if not self.ready:
+            if _recv(self.proc.stdout) != "ready":
+                raise RuntimeError("MLP worker failed to start")
+            self.ready = True
+        _send(self.proc.stdin, args)
+        status, payload = _recv(self.proc.stdout)
+        if status != "ok":
+            raise RuntimeError(f"MLP worker: {payload}")
+        return payload
+
+    def close(self):
+        try:
+            self.proc.stdin.close()
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+
+
+class _Pool:
+    def __init__(self, n: int):
+        self.n = n
+        self.idle: queue.Queue = queue.Queue()
+        self.all = [_Worker() for _ in range(n)]  # start every interpreter now: their imports run concurrently
+        for w in self.all:
+            self.idle.put(w)
+        self.threads = ThreadPoolExecutor(max_workers=n, thread_name_prefix="dj-mlp")
+        self.lock = threading.Lock()
+
+    def _run(self, args):
+        w = self.idle.get()
+        try:
+            return w.call(args)
+        finally:
+            self.idle.put(w)
+
+    def submit(self, args) -> Future:
+        return self.threads.submit(self._run, args)
+
+    def close(self):
+        self.threads.shutdown(wait=False, cancel_futures=True)
+        for w in self.all:
+            w.close()
+
+
+_pool: _Pool | None = None
+
+
+def _shutdown() -> None:
+    global _pool
+    if _pool is not None:
+        _pool.close()
+        _pool = None
+
+
+def submit(sample: np.ndarray, control: np.ndarray, threshold: float) -> Future:
+    """Start one fit; ``.result()`` gives the boolean candidate mask."""
+    global _pool
+    n = workers()
+    if n == 0:
+        fut: Future = Future()
+        try:
+            fut.set_result(fit_predict(sample, control, threshold))
+        except BaseException as exc:  # noqa: BLE001 - handed to the caller through the future
+            fut.set_exception(exc)
+        return fut
+    if _pool is None or _pool.n != n:
+        _shutdown()
+        _pool = _Pool(n)
+        atexit.register(_shutdown)
+    return _pool.submit((np.ascontiguousarray(sample, dtype=np.float64),
+                         np.ascontiguousarray(control, dtype=np.float64), float(threshold)))
+
+
+def warm_up() -> None:
+    """Start the workers and import scikit-learn in each of them (first use otherwise pays ~1-2 s)."""
+    n = workers()
+    if n == 0:
+        return
+    tiny = np.zeros(4)
+    for f in [submit(tiny, tiny, 0.1) for _ in range(n)]:
+        f.result()
+
+
+if __name__ == "__main__":
+    if "--worker" in sys.argv:
+        _worker_main()
