@@ -42,7 +42,9 @@ class RowSet:
 def dedup_rows(ids: torch.Tensor, strand: torch.Tensor, rows: torch.Tensor | None) -> RowSet:
     dev = require_cuda()
     n_rows, n_cols = int(ids.shape[0]), int(ids.shape[1])
-    capacity = max(1 << 12, _next_pow2(min(2 * n_rows, 1 << 22)))
+    # score rows are discrete: a few dozen to a few hundred distinct rows whatever N is, so start with
+    # a small table (everything sized by `capacity` below is host memory and H2D traffic) and grow it on demand
+    capacity = max(1 << 12, min(1 << 14, _next_pow2(2 * n_rows)))
     while True:
         table = torch.empty(_cabi.call("dj_row_table_bytes", capacity), dtype=torch.uint8, device=dev)
         _cabi.call("dj_row_table_clear", _p(table), capacity, _stream())
@@ -279,13 +281,10 @@ def remove_biased_clusters(labels_pts: np.ndarray, rs: RowSet, X_pts_dense_fn, s
     return labels
 
 
-def cluster_rows(ids_sample: torch.Tensor, strand_sample: torch.Tensor, rows_sample: torch.Tensor | None,
-                 ids_control: torch.Tensor, strand_control: torch.Tensor, model: KmerModel,
-                 strand_all: dict[str, int]) -> tuple[torch.Tensor, dict]:
-    """``return_labels`` + ``relabel_with_consective_order``: device labels (int32, 1-based, in first-occurrence
-    order) for every sample row plus a small summary dict."""
-    dev = require_cuda()
-    rs = dedup_rows(ids_sample, strand_sample, rows_sample)
+def cluster_points(rs: RowSet, ids_control: torch.Tensor, strand_control: torch.Tensor, model: KmerModel,
+                   strand_all: dict[str, int]) -> tuple[np.ndarray, dict]:
+    """``return_labels`` + ``relabel_with_consective_order`` on the de-duplicated sample rows ``rs`` (local rows of one
+    GPU, or the merged rows of every shard).  Returns the final 1-based label of every sample point."""
     Xs = _values_matrix(rs.point_ids, model.value_of_id)
     Xc, wc, ctrl_rows = control_subset(ids_control, strand_control, model)
     labels_pts = optimize_labels_points(Xs, rs.count, Xc, wc, ctrl_rows, rs)
@@ -300,10 +299,25 @@ def cluster_rows(ids_sample: torch.Tensor, strand_sample: torch.Tensor, rows_sam
     order = sorted(set(labels_pts.tolist()), key=lambda v: rs.first_row[labels_pts == v].min())
     rank = {v: k + 1 for k, v in enumerate(order)}
     final_pts = np.array([rank[v] for v in labels_pts.tolist()], dtype=np.int32)
+    sizes = np.bincount(final_pts, weights=rs.count, minlength=len(order) + 1)[1:].astype(np.int64)
+    return final_pts, {"n_points": len(Xs), "n_control_points": len(Xc), "cluster_sizes": sizes.tolist()}
+
+
+def labels_of_rows(rs: RowSet, final_pts: np.ndarray) -> torch.Tensor:
+    """Device labels (int32) of every row of ``rs`` from the labels of its points."""
+    dev = require_cuda()
     label_of_slot = np.zeros(rs.point_of_slot.shape[0], dtype=np.int32)
     label_of_slot[rs.slots] = final_pts
     labels_d = torch.empty(max(rs.n_rows, 1), dtype=torch.int32, device=dev)
     label_of_slot_d = torch.as_tensor(label_of_slot, device=dev)
     _cabi.call("dj_gather_labels", _p(rs.slot_of_row), rs.n_rows, _p(label_of_slot_d), _p(labels_d), _stream())
-    sizes = np.bincount(final_pts, weights=rs.count, minlength=len(order) + 1)[1:].astype(np.int64)
-    return labels_d[: rs.n_rows], {"n_points": len(Xs), "n_control_points": len(Xc), "cluster_sizes": sizes.tolist()}
+    return labels_d[: rs.n_rows]
+
+
+def cluster_rows(ids_sample: torch.Tensor, strand_sample: torch.Tensor, rows_sample: torch.Tensor | None,
+                 ids_control: torch.Tensor, strand_control: torch.Tensor, model: KmerModel,
+                 strand_all: dict[str, int]) -> tuple[torch.Tensor, dict]:
+    """Device labels (int32, 1-based, in first-occurrence order) for every sample row plus a small summary dict."""
+    rs = dedup_rows(ids_sample, strand_sample, rows_sample)
+    final_pts, info = cluster_points(rs, ids_control, strand_control, model, strand_all)
+    return labels_of_rows(rs, final_pts), info

@@ -1,15 +1,280 @@
-"""Read-sharded multi-GPU execution of the hot path: one process per GPU, NCCL through
-``torch.distributed``.  Filled in below; the single-GPU path never imports this module."""
+"""Read-sharded multi-GPU execution of the hot path: one process per GPU, ``torch.distributed``.
+
+Every read-scale stage is independent per read; what crosses GPUs are per-locus and per-row *summaries*:
+
+  1. the 10 x L int32 histogram of the sample shard (+ the strand totals)            -> all-reduce (sum)
+  2. the selected loci (decided on rank 0 from the reduced histogram)                 -> broadcast
+  3. the distinct 3-mers at the selected loci with their counts                       -> all-gather, merged by name
+  4. the distinct score rows of the shard (value ids, multiplicities, first position) -> all-gather, merged by content
+  5. the point of every read, in global read order (4 bytes per read)                 -> all-gather
+
+after which every rank clusters the same few hundred weighted points and labels its own reads.  The control file
+(<= 10^4 reads) is replicated.  The arithmetic of every step is the single-GPU one, so a sharded run returns exactly
+the labels of the unsharded run; ``tests/test_gpu_parity.py::test_sharded_equals_unsharded`` checks that by driving
+two shards through these phases on one GPU, and ``tests/test_distributed_cpu.py`` runs the merges and the collectives
+under gloo with two processes.
+"""
 
 from __future__ import annotations
 
+from dataclasses import dataclass
+
+import numpy as np
+
+MUTS = ("+", "-", "*")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# communicator: the handful of collectives the path needs, on NCCL (GPU tensors) or gloo (CPU tensors)
+# ---------------------------------------------------------------------------------------------------------
+
 
 class Communicator:
-    def __init__(self, dist):
+    def __init__(self, dist, device=None):
+        import torch
+
         self.dist = dist
         self.rank = dist.get_rank()
         self.world = dist.get_world_size()
+        self.backend = dist.get_backend()
+        self.device = device if device is not None else (
+            torch.device("cuda", torch.cuda.current_device()) if self.backend == "nccl" else torch.device("cpu"))
+        self.collectives = 0
+
+    def allreduce_sum(self, t):
+        """In-place sum of an integer tensor living on ``self.device``."""
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        self.collectives += 1
+        return t
+
+    def allgather_object(self, obj) -> list:
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        self.collectives += 1
+        return out
+
+    def broadcast_object(self, obj, src: int = 0):
+        box = [obj if self.rank == src else None]
+        self.dist.broadcast_object_list(box, src=src)
+        self.collectives += 1
+        return box[0]
+
+    def allgather_rows(self, t, sizes: list[int]):
+        """Concatenation over ranks of 1-D tensors of the given per-rank sizes (padded all-gather)."""
+        import torch
+
+        width = max(sizes)
+        buf = torch.zeros(width, dtype=t.dtype, device=t.device)
+        buf[: t.shape[0]] = t
+        parts = [torch.empty_like(buf) for _ in range(self.world)]
+        self.dist.all_gather(parts, buf)
+        self.collectives += 1
+        return torch.cat([p[:n] for p, n in zip(parts, sizes)])
 
 
-def run_device_sharded(*args, **kwargs):
-    raise NotImplementedError("multi-GPU path is being built")
+# ---------------------------------------------------------------------------------------------------------
+# merges (pure numpy / python: covered on CPU)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def kmer_payload(kc) -> list[tuple[int, str, int, int]]:
+    """(locus, "prev,cur,next", sample count, control count) of every distinct 3-mer of one shard."""
+    out = []
+    for locus, ks in kc.per_locus.items():
+        for k in ks:
+            out.append((int(locus), kc.names[k], int(kc.records["count_sample"][k]), int(kc.records["count_control"][k])))
+    return out
+
+
+@dataclass
+class MergedKmers:
+    """What ``engine.score_from_counts`` reads of a ``KmerCounts``, for the union of all shards."""
+
+    n_loci: int
+    names: list
+    per_locus: dict
+    records: dict
+
+
+def merge_kmers(payloads: list[list[tuple[int, str, int, int]]], n_loci: int) -> MergedKmers:
+    """Sum the sample counts over shards; the control file is replicated, so its counts are taken once (from the
+    first shard that reports the 3-mer with a non-zero control count — they are all equal)."""
+    table: dict[tuple[int, str], list[int]] = {}
+    for payload in payloads:
+        seen: dict[tuple[int, str], list[int]] = {}
+        for locus, name, cs, cc in payload:  # a shard may hold one name under several table slots (raw insertions)
+            cell = seen.setdefault((locus, name), [0, 0])
+            cell[0] += cs
+            cell[1] += cc
+        for key, (cs, cc) in seen.items():
+            cell = table.setdefault(key, [0, 0])
+            cell[0] += cs
+            cell[1] = max(cell[1], cc)
+    keys = sorted(table)
+    names = [k[1] for k in keys]
+    per_locus: dict[int, list[int]] = {}
+    for idx, (locus, _) in enumerate(keys):
+        per_locus.setdefault(locus, []).append(idx)
+    records = {"count_sample": np.array([table[k][0] for k in keys], dtype=np.int64),
+               "count_control": np.array([table[k][1] for k in keys], dtype=np.int64)}
+    return MergedKmers(n_loci, names, per_locus, records)
+
+
+def merge_points(payloads: list[tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]]):
+    """Union of the shards' distinct score rows.  Each payload = (point_ids [U, K] uint16, count [U], count_plus [U],
+    first global position [U]).  Returns (point_ids, count, count_plus, first, maps) with the points ordered by
+    first global position — the order ``dedup_rows`` gives an unsharded run — and, per shard, local -> merged."""
+    index: dict[bytes, int] = {}
+    rows, count, plus, first = [], [], [], []
+    for ids, c, p, f in payloads:
+        for u in range(ids.shape[0]):
+            key = ids[u].tobytes()
+            k = index.get(key)
+            if k is None:
+                index[key] = len(rows)
+                rows.append(ids[u])
+                count.append(int(c[u]))
+                plus.append(int(p[u]))
+                first.append(int(f[u]))
+            else:
+                count[k] += int(c[u])
+                plus[k] += int(p[u])
+                first[k] = min(first[k], int(f[u]))
+    order = np.argsort(np.array(first, dtype=np.int64), kind="stable") if rows else np.zeros(0, dtype=np.int64)
+    new_of_old = np.empty(len(rows), dtype=np.int64)
+    new_of_old[order] = np.arange(len(rows))
+    n_cols = payloads[0][0].shape[1] if payloads else 0
+    ids_m = np.stack([rows[i] for i in order]) if rows else np.zeros((0, n_cols), dtype=np.uint16)
+    maps = [np.array([new_of_old[index[ids[u].tobytes()]] for u in range(ids.shape[0])], dtype=np.int32)
+            for ids, _, _, _ in payloads]
+    return (ids_m, np.array(count, dtype=np.int64)[order], np.array(plus, dtype=np.int64)[order],
+            np.array(first, dtype=np.int64)[order], maps)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the sharded run, phase by phase (a phase ends where a collective is needed)
+# ---------------------------------------------------------------------------------------------------------
+
+
+class ShardRun:
+    """One shard's side of the hot path.  ``gpos[r]`` is the position of local read r in the global label order
+    (QNAME order over all shards, reference classifier.py:38-46)."""
+
+    def __init__(self, sample, control, sequence: str, knockin, gpos: np.ndarray):
+        import torch
+
+        from . import engine
+
+        self.engine = engine
+        self.dev = engine.require_cuda()
+        self.sample, self.control, self.sequence = sample, control, sequence
+        self.knockin = set(knockin) if knockin else None
+        local_order = np.argsort(gpos, kind="stable")
+        self.rows = torch.as_tensor(local_order.astype(np.int32), device=self.dev)  # local reads in global order
+        self.gpos_sorted = np.asarray(gpos, dtype=np.int64)[local_order]
+
+    # phase 1 -> all-reduce
+    def histogram_and_strands(self):
+        import torch
+
+        hist = self.sample.histogram_device().flatten()
+        n_plus = int((self.sample.strand_host == ord("+")).sum())
+        tail = torch.tensor([n_plus, self.sample.n_reads], dtype=torch.int32, device=self.dev)
+        return torch.cat([hist, tail])
+
+    # rank 0 between phase 1 and 2
+    def select_loci(self, reduced) -> list[set[str]]:
+        eng = self.engine
+        L = self.sample.n_loci
+        host = reduced.cpu().numpy()
+        hist_s = host[: 10 * L].reshape(10, L)
+        n_plus, n_total = int(host[10 * L]), int(host[10 * L + 1])
+        hist_c = self.control.histogram()
+        norm_s = eng.normalize_indels(eng.counts_from_histogram(hist_s))
+        norm_c = eng.normalize_indels(eng.counts_from_histogram(hist_c))
+        return eng.select_mutation_loci(hist_s, (n_plus, n_total - n_plus), self.sequence, norm_s, norm_c, self.knockin)
+
+    # phase 2 -> all-gather of 3-mer payloads
+    def count_kmers(self, reduced, loci_t: list[set[str]]):
+        L = self.sample.n_loci
+        host = reduced[10 * L :].cpu().numpy()
+        self.n_plus, self.n_total = int(host[0]), int(host[1])
+        self.loci_t = loci_t
+        self.kc = self.engine.count_kmers(self.sample, self.rows, self.control, loci_t)
+        return kmer_payload(self.kc)
+
+    # phase 3 -> all-gather of distinct rows
+    def score_rows(self, kmer_payloads: list):
+        from . import clusterer
+
+        eng = self.engine
+        merged = merge_kmers(kmer_payloads, self.sample.n_loci)
+        score = eng.score_from_counts(merged, self.n_total, self.control.n_reads, self.loci_t, self.knockin or set())
+        self.model = eng.model_from_score(self.kc, score)
+        self.ids_s = eng.annotate_ids(self.sample, self.rows, self.model, False)
+        self.ids_c = eng.annotate_ids(self.control, None, self.model, True)
+        self.rs = clusterer.dedup_rows(self.ids_s, self.sample.strand, self.rows)
+        first_global = self.gpos_sorted[self.rs.first_row] if len(self.rs.first_row) else np.zeros(0, dtype=np.int64)
+        return (self.rs.point_ids, self.rs.count, self.rs.count_plus, first_global)
+
+    # phase 4 -> all-gather of (global position, merged point) per read
+    def points_of_reads(self, point_payloads: list, shard_index: int):
+        import torch
+
+        self.merged_points = merge_points(point_payloads)
+        local_to_merged = self.merged_points[4][shard_index]
+        lut = np.full(self.rs.point_of_slot.shape[0], -1, dtype=np.int32)
+        lut[self.rs.slots] = local_to_merged
+        lut_d = torch.as_tensor(lut, device=self.dev)
+        self.point_of_row = lut_d[self.rs.slot_of_row.long()].to(torch.int32)  # local reads in global order
+        return torch.as_tensor(self.gpos_sorted, device=self.dev), self.point_of_row
+
+    # phase 5: every rank clusters the merged points and labels its reads
+    def cluster(self, gpos_all, point_all):
+        import torch
+
+        from . import clusterer
+
+        ids_m, count, plus, first, _ = self.merged_points
+        n_points = int(ids_m.shape[0])
+        point_of_global_row = torch.empty(self.n_total, dtype=torch.int32, device=self.dev)
+        point_of_global_row[gpos_all.long()] = point_all
+        rs_global = clusterer.RowSet(self.n_total, point_of_global_row, np.arange(n_points, dtype=np.uint32), count, plus,
+                                     first, ids_m, np.arange(n_points, dtype=np.int32))
+        final_pts, info = clusterer.cluster_points(rs_global, self.ids_c, self.control.strand, self.model,
+                                                   {"+": self.n_plus, "-": self.n_total - self.n_plus})
+        labels_d = torch.as_tensor(final_pts, device=self.dev)[self.point_of_row.long()]
+        return labels_d, info
+
+
+def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, gpos: np.ndarray,
+                       fetch_labels: bool = True):
+    """Drive one shard through the phases with real collectives.  Returns a ``pipeline.HotPathResult`` whose labels
+    refer to the local reads in global order (``order`` = the local read index of each label)."""
+    import torch
+
+    from .pipeline import HotPathResult
+
+    run = ShardRun(sample, control, sequence, knockin, gpos)
+    reduced = comm.allreduce_sum(run.histogram_and_strands())
+    loci_mask = None
+    if comm.rank == 0:
+        loci_mask = ["".join(sorted(m)) for m in run.select_loci(reduced)]
+    loci_t = [set(m) for m in comm.broadcast_object(loci_mask)]
+    order = run.rows.cpu().numpy()
+    n_total = int(reduced[-1].item())
+    if all(not m for m in loci_t) or n_total < 5:
+        labels = np.ones(sample.n_reads, dtype=np.int32) if fetch_labels else None
+        return HotPathResult(labels, order, [n_total], [100.0], loci_t, None, {"collectives": comm.collectives})
+    kmers = comm.allgather_object(run.count_kmers(reduced, loci_t))
+    points = comm.allgather_object(run.score_rows(kmers))
+    gpos_d, point_d = run.points_of_reads(points, comm.rank)
+    sizes = [int(p[1].sum()) for p in points]
+    gpos_all = comm.allgather_rows(gpos_d, sizes)
+    point_all = comm.allgather_rows(point_d, sizes)
+    labels_d, info = run.cluster(gpos_all, point_all)
+    labels = labels_d.cpu().numpy() if fetch_labels else None
+    sizes_c = info["cluster_sizes"]
+    pct = [round(s / n_total * 100, 3) for s in sizes_c]
+    timings = {"n_points": info["n_points"], "n_cols": run.model.n_cols, "collectives": comm.collectives}
+    return HotPathResult(labels, order, sizes_c, pct, loci_t, run.model, timings)

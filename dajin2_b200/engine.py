@@ -100,13 +100,16 @@ class EncodedReads:
         """calc_match of every read (reference ``classification/classifier.py:11-24``)."""
         return self.match_score[: self.n_reads].cpu().numpy()
 
-    def histogram(self, rows: torch.Tensor | None = None) -> np.ndarray:
-        """int32[10, L]: rows 0-3 = count_indels classes '=', '+', '-', '*' (skip rule applied); rows 4-9 =
-        startswith('+','-','*') counts on '+' then '-' strand reads (no skip rule)."""
+    def histogram_device(self, rows: torch.Tensor | None = None) -> torch.Tensor:
+        """int32[10, L] on the device: rows 0-3 = count_indels classes '=', '+', '-', '*' (skip rule applied); rows
+        4-9 = startswith('+','-','*') counts on '+' then '-' strand reads (no skip rule)."""
         out = torch.empty((_cabi.HIST_ROWS, self.n_loci), dtype=torch.int32, device=self.codes.device)
         n = self.n_reads if rows is None else int(rows.shape[0])
         _cabi.call("dj_hist", _p(self.codes), self.pitch, _p(self.strand), _p(rows), n, self.n_loci, _p(out), _stream())
-        return out.cpu().numpy()
+        return out
+
+    def histogram(self, rows: torch.Tensor | None = None) -> np.ndarray:
+        return self.histogram_device(rows).cpu().numpy()
 
     def fetch_tokens(self, reads, loci) -> list[str]:
         """Raw text of token ``loci[k]`` of read ``reads[k]`` (used to print raw insertion tokens)."""
@@ -242,12 +245,20 @@ def homopolymer_errors(sequence: str, norm_sample, norm_control, loci: dict[str,
     return out
 
 
-def strand_biased_loci(hist_sample: np.ndarray, strand_host: np.ndarray, loci_t: list[set[str]]) -> dict[str, set[int]]:
-    """Reference ``error_correction/strand_bias_handler.py:36-61`` on the histogram's startswith rows."""
+def strand_totals(strand_host) -> tuple[int, int]:
+    """(reads on '+', reads on '-') from the per-read strand bytes, or the pair itself when already counted."""
+    if isinstance(strand_host, tuple):
+        return int(strand_host[0]), int(strand_host[1])
+    n_plus = int((strand_host == ord("+")).sum())
+    return n_plus, int(strand_host.shape[0]) - n_plus
+
+
+def strand_biased_loci(hist_sample: np.ndarray, strand_host, loci_t: list[set[str]]) -> dict[str, set[int]]:
+    """Reference ``error_correction/strand_bias_handler.py:36-61`` on the histogram's startswith rows.
+    ``strand_host``: the per-read strand bytes, or the (plus, minus) totals (read-sharded runs)."""
     from scipy.stats import fisher_exact
 
-    n_plus = int((strand_host == ord("+")).sum())
-    n_minus = int(strand_host.shape[0]) - n_plus
+    n_plus, n_minus = strand_totals(strand_host)
     biased = {op: set() for op in MUTS}
     for i, per_op in strand_table(hist_sample, loci_t).items():
         for op, c in per_op.items():

@@ -77,13 +77,21 @@ def _finish(timings: dict) -> None:
 
 def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequence: str, knockin: set[int] | None = None,
                order: np.ndarray | None = None, fetch_labels: bool = True, reencode: bool = True,
-               comm=None) -> HotPathResult:
-    """Hot path on reads whose text already sits in HBM."""
+               comm=None, gpos: np.ndarray | None = None) -> HotPathResult:
+    """Hot path on reads whose text already sits in HBM.  With ``comm`` (a ``distributed.Communicator``) the sample
+    is one shard of a read-sharded run and ``gpos`` gives the global label-order position of each local read."""
     dev = engine.require_cuda()
     if comm is not None:
         from . import distributed
 
-        return distributed.run_device_sharded(sample, control, sequence, knockin, comm, fetch_labels, reencode)
+        if reencode:
+            sample.encode()
+            control.encode()
+            sample.validate()
+            control.validate()
+        if gpos is None:
+            raise ValueError("a sharded run needs the global position of every local read (gpos)")
+        return distributed.run_device_sharded(sample, control, sequence, knockin, comm, gpos, fetch_labels)
     timings: dict = {}
     tm = _Timer(timings)
     if reencode:
@@ -129,14 +137,14 @@ def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequen
 
 
 def run_host(sample: HostReads, control: HostReads, sequence: str, knockin: set[int] | None = None,
-             order: np.ndarray | None = None, comm=None) -> HotPathResult:
+             order: np.ndarray | None = None, comm=None, gpos: np.ndarray | None = None) -> HotPathResult:
     """Hot path from packed HOST buffers: host->device copies, the device path, label read-back."""
     t0 = time.perf_counter()
     enc_s = engine.EncodedReads(sample, len(sequence), validate=False, encode=False)
     enc_c = engine.EncodedReads(control, len(sequence), validate=False, encode=False)
     torch.cuda.synchronize()
     h2d_ms = (time.perf_counter() - t0) * 1e3
-    res = run_device(enc_s, enc_c, sequence, knockin, order, comm=comm)
+    res = run_device(enc_s, enc_c, sequence, knockin, order, comm=comm, gpos=gpos)
     res.timings["h2d_ms"] = h2d_ms
     res.timings["h2d_bytes"] = enc_s.h2d_bytes + enc_c.h2d_bytes
     res.timings["d2h_bytes"] = int(res.labels.nbytes) if res.labels is not None else 0

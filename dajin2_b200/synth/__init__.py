@@ -147,6 +147,14 @@ class MidsvBatch:
         return path
 
 
+def qnames(seed: int, first_read: int, stride: int, n_reads: int) -> np.ndarray:
+    """QNAMEs of reads first_read, first_read + stride, ... of the stream with this seed (a function of the index)."""
+    out = np.empty(n_reads, dtype="S36")
+    if n_reads:
+        _load().dj_synth_qnames(seed, first_read, stride, n_reads, out.ctypes.data)
+    return out
+
+
 def generate(pop: Population, n_reads: int, seed: int = SEED, first_read: int = 0, stride: int = 1,
              text_alloc=None) -> MidsvBatch:
     """``text_alloc(nbytes)`` may supply the uint8 buffer for the text (e.g. a view of pinned host memory)."""

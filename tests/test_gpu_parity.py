@@ -286,3 +286,45 @@ def test_first_token_raw_insertion_quirk():
     assert model.score == want
     rows = engine.dense_score_rows(engine.annotate_ids(es, None, model, False), model)
     assert rows == list(orc.annotate_score(sample, want, loci))
+
+
+@pytest.mark.parametrize("name,n_shards", [("tp_L1000_N2000_r10", 2), ("tp_L1000_N1200_r9", 3), ("point_L900_N1500", 2)])
+def test_sharded_equals_unsharded(name, n_shards):
+    """The read-sharded path (dajin2_b200/distributed.py) returns exactly the labels of the unsharded run: the
+    shards are driven through its phases on one GPU, with the collectives replaced by local sums / lists."""
+    import torch
+
+    from dajin2_b200 import distributed as dj
+    from dajin2_b200 import engine, pipeline
+    from dajin2_b200.ingest import pack_rows
+
+    alleles, golden = load_case(name)
+    a = alleles["control"]
+    L = len(a["sequence"])
+    part = a["sample"]
+    es, ec = _enc(part, L), _enc(a["control"], L)
+    full = pipeline.run_device(es, ec, a["sequence"], a.get("knockin"), None)
+    n = len(part["rows"])
+    position = np.empty(n, dtype=np.int64)
+    position[full.order] = np.arange(n)  # global label-order position of every read
+
+    runs = []
+    for k in range(n_shards):
+        idx = list(range(k, n, n_shards))
+        host = pack_rows([part["rows"][i] for i in idx], [part["strands"][i] for i in idx], [part["qnames"][i] for i in idx])
+        runs.append(dj.ShardRun(engine.EncodedReads(host, L), ec, a["sequence"], a.get("knockin"), position[idx]))
+    reduced = sum(r.histogram_and_strands() for r in runs)
+    loci = runs[0].select_loci(reduced)
+    assert loci == full.mutation_loci
+    kmers = [r.count_kmers(reduced, loci) for r in runs]
+    points = [r.score_rows(kmers) for r in runs]
+    assert all(r.model.score == full.model.score for r in runs)
+    per_read = [r.points_of_reads(points, k) for k, r in enumerate(runs)]
+    gpos_all = torch.cat([g for g, _ in per_read])
+    point_all = torch.cat([p for _, p in per_read])
+    labels = np.zeros(n, dtype=np.int64)
+    for r in runs:
+        lab, info = r.cluster(gpos_all, point_all)
+        labels[r.gpos_sorted] = lab.cpu().numpy()
+        assert info["cluster_sizes"] == full.cluster_sizes
+    assert labels.tolist() == full.labels.tolist()
