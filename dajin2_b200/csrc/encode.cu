@@ -368,7 +368,7 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
         if (!broken) {  // what is left is less than one sector: pad it (deterministically) and store it
             __syncwarp();
             const int staged = tokbase & 31;
-            if (lane < 32 - staged) stage[staged + lane] = DJ_CODE_INVALID;
+            if (lane < 32 - staged) stage[staged + lane] = 0;  // reads as a plain match: dj_hist looks at every byte of the pitch
             __syncwarp();
             if (staged > 0 && lane < 2 && (tokbase & ~31) < code_pitch)
                 *reinterpret_cast<uint4 *>(outp) = *reinterpret_cast<const uint4 *>(stage + lane * 16);
