@@ -29,6 +29,21 @@ int dj_sm_count() {
     return sms;
 }
 
+// Scratch buffers come from the device's stream-ordered pool (cudaMallocAsync): keep freed blocks in the pool across
+// synchronisations instead of returning them to the driver.
+int dj_scratch_pool_init() {
+    static bool done = false;
+    if (done) return 0;
+    int dev = 0;
+    cudaMemPool_t pool;
+    DJ_CUDA_CHECK(cudaGetDevice(&dev));
+    DJ_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = UINT64_MAX;
+    DJ_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done = true;
+    return 0;
+}
+
 extern "C" int dj_abi_version(void) { return DJ_ABI_VERSION; }
 
 extern "C" const char *dj_last_error(void) { return g_error; }

@@ -505,16 +505,18 @@ extern "C" int dj_dedup_export(const void *table, uint32_t capacity, DjRowRecord
     }
     DjRowRecord *d_out = nullptr;
     uint32_t *d_n = nullptr;
-    DJ_CUDA_CHECK(cudaMalloc(&d_out, sizeof(DjRowRecord) * (size_t)header[0]));
-    DJ_CUDA_CHECK(cudaMalloc(&d_n, sizeof(uint32_t)));
+    if (dj_scratch_pool_init() != 0) return 1;
+    // stream-ordered scratch: cudaMalloc / cudaFree synchronise the device and cost tens of milliseconds in a
+    // process that holds gigabytes of allocations
+    DJ_CUDA_CHECK(cudaMallocAsync(&d_out, sizeof(DjRowRecord) * (size_t)header[0] + 16, st));
+    d_n = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(d_out) + sizeof(DjRowRecord) * (size_t)header[0]);
     DJ_CUDA_CHECK(cudaMemsetAsync(d_n, 0, sizeof(uint32_t), st));
     dedup_export_kernel<<<grid_for(capacity, kThreads), kThreads, 0, st>>>(tb, d_out, header[0], d_n);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess)
         err = cudaMemcpyAsync(h_out, d_out, sizeof(DjRowRecord) * (size_t)header[0], cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
-    cudaFree(d_out);
-    cudaFree(d_n);
+    cudaFreeAsync(d_out, st);
     if (err != cudaSuccess) {
         dj_set_error("dj_dedup_export: %s", cudaGetErrorString(err));
         return 1;

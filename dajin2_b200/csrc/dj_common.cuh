@@ -23,6 +23,7 @@ void dj_set_error(const char *fmt, ...);
 #define DJ_LAUNCH_CHECK() DJ_CUDA_CHECK(cudaGetLastError())
 
 int dj_sm_count();
+int dj_scratch_pool_init();  // 0 on success; call before cudaMallocAsync
 
 // ---------------------------------------------------------------------------------------------------------
 // code byte arithmetic (see include/dajin2_b200.h for the layout)

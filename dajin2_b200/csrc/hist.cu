@@ -297,13 +297,7 @@ extern "C" int dj_hist(const uint8_t *codes, int32_t code_pitch, const uint8_t *
                                            (int)sizeof(HistSmem)));
         DJ_CUDA_CHECK(cudaFuncSetAttribute(hist_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)sizeof(HistSmem)));
-        // keep the scratch (global tile, column counters) in the stream-ordered pool across synchronisations
-        int dev = 0;
-        cudaMemPool_t pool;
-        DJ_CUDA_CHECK(cudaGetDevice(&dev));
-        DJ_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
-        uint64_t keep = UINT64_MAX;
-        DJ_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        if (dj_scratch_pool_init() != 0) return 1;
         configured = true;
     }
     const int n_cols = (code_pitch + kTileLoci - 1) / kTileLoci;
