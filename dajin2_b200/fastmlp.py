@@ -1,0 +1,189 @@
+"""A faster evaluation of scikit-learn's lbfgs MLP loss/gradient that is bit-identical to scikit-learn's own.
+
+``detect_anomalies`` of the reference (``mutation_processing/anomaly_detector.py:61-94``) fits
+``MLPClassifier(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)`` on
+2 x (10 000 + L) two-dimensional points, three times per allele: ~0.6 s of single-threaded host time that does not
+depend on the number of reads and dominates a step once the read-scale passes run on the GPU.  The fit is chaotic in
+its rounding (profiles/r01_mlp_stability.log), so anything short of the same floating-point operations in the same
+order selects different candidate loci.  ``FastMLPClassifier`` therefore changes nothing about the model, the
+initialisation or the optimiser (all inherited from scikit-learn / scipy); it only replaces the ~60 numpy calls of
+one loss/gradient evaluation (``_loss_grad_lbfgs``) by the same arithmetic fused into three C passes
+(``hostc/fastmlp.c``: hidden layers forward; logistic + log-loss + output delta; backward), about ten times faster:
+
+  * the matrix products numpy hands to dgemm are single fused-multiply-add chains over the inner dimension
+    (``scripts/micro/blas_order_probe.py``) and are restated as such; the two matrix x vector products of the output
+    unit (dgemv: another order) are still made by numpy, exactly as scikit-learn's ``safe_sparse_dot`` makes them;
+  * sums are numpy's pairwise summation or row-by-row accumulation, whichever numpy uses for that shape;
+  * ``expit`` / ``xlogy`` are libm's ``exp`` / ``log`` as in scipy.special; these two take most of the time left and
+    run on ``DAJIN2_B200_MLP_THREADS`` threads (element-wise, so the thread count cannot change a bit).
+
+Trust, but verify: every fit evaluates scikit-learn's original ``_loss_grad_lbfgs`` at the first and at the last
+iterate and compares loss and gradient bit for bit; on any difference (another numpy / scipy / libm than the ones
+this was written against) the fit is redone with scikit-learn's own evaluation, so the result is always
+scikit-learn's.  ``tests/test_fastmlp.py`` compares complete fits.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+from sklearn.neural_network import MLPClassifier
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "hostc" / "fastmlp.c"
+LIB = HERE / "hostc" / "libdjhost.so"
+
+_lib = None
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+def build(force: bool = False) -> Path:
+    """gcc -O2 without fast-math and without FMA contraction: the C code must round exactly like numpy does."""
+    if force or not LIB.exists() or LIB.stat().st_mtime < SRC.stat().st_mtime:
+        tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
+        flags = ["-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp"]
+        try:
+            if " fma " in Path("/proc/cpuinfo").read_text():
+                flags.append("-mfma")  # fma() inlines to vfmadd; without it libm's (exact, slow) fma is called
+        except OSError:
+            pass
+        subprocess.run(["gcc", *flags, "-o", str(tmp), str(SRC), "-lm"], check=True)
+        tmp.replace(LIB)
+    return LIB
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = ctypes.CDLL(str(LIB))
+        vp, i64, ci, cd = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
+        lib.fm_set_threads.argtypes = [ci]
+        lib.fm_set_threads.restype = None
+        lib.fm_forward_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, vp, vp, vp]
+        lib.fm_forward_packed.restype = ci
+        lib.fm_output.argtypes = [vp, cd, vp, i64, vp, vp, vp]
+        lib.fm_output.restype = cd
+        lib.fm_backward_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, cd, cd, vp]
+        lib.fm_backward_packed.restype = ci
+        lib.fm_set_threads(max(1, int(os.environ.get("DAJIN2_B200_MLP_THREADS", "4"))))
+        lib.fm_pairwise_sum.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        lib.fm_pairwise_sum.restype = ctypes.c_double
+        _lib = lib
+    return _lib
+
+
+def _ptr(a: np.ndarray) -> int:
+    return a.ctypes.data
+
+
+class FastMLPClassifier(MLPClassifier):
+    """``MLPClassifier`` whose lbfgs loss/gradient evaluation is fused (two hidden relu layers, one logistic output,
+    float64, no sample weights); any other configuration uses scikit-learn's evaluation."""
+
+    fast_path_used_: bool = False
+
+    def _fast_applicable(self, X, y, sample_weight) -> bool:
+        return (sample_weight is None and self.activation == "relu" and self.out_activation_ == "logistic"
+                and self.n_layers_ == 4 and self.n_outputs_ == 1 and isinstance(X, np.ndarray)
+                and X.dtype == np.float64 and X.ndim == 2 and self.loss == "log_loss")
+
+    def _fast_setup(self, X, y):
+        n, n_in = X.shape
+        h1, h2 = self.coefs_[0].shape[1], self.coefs_[1].shape[1]
+        f = lambda *shape: np.empty(shape, dtype=np.float64)  # noqa: E731
+        fm = {
+            "n": n, "lib": _load(), "dims": (n_in, h1, h2), "y": np.ascontiguousarray(y, dtype=np.float64).reshape(n, 1),
+            "a1": f(n, h1), "a2": f(n, h2), "d3": f(n, 1), "d2": f(n, h2), "d1": f(n, h1), "terms": f(n), "sum3": f(1),
+            "xs": (X.strides[0] // 8, X.strides[1] // 8), "X": X,
+            # offsets of W1, W2, W3, b1, b2, b3 in scikit-learn's packed parameter vector (_pack / _unpack)
+            "o_w3": n_in * h1 + h1 * h2, "o_b3": n_in * h1 + h1 * h2 + h2 + h1 + h2,
+            "n_par": n_in * h1 + h1 * h2 + h2 + h1 + h2 + 1,
+        }
+        fm["a2T"] = fm["a2"].T
+        fm["ptr"] = {k: _ptr(fm[k]) for k in ("a1", "a2", "d3", "d2", "d1", "terms", "sum3", "y", "X")}
+        self._fm = fm
+
+    def _fast_loss_grad(self, packed, X):
+        fm = self._fm
+        lib, n, ptr = fm["lib"], fm["n"], fm["ptr"]
+        n_in, h1, h2 = fm["dims"]
+        xs_row, xs_col = fm["xs"]
+        if X is not fm["X"] or packed.dtype != np.float64 or not packed.flags.c_contiguous or packed.shape[0] != fm["n_par"]:
+            raise RuntimeError("unexpected arguments for the fused evaluation")
+        pp = _ptr(packed)
+        o_w3, o_b3 = fm["o_w3"], fm["o_b3"]
+        if lib.fm_forward_packed(ptr["X"], xs_row, xs_col, n, n_in, h1, h2, pp, ptr["a1"], ptr["a2"]) != 0:
+            raise RuntimeError("layer too wide for the fused evaluation")
+        W3 = packed[o_w3:o_w3 + h2].reshape(h2, 1)  # the view _unpack makes of the output unit's weights
+        a3 = fm["a2"] @ W3  # (n, h2) @ (h2, 1): numpy -> dgemv, as safe_sparse_dot does
+        loss = np.float64(lib.fm_output(_ptr(a3), float(packed[o_b3]), ptr["y"], n, ptr["d3"], ptr["terms"], ptr["sum3"]))
+        values = 0
+        lo = 0
+        for size in (n_in * h1, h1 * h2, h2):  # for s in self.coefs_: values += np.dot(s.ravel(), s.ravel())
+            sl = packed[lo:lo + size]
+            values += np.dot(sl, sl)
+            lo += size
+        loss += (0.5 * self.alpha) * values / n
+        g3_raw = fm["a2T"] @ fm["d3"]  # (h2, n) @ (n, 1): numpy -> dgemv
+        grad = np.empty(fm["n_par"], dtype=np.float64)
+        if lib.fm_backward_packed(ptr["X"], xs_row, xs_col, n, n_in, h1, h2, pp, ptr["a1"], ptr["a2"], ptr["d3"], ptr["d2"],
+                                  ptr["d1"], _ptr(g3_raw), float(fm["sum3"][0]), float(self.alpha), _ptr(grad)) != 0:
+            raise RuntimeError("layer too wide for the fused evaluation")
+        return loss, grad
+
+    def _loss_grad_lbfgs(self, packed_coef_inter, X, y, sample_weight, activations, deltas, coef_grads, intercept_grads):
+        mode = getattr(self, "_fm_mode", None)
+        if mode is None:  # first evaluation of this fit: decide, and check against scikit-learn's own evaluation
+            mode = "sklearn"
+            if self._fast_applicable(X, y, sample_weight):
+                self._fast_setup(X, y)
+                ref = super()._loss_grad_lbfgs(packed_coef_inter.copy(), X, y, sample_weight, activations, deltas,
+                                               coef_grads, intercept_grads)
+                try:
+                    got = self._fast_loss_grad(packed_coef_inter, X)
+                    if _same_bits(ref, got):
+                        mode = "fast"
+                except Exception:  # noqa: BLE001 - anything unexpected: scikit-learn's own evaluation is always right
+                    mode = "sklearn"
+            self._fm_mode = mode
+        if mode == "fast":
+            self._fm_last = packed_coef_inter.copy()
+            return self._fast_loss_grad(packed_coef_inter, X)
+        return super()._loss_grad_lbfgs(packed_coef_inter, X, y, sample_weight, activations, deltas, coef_grads,
+                                        intercept_grads)
+
+    def _fit_lbfgs(self, X, y, sample_weight, activations, deltas, coef_grads, intercept_grads, layer_units):
+        self._fm_mode = None
+        start = [c.copy() for c in self.coefs_], [b.copy() for b in self.intercepts_]
+        super()._fit_lbfgs(X, y, sample_weight, activations, deltas, coef_grads, intercept_grads, layer_units)
+        self.fast_path_used_ = self._fm_mode == "fast"
+        if self._fm_mode == "fast":
+            # check the last evaluated point as well (late iterates exercise the clipped / saturated branches)
+            last = self._fm_last
+            final = [c.copy() for c in self.coefs_], [b.copy() for b in self.intercepts_]
+            ref = super()._loss_grad_lbfgs(last.copy(), X, y, sample_weight, activations, deltas, coef_grads,
+                                           intercept_grads)
+            got = self._fast_loss_grad(last, X)
+            if _same_bits(ref, got):
+                self.coefs_, self.intercepts_ = final
+            else:  # not the arithmetic this was written against: redo the fit with scikit-learn's evaluation
+                self.coefs_, self.intercepts_ = start
+                self._fm_mode = "sklearn"
+                self.fast_path_used_ = False
+                MLPClassifier._fit_lbfgs(self, X, y, sample_weight, activations, deltas, coef_grads, intercept_grads,
+                                         layer_units)
+        self._fm = None
+
+
+def _same_bits(ref, got) -> bool:
+    (l0, g0), (l1, g1) = ref, got
+    a = np.asarray(l0, dtype=np.float64).reshape(1).view(np.uint64)
+    b = np.asarray(l1, dtype=np.float64).reshape(1).view(np.uint64)
+    return bool(a[0] == b[0]) and g0.shape == g1.shape and bool(
+        np.array_equal(np.ascontiguousarray(g0, dtype=np.float64).view(np.uint64),
+                       np.ascontiguousarray(g1, dtype=np.float64).view(np.uint64)))

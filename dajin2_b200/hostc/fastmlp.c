@@ -1,0 +1,253 @@
+/* scikit-learn's lbfgs MLP loss/gradient (float64, two relu hidden layers, one logistic output), bit for bit.
+ *
+ * The reference selects candidate loci with sklearn's MLPClassifier(solver="lbfgs", hidden_layer_sizes=(5, 2))
+ * (src/DAJIN2/core/preprocess/mutation_processing/anomaly_detector.py:89-92).  One loss/gradient evaluation of
+ * that model on the 2 x (10 000 + L) training points is ~60 numpy calls on (n, 5) arrays and costs ~4.5 ms, almost
+ * all of it numpy's per-call and per-element overhead.  This file restates the arithmetic of
+ * sklearn/neural_network/_multilayer_perceptron.py (_forward_pass, _backprop, _compute_loss_grad) and _base.py
+ * (binary_log_loss, inplace_relu, inplace_relu_derivative) with the SAME floating-point operations in the SAME
+ * order, so that the optimiser follows the same trajectory to the last bit:
+ *   - matrix products (numpy -> OpenBLAS dgemm): every output element is ONE chain of fused multiply-adds over
+ *     the inner dimension, started from +0.0 (probed with scripts/micro/blas_order_probe.py: no k-blocking and no
+ *     split accumulators are visible up to K = 30 000).  The two matrix x vector products of the output unit go
+ *     through dgemv, whose order differs, and stay with numpy (called from Python between the stages here);
+ *   - an inner dimension of 1 takes numpy's non-BLAS loop: out = 0 + a * b;
+ *   - np.sum / np.mean over a contiguous axis is numpy's pairwise summation (blocks of 128, 8 accumulators),
+ *     restated in pairwise_sum(); a sum over axis 0 of an (n, h > 1) array is a plain row-by-row accumulation;
+ *   - expit and xlogy are scipy.special's: 1 / (1 + exp(-x)) and x * log(y) with libm's exp / log.
+ * None of this is taken on trust: dajin2_b200/fastmlp.py compares loss and gradient with scikit-learn's own function
+ * at the first and the last iterate of every fit and falls back to scikit-learn on any difference.
+ * Compile WITHOUT -ffast-math, with -ffp-contract=off (and -mfma where the CPU has it).
+ */
+#include <math.h>
+#include <stdint.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+static int g_threads = 1;
+void fm_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+
+/* numpy/_core/src/umath/loops_utils.h.src: @TYPE@_pairwise_sum */
+static double pairwise_sum(const double *a, int64_t n) {
+    if (n < 8) {
+        double res = 0.;
+        for (int64_t i = 0; i < n; i++) res += a[i];
+        return res;
+    } else if (n <= 128) {
+        double r[8], res;
+        int64_t i;
+        r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = a[3];
+        r[4] = a[4]; r[5] = a[5]; r[6] = a[6]; r[7] = a[7];
+        for (i = 8; i < n - (n % 8); i += 8) {
+            r[0] += a[i + 0]; r[1] += a[i + 1]; r[2] += a[i + 2]; r[3] += a[i + 3];
+            r[4] += a[i + 4]; r[5] += a[i + 5]; r[6] += a[i + 6]; r[7] += a[i + 7];
+        }
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    } else {
+        int64_t n2 = n / 2;
+        n2 -= n2 % 8;
+        return pairwise_sum(a, n2) + pairwise_sum(a + n2, n - n2);
+    }
+}
+
+/* np.maximum(v, 0): v unless v < 0 (NaN and -0.0 pass through, as numpy's loop does) */
+static inline double relu(double v) { return v < 0.0 ? 0.0 : v; }
+
+#define FM_MAX_H 16
+
+/* Forward pass through the two hidden layers:
+ *   a1 = relu(X @ W1 + b1)   (n x h1),   a2 = relu(a1 @ W2 + b2)   (n x h2)
+ * X has n_in columns and arbitrary element strides (xs_row, xs_col, in doubles); W row-major. */
+/* rows [i0, i1) of the forward pass; called with literal layer sizes for the reference's model so that the inner
+ * loops unroll (the OpenMP region is outside: an outlined region would turn the sizes back into variables) */
+static inline __attribute__((always_inline)) void forward_rows(
+    int64_t i0, int64_t i1, const double *X, int64_t xs_row, int64_t xs_col, const int n_in, const double *W1,
+    const double *b1, const int h1, const double *W2, const double *b2, const int h2, double *a1, double *a2) {
+    for (int64_t i = i0; i < i1; i++) {
+        double *r1 = a1 + i * h1, *r2 = a2 + i * h2;
+        for (int j = 0; j < h1; j++) {
+            double acc = 0.0;
+            for (int k = 0; k < n_in; k++) acc = fma(X[i * xs_row + k * xs_col], W1[k * h1 + j], acc);
+            r1[j] = relu(acc + b1[j]);
+        }
+        for (int j = 0; j < h2; j++) {
+            double acc = 0.0;
+            for (int k = 0; k < h1; k++) acc = fma(r1[k], W2[k * h2 + j], acc);
+            r2[j] = relu(acc + b2[j]);
+        }
+    }
+}
+
+#define FM_CHUNKS 64
+
+int fm_forward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n_in, const double *W1, const double *b1,
+               int h1, const double *W2, const double *b2, int h2, double *a1, double *a2) {
+    if (h1 > FM_MAX_H || h2 > FM_MAX_H || n_in > FM_MAX_H) return 1;
+    const int64_t step = (n + FM_CHUNKS - 1) / FM_CHUNKS;
+    if (n_in == 2 && h1 == 5 && h2 == 2) {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+        for (int c = 0; c < FM_CHUNKS; c++)
+            forward_rows(c * step, (c + 1) * step < n ? (c + 1) * step : n, X, xs_row, xs_col, 2, W1, b1, 5, W2, b2, 2, a1, a2);
+    } else {
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+        for (int c = 0; c < FM_CHUNKS; c++)
+            forward_rows(c * step, (c + 1) * step < n ? (c + 1) * step : n, X, xs_row, xs_col, n_in, W1, b1, h1, W2, b2, h2,
+                         a1, a2);
+    }
+    return 0;
+}
+
+/* Output unit: a = expit(z + b); binary_log_loss(y, a); delta = a - y.
+ * Returns -mean(xlogy(y, p) + xlogy(1 - y, 1 - p)) with p = clip(a, eps, 1 - eps); *sum_delta = np.sum(delta, axis=0).
+ * z is overwritten with a; `terms` is scratch of n doubles. */
+double fm_output(double *z, double b, const double *y, int64_t n, double *delta, double *terms, double *sum_delta) {
+    const double eps = 2.220446049250313e-16;
+    const double hi = 1.0 - eps;
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        double v = z[i] + b;
+        double a = 1.0 / (1.0 + exp(-v));
+        z[i] = a;
+        double p = a < eps ? eps : (a > hi ? hi : a);
+        double yi = y[i], t1, t2;
+        /* scipy.special.xlogy: 0 when x == 0 and y is not NaN, else x * log(y) */
+        t1 = (yi == 0.0 && p == p) ? 0.0 : yi * log(p);
+        double q = 1.0 - p, w = 1.0 - yi;
+        t2 = (w == 0.0 && q == q) ? 0.0 : w * log(q);
+        terms[i] = t1 + t2;
+        delta[i] = a - yi;
+    }
+    *sum_delta = pairwise_sum(delta, n);
+    return -(pairwise_sum(terms, n) / (double)n);
+}
+
+/* Backward pass below the output unit (d3 = delta of the output unit, n x 1; W3 = h2 weights of the output unit):
+ *   d2 = (d3 @ W3.T) with d2[a2 == 0] = 0          cs2 = sum(d2, axis=0)        g2 = a1.T @ d2   (h1 x h2)
+ *   d1 = (d2 @ W2.T) with d1[a1 == 0] = 0          cs1 = sum(d1, axis=0)        g1 = X.T @ d1    (n_in x h1)
+ * d2 / d1 are scratch (n x h2, n x h1).  The column sums and the products over n are sequential chains. */
+static inline __attribute__((always_inline)) void backward_rows(
+    int64_t i0, int64_t i1, const double *a1, const int h1, const double *a2, const int h2, const double *W2,
+    const double *W3, const double *d3, double *d2, double *d1) {
+    for (int64_t i = i0; i < i1; i++) {
+        double *r2 = d2 + i * h2, *r1 = d1 + i * h1;
+        for (int j = 0; j < h2; j++) {
+            double v = 0.0 + d3[i] * W3[j];
+            r2[j] = a2[i * h2 + j] == 0.0 ? 0.0 : v;
+        }
+        for (int j = 0; j < h1; j++) {
+            double acc = 0.0;
+            for (int k = 0; k < h2; k++) acc = fma(r2[k], W2[j * h2 + k], acc);
+            r1[j] = a1[i * h1 + j] == 0.0 ? 0.0 : acc;
+        }
+    }
+}
+
+/* The reductions over the n rows: one sequential chain per output element.  Chains are independent of each other, so
+ * they are dealt to threads in four tasks (a chain is never split: its order is the result). */
+static inline __attribute__((always_inline)) void reduce_colsums(int64_t n, const int h1, const int h2, const double *d2,
+                                                                 const double *d1, double *cs2, double *cs1) {
+    double s2[FM_MAX_H], s1[FM_MAX_H];
+    for (int j = 0; j < h2; j++) s2[j] = 0.0;
+    for (int j = 0; j < h1; j++) s1[j] = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        for (int j = 0; j < h2; j++) s2[j] += d2[i * h2 + j];
+        for (int j = 0; j < h1; j++) s1[j] += d1[i * h1 + j];
+    }
+    for (int j = 0; j < h2; j++) cs2[j] = s2[j];
+    for (int j = 0; j < h1; j++) cs1[j] = s1[j];
+}
+
+/* g[k, j] = sum_i left[i, k] * right[i, j] for k in [k0, k1): fma chains over i (left has element strides) */
+static inline __attribute__((always_inline)) void reduce_product(int64_t n, const double *left, int64_t ls_row,
+                                                                 int64_t ls_col, const int k0, const int k1,
+                                                                 const double *right, const int h, double *g) {
+    double acc[FM_MAX_H * FM_MAX_H];
+    for (int c = 0; c < (k1 - k0) * h; c++) acc[c] = 0.0;
+    for (int64_t i = 0; i < n; i++) {
+        for (int k = k0; k < k1; k++) {
+            const double x = left[i * ls_row + k * ls_col];
+            for (int j = 0; j < h; j++) acc[(k - k0) * h + j] = fma(x, right[i * h + j], acc[(k - k0) * h + j]);
+        }
+    }
+    for (int k = k0; k < k1; k++)
+        for (int j = 0; j < h; j++) g[k * h + j] = acc[(k - k0) * h + j];
+}
+
+/* one of the four reduction tasks; called with literal sizes for the reference's model */
+static inline __attribute__((always_inline)) void reduce_task(
+    const int task, const double *X, int64_t xs_row, int64_t xs_col, int64_t n, const int n_in, const int half,
+    const double *a1, const int h1, const int h2, const double *d2, const double *d1, double *cs2, double *g2,
+    double *cs1, double *g1) {
+    if (task == 0) reduce_product(n, a1, h1, 1, 0, h1, d2, h2, g2);
+    else if (task == 1) reduce_product(n, X, xs_row, xs_col, 0, half, d1, h1, g1);
+    else if (task == 2) reduce_product(n, X, xs_row, xs_col, half, n_in, d1, h1, g1);
+    else reduce_colsums(n, h1, h2, d2, d1, cs2, cs1);
+}
+
+int fm_backward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n_in, const double *a1, int h1,
+                const double *a2, int h2, const double *W2, const double *W3, const double *d3, double *d2, double *d1,
+                double *cs2, double *g2, double *cs1, double *g1) {
+    if (h1 > FM_MAX_H || h2 > FM_MAX_H || n_in > FM_MAX_H) return 1;
+    const int64_t step = (n + FM_CHUNKS - 1) / FM_CHUNKS;
+    if (n_in == 2 && h1 == 5 && h2 == 2) {
+#pragma omp parallel num_threads(g_threads)
+        {
+#pragma omp for schedule(static)
+            for (int c = 0; c < FM_CHUNKS; c++)
+                backward_rows(c * step, (c + 1) * step < n ? (c + 1) * step : n, a1, 5, a2, 2, W2, W3, d3, d2, d1);
+#pragma omp for schedule(dynamic, 1)
+            for (int task = 0; task < 4; task++) {
+                if (task == 0) reduce_task(0, X, xs_row, xs_col, n, 2, 1, a1, 5, 2, d2, d1, cs2, g2, cs1, g1);
+                else if (task == 1) reduce_task(1, X, xs_row, xs_col, n, 2, 1, a1, 5, 2, d2, d1, cs2, g2, cs1, g1);
+                else if (task == 2) reduce_task(2, X, xs_row, xs_col, n, 2, 1, a1, 5, 2, d2, d1, cs2, g2, cs1, g1);
+                else reduce_task(3, X, xs_row, xs_col, n, 2, 1, a1, 5, 2, d2, d1, cs2, g2, cs1, g1);
+            }
+        }
+    } else {
+        const int half = (n_in + 1) / 2;
+#pragma omp parallel num_threads(g_threads)
+        {
+#pragma omp for schedule(static)
+            for (int c = 0; c < FM_CHUNKS; c++)
+                backward_rows(c * step, (c + 1) * step < n ? (c + 1) * step : n, a1, h1, a2, h2, W2, W3, d3, d2, d1);
+#pragma omp for schedule(dynamic, 1)
+            for (int task = 0; task < 4; task++)
+                reduce_task(task, X, xs_row, xs_col, n, n_in, half, a1, h1, h2, d2, d1, cs2, g2, cs1, g1);
+        }
+    }
+    return 0;
+}
+
+/* ---- entry points on scikit-learn's packed parameter vector: [W1 | W2 | W3 | b1 | b2 | b3], row-major ---- */
+
+int fm_forward_packed(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n_in, int h1, int h2,
+                      const double *packed, double *a1, double *a2) {
+    const double *W1 = packed, *W2 = W1 + n_in * h1, *W3 = W2 + h1 * h2, *b1 = W3 + h2, *b2 = b1 + h1;
+    return fm_forward(X, xs_row, xs_col, n, n_in, W1, b1, h1, W2, b2, h2, a1, a2);
+}
+
+/* g3_raw = a2.T @ d3 (numpy's dgemv), sum3 = np.sum(d3, axis=0).  Writes the packed gradient:
+ * coef_grads[l] = (raw + alpha * W_l) / n, intercept_grads[l] = colsum / n (_compute_loss_grad). */
+int fm_backward_packed(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n_in, int h1, int h2,
+                       const double *packed, const double *a1, const double *a2, const double *d3, double *d2, double *d1,
+                       const double *g3_raw, double sum3, double alpha, double *grad) {
+    const double *W1 = packed, *W2 = W1 + n_in * h1, *W3 = W2 + h1 * h2;
+    double cs1[FM_MAX_H], cs2[FM_MAX_H], g1[FM_MAX_H * FM_MAX_H], g2[FM_MAX_H * FM_MAX_H];
+    int rc = fm_backward(X, xs_row, xs_col, n, n_in, a1, h1, a2, h2, W2, W3, d3, d2, d1, cs2, g2, cs1, g1);
+    if (rc) return rc;
+    const double dn = (double)n;
+    double *o = grad;
+    for (int c = 0; c < n_in * h1; c++) *o++ = (g1[c] + alpha * W1[c]) / dn;
+    for (int c = 0; c < h1 * h2; c++) *o++ = (g2[c] + alpha * W2[c]) / dn;
+    for (int c = 0; c < h2; c++) *o++ = (g3_raw[c] + alpha * W3[c]) / dn;
+    for (int c = 0; c < h1; c++) *o++ = cs1[c] / dn;
+    for (int c = 0; c < h2; c++) *o++ = cs2[c] / dn;
+    *o++ = sum3 / dn;
+    return 0;
+}
+
+double fm_pairwise_sum(const double *a, int64_t n) { return pairwise_sum(a, n); }

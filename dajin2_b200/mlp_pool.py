@@ -5,9 +5,11 @@ fixed ~0.3-1.2 s of single-threaded host arithmetic per fit that does not depend
 chaotic in its floating-point summation order (profiles/r01_mlp_stability.log: shuffling the training rows or a 1e-13
 perturbation of the inputs changes the predicted candidate loci), so it cannot be re-implemented on the device and
 stay bit-exact with the reference; it is therefore kept on scikit-learn, the reference's own dependency, with the
-BLAS thread count pinned to 1 exactly as the reference pins it (``main.py:5-9``).  What this module adds is
-concurrency: the three fits of an allele (and the fits of further alleles / samples) run side by side in a small pool
-of spawned workers while the GPU and the calling thread carry on.
+BLAS thread count pinned to 1 exactly as the reference pins it (``main.py:5-9``).  Two things are added here:
+``fastmlp.FastMLPClassifier`` evaluates scikit-learn's loss/gradient with the same floating-point operations in fused
+C passes (4-5x faster, checked against scikit-learn's own function in every fit), and the three fits of an allele
+(and the fits of further alleles / samples) run side by side in a small pool of spawned workers while the GPU and
+the calling thread carry on.
 
 ``DAJIN2_B200_MLP_WORKERS=0`` keeps the fits in the calling process.
 """
@@ -31,7 +33,7 @@ def fit_predict(sample: np.ndarray, control: np.ndarray, threshold: float) -> np
     """Candidate loci proposed by the reference's MLP; the training set is rebuilt exactly as the reference does."""
     import warnings
 
-    from sklearn.neural_network import MLPClassifier
+    from .fastmlp import FastMLPClassifier  # scikit-learn's MLPClassifier with a fused, bit-identical loss/gradient
 
     rng = np.random.default_rng(seed=1)
     n_rand, n_ctrl = 10_000, len(control)
@@ -44,7 +46,7 @@ def fit_predict(sample: np.ndarray, control: np.ndarray, threshold: float) -> np
     mut = np.concatenate([np.array([base, base_mut]).T, np.array([control, ctrl_mut]).T], axis=0)
     X = np.concatenate([err, mut], axis=0)
     y = [0] * (n_rand + n_ctrl) + [1] * (n_rand + n_ctrl)
-    clf = MLPClassifier(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
+    clf = FastMLPClassifier(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")  # ConvergenceWarning, as the reference silences it (utils/config.py:79-83)
         clf.fit(X, y)
@@ -188,8 +190,8 @@ def warm_up() -> None:
     n = workers()
     if n == 0:
         return
-    tiny = np.zeros(4)
-    for f in [submit(tiny, tiny, 0.1) for _ in range(n)]:
+    probe = np.linspace(0.0, 3.0, 256)  # a real (small) fit: imports, the C helper's build and its thread team
+    for f in [submit(probe, probe * 0.5, 0.1) for _ in range(n)]:
         f.result()
 
 

@@ -1,0 +1,91 @@
+"""FastMLPClassifier must reproduce scikit-learn's MLPClassifier bit for bit (reference: ``detect_anomalies``,
+src/DAJIN2/core/preprocess/mutation_processing/anomaly_detector.py:61-94)."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, "1")
+
+from sklearn.neural_network import MLPClassifier  # noqa: E402
+
+from dajin2_b200 import fastmlp  # noqa: E402
+
+KW = dict(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
+
+
+def training_set(n_loci: int, seed: int, threshold: float = 0.1):
+    """The reference's training set (anomaly_detector.py:65-87) on a synthetic control profile."""
+    g = np.random.default_rng(seed)
+    control = np.abs(g.normal(0.8, 0.2, n_loci))
+    sample = np.clip(control + g.normal(0, 0.05, n_loci), 0, 100)
+    sample[[n_loci // 5, n_loci // 3, n_loci // 2]] += [25, 15, 10]
+    control = np.minimum(control, sample)
+    rng = np.random.default_rng(seed=1)
+    n_rand, n_ctrl = 10_000, len(control)
+    base = rng.uniform(0, 100, n_rand)
+    base_err = np.clip(base + rng.uniform(0, threshold, n_rand), 0, 100)
+    base_mut = np.clip(base + rng.uniform(threshold, 100, n_rand), 0, 100)
+    ctrl_err = np.clip(control + rng.uniform(0, threshold, n_ctrl), 0, 100)
+    ctrl_mut = np.clip(control + rng.uniform(threshold, 100, n_ctrl), 0, 100)
+    err = np.concatenate([np.array([base, base_err]).T, np.array([control, ctrl_err]).T], axis=0)
+    mut = np.concatenate([np.array([base, base_mut]).T, np.array([control, ctrl_mut]).T], axis=0)
+    X = np.concatenate([err, mut], axis=0)
+    y = [0] * (n_rand + n_ctrl) + [1] * (n_rand + n_ctrl)
+    return X, y, np.array([control, sample]).T
+
+
+def _fit(cls, X, y):
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return cls(**KW).fit(X, y)
+
+
+@pytest.mark.parametrize("n_loci,seed", [(300, 9), (1000, 7), (2832, 8)])
+def test_same_parameters_and_predictions(n_loci, seed):
+    X, y, probe = training_set(n_loci, seed)
+    ref, fast = _fit(MLPClassifier, X, y), _fit(fastmlp.FastMLPClassifier, X, y)
+    for a, b in zip(ref.coefs_ + ref.intercepts_, fast.coefs_ + fast.intercepts_):
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64))
+    assert ref.n_iter_ == fast.n_iter_ and ref.loss_ == fast.loss_
+    assert np.array_equal(ref.predict(probe), fast.predict(probe))
+
+
+def test_every_evaluation_matches_sklearn():
+    """Loss and gradient of the fused evaluation equal scikit-learn's at every iterate of a fit, bit for bit."""
+    X, y, _ = training_set(500, 3)
+    mismatches = []
+
+    class Checked(fastmlp.FastMLPClassifier):
+        def _loss_grad_lbfgs(self, packed, X, y, sw, act, deltas, cg, ig):
+            if getattr(self, "_fm", None) is None:
+                self._fast_setup(X, y)
+            ref = MLPClassifier._loss_grad_lbfgs(self, packed.copy(), X, y, sw, act, deltas, cg, ig)
+            got = self._fast_loss_grad(packed, X)
+            if not fastmlp._same_bits(ref, got):
+                mismatches.append(len(mismatches))
+            return ref
+
+        def _fit_lbfgs(self, *a):
+            return MLPClassifier._fit_lbfgs(self, *a)
+
+    m = _fit(Checked, X, y)
+    assert m.n_iter_ > 10 and not mismatches
+
+
+def test_fallback_when_the_fused_path_does_not_apply():
+    """Other layer sizes may take other BLAS paths: the self-check must notice and leave the fit to scikit-learn."""
+    X, y, _ = training_set(400, 11)
+    kw = dict(solver="lbfgs", alpha=1e-4, hidden_layer_sizes=(4, 3), random_state=3, max_iter=200)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref, got = MLPClassifier(**kw).fit(X, y), fastmlp.FastMLPClassifier(**kw).fit(X, y)
+    for a, b in zip(ref.coefs_ + ref.intercepts_, got.coefs_ + got.intercepts_):
+        assert np.array_equal(a, b)
+
+
+def test_fast_path_is_taken_here():
+    X, y, _ = training_set(300, 5)
+    assert _fit(fastmlp.FastMLPClassifier, X, y).fast_path_used_
