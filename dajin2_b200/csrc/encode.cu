@@ -49,9 +49,6 @@
 #ifndef DJ_ENC_HASH_MODE
 #define DJ_ENC_HASH_MODE 1  // 0: mul, shr, and   1: mul, shr, mad   2: mul, mul.hi, mad (no ALU-pipe op)
 #endif
-#ifndef DJ_ENC_V6
-#define DJ_ENC_V6 1  // 1: six 3-byte windows per chunk, mul.hi + and hash, predicated table reads; 0: eight word slots
-#endif
 
 namespace {
 
@@ -74,15 +71,7 @@ constexpr uint32_t kStatSub = 1u << 18;       // bits 18..22: anchor is a substi
 constexpr uint32_t kStatSpecial = 1u << 23;   // bits 23..27: empty slot (unknown anchor) or lowercase insertion
 constexpr uint32_t kStickyBroken = 1u << 16;  // per-row flag word: see the main loop
 
-#if DJ_ENC_V6
-// v6 hash: byte offset of the entry = bits 2..14 of the HIGH word of key * kLutMagicHi (one IMAD.HI + one LOP3; the
-// table sits at shared-memory offset 0).  Keys that share a slot carry the same entry (they differ only in the
-// nibble that is irrelevant for "=X" / "-X" anchors); tests/test_host_logic.py re-derives this and the bank spread.
-constexpr uint32_t kLutMagicHi = 0xee953fe9u;
-__device__ __forceinline__ uint32_t lut_slot(uint32_t key) { return (__umulhi(key, kLutMagicHi) >> 2) & (kLutSize - 1); }
-#else
 __device__ __forceinline__ uint32_t lut_slot(uint32_t key) { return (key * kLutMagic) >> (32 - kLutBits); }
-#endif
 
 // Key of the token closed by a comma: high nibble of the byte four positions before the comma, then the three
 // bytes in front of the comma, then the comma's own low nibble (0xC).  For "=X"/"-X" anchors the three bytes are
@@ -264,60 +253,6 @@ __device__ __forceinline__ uint32_t emit_chunk(uint32_t &acc, uint32_t sp, uint3
     return sp - sp0;
 }
 
-
-#if DJ_ENC_V6
-// ---- v6 slots -------------------------------------------------------------------------------------------------
-// A token is at least two characters long, so any three consecutive bytes hold at most one comma: a 16-byte chunk
-// is cut into six windows (bytes 0-2, 3-5, 6-8, 9-11, 12-14, 15) = six predicated slots instead of eight.
-__device__ __forceinline__ void emit_token6(uint32_t &acc, uint32_t &sp, uint32_t key, uint32_t flag) {
-    asm volatile(
-        "{\n .reg .pred p;\n .reg .u32 h, e;\n"
-        " setp.ne.u32 p, %3, 0;\n"
-        " mul.hi.u32 h, %2, %4;\n"
-        " and.b32 h, h, %5;\n"
-        " @p ld.shared.u32 e, [h];\n"
-        " @p add.u32 %0, %0, e;\n"
-        " @p st.shared.u8 [%1], e;\n"
-        " @p add.u32 %1, %1, 1;\n}\n"
-        : "+r"(acc), "+r"(sp)
-        : "r"(key), "r"(flag), "n"(kLutMagicHi), "n"((kLutSize - 1) << 2)
-        : "memory");
-}
-
-// window whose three bytes are bytes 0..2 (mask 0x00808080) or 1..3 (0x80808000) of `word`; `prev` = the four
-// bytes in front of `word`; `cf` = comma flags of `word`
-__device__ __forceinline__ void emit_window(uint32_t &acc, uint32_t &sp, uint32_t prev, uint32_t word, uint32_t cf,
-                                            uint32_t mask) {
-    const uint32_t m = cf & mask;
-    emit_token6(acc, sp, __funnelshift_r(prev, word, find_msb(m) - 3u), m);
-}
-
-__device__ __forceinline__ uint32_t emit_chunk6(uint32_t &acc, uint32_t sp, uint32_t wp, const uint4 &c,
-                                                const uint32_t (&cf)[4]) {
-    const uint32_t sp0 = sp;
-    emit_window(acc, sp, wp, c.x, cf[0], 0x00808080u);                                        // bytes 0..2
-    emit_window(acc, sp, __funnelshift_r(wp, c.x, 24), __funnelshift_r(c.x, c.y, 24),         // bytes 3..5
-                __funnelshift_r(cf[0], cf[1], 24), 0x00808080u);
-    emit_window(acc, sp, __funnelshift_r(c.x, c.y, 16), __funnelshift_r(c.y, c.z, 16),        // bytes 6..8
-                __funnelshift_r(cf[1], cf[2], 16), 0x00808080u);
-    emit_window(acc, sp, c.y, c.z, cf[2], 0x80808000u);                                       // bytes 9..11
-    emit_window(acc, sp, c.z, c.w, cf[3], 0x00808080u);                                       // bytes 12..14
-    emit_token6(acc, sp, __funnelshift_r(c.z, c.w, 28), cf[3] & 0x80000000u);                 // byte 15
-    return sp - sp0;
-}
-
-// comma flags of the four words and their number
-__device__ __forceinline__ uint32_t chunk_commas6(const uint4 &c, uint32_t &high, uint32_t (&cf)[4]) {
-    high |= c.x | c.y;
-    high |= c.z | c.w;
-    cf[0] = comma_flags(c.x);
-    cf[1] = comma_flags(c.y);
-    cf[2] = comma_flags(c.z);
-    cf[3] = comma_flags(c.w);
-    return __popc(cf[0] | (cf[1] >> 1) | (cf[2] >> 2) | (cf[3] >> 3));
-}
-#endif
-
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
 encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_off,
               const int32_t *__restrict__ row_len, int64_t n_reads, int n_loci, int code_pitch, int ckpt_pitch,
@@ -325,22 +260,14 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
               uint32_t *__restrict__ flags, uint32_t *__restrict__ ckpt, uint32_t c_four, uint32_t c_shift) {
     // c_four = 4 and c_shift = 2^kLutBits arrive as arguments so that the table address is computed with integer
     // multiply-adds (FMA pipe) instead of being strength-reduced to shifts and masks on the saturated ALU pipe
-    // one object, so that the table sits at shared-memory offset 0 (the v6 slot addresses it without a base)
-    __shared__ __align__(16) struct {
-        uint32_t lut[kLutSize];
-        uint8_t stage_all[kWarpsPerCta][kStageBytes];
-    } sm;
-    uint32_t *lut = sm.lut;
-    uint8_t(*stage_all)[kStageBytes] = sm.stage_all;
+    __shared__ uint32_t lut[kLutSize];
+    __shared__ __align__(16) uint8_t stage_all[kWarpsPerCta][kStageBytes];
     build_token_lut(lut);
 
     const int lane = threadIdx.x & 31;
     uint8_t *stage = stage_all[threadIdx.x >> 5];
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(lut);
-#if DJ_ENC_V6
-    if (lut_s != 0) __trap();  // the table must start the CTA's shared memory
-#endif
     const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
 
@@ -365,12 +292,7 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
 
         // One trip = two chunks of 512 bytes.  stage[0] always holds locus (tokbase & ~31) of the row.
         auto trip = [&](const uint4 &ca, const uint4 &cb) {
-#if DJ_ENC_V6
-            uint32_t cfa[4], cfb[4];
-            const uint32_t cnt_a = chunk_commas6(ca, high, cfa), cnt_b = chunk_commas6(cb, high, cfb);
-#else
             const uint32_t zza = chunk_commas(ca, high), zzb = chunk_commas(cb, high);
-#endif
             // the word in front of each lane's chunk
             uint32_t wpa = __shfl_up_sync(0xffffffffu, ca.w, 1);
             uint32_t wpb = __shfl_up_sync(0xffffffffu, cb.w, 1);
@@ -384,9 +306,7 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
             carry_w = __shfl_sync(0xffffffffu, cb.w, 31);
 
             // ranks of this lane's commas: one scan for both chunks (16-bit fields)
-#if !DJ_ENC_V6
             const uint32_t cnt_a = __popc(zza), cnt_b = __popc(zzb);
-#endif
             const uint32_t cnt = cnt_a | (cnt_b << 16);
             uint32_t incl = cnt;
 #pragma unroll
@@ -406,14 +326,9 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
             }
             uint32_t acc = 0;
             const uint32_t sp = stage_s + (uint32_t)(tokbase & 31);
-#if DJ_ENC_V6
-            const uint32_t wrote_a = emit_chunk6(acc, sp + (excl & 0xFFFFu), wpa, ca, cfa);
-            const uint32_t wrote_b = emit_chunk6(acc, sp + (uint32_t)total_a + (excl >> 16), wpb, cb, cfb);
-#else
             const uint32_t wrote_a = emit_chunk(acc, sp + (excl & 0xFFFFu), lut_s, wpa, ca, zza, c_four, c_shift);
             const uint32_t wrote_b =
                 emit_chunk(acc, sp + (uint32_t)total_a + (excl >> 16), lut_s, wpb, cb, zzb, c_four, c_shift);
-#endif
             // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV: bits 0..3;
             // the table's "special" counter: bits 8..12
             sticky |= (wrote_a ^ cnt_a) | (wrote_b ^ cnt_b) | ((acc >> 15) & 0x1F00u);
