@@ -76,6 +76,26 @@ def dedup_rows(ids: torch.Tensor, strand: torch.Tensor, rows: torch.Tensor | Non
                   rec["count_plus"].astype(np.int64), first, point_ids, point_of_slot)
 
 
+def uniform_choice2(rng: np.random.RandomState, n: int) -> np.ndarray:
+    """``rng.choice(n, size=2, replace=False, p=np.ones(n) / np.ones(n).sum())`` -- the draw scikit-learn makes to seed
+    a bisection (``sklearn/cluster/_kmeans.py:1030-1037`` with unit sample weights) -- without numpy's O(n)
+    temporaries: same generator state afterwards, same indices (``hostc/choice.c`` restates the cumulative-sum
+    search; ``tests/test_host_logic.py`` compares them).  Falls back to numpy for n > 4M and when the two draws
+    coincide (numpy then redraws)."""
+    from .fastmlp import load_host_lib
+
+    if n < 2 or n > 4_000_000:
+        return rng.choice(n, size=2, replace=False, p=np.ones(n) / np.ones(n).sum())
+    state = rng.get_state()
+    x = rng.random_sample(2)
+    out = np.empty(2, dtype=np.int64)
+    rc = load_host_lib().fm_uniform_choice(n, x.ctypes.data, 2, out.ctypes.data)
+    if rc != 0 or out[0] == out[1]:
+        rng.set_state(state)
+        return rng.choice(n, size=2, replace=False, p=np.ones(n) / np.ones(n).sum())
+    return out
+
+
 def _bisect(X_d, w_d, leaf_host: np.ndarray, target: int, seed0: int, seed1: int):
     dev = X_d.device
     n_points, n_cols = int(X_d.shape[0]), int(X_d.shape[1])
@@ -169,7 +189,7 @@ def control_subset(ids_control: torch.Tensor, strand_control: torch.Tensor, mode
     slot_rows = rs_c.slot_of_row.cpu().numpy()
     point_rows = rs_c.point_of_slot[slot_rows]  # point of every control row, file order
     rng = np.random.RandomState(1)
-    seeds = rng.choice(n_c, size=2, replace=False, p=np.ones(n_c) / np.ones(n_c).sum())
+    seeds = uniform_choice2(rng, n_c)
     X_d = torch.as_tensor(Xc, device=dev)
     w_d = torch.as_tensor(rs_c.count.astype(np.float64), device=dev)
     sub, _ = _bisect(X_d, w_d, np.zeros(len(Xc), dtype=np.int32), 0, int(point_rows[seeds[0]]), int(point_rows[seeds[1]]))
@@ -209,7 +229,7 @@ def optimize_labels_points(Xs: np.ndarray, ws: np.ndarray, Xc: np.ndarray, wc: n
         ns_leaf = int(ws[members[:n_s_pts]].sum())
         nc_leaf = int(wc[members[n_s_pts:]].sum()) if n_c_pts else 0
         n_sub = ns_leaf + nc_leaf
-        seeds = rng.choice(n_sub, size=2, replace=False, p=np.ones(n_sub) / np.ones(n_sub).sum())
+        seeds = uniform_choice2(rng, n_sub)
         seed_points = []
         leaf_of_slot_d = None
         for j in seeds.tolist():

@@ -34,7 +34,7 @@ import numpy as np
 from sklearn.neural_network import MLPClassifier
 
 HERE = Path(__file__).resolve().parent
-SRC = HERE / "hostc" / "fastmlp.c"
+SOURCES = [HERE / "hostc" / "fastmlp.c", HERE / "hostc" / "choice.c"]  # one small host library
 LIB = HERE / "hostc" / "libdjhost.so"
 
 _lib = None
@@ -43,7 +43,7 @@ _c_double_p = ctypes.POINTER(ctypes.c_double)
 
 def build(force: bool = False) -> Path:
     """gcc -O2 without fast-math and without FMA contraction: the C code must round exactly like numpy does."""
-    if force or not LIB.exists() or LIB.stat().st_mtime < SRC.stat().st_mtime:
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime for src in SOURCES):
         tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
         flags = ["-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp"]
         try:
@@ -51,12 +51,12 @@ def build(force: bool = False) -> Path:
                 flags.append("-mfma")  # fma() inlines to vfmadd; without it libm's (exact, slow) fma is called
         except OSError:
             pass
-        subprocess.run(["gcc", *flags, "-o", str(tmp), str(SRC), "-lm"], check=True)
+        subprocess.run(["gcc", *flags, "-o", str(tmp), *map(str, SOURCES), "-lm"], check=True)
         tmp.replace(LIB)
     return LIB
 
 
-def _load():
+def load_host_lib():
     global _lib
     if _lib is None:
         build()
@@ -70,6 +70,8 @@ def _load():
         lib.fm_output.restype = cd
         lib.fm_backward_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, cd, cd, vp]
         lib.fm_backward_packed.restype = ci
+        lib.fm_uniform_choice.argtypes = [i64, vp, ci, vp]
+        lib.fm_uniform_choice.restype = ci
         lib.fm_set_threads(max(1, int(os.environ.get("DAJIN2_B200_MLP_THREADS", "4"))))
         lib.fm_pairwise_sum.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         lib.fm_pairwise_sum.restype = ctypes.c_double
@@ -97,7 +99,7 @@ class FastMLPClassifier(MLPClassifier):
         h1, h2 = self.coefs_[0].shape[1], self.coefs_[1].shape[1]
         f = lambda *shape: np.empty(shape, dtype=np.float64)  # noqa: E731
         fm = {
-            "n": n, "lib": _load(), "dims": (n_in, h1, h2), "y": np.ascontiguousarray(y, dtype=np.float64).reshape(n, 1),
+            "n": n, "lib": load_host_lib(), "dims": (n_in, h1, h2), "y": np.ascontiguousarray(y, dtype=np.float64).reshape(n, 1),
             "a1": f(n, h1), "a2": f(n, h2), "d3": f(n, 1), "d2": f(n, h2), "d1": f(n, h1), "terms": f(n), "sum3": f(1),
             "xs": (X.strides[0] // 8, X.strides[1] // 8), "X": X,
             # offsets of W1, W2, W3, b1, b2, b3 in scikit-learn's packed parameter vector (_pack / _unpack)

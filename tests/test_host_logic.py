@@ -112,3 +112,16 @@ def test_encoder_token_table_is_collision_free():
     assert len({slot(k) for k in keys}) == 320
     hot = [key(ord(p), ord(","), ord("="), ord(x)) for p in "AT" for x in "ACGT"]
     assert len({slot(k) & 31 for k in hot}) == len(hot)
+
+
+def test_uniform_choice_matches_numpy_legacy_choice():
+    """clusterer.uniform_choice2 == RandomState.choice(n, 2, replace=False, p=uniform): indices and generator state."""
+    from dajin2_b200.clusterer import uniform_choice2
+
+    for n in (2, 3, 7, 100, 4095, 4096, 4097, 10_000, 99_999, 433_328, 1_000_000):
+        for seed in range(3):
+            r1, r2 = np.random.RandomState(seed), np.random.RandomState(seed)
+            for _ in range(3):
+                want = r1.choice(n, size=2, replace=False, p=np.ones(n) / np.ones(n).sum())
+                assert uniform_choice2(r2, n).tolist() == want.tolist()
+            assert r1.random_sample() == r2.random_sample()
