@@ -34,7 +34,7 @@ import numpy as np
 from sklearn.neural_network import MLPClassifier
 
 HERE = Path(__file__).resolve().parent
-SOURCES = [HERE / "hostc" / "fastmlp.c", HERE / "hostc" / "choice.c"]  # one small host library
+SOURCES = [HERE / "hostc" / "fastmlp.c", HERE / "hostc" / "choice.c", HERE / "hostc" / "ingest.c"]  # one small host library
 LIB = HERE / "hostc" / "libdjhost.so"
 
 _lib = None
@@ -72,6 +72,12 @@ def load_host_lib():
         lib.fm_backward_packed.restype = ci
         lib.fm_uniform_choice.argtypes = [i64, vp, ci, vp]
         lib.fm_uniform_choice.restype = ci
+        lib.dj_jsonl_count_lines.argtypes = [vp, i64, ci]
+        lib.dj_jsonl_count_lines.restype = i64
+        lib.dj_jsonl_index.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, ci]
+        lib.dj_jsonl_index.restype = i64
+        lib.dj_gather_fixed.argtypes = [vp, vp, vp, i64, ctypes.c_int32, vp, ci]
+        lib.dj_gather_fixed.restype = None
         lib.fm_set_threads(max(1, int(os.environ.get("DAJIN2_B200_MLP_THREADS", "4"))))
         lib.fm_pairwise_sum.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         lib.fm_pairwise_sum.restype = ctypes.c_double

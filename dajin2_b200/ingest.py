@@ -4,16 +4,13 @@ the (offset, length) of its MIDSV string inside them — no re-serialisation, no
 
 from __future__ import annotations
 
+import ctypes
 import json
-import re
+import os
 from dataclasses import dataclass
 from pathlib import Path
 
 import numpy as np
-
-_RE_MIDSV = re.compile(rb'"MIDSV": ?"([^"\\]*)"')
-_RE_QNAME = re.compile(rb'"QNAME": ?"([^"\\]*)"')
-_RE_STRAND = re.compile(rb'"STRAND": ?"([+-])"')
 
 SLACK = 64  # readable bytes after the last row (the encoder loads aligned 16-byte chunks)
 
@@ -51,26 +48,45 @@ def pack_rows(rows: list[str], strands: list[str] | None = None, qnames: list[st
     return HostReads(text, offs, lens, st, qn)
 
 
-def read_midsv_jsonl(path: str | Path, keep_records: bool = False) -> HostReads:
-    """Locate the MIDSV / QNAME / STRAND values of every line of a JSONL file without re-encoding the text."""
-    raw = Path(path).read_bytes()
-    n_lines = raw.count(b"\n") + (1 if raw and not raw.endswith(b"\n") else 0)
-    spans = [(m.start(1), m.end(1)) for m in _RE_MIDSV.finditer(raw)]
-    qn = [m.group(1) for m in _RE_QNAME.finditer(raw)]
-    st = [m.group(1) for m in _RE_STRAND.finditer(raw)]
+def read_midsv_jsonl(path: str | Path, keep_records: bool = False, text_alloc=None) -> HostReads:
+    """Locate the MIDSV / QNAME / STRAND values of every line of a JSONL file without re-encoding the text.
+
+    The file is read once into one buffer (``text_alloc(nbytes)`` may supply pinned memory) and indexed by the
+    multi-threaded C tokenizer ``hostc/ingest.c``; lines it reports as irregular (escapes, missing keys) send the
+    whole file through ``json.loads`` instead."""
+    from .fastmlp import load_host_lib
+
+    path = Path(path)
+    size = path.stat().st_size
+    text = text_alloc(size + SLACK) if text_alloc is not None else np.empty(size + SLACK, dtype=np.uint8)
+    with open(path, "rb") as f:
+        got = f.readinto(memoryview(text)[:size]) if size else 0
+    if got != size:
+        raise OSError(f"short read of {path}: {got} of {size} bytes")
+    text[size:] = ord("\n")
+    lib = load_host_lib()
+    threads = max(1, min(16, os.cpu_count() or 1))
+    ptr = text.ctypes.data
+    n_lines = int(lib.dj_jsonl_count_lines(ptr, size, threads))
+    off = np.empty(n_lines, dtype=np.int64)
+    ln = np.empty(n_lines, dtype=np.int32)
+    q_off = np.empty(n_lines, dtype=np.int64)
+    q_len = np.empty(n_lines, dtype=np.int32)
+    strand = np.empty(n_lines, dtype=np.uint8)
+    has_strand = ctypes.c_int32(0)
+    irregular = int(lib.dj_jsonl_index(ptr, size, n_lines, off.ctypes.data, ln.ctypes.data, q_off.ctypes.data,
+                                       q_len.ctypes.data, strand.ctypes.data, ctypes.byref(has_strand), threads))
     records = None
-    if len(spans) != n_lines or len(qn) != n_lines or (st and len(st) != n_lines) or keep_records:
-        # unusual formatting (escapes, different separators, missing keys): fall back to a real JSON parse per line
-        records = [json.loads(line) for line in raw.splitlines() if line.strip()]
-        if len(spans) != len(records) or len(qn) != len(records) or (st and len(st) != len(records)):
+    if irregular != 0 or keep_records:
+        # unusual formatting (escapes, different separators, missing keys): a real JSON parse per line
+        records = [json.loads(line) for line in bytes(memoryview(text)[:size]).splitlines() if line.strip()]
+        if irregular != 0:
             return _from_records(records, keep_records)
-    text = np.empty(len(raw) + SLACK, dtype=np.uint8)
-    text[: len(raw)] = np.frombuffer(raw, dtype=np.uint8)
-    text[len(raw) :] = ord("\n")
-    off = np.array([s for s, _ in spans], dtype=np.int64)
-    ln = np.array([e - s for s, e in spans], dtype=np.int32)
-    strand = np.frombuffer(b"".join(st), dtype=np.uint8).copy() if st else np.full(len(spans), ord("+"), np.uint8)
-    return HostReads(text, off, ln, strand, np.array(qn, dtype="S"), records if keep_records else None)
+    width = int(q_len.max()) if n_lines else 1
+    names = np.empty((n_lines, max(width, 1)), dtype=np.uint8)
+    lib.dj_gather_fixed(ptr, q_off.ctypes.data, q_len.ctypes.data, n_lines, max(width, 1), names.ctypes.data, threads)
+    qnames = names.view(f"S{max(width, 1)}").reshape(n_lines)
+    return HostReads(text, off, ln, strand, qnames, records if keep_records else None)
 
 
 def _from_records(records: list[dict], keep_records: bool) -> HostReads:

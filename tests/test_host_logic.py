@@ -125,3 +125,33 @@ def test_uniform_choice_matches_numpy_legacy_choice():
                 want = r1.choice(n, size=2, replace=False, p=np.ones(n) / np.ones(n).sum())
                 assert uniform_choice2(r2, n).tolist() == want.tolist()
             assert r1.random_sample() == r2.random_sample()
+
+
+def test_jsonl_tokenizer_irregular_lines(tmp_path):
+    """hostc/ingest.c: escapes, missing keys, nested objects, blank lines and a missing final newline."""
+    p = tmp_path / "y.jsonl"
+    p.write_text('{"MIDSV":"=A,=C","QNAME":"a\\"b","STRAND":"-"}\n\n{"QNAME": "x", "MIDSV": "=G,=T"}')
+    host = read_midsv_jsonl(p)  # escaped quote -> JSON fallback for the file
+    got = [host.text[o : o + n].tobytes().decode() for o, n in zip(host.row_off, host.row_len)]
+    assert got == ["=A,=C", "=G,=T"] and host.strand.tobytes() == b"-+" and host.qnames.tolist() == [b'a"b', b"x"]
+    p.write_text('{"extra": {"MIDSV": "zz"}, "MIDSV":"=A,=C" , "QNAME" :"r1"}\n'
+                 '{"QNAME": "x", "MIDSV": "=G,=T", "STRAND": "-"}\n')
+    host = read_midsv_jsonl(p)  # nested key is ignored, spans are taken in place
+    got = [host.text[o : o + n].tobytes().decode() for o, n in zip(host.row_off, host.row_len)]
+    assert got == ["=A,=C", "=G,=T"] and host.strand.tobytes() == b"+-" and host.qnames.tolist() == [b"r1", b"x"]
+    p.write_text("")
+    assert read_midsv_jsonl(p).n_reads == 0
+
+
+def test_jsonl_tokenizer_matches_json_loads(tmp_path):
+    b = synth.generate(synth.throughput_population(300), 257, seed=7)
+    p = tmp_path / "z.jsonl"
+    with open(p, "w") as f:
+        for r in range(257):
+            f.write(json.dumps({"QNAME": b.qnames()[r].decode(), "RNAME": "control", "MIDSV": b.midsv(r),
+                                "STRAND": chr(b.strand[r]), "PRESET": "map-ont"}) + "\n")
+    host = read_midsv_jsonl(p, keep_records=True)
+    assert [r["MIDSV"] for r in host.records] == [
+        host.text[o : o + n].tobytes().decode() for o, n in zip(host.row_off, host.row_len)]
+    assert host.qnames.tolist() == [r["QNAME"].encode() for r in host.records]
+    assert host.strand.tobytes().decode() == "".join(r["STRAND"] for r in host.records)
