@@ -358,18 +358,6 @@ def run_ours(args):
     pop, hs, hc, keep = make_workload(args, rank, world, pinned=True)
     sequence = pop.reference
     comm = djdist.Communicator(dist) if dist is not None else None
-    gpos = None
-    if world > 1:
-        # global label order = QNAME order over all shards (reference classifier.py:38-46).  Rank r holds reads
-        # r, r + world, ...; the names are a function of the read index, so every rank can rank its own reads.
-        from dajin2_b200 import synth
-
-        names = synth.qnames(synth.SEED + 1, 0, 1, args.reads * world)
-        position = np.empty(args.reads * world, dtype=np.int64)
-        position[np.argsort(names, kind="stable")] = np.arange(args.reads * world)
-        gpos = position[rank::world][: hs.n_reads]
-        del names, position
-
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -378,7 +366,6 @@ def run_ours(args):
     # ---- device-resident arm -------------------------------------------------------------------------------
     enc_s = engine.EncodedReads(hs, len(sequence), validate=False, encode=False)
     enc_c = engine.EncodedReads(hc, len(sequence), validate=False, encode=False)
-    order = pipeline.qname_order(hs.qnames) if world == 1 else None
     text_bytes = int(hs.row_len.astype(np.int64).sum())
     enc_bytes = text_bytes + hs.n_reads * (len(sequence) + 16)
 
@@ -388,8 +375,8 @@ def run_ours(args):
         enc_s.encode()
         ev[1].record()
         enc_c.encode()
-        res = pipeline.run_device(enc_s, enc_c, sequence, None, None if comm else order, fetch_labels=False,
-                                  reencode=False, comm=comm, gpos=gpos)
+        # the label order (QNAME order, over all shards) is established inside the step, on the device
+        res = pipeline.run_device(enc_s, enc_c, sequence, None, None, fetch_labels=False, reencode=False, comm=comm)
         return res, ev
 
     for _ in range(args.warmup):
@@ -422,7 +409,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     def e2e_step():
-        return pipeline.run_host(hs, hc, sequence, None, None if comm else order, comm=comm, gpos=gpos)
+        return pipeline.run_host(hs, hc, sequence, None, None, comm=comm)
 
     e2e_steps = max(2, min(args.steps, 3))
     e2e_step()

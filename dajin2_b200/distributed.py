@@ -160,18 +160,24 @@ class ShardRun:
     """One shard's side of the hot path.  ``gpos[r]`` is the position of local read r in the global label order
     (QNAME order over all shards, reference classifier.py:38-46)."""
 
-    def __init__(self, sample, control, sequence: str, knockin, gpos: np.ndarray):
-        import torch
-
+    def __init__(self, sample, control, sequence: str, knockin, gpos=None):
         from . import engine
 
         self.engine = engine
         self.dev = engine.require_cuda()
         self.sample, self.control, self.sequence = sample, control, sequence
         self.knockin = set(knockin) if knockin else None
-        local_order = np.argsort(gpos, kind="stable")
-        self.rows = torch.as_tensor(local_order.astype(np.int32), device=self.dev)  # local reads in global order
-        self.gpos_sorted = np.asarray(gpos, dtype=np.int64)[local_order]
+        if gpos is not None:
+            self.set_positions(gpos)
+
+    def set_positions(self, gpos) -> None:
+        """``gpos``: global label-order position of every local read (numpy array or device tensor)."""
+        import torch
+
+        g = torch.as_tensor(gpos, device=self.dev).to(torch.int64)
+        local_order = torch.argsort(g, stable=True)
+        self.rows = local_order.to(torch.int32)  # local reads in global order
+        self.gpos_sorted = g[local_order]  # int64 on the device
 
     # phase 1 -> all-reduce
     def histogram_and_strands(self):
@@ -183,7 +189,7 @@ class ShardRun:
         return torch.cat([hist, tail])
 
     # rank 0 between phase 1 and 2
-    def select_loci(self, reduced) -> list[set[str]]:
+    def select_loci(self, reduced, while_waiting=None) -> list[set[str]]:
         eng = self.engine
         L = self.sample.n_loci
         host = reduced.cpu().numpy()
@@ -192,7 +198,8 @@ class ShardRun:
         hist_c = self.control.histogram()
         norm_s = eng.normalize_indels(eng.counts_from_histogram(hist_s))
         norm_c = eng.normalize_indels(eng.counts_from_histogram(hist_c))
-        return eng.select_mutation_loci(hist_s, (n_plus, n_total - n_plus), self.sequence, norm_s, norm_c, self.knockin)
+        return eng.select_mutation_loci(hist_s, (n_plus, n_total - n_plus), self.sequence, norm_s, norm_c, self.knockin,
+                                        while_waiting=while_waiting)
 
     # phase 2 -> all-gather of 3-mer payloads
     def count_kmers(self, reduced, loci_t: list[set[str]]):
@@ -214,7 +221,10 @@ class ShardRun:
         self.ids_s = eng.annotate_ids(self.sample, self.rows, self.model, False)
         self.ids_c = eng.annotate_ids(self.control, None, self.model, True)
         self.rs = clusterer.dedup_rows(self.ids_s, self.sample.strand, self.rows)
-        first_global = self.gpos_sorted[self.rs.first_row] if len(self.rs.first_row) else np.zeros(0, dtype=np.int64)
+        import torch
+
+        first_global = (self.gpos_sorted[torch.as_tensor(self.rs.first_row, device=self.dev)].cpu().numpy()
+                        if len(self.rs.first_row) else np.zeros(0, dtype=np.int64))
         return (self.rs.point_ids, self.rs.count, self.rs.count_plus, first_global)
 
     # phase 4 -> all-gather of (global position, merged point) per read
@@ -227,7 +237,7 @@ class ShardRun:
         lut[self.rs.slots] = local_to_merged
         lut_d = torch.as_tensor(lut, device=self.dev)
         self.point_of_row = lut_d[self.rs.slot_of_row.long()].to(torch.int32)  # local reads in global order
-        return torch.as_tensor(self.gpos_sorted, device=self.dev), self.point_of_row
+        return self.gpos_sorted, self.point_of_row
 
     # phase 5: every rank clusters the merged points and labels its reads
     def cluster(self, gpos_all, point_all):
@@ -247,19 +257,28 @@ class ShardRun:
         return labels_d, info
 
 
-def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, gpos: np.ndarray,
+def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, gpos=None,
                        fetch_labels: bool = True):
     """Drive one shard through the phases with real collectives.  Returns a ``pipeline.HotPathResult`` whose labels
-    refer to the local reads in global order (``order`` = the local read index of each label)."""
+    refer to the local reads in global order (``order`` = the local read index of each label).  Without ``gpos`` the
+    global label order (QNAME order over all shards) is established here, on every rank while rank 0 waits for the
+    loci selection."""
     import torch
 
-    from .pipeline import HotPathResult
+    from .pipeline import HotPathResult, global_positions
 
     run = ShardRun(sample, control, sequence, knockin, gpos)
     reduced = comm.allreduce_sum(run.histogram_and_strands())
+
+    def positions():
+        if gpos is None:
+            run.set_positions(global_positions(sample, comm))
+
     loci_mask = None
     if comm.rank == 0:
-        loci_mask = ["".join(sorted(m)) for m in run.select_loci(reduced)]
+        loci_mask = ["".join(sorted(m)) for m in run.select_loci(reduced, while_waiting=positions)]
+    else:
+        positions()
     loci_t = [set(m) for m in comm.broadcast_object(loci_mask)]
     order = run.rows.cpu().numpy()
     n_total = int(reduced[-1].item())

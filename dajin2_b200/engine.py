@@ -43,6 +43,35 @@ def _to_device(arr: np.ndarray | torch.Tensor, device) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------------------
+# read names as sort keys (the label order of the path is the QNAME order, reference classifier.py:38-46)
+# ---------------------------------------------------------------------------------------------------------
+
+
+def qname_keys(qnames: np.ndarray, device) -> torch.Tensor:
+    """The names as int64 sort keys [N, ceil(W / 8)] on ``device``: eight bytes per key, big-endian, sign bit flipped,
+    so that signed comparison of the key tuples is bytewise comparison of the (NUL-padded) names."""
+    n = int(qnames.shape[0])
+    width = max(int(qnames.dtype.itemsize), 1)
+    host = np.ascontiguousarray(qnames).view(np.uint8).reshape(n, width) if n else np.zeros((0, width), dtype=np.uint8)
+    raw = torch.from_numpy(host).to(device, non_blocking=True)
+    padded = (width + 7) // 8 * 8
+    if padded != width:
+        raw = torch.nn.functional.pad(raw, (0, padded - width))
+    keys = raw.view(n, padded // 8, 8).flip(-1).contiguous().view(torch.int64).reshape(n, padded // 8)
+    return keys ^ torch.tensor(-(2 ** 63), dtype=torch.int64, device=raw.device)
+
+
+def order_of_keys(keys: torch.Tensor) -> torch.Tensor:
+    """Stable lexicographic argsort of the key tuples (least-significant key first): int64[N] on the keys' device."""
+    n = int(keys.shape[0])
+    perm = torch.arange(n, dtype=torch.int64, device=keys.device)
+    for c in reversed(range(keys.shape[1])):
+        _, idx = torch.sort(keys[perm, c], stable=True)
+        perm = perm[idx]
+    return perm
+
+
+# ---------------------------------------------------------------------------------------------------------
 # encode
 # ---------------------------------------------------------------------------------------------------------
 
@@ -57,7 +86,9 @@ class EncodedReads:
         self.qnames = host.qnames
         self.records = host.records
         self.strand_host = host.strand
-        self.h2d_bytes = int(host.text.nbytes + host.row_off.nbytes + host.row_len.nbytes + host.strand.nbytes)
+        self.h2d_bytes = int(host.text.nbytes + host.row_off.nbytes + host.row_len.nbytes + host.strand.nbytes
+                             + host.qnames.nbytes)
+        self.name_keys = qname_keys(host.qnames, dev)  # int64[N, ceil(W / 8)]: the label order is the QNAME order
         self.text = _to_device(host.text, dev)
         self.row_off = _to_device(host.row_off, dev)
         self.row_len = _to_device(host.row_len, dev)
@@ -207,9 +238,10 @@ def mlp_candidates(sample: np.ndarray, control: np.ndarray, threshold: float) ->
     return mlp_pool.submit(sample, control, threshold).result()
 
 
-def extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False) -> dict[str, set[int]]:
+def extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False,
+                        while_waiting=None) -> dict[str, set[int]]:
     """``extract_anomal_loci`` (reference ``anomaly_detector.py:99-109``): the three MLP fits run concurrently in the
-    worker pool while the window distances are computed on the device."""
+    worker pool while the window distances are computed on the device (and ``while_waiting()`` is called)."""
     from . import mlp_pool
 
     pending = {}
@@ -219,6 +251,8 @@ def extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: boo
         pending[op] = (s, c, mlp_pool.submit(s, c, thresholds[op]))
     out = {}
     masks = {op: dissimilar_mask(s, c, is_consensus) for op, (s, c, _) in pending.items()}
+    if while_waiting is not None:
+        while_waiting()
     for op, (_, _, fut) in pending.items():
         out[op] = set(np.flatnonzero(fut.result() & masks[op]).tolist())
     return out
@@ -312,12 +346,12 @@ def transpose_loci(loci: dict[str, set[int]], n_loci: int) -> list[set[str]]:
 
 def select_mutation_loci(hist_sample: np.ndarray, strand_host: np.ndarray, sequence: str, norm_sample, norm_control_raw,
                          knockin: set[int] | None = None, thresholds=None, is_consensus: bool = False,
-                         insample_filter=None) -> list[set[str]]:
+                         insample_filter=None, while_waiting=None) -> list[set[str]]:
     """``extract_mutation_loci`` (reference ``mutation_processing/mutation_extractor.py:28-87``) fed by the device
     histogram of the sample file instead of two more passes over its JSONL."""
     thresholds = thresholds or {"*": 0.1, "-": 0.1, "+": 0.1}
     norm_control = {op: np.minimum(norm_control_raw[op], norm_sample[op]) for op in MUTS}
-    loci = extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus)
+    loci = extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus, while_waiting)
     if knockin is not None:
         loci = {op: loci[op] | set(knockin) for op in MUTS}
     homo = homopolymer_errors(sequence, norm_sample, norm_control, loci)

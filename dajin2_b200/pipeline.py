@@ -33,6 +33,26 @@ def qname_order(qnames: np.ndarray) -> np.ndarray:
     return np.argsort(qnames, kind="stable").astype(np.int32)
 
 
+def qname_order_device(sample: engine.EncodedReads) -> torch.Tensor:
+    """``qname_order`` on the device (int32 tensor): the stable sort by QNAME of ``extract_alleles_with_max_score``
+    (reference classifier.py:38-46) as ceil(W / 8) stable 64-bit sorts instead of a host sort of a million strings."""
+    return engine.order_of_keys(sample.name_keys).to(torch.int32)
+
+
+def global_positions(sample: engine.EncodedReads, comm) -> torch.Tensor:
+    """Position of every local read in the QNAME order over all shards (int64 tensor on the device): the keys of all
+    shards are gathered (8 x ceil(W / 8) bytes per read) and every rank sorts the union; names are unique read ids."""
+    keys = sample.name_keys
+    n_local, n_keys = int(keys.shape[0]), int(keys.shape[1])
+    sizes = [int(x) for x in comm.allgather_object(n_local)]
+    gathered = comm.allgather_rows(keys.reshape(-1), [sz * n_keys for sz in sizes]).reshape(-1, n_keys)
+    perm = engine.order_of_keys(gathered)
+    position = torch.empty_like(perm)
+    position[perm] = torch.arange(perm.shape[0], dtype=torch.int64, device=perm.device)
+    start = sum(sizes[: comm.rank])
+    return position[start : start + n_local]
+
+
 class _Timer:
     def __init__(self, timings: dict):
         self.timings = timings
@@ -89,8 +109,6 @@ def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequen
             control.encode()
             sample.validate()
             control.validate()
-        if gpos is None:
-            raise ValueError("a sharded run needs the global position of every local read (gpos)")
         return distributed.run_device_sharded(sample, control, sequence, knockin, comm, gpos, fetch_labels)
     timings: dict = {}
     tm = _Timer(timings)
@@ -103,6 +121,9 @@ def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequen
     with tm.device("hist_ms"):
         hist_s = sample.histogram()
         hist_c = control.histogram()
+    rows = None
+    if order is None:  # launched now: the sorts run on the device while the host waits for the loci selection
+        rows = qname_order_device(sample)
     with tm.host("loci_host_ms"):
         count_s = engine.counts_from_histogram(hist_s)
         count_c = engine.counts_from_histogram(hist_c)
@@ -110,9 +131,10 @@ def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequen
         norm_c = engine.normalize_indels(count_c)
         loci = engine.select_mutation_loci(hist_s, sample.strand_host, sequence, norm_s, norm_c, knockin)
     with tm.host("order_host_ms"):
-        if order is None:
-            order = qname_order(sample.qnames)
-        rows = torch.as_tensor(order, device=dev)
+        if rows is not None:
+            order = rows.cpu().numpy()
+        else:
+            rows = torch.as_tensor(order, device=dev)
     n = sample.n_reads
     if all(not m for m in loci) or n < 5:
         labels = np.ones(n, dtype=np.int32) if fetch_labels else None

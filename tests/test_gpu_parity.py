@@ -325,6 +325,6 @@ def test_sharded_equals_unsharded(name, n_shards):
     labels = np.zeros(n, dtype=np.int64)
     for r in runs:
         lab, info = r.cluster(gpos_all, point_all)
-        labels[r.gpos_sorted] = lab.cpu().numpy()
+        labels[r.gpos_sorted.cpu().numpy()] = lab.cpu().numpy()
         assert info["cluster_sizes"] == full.cluster_sizes
     assert labels.tolist() == full.labels.tolist()

@@ -46,6 +46,20 @@ def test_qname_order_is_python_sort():
     assert qname_order(q).tolist() == sorted(range(len(names)), key=lambda i: names[i])
 
 
+def test_device_qname_sort_is_python_sort():
+    """The radix passes of qname_order_device (run on the CPU here) give Python's sorted() order, ties included."""
+    import torch
+
+    def order(q):
+        return engine.order_of_keys(engine.qname_keys(q, torch.device("cpu"))).tolist()
+
+    q = synth.generate(synth.throughput_population(50), 700).qnames()
+    names = [x.decode() for x in q]
+    assert order(q) == sorted(range(len(names)), key=lambda i: names[i])
+    odd = np.array([b"b", b"a", b"ab", b"", b"a", b"abcdefghi", b"abcdefgh", b"\xff", b"B"], dtype="S")
+    assert order(odd) == sorted(range(len(odd)), key=lambda i: bytes(odd[i]))
+
+
 def test_generator_is_shard_invariant():
     pop = synth.throughput_population(200)
     whole = synth.generate(pop, 64)
