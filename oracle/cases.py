@@ -79,6 +79,32 @@ def flox_like_case(n_sample: int = 400, n_control: int = 300, profile: str = "r1
     return out
 
 
+def single_like_case(n_sample: int = 900, n_control: int = 500, profile: str = "r10") -> dict:
+    """Three FASTA alleles as in examples/example_single (control, large deletion, inversion); the sample is a 1:1:1
+    mixture of a point mutant of the control, the deletion allele and the inversion allele, every read expressed
+    against each FASTA allele (BASELINE.json configs[0] stand-in: exercises classify_alleles over three alleles)."""
+    base = synth.random_reference(1000)
+    deletion = base[:300] + base[450:]
+    S, D, I, V = synth.SUB, synth.DEL, synth.INS, synth.INV  # noqa: E741
+    fr = [1 / 3, 1 / 3, 1 / 3]
+    truth = {  # true allele (point mutant, deletion, inversion) against each FASTA allele
+        "control": (base, [[(S, 500, 1)], [(D, 300, 150)], [(V, 600, 200)]], [[]]),
+        "deletion": (deletion, [[(I, 300, 150), (S, 350, 1)], [], [(I, 300, 150), (V, 450, 200)]], [[(I, 300, 150)]]),
+        "inversion": (base, [[(V, 600, 200), (S, 500, 1)], [(D, 300, 150), (V, 600, 200)], []], [[(V, 600, 200)]]),
+    }
+    out = {"alleles": {}}
+    for name, (seq, sample_alleles, control_alleles) in truth.items():
+        ps = synth.Population(seq, sample_alleles, fr, profile, rname=name)
+        pc = synth.Population(seq, control_alleles, [1.0], profile, rname=name)
+        out["alleles"][name] = {
+            "sequence": seq,
+            "sample": _pack(synth.generate(ps, n_sample, seed=synth.SEED + 1)),
+            "control": _pack(synth.generate(pc, n_control, seed=synth.SEED + 99)),
+            "knockin": None,
+        }
+    return out
+
+
 def kat_case() -> dict:
     """SURVEY.md §8c extra known-answer case (quirk ii: '@,@,@' is a scored k-mer)."""
     sample = ["=A,=C,-G,+T|+T|=T,=A,=C"] * 3 + ["=A,=C,-G,+A|=T,=A,=C"] * 2 + ["=A,=C,=G,=T,=A,=C"] * 5
@@ -96,7 +122,13 @@ RECIPES = {
     "inv_L2724_N300": (synthetic_case, dict(length=2724, n_sample=300, n_control=300, profile="r10", kind="inversion")),
     "point_L900_N1500": (synthetic_case, dict(length=900, n_sample=1500, n_control=1000, profile="r10", kind="point",
                                               fraction=0.1)),
+    # batch-like (BASELINE.json configs[3]): the same control with the point mutation at 1 % and at 50 %
+    "point_L900_N1500_f01": (synthetic_case, dict(length=900, n_sample=1500, n_control=1000, profile="r10", kind="point",
+                                                  fraction=0.01)),
+    "point_L900_N1500_f50": (synthetic_case, dict(length=900, n_sample=1500, n_control=1000, profile="r10", kind="point",
+                                                  fraction=0.5)),
     "flox_like": (flox_like_case, dict()),
+    "single_like": (single_like_case, dict()),
     "kat": (kat_case, dict()),
 }
 

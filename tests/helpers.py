@@ -45,7 +45,7 @@ def golden_score(g, n_loci):
 
 
 SINGLE_CASES = ["kat", "fixture_flox100", "tp_L1000_N2000_r10", "tp_L1000_N1200_r9", "inv_L2724_N300",
-                "point_L900_N1500"]
+                "point_L900_N1500", "point_L900_N1500_f01", "point_L900_N1500_f50"]
 
 
 _B = "ACGTN"

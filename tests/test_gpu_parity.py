@@ -40,7 +40,7 @@ def _percent_gap(ref_labels, got_labels):
     return max(abs(x - y) for x, y in zip(pr, pg))
 
 
-@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like"])
+@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like", "single_like"])
 def test_encode_codes_and_scalars(name):
     alleles, golden = load_case(name)
     for aname, a in alleles.items():
@@ -55,7 +55,7 @@ def test_encode_codes_and_scalars(name):
         assert enc.match_scores().tolist() == golden["alleles"][aname]["calc_match"]
 
 
-@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like"])
+@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like", "single_like"])
 def test_histogram_counts(name):
     from dajin2_b200 import engine
 
@@ -76,7 +76,7 @@ def test_histogram_counts(name):
         assert {str(i): v for i, v in got.items()} == g["strand_counts"]
 
 
-@pytest.mark.parametrize("name", [n for n in SINGLE_CASES if n != "kat"] + ["flox_like"])
+@pytest.mark.parametrize("name", [n for n in SINGLE_CASES if n != "kat"] + ["flox_like", "single_like"])
 def test_mutation_loci(name):
     from dajin2_b200 import engine
 
@@ -92,7 +92,7 @@ def test_mutation_loci(name):
         assert ["".join(sorted(s)) for s in loci] == g["mutation_loci"]
 
 
-@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like"])
+@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like", "single_like"])
 def test_scores_and_rows(name):
     from dajin2_b200 import engine
 
@@ -154,7 +154,8 @@ def _write_tree(tmp_path, alleles, sname="sample", cname="ctrl"):
                            fasta_alleles={n: a["sequence"] for n, a in alleles.items()})
 
 
-@pytest.mark.parametrize("name", ["flox_like", "tp_L1000_N2000_r10", "tp_L1000_N1200_r9", "point_L900_N1500",
+@pytest.mark.parametrize("name", ["flox_like", "single_like", "tp_L1000_N2000_r10", "tp_L1000_N1200_r9",
+                                  "point_L900_N1500", "point_L900_N1500_f01", "point_L900_N1500_f50",
                                   "fixture_flox100", "inv_L2724_N300"])
 def test_dropin_entry_points_on_files(name, tmp_path):
     """The reference's own call sequence (core.py:95,161,217-233) through the drop-in functions, on JSONL files."""

@@ -71,8 +71,9 @@ def test_return_labels(name):
         assert orc.return_labels(xs, xc, strands, strand_all) == g["return_labels"]
 
 
-def test_flox_like_multi_allele():
-    alleles, golden = load_case("flox_like")
+@pytest.mark.parametrize("name", ["flox_like", "single_like"])
+def test_multi_allele(name):
+    alleles, golden = load_case(name)
     for aname, a in alleles.items():
         g = golden["alleles"][aname]
         L = len(a["sequence"])
