@@ -368,6 +368,7 @@ def run_ours(args):
     enc_c = engine.EncodedReads(hc, len(sequence), validate=False, encode=False)
     text_bytes = int(hs.row_len.astype(np.int64).sum())
     enc_bytes = text_bytes + hs.n_reads * (len(sequence) + 16)
+    enc_pitch = int(enc_s.pitch)
 
     def device_step():
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -437,6 +438,25 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = enc_bytes / (enc_ms * 1e-3) / 1e9
     total_reads = args.reads * world
+    # DRAM traffic of one launch from the committed ncu --set full capture of this workload (scripts/ncu_traffic.py)
+    traffic, traffic_hist = None, None
+    tpath = ROOT / "profiles" / "ncu_traffic.json"
+    if tpath.exists():
+        cap = json.loads(tpath.read_text())
+        enc_cap, hist_cap = cap.get("encode_kernel"), cap.get("hist_tile_kernel")
+        if enc_cap and enc_cap["reads_per_launch"] == args.reads and cap.get("n_loci", args.loci) == args.loci:
+            traffic = enc_cap["dram_bytes_per_launch"]
+        if hist_cap and hist_cap["reads_per_launch"] == args.reads and cap.get("n_loci", args.loci) == args.loci:
+            traffic_hist = hist_cap["dram_bytes_per_launch"]
+    # second read-scale kernel: the histogram (sample launch; CUDA events of pipeline.run_device, single GPU only)
+    hist_roofline = None
+    if stage.get("hist_ms"):
+        hist_ms = stage["hist_ms"] / args.steps
+        hist_bytes = (args.reads + N_CONTROL) * (enc_pitch + 1)
+        hist_roofline = {"kernel": "hist_tile_kernel + hist_reduce_kernel (sample and control launches)", "bound": "hbm",
+                         "achieved": hist_bytes / (hist_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": hist_bytes / (hist_ms * 1e-3) / 1e9 / peak, "traffic": traffic_hist,
+                         "algorithmic_bytes_per_step": hist_bytes, "ms_per_step": hist_ms}
     line = {
         "metric": METRIC, "value": total_reads * args.steps / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -452,10 +472,12 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(r2.timings.get("d2h_bytes", 0))},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "encode_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                     "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes_per_launch": enc_bytes, "ms_per_launch": enc_ms},
         "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage.items()},
     }
+    if hist_roofline is not None:
+        line["roofline_hist"] = hist_roofline
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, hs, hc, sequence)
     print(json.dumps(line), flush=True)
