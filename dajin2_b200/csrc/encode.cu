@@ -41,7 +41,9 @@
 #ifndef DJ_ENC_PRED_LDS
 #define DJ_ENC_PRED_LDS 0  // 1: slots without a comma do not read the table (fewer bank conflicts, one more move)
 #endif
-#if DJ_ENC_PRED_LDS
+#if DJ_ENC_PRED_LDS == 2
+#define DJ_ENC_LDS " @p ld.shared.u32 e, [h];\n"
+#elif DJ_ENC_PRED_LDS
 #define DJ_ENC_LDS " mov.u32 e, 0;\n @p ld.shared.u32 e, [h];\n"
 #else
 #define DJ_ENC_LDS " ld.shared.u32 e, [h];\n"
@@ -52,7 +54,10 @@
 
 namespace {
 
-constexpr int kWarpsPerCta = 16;
+#ifndef DJ_ENC_WARPS
+#define DJ_ENC_WARPS 20  // warps per CTA; two CTAs per SM = 40 warps at 48 registers (16: 63 registers, 1 % slower)
+#endif
+constexpr int kWarpsPerCta = DJ_ENC_WARPS;
 constexpr int kLutBits = 13;
 constexpr int kLutSize = 1 << kLutBits;
 // (key * kLutMagic) >> 19 is injective over the 320 keys enumerated in build_token_lut and spreads the frequent
