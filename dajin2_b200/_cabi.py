@@ -57,6 +57,9 @@ SIGNATURES = {
     "dj_ckpt_pitch": (c_int32, [c_int32]),
     "dj_encode": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dj_encode_ref": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dj_encode_ref_smem_bytes": (c_int64, [c_int32, c_int32]),
     "dj_hist": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "dj_window_cosine": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "dj_kmer_table_bytes": (c_int64, [c_uint32]),
@@ -84,12 +87,13 @@ SIGNATURES = {
     "dj_gather_labels": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
 }
 
-_NO_STATUS = {"dj_abi_version", "dj_last_error", "dj_code_pitch", "dj_ckpt_pitch", "dj_kmer_table_bytes",
+_NO_STATUS = {"dj_abi_version", "dj_last_error", "dj_code_pitch", "dj_ckpt_pitch", "dj_encode_ref_smem_bytes",
+              "dj_kmer_table_bytes",
               "dj_row_table_bytes"}
 
 # kernels launched per call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    "dj_encode": 1, "dj_hist": 2, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
+    "dj_encode": 1, "dj_encode_ref": 1, "dj_hist": 2, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
     "dj_fetch_tokens": 1, "dj_dedup_rows": 1, "dj_dedup_export": 1, "dj_bisect": 1, "dj_assign_rows": 1,
     "dj_silhouette": 2, "dj_member_counts": 1, "dj_member_locate": 1, "dj_gather_labels": 1,
 }

@@ -13,7 +13,8 @@ _CACHE: "OrderedDict[tuple, EncodedReads]" = OrderedDict()
 MAX_ENTRIES = 16
 
 
-def encoded_file(path: str | Path, n_loci: int | None = None, keep_records: bool = False) -> EncodedReads:
+def encoded_file(path: str | Path, n_loci: int | None = None, keep_records: bool = False,
+                 sequence: str | None = None) -> EncodedReads:
     path = Path(path)
     st = path.stat()
     key = (str(path.resolve()), st.st_size, st.st_mtime_ns)
@@ -28,7 +29,7 @@ def encoded_file(path: str | Path, n_loci: int | None = None, keep_records: bool
         else:
             o, n = int(host.row_off[0]), int(host.row_len[0])
             n_loci = int((host.text[o : o + n] == ord(",")).sum()) + 1
-    enc = EncodedReads(host, n_loci)
+    enc = EncodedReads(host, n_loci, sequence=sequence)  # the sequence only speeds the encoder up (dj_encode_ref)
     _CACHE[key] = enc
     while len(_CACHE) > MAX_ENTRIES:
         _CACHE.popitem(last=False)

@@ -401,6 +401,256 @@ encode_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Reference-assisted encoder (dj_encode_ref)
+//
+// 98 tokens in 100 are plain matches "=X" whose X is, by the definition of MIDSV, the reference base of their locus:
+// a stretch of plain tokens is byte for byte the reference rendered as "=X,=X,...".  So when the caller supplies
+// the allele sequence, a lane does not translate its tokens one by one; it VERIFIES them: the 16 bytes of its chunk
+// plus the 4 bytes in front of them are compared with the rendered reference at the offset the token ranks dictate
+// (20 bytes, six conflict-free shared-memory loads, five funnel shifts, five XOR/ORs).  If they are equal, every
+// token that closes in the chunk is a plain match of the reference and its code is already in the row: each row
+// starts as a copy of the reference's code row (coalesced 16-byte stores).  If they differ -- a mismatch, an indel,
+// an inversion, an N, a row edge -- the chunk goes to the warp's queue (32 bytes in shared memory), and whenever
+// 32 chunks are queued the warp translates them with the eight-slot code of the generic kernel, one chunk per
+// lane, all lanes busy, and patches the row with byte stores.  Nothing is taken on trust: a read whose plain
+// tokens disagree with the sequence just takes the generic path chunk by chunk.  Output identical to dj_encode.
+// ---------------------------------------------------------------------------------------------------------
+
+constexpr int kRefFrontPad = 32;   // ' ' bytes in front of the rendered reference (a row starts after the filler)
+constexpr int kRefBlockWords = 41; // a block = 32 words of text + 9 words repeated from the next block: lanes read
+                                   // 4 words apart, the 9-word skew puts the 32 lanes of a request in 32 banks, and
+                                   // a 6-word window never leaves its block
+constexpr int kQueueEntries = 64;  // per warp; an entry = 2 x uint4: (prev word, chunk), (first locus, comma flags)
+
+__host__ __device__ inline int ref_text_blocks(int n_loci) { return (kRefFrontPad + 3 * n_loci + 64 + 127) / 128; }
+
+// byte k of the padded rendered reference: ' ' x 32, then "=X," per locus, then ' '.  Loci whose base is not one of
+// ACGTN (upper case) get a byte no text holds, so their tokens always take the generic path.
+__device__ __forceinline__ uint32_t ref_text_byte(const uint8_t *__restrict__ ref, int n_loci, int k) {
+    const int pos = k - kRefFrontPad;
+    if (pos < 0 || pos >= 3 * n_loci) return ' ';
+    const int locus = pos / 3, m = pos - 3 * locus;
+    if (m == 0) return '=';
+    if (m == 2) return ',';
+    const uint32_t b = ref[locus];
+    return (b == 'A' || b == 'C' || b == 'G' || b == 'T' || b == 'N') ? b : 0x01u;
+}
+
+__device__ __forceinline__ uint32_t ref_code(uint32_t b) {
+    return b == 'A' ? 0u : b == 'C' ? 1u : b == 'G' ? 2u : b == 'T' ? 3u : b == 'N' ? 4u : 0u;
+}
+
+// the generic slot with the code byte going to global memory (queued chunks patch the row)
+__device__ __forceinline__ void emit_token_g(uint32_t &acc, uint8_t *&gp, uint32_t lut_s, uint32_t key, uint32_t flag,
+                                             uint32_t c_four) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .u32 h, e;\n"
+        " setp.ne.u32 p, %4, 0;\n"
+        " mul.lo.u32 h, %2, %6;\n"
+        " shr.u32 h, h, %7;\n"
+        " mad.lo.u32 h, h, %5, %3;\n"
+        " ld.shared.u32 e, [h];\n"
+        " @p add.u32 %0, %0, e;\n"
+        " @p st.global.u8 [%1], e;\n"
+        " @p add.u64 %1, %1, 1;\n}\n"
+        : "+r"(acc), "+l"(gp)
+        : "r"(key), "r"(lut_s), "r"(flag), "r"(c_four), "n"(kLutMagic), "n"(32 - kLutBits)
+        : "memory");
+}
+
+template <int k>
+__device__ __forceinline__ void emit_word_g(uint32_t &acc, uint8_t *&gp, uint32_t lut_s, uint32_t prev, uint32_t word,
+                                            uint32_t zz, uint32_t c_four) {
+    emit_token_g(acc, gp, lut_s, __funnelshift_r(prev, word, 4), zz & (0x80u >> k), c_four);
+    const uint32_t m = zz & (0x80808000u >> k);
+    emit_token_g(acc, gp, lut_s, __funnelshift_r(prev, word, find_msb(m) + (uint32_t)(k - 3)), m, c_four);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+encode_ref_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_off,
+                  const int32_t *__restrict__ row_len, int64_t n_reads, int n_loci, int code_pitch, int ckpt_pitch,
+                  const uint8_t *__restrict__ ref, uint8_t *__restrict__ codes, int32_t *__restrict__ match_score,
+                  int32_t *__restrict__ n_tokens, uint32_t *__restrict__ flags, uint32_t *__restrict__ ckpt,
+                  uint32_t c_four) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    // layout: token table | per-warp queues | code row of the reference | rendered reference (swizzled)
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem_raw);
+    uint4 *queue_all = reinterpret_cast<uint4 *>(smem_raw + kLutSize * 4);
+    uint8_t *ref_codes = smem_raw + kLutSize * 4 + kWarpsPerCta * kQueueEntries * 32;
+    uint32_t *ref_text = reinterpret_cast<uint32_t *>(ref_codes + code_pitch);
+    build_token_lut(lut);
+    for (int i = threadIdx.x; i < code_pitch; i += blockDim.x) ref_codes[i] = i < n_loci ? (uint8_t)ref_code(ref[i]) : 0;
+    const int n_blocks = ref_text_blocks(n_loci);
+    for (int w = threadIdx.x; w < n_blocks * kRefBlockWords; w += blockDim.x) {
+        const int blk = w / kRefBlockWords, in = w - blk * kRefBlockWords;
+        const int k = (blk * 32 + in) * 4;  // words 32..40 of a block repeat the head of the next one
+        ref_text[w] = ref_text_byte(ref, n_loci, k) | (ref_text_byte(ref, n_loci, k + 1) << 8) |
+                      (ref_text_byte(ref, n_loci, k + 2) << 16) | (ref_text_byte(ref, n_loci, k + 3) << 24);
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    uint4 *queue = queue_all + (threadIdx.x >> 5) * (kQueueEntries * 2);
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(lut);
+    const uint32_t ref_text_s = (uint32_t)__cvta_generic_to_shared(ref_text);
+    const uint32_t lanes_below = (1u << lane) - 1u;
+    const int64_t warp = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerCta;
+
+    for (int64_t r = warp; r < n_reads; r += n_warps) {
+        const int64_t off = row_off[r];
+        const int len = row_len[r];
+        const int head = (int)(off & 15);
+        const uint4 *base = reinterpret_cast<const uint4 *>(text + (off - head));
+        const int nbytes = head + len;
+        const int n_iter = (nbytes >> 9) + 1;
+        const int n_pairs = (n_iter + 1) >> 1;
+        uint8_t *out = codes + r * (int64_t)code_pitch;
+        uint32_t *ck = ckpt + r * (int64_t)ckpt_pitch;
+
+        // the row starts as the reference's code row
+        for (int b = lane * 16; b < code_pitch; b += 512)
+            *reinterpret_cast<uint4 *>(out + b) = *reinterpret_cast<const uint4 *>(ref_codes + b);
+        __syncwarp();
+
+        int tokbase = 0;
+        uint32_t counts = 0, sticky = 0, high = 0;
+        uint32_t carry_w = kFill;
+        uint32_t q_in = 0, q_out = 0;  // chunks queued / translated so far (warp-uniform)
+        int pair = 0;
+
+        // translate (up to) 32 queued chunks, one per lane, with the generic slots; codes go to the row
+        auto drain = [&](uint32_t n) {
+            __syncwarp();
+            if ((uint32_t)lane < n) {
+                const uint32_t slot = (q_out + lane) & (kQueueEntries - 1);
+                const uint4 e0 = queue[slot * 2], e1 = queue[slot * 2 + 1];
+                const uint32_t first = e1.y, zz = e1.z;
+                const uint32_t cnt = __popc(zz);
+                if (first + cnt <= (uint32_t)code_pitch) {
+                    uint8_t *gp = out + first;
+                    uint8_t *const gp0 = gp;
+                    uint32_t acc = 0;
+                    emit_word_g<0>(acc, gp, lut_s, e0.x, e0.y, zz, c_four);
+                    emit_word_g<1>(acc, gp, lut_s, e0.y, e0.z, zz, c_four);
+                    emit_word_g<2>(acc, gp, lut_s, e0.z, e0.w, zz, c_four);
+                    emit_word_g<3>(acc, gp, lut_s, e0.w, e1.x, zz, c_four);
+                    sticky |= ((uint32_t)(gp - gp0) ^ cnt) | ((acc >> 15) & 0x1F00u);
+                    counts += ((acc >> kStatShift) & 0x3Fu) | ((acc >> 2) & 0x1F0000u);
+                } else {
+                    sticky |= kStickyBroken;
+                }
+            }
+            q_out += n;
+            __syncwarp();
+        };
+
+        // One chunk: verify it against the rendered reference or queue it.  `first` = rank of the first token that
+        // closes in the chunk, `wp` = the word in front of the chunk.
+        auto check = [&](const uint4 &c, uint32_t wp, uint32_t zz, uint32_t cnt, uint32_t first) {
+            const uint32_t t = zz & 0x00808080u;     // a plain chunk closes a token within its first three bytes
+            const uint32_t p8 = t ? find_msb(t) - 7u : 0u;  // 8 x (position of that comma)
+            // byte offset, in the padded rendered reference, of the byte 4 in front of the chunk (ranks past the
+            // reference are clamped: such a chunk is never plain, the loads just have to stay inside the table)
+            const uint32_t a = 3u * min(first, (uint32_t)n_loci) + (uint32_t)(kRefFrontPad + 2 - 4) - (p8 >> 3);
+            const uint32_t q = a >> 2, sh = (a & 3u) << 3;
+            const uint32_t addr = ref_text_s + ((q + 9u * (q >> 5)) << 2);
+            uint32_t r0, r1, r2, r3, r4, r5;
+            asm volatile("ld.shared.u32 %0, [%6];\n ld.shared.u32 %1, [%6+4];\n ld.shared.u32 %2, [%6+8];\n"
+                         " ld.shared.u32 %3, [%6+12];\n ld.shared.u32 %4, [%6+16];\n ld.shared.u32 %5, [%6+20];\n"
+                         : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3), "=r"(r4), "=r"(r5) : "r"(addr));
+            uint32_t d = (wp ^ __funnelshift_r(r0, r1, sh)) & (0xFFFFFFFFu << ((p8 + 8u) & 31u));
+            d |= c.x ^ __funnelshift_r(r1, r2, sh);
+            d |= c.y ^ __funnelshift_r(r2, r3, sh);
+            d |= c.z ^ __funnelshift_r(r3, r4, sh);
+            d |= c.w ^ __funnelshift_r(r4, r5, sh);
+            const bool plain = d == 0 && t != 0 && first < (uint32_t)n_loci;
+            const bool push = !plain && cnt != 0;
+            const uint32_t vote = __ballot_sync(0xffffffffu, push);
+            if (push) {
+                const uint32_t slot = (q_in + __popc(vote & lanes_below)) & (kQueueEntries - 1);
+                queue[slot * 2] = make_uint4(wp, c.x, c.y, c.z);
+                queue[slot * 2 + 1] = make_uint4(c.w, first, zz, 0u);
+            }
+            q_in += __popc(vote);
+            if (q_in - q_out >= 32) drain(32);
+        };
+
+        auto trip = [&](const uint4 &ca, const uint4 &cb) {
+            const uint32_t zza = chunk_commas(ca, high), zzb = chunk_commas(cb, high);
+            uint32_t wpa = __shfl_up_sync(0xffffffffu, ca.w, 1);
+            uint32_t wpb = __shfl_up_sync(0xffffffffu, cb.w, 1);
+            const uint32_t last_a = __shfl_sync(0xffffffffu, ca.w, 31);
+            if (lane == 0) {
+                ck[pair] = pair == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
+                wpa = carry_w;
+                wpb = last_a;
+            }
+            carry_w = __shfl_sync(0xffffffffu, cb.w, 31);
+
+            const uint32_t cnt_a = __popc(zza), cnt_b = __popc(zzb);
+            const uint32_t cnt = cnt_a | (cnt_b << 16);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const uint32_t totals = __shfl_sync(0xffffffffu, incl, 31);
+            const int total_a = (int)(totals & 0xFFFFu), total_b = (int)(totals >> 16);
+            const uint32_t excl = incl - cnt;
+            if (total_a > kMaxTokensPerChunk || total_b > kMaxTokensPerChunk || tokbase >= code_pitch) {
+                sticky |= kStickyBroken;
+                pair = 0x3FFFFFFF;
+                return;
+            }
+            check(ca, wpa, zza, cnt_a, (uint32_t)tokbase + (excl & 0xFFFFu));
+            check(cb, wpb, zzb, cnt_b, (uint32_t)tokbase + (uint32_t)total_a + (excl >> 16));
+            tokbase += total_a + total_b;
+        };
+
+        trip(load_chunk(base, lane, head, nbytes), load_chunk(base, 32 + lane, head, nbytes));
+        const int n_inside = nbytes >> 10;
+#pragma unroll 1
+        for (++pair; pair < n_inside; ++pair) {
+            const uint4 *p = base + pair * 64 + lane;
+#if DJ_ENC_PREFETCH_DIST > 0
+            if (pair + DJ_ENC_PREFETCH_DIST < n_inside) {
+                asm volatile("prefetch.global." DJ_ENC_PREFETCH_LEVEL " [%0];" ::"l"(p + 64 * DJ_ENC_PREFETCH_DIST));
+                asm volatile("prefetch.global." DJ_ENC_PREFETCH_LEVEL " [%0];" ::"l"(p + 64 * DJ_ENC_PREFETCH_DIST + 32));
+            }
+#endif
+            trip(__ldg(p), __ldg(p + 32));
+        }
+#pragma unroll 1
+        for (; pair < n_pairs; ++pair)
+            trip(load_chunk(base, pair * 64 + lane, head, nbytes), load_chunk(base, pair * 64 + 32 + lane, head, nbytes));
+        drain(q_in - q_out);
+
+        const bool broken = (__reduce_or_sync(0xffffffffu, sticky) & kStickyBroken) != 0;
+        counts = __reduce_add_sync(0xffffffffu, counts);
+        sticky = __reduce_or_sync(0xffffffffu, sticky | (high & 0x80808080u));
+        const uint32_t mism = counts & 0xFFFFu, n_sub = counts >> 16;
+        const int ins3 = len - 3 * tokbase + 1 - (int)n_sub;
+        bool bad = (sticky & (kStickyBroken | 0x8080808Fu)) != 0 || ins3 < 0 || ins3 % 3 != 0;
+        uint32_t mismatches = mism + (uint32_t)(ins3 / 3);
+        if ((sticky & 0x1F00u) != 0 && !broken) {
+            __syncwarp();
+            bool has_invalid = false;
+            mismatches = recheck_row(text + off, len, out, min(tokbase, code_pitch), lane, &has_invalid);
+            bad = bad || has_invalid;
+        }
+        if (lane == 0) {
+            match_score[r] = -(int32_t)mismatches;
+            n_tokens[r] = tokbase;
+            flags[r] = (tokbase != n_loci ? DJ_FLAG_TOKEN_COUNT : 0u) | (bad ? DJ_FLAG_BAD_TOKEN : 0u);
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
 extern "C" int32_t dj_code_pitch(int32_t n_loci) { return (n_loci + 31) & ~31; }
@@ -431,6 +681,46 @@ extern "C" int dj_encode(const uint8_t *text, const int64_t *row_off, const int3
     encode_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, 0, (cudaStream_t)stream>>>(
         text, row_off, row_len, n_reads, n_loci, code_pitch, ckpt_pitch, codes, match_score, n_tokens, flags, ckpt, 4u,
         (uint32_t)kLutSize);
+    DJ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int64_t dj_encode_ref_smem_bytes(int32_t n_loci, int32_t code_pitch) {
+    return (int64_t)kLutSize * 4 + (int64_t)kWarpsPerCta * kQueueEntries * 32 + code_pitch +
+           (int64_t)ref_text_blocks(n_loci) * kRefBlockWords * 4;
+}
+
+extern "C" int dj_encode_ref(const uint8_t *text, const int64_t *row_off, const int32_t *row_len, int64_t n_reads,
+                             int32_t n_loci, int32_t code_pitch, int32_t ckpt_pitch, const uint8_t *ref_seq,
+                             uint8_t *codes, int32_t *match_score, int32_t *n_tokens, uint32_t *flags, uint32_t *ckpt,
+                             void *stream) {
+    const int64_t smem = dj_encode_ref_smem_bytes(n_loci, code_pitch);
+    // without a reference, or when the rendered reference does not fit next to a second CTA: the generic kernel
+    if (ref_seq == nullptr || smem > 110 * 1024)
+        return dj_encode(text, row_off, row_len, n_reads, n_loci, code_pitch, ckpt_pitch, codes, match_score, n_tokens,
+                         flags, ckpt, stream);
+    if (n_reads <= 0) return 0;
+    if (((uintptr_t)text & 15) != 0 || ((uintptr_t)codes & 15) != 0) {
+        dj_set_error("dj_encode_ref: text and codes must be 16-byte aligned");
+        return 1;
+    }
+    if (code_pitch < n_loci || (code_pitch & 31) != 0) {
+        dj_set_error("dj_encode_ref: code_pitch %d must be a multiple of 32 and >= n_loci %d", code_pitch, n_loci);
+        return 1;
+    }
+    const int sms = dj_sm_count();
+    if (sms <= 0) return 1;
+    static int64_t configured = 0;
+    if (configured < smem) {
+        DJ_CUDA_CHECK(cudaFuncSetAttribute(encode_ref_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int64_t ctas = (n_reads + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int64_t resident = (int64_t)sms * 2;
+    if (ctas > resident) ctas = resident;
+    encode_ref_kernel<<<(unsigned)ctas, kWarpsPerCta * 32, (size_t)smem, (cudaStream_t)stream>>>(
+        text, row_off, row_len, n_reads, n_loci, code_pitch, ckpt_pitch, ref_seq, codes, match_score, n_tokens, flags,
+        ckpt, 4u);
     DJ_LAUNCH_CHECK();
     return 0;
 }

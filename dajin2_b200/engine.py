@@ -79,7 +79,11 @@ def order_of_keys(keys: torch.Tensor) -> torch.Tensor:
 class EncodedReads:
     """One MIDSV file on the device: text, row index, read x locus code matrix and per-read scalars."""
 
-    def __init__(self, host: HostReads, n_loci: int, validate: bool = True, encode: bool = True):
+    def __init__(self, host: HostReads, n_loci: int, validate: bool = True, encode: bool = True,
+                 sequence: str | None = None):
+        """``sequence`` (the allele the reads were aligned to, when the caller has it) lets the encoder verify plain
+        stretches against the rendered reference instead of translating them (``dj_encode_ref``); the codes are the
+        same with or without it."""
         dev = require_cuda()
         self.n_reads = host.n_reads
         self.n_loci = int(n_loci)
@@ -102,12 +106,20 @@ class EncodedReads:
         self.n_tokens = torch.empty(n, dtype=torch.int32, device=dev)
         self.flags = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ckpt = torch.empty((n, self.ckpt_pitch), dtype=torch.int32, device=dev)
+        self.ref = None
+        if sequence is not None and len(sequence) == self.n_loci:
+            self.ref = torch.from_numpy(np.frombuffer(sequence.encode("ascii", "replace"), dtype=np.uint8).copy()).to(dev)
         if encode:
             self.encode()
             if validate:
                 self.validate()
 
     def encode(self) -> None:
+        if self.ref is not None:
+            _cabi.call("dj_encode_ref", _p(self.text), _p(self.row_off), _p(self.row_len), self.n_reads, self.n_loci,
+                       self.pitch, self.ckpt_pitch, _p(self.ref), _p(self.codes), _p(self.match_score),
+                       _p(self.n_tokens), _p(self.flags), _p(self.ckpt), _stream())
+            return
         _cabi.call("dj_encode", _p(self.text), _p(self.row_off), _p(self.row_len), self.n_reads, self.n_loci,
                    self.pitch, self.ckpt_pitch, _p(self.codes), _p(self.match_score), _p(self.n_tokens),
                    _p(self.flags), _p(self.ckpt), _stream())

@@ -162,8 +162,8 @@ def run_host(sample: HostReads, control: HostReads, sequence: str, knockin: set[
              order: np.ndarray | None = None, comm=None, gpos: np.ndarray | None = None) -> HotPathResult:
     """Hot path from packed HOST buffers: host->device copies, the device path, label read-back."""
     t0 = time.perf_counter()
-    enc_s = engine.EncodedReads(sample, len(sequence), validate=False, encode=False)
-    enc_c = engine.EncodedReads(control, len(sequence), validate=False, encode=False)
+    enc_s = engine.EncodedReads(sample, len(sequence), validate=False, encode=False, sequence=sequence)
+    enc_c = engine.EncodedReads(control, len(sequence), validate=False, encode=False, sequence=sequence)
     torch.cuda.synchronize()
     h2d_ms = (time.perf_counter() - t0) * 1e3
     res = run_device(enc_s, enc_c, sequence, knockin, order, comm=comm, gpos=gpos)

@@ -49,7 +49,7 @@ def minimize_mutation_counts(indels_control, indels_sample):
 
 def summarize_indels(path_midsv: Path, sequence: str) -> tuple:
     """indel_counter.py:58-62."""
-    enc = encoded_file(path_midsv, len(sequence))
+    enc = encoded_file(path_midsv, len(sequence), sequence=sequence)
     count = engine.counts_from_histogram(enc.histogram())
     return count, engine.normalize_indels(count)
 
@@ -73,7 +73,7 @@ def extract_mutation_loci(path_midsv_sample: Path, sequence: str, path_indels_no
     norm_sample = _load_pickle(path_indels_normalized_sample)
     norm_control = _load_pickle(path_indels_normalized_control)
     knockin = _load_pickle(path_knockin) if Path(path_knockin).exists() else None
-    enc = encoded_file(path_midsv_sample, len(sequence))
+    enc = encoded_file(path_midsv_sample, len(sequence), sequence=sequence)
     insample = None
     if is_consensus:
         # consensus-only Gaussian-process filter stays in the reference (out of scope)

@@ -108,6 +108,18 @@ int dj_encode(const uint8_t *text, const int64_t *row_off, const int32_t *row_le
               int32_t n_loci, int32_t code_pitch, int32_t ckpt_pitch, uint8_t *codes, int32_t *match_score,
               int32_t *n_tokens, uint32_t *flags, uint32_t *ckpt, void *stream);
 
+/* dj_encode with the allele sequence as an accelerator: ref_seq[n_loci] (device, ASCII bases).  Stretches of plain
+ * matches are verified against the reference rendered as "=X,=X,..." instead of being translated token by token;
+ * everything else -- and every read whose text disagrees with the sequence -- takes the path of dj_encode.  Output
+ * identical to dj_encode for any input; ref_seq == NULL (or a sequence too long for shared memory) calls dj_encode.
+ * Same reference interface as dj_encode; the sequence is the `sequence` argument the reference passes next to the
+ * file (summarize_indels(path, sequence), indel_counter.py:58; score_allele, classifier.py:27). */
+int dj_encode_ref(const uint8_t *text, const int64_t *row_off, const int32_t *row_len, int64_t n_reads,
+                  int32_t n_loci, int32_t code_pitch, int32_t ckpt_pitch, const uint8_t *ref_seq, uint8_t *codes,
+                  int32_t *match_score, int32_t *n_tokens, uint32_t *flags, uint32_t *ckpt, void *stream);
+/* dynamic shared memory dj_encode_ref needs per CTA for this reference length */
+int64_t dj_encode_ref_smem_bytes(int32_t n_loci, int32_t code_pitch);
+
 /*
  * Per-locus histograms of the code matrix over `rows` (NULL = all n_rows reads in order).
  * counts[DJ_HIST_ROWS][n_loci] is zeroed and filled.  Replaces count_indels (indel_counter.py:15-31) and the

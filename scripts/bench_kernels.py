@@ -51,6 +51,14 @@ def timeit(fn, nbytes, name):
 
 
 timeit(enc.encode, text_bytes + args.reads * (args.loci + 16), "encode")
+enc_ref = engine.EncodedReads(hs, args.loci, validate=True, encode=True, sequence=pop.reference)
+timeit(enc_ref.encode, text_bytes + args.reads * (args.loci + 16), "encode_ref")
+for name in ("codes", "match_score", "n_tokens", "flags"):
+    a, b = getattr(enc, name), getattr(enc_ref, name)
+    if name == "codes":
+        a, b = a[:, : args.loci], b[:, : args.loci]
+    print("encode_ref ==", name, bool(torch.equal(a, b)))
+del enc_ref
 hist = torch.empty((_cabi.HIST_ROWS, args.loci), dtype=torch.int32, device="cuda")
 timeit(lambda: _cabi.call("dj_hist", engine._p(enc.codes), enc.pitch, engine._p(enc.strand), engine._p(None), enc.n_reads,
                           enc.n_loci, engine._p(hist), engine._stream()), args.reads * (args.loci + 1), "hist")

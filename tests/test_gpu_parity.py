@@ -186,6 +186,64 @@ def test_dropin_entry_points_on_files(name, tmp_path):
         assert abs(pr - pg) <= 0.5
 
 
+@pytest.mark.parametrize("name", SINGLE_CASES + ["flox_like", "single_like"])
+def test_encode_ref_equals_generic(name):
+    """dj_encode_ref (plain stretches verified against the rendered reference) == dj_encode, with the right
+    sequence, with a wrong one, and with one that holds N / lower-case / IUPAC letters."""
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+
+    alleles, _ = load_case(name)
+    for a in alleles.values():
+        L = len(a["sequence"])
+        for part in (a["sample"], a["control"]):
+            host = pack_rows(part["rows"], part["strands"], part["qnames"])
+            want = engine.EncodedReads(host, L)
+            seq = a["sequence"]
+            shuffled = seq[7:] + seq[:7]
+            odd = "".join("NnRa"[i % 4] if i % 5 == 0 else ch for i, ch in enumerate(seq))
+            for ref in (seq, shuffled, odd):
+                got = engine.EncodedReads(host, L, sequence=ref)
+                assert got.ref is not None
+                assert torch.equal(got.codes[:, :L], want.codes[:, :L])
+                assert torch.equal(got.match_score, want.match_score)
+                assert torch.equal(got.n_tokens, want.n_tokens) and torch.equal(got.flags, want.flags)
+                assert torch.equal(got.ckpt, want.ckpt)
+
+
+def test_encode_ref_edge_cases():
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+
+    rng = np.random.default_rng(3)
+    for L in (1, 2, 3, 5, 16, 31, 32, 33, 171, 342, 343, 1000, 2049):
+        seq = "".join("ACGT"[i] for i in rng.integers(0, 4, L))
+        plain = ",".join("=" + c for c in seq)
+        toks = ["=" + c for c in seq]
+        variants = [plain]
+        for _ in range(12):
+            t = list(toks)
+            for i in rng.integers(0, L, max(1, L // 40)):
+                kind = int(rng.integers(0, 6))
+                c = seq[i]
+                t[i] = [f"-{c}", f"*{c}{'ACGT'[("ACGT".index(c) + 1) % 4]}", f"+A|+C|={c}", "=N", f"={c.lower()}",
+                        f"+T|*{c}{'ACGT'[("ACGT".index(c) + 2) % 4]}"][kind]
+            variants.append(",".join(t))
+        variants.append(",".join(["=N"] * L))                       # nothing matches
+        variants.append(",".join("=" + c.lower() for c in seq))      # an inverted read
+        host = pack_rows(variants)
+        want = engine.EncodedReads(host, L)
+        got = engine.EncodedReads(host, L, sequence=seq)
+        assert torch.equal(got.codes[:, :L], want.codes[:, :L]), L
+        assert torch.equal(got.match_score, want.match_score), L
+        assert torch.equal(got.n_tokens, want.n_tokens) and torch.equal(got.flags, want.flags)
+    # rows with a wrong token count / a bad token are flagged the same way
+    host = pack_rows(["=A,=C,=G", "=A,=C", "=A,=R,=G", "=A,=C,=G,=T"])
+    a = engine.EncodedReads(host, 3, validate=False)
+    b = engine.EncodedReads(host, 3, validate=False, sequence="ACG")
+    assert torch.equal(a.flags, b.flags) and torch.equal(a.n_tokens, b.n_tokens)
+
+
 def test_window_cosine_matches_oracle():
     from dajin2_b200 import engine
     from oracle import dajin2_oracle as orc
