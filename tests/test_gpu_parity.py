@@ -10,6 +10,7 @@ from types import SimpleNamespace
 
 import numpy as np
 import pytest
+import torch
 
 from tests.helpers import (SINGLE_CASES, encode_rows, golden_loci, golden_score, load_case, sparse_rows)
 
@@ -190,6 +191,8 @@ def test_dropin_entry_points_on_files(name, tmp_path):
 def test_encode_ref_equals_generic(name):
     """dj_encode_ref (plain stretches verified against the rendered reference) == dj_encode, with the right
     sequence, with a wrong one, and with one that holds N / lower-case / IUPAC letters."""
+    import torch
+
     from dajin2_b200 import engine
     from dajin2_b200.ingest import pack_rows
 
