@@ -471,7 +471,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(r2.timings.get("h2d_bytes", 0)),
                 "d2h_bytes_per_step": int(r2.timings.get("d2h_bytes", 0))},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "encode_ref_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": "encode_ref_kernel" if enc_s.ref is not None else "encode_kernel", "bound": "hbm",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes_per_launch": enc_bytes, "ms_per_launch": enc_ms},
         "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage.items()},

@@ -85,17 +85,21 @@ SIGNATURES = {
     "dj_member_counts": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "dj_member_locate": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dj_gather_labels": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "dj_read_n_features": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dj_loci_words": (c_int32, [c_int32]),
+    "dj_sv_scan": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                             c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_void_p, c_void_p]),
 }
 
 _NO_STATUS = {"dj_abi_version", "dj_last_error", "dj_code_pitch", "dj_ckpt_pitch", "dj_encode_ref_smem_bytes",
-              "dj_kmer_table_bytes",
-              "dj_row_table_bytes"}
+              "dj_kmer_table_bytes", "dj_row_table_bytes", "dj_loci_words"}
 
 # kernels launched per call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
     "dj_encode": 1, "dj_encode_ref": 1, "dj_hist": 2, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
     "dj_fetch_tokens": 1, "dj_dedup_rows": 1, "dj_dedup_export": 1, "dj_bisect": 1, "dj_assign_rows": 1,
     "dj_silhouette": 2, "dj_member_counts": 1, "dj_member_locate": 1, "dj_gather_labels": 1,
+    "dj_read_n_features": 1, "dj_sv_scan": 1,
 }
 launch_count = 0
 

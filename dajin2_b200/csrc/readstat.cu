@@ -1,0 +1,314 @@
+// Per-read scans of the code matrix that the reference makes as further passes over the MIDSV text:
+//
+//   dj_read_n_features   N count and longest N run of every read -- the two features of the sequence-error read
+//                        filter (convert_nm_tag / extract_n_features,
+//                        src/DAJIN2/core/preprocess/error_correction/sequence_error_handler.py:26-41) and the N
+//                        count of the consensus stage's control filter
+//                        (consensus/consensus_mutation_analyzer.py:85-88);
+//   dj_sv_scan           start index and size of every structural-variant feature of every read
+//                        (get_index_and_sv_size, preprocess/structural_variants/sv_detector.py:53-97): runs of >= 10
+//                        deletions on loci that carry '-' in mutation_loci, runs of >= 10 lowercase (inverted)
+//                        tokens, insertions of >= 10 bases on loci that carry '+'.  The reference makes twelve passes
+//                        over the two files for this (three SV types x {collect indices, extract features} x
+//                        {sample, control}); the records of ONE scan serve all of them.
+//
+// Both kernels are one warp per read: the row is turned into bit strings in shared memory (one bit per locus and
+// token class, found sixteen code bytes at a time with byte-parallel range tests), and runs are then found with
+// word-parallel shifts -- no per-token loop anywhere.  Reads are independent; HBM traffic is the code matrix once
+// (algorithmic bytes per read: code_pitch).
+#include "dj_common.cuh"
+
+namespace {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr uint32_t kOnes = 0x01010101u;
+constexpr uint32_t kHigh = 0x80808080u;
+
+// 0x80 in every byte of y (7-bit values) that lies in [lo, hi)
+template <int lo, int hi>
+__device__ __forceinline__ uint32_t bytes_in_range(uint32_t y) {
+    const uint32_t ge = y + (uint32_t)(0x80 - lo) * kOnes;
+    const uint32_t lt = ~(y + (uint32_t)(0x80 - hi) * kOnes);
+    return ge & lt & kHigh;
+}
+
+// bit j = bit 7 of byte j
+__device__ __forceinline__ uint32_t movemask4(uint32_t z) { return ((z >> 7) * 0x01020408u) >> 24; }
+
+enum { kClassN = 0, kClassDel = 1, kClassLower = 2, kClassIns = 3, kClasses = 4 };
+
+// bit 7 of each byte: the token class tests on four code bytes
+__device__ __forceinline__ uint32_t class_flags(uint32_t w, int cls) {
+    const uint32_t y = w & 0x7F7F7F7Fu;
+    switch (cls) {
+        case kClassN:  // is_n_tag (utils/midsv_handler.py:8-14): anchor "=N" / "=n", inserted or not
+            return bytes_in_range<4, 5>(y) | bytes_in_range<9, 10>(y);
+        case kClassDel:  // startswith("-"): a deletion anchor that is not an insertion's anchor
+            return bytes_in_range<10, 20>(y) & ~w;
+        case kClassLower:  // str.islower(): the lowercase anchors (an insertion takes the case of its anchor)
+            return bytes_in_range<5, 10>(y) | bytes_in_range<15, 20>(y) | bytes_in_range<45, 70>(y);
+        default:  // startswith("+")
+            return w & kHigh;
+    }
+}
+
+__device__ __forceinline__ uint32_t class_mask16(const uint4 &v, int cls) {
+    return movemask4(class_flags(v.x, cls)) | (movemask4(class_flags(v.y, cls)) << 4) |
+           (movemask4(class_flags(v.z, cls)) << 8) | (movemask4(class_flags(v.w, cls)) << 12);
+}
+
+// Bit strings of one row: bits[c][k] bit b = token 32 * k + b belongs to class c.  `words` words per class plus two
+// zero words behind them.  Returns, per class, whether any bit is set (warp-uniform).
+template <int kFirst, int kLast>
+__device__ __forceinline__ uint32_t build_bits(const uint8_t *__restrict__ row, int code_pitch, int n_loci, int words,
+                                               uint32_t *bits, int stride, int lane) {
+    uint32_t any = 0;
+    for (int base = 0; base < words * 32; base += 512) {
+        const int pos = base + lane * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (pos < code_pitch) v = __ldg(reinterpret_cast<const uint4 *>(row + pos));
+        // tokens past n_loci (row padding) never count
+        uint32_t valid = 0xFFFFu;
+        if (pos + 16 > n_loci) valid = pos >= n_loci ? 0u : (0xFFFFu >> (pos + 16 - n_loci));
+#pragma unroll
+        for (int c = kFirst; c <= kLast; ++c) {
+            uint32_t m = 0;
+            if (((v.x | v.y | v.z | v.w) & 0xFCFCFCFCu) != 0) m = class_mask16(v, c) & valid;  // plain matches: no class
+            const uint32_t hi = __shfl_down_sync(0xffffffffu, m, 1);
+            const int k = (base >> 5) + (lane >> 1);
+            if ((lane & 1) == 0 && k < words) bits[c * stride + k] = m | (hi << 16);
+            any |= (__ballot_sync(0xffffffffu, m != 0) != 0 ? 1u : 0u) << c;
+        }
+    }
+    return any;
+}
+
+struct RunSummary {  // of a bit string: leading run (from bit 0), trailing run, longest run, length
+    int pre, suf, best, len;
+};
+
+__device__ __forceinline__ RunSummary combine(const RunSummary &a, const RunSummary &b) {  // a then b
+    RunSummary r;
+    r.pre = a.pre == a.len ? a.len + b.pre : a.pre;
+    r.suf = b.suf == b.len ? b.len + a.suf : b.suf;
+    r.best = max(max(a.best, b.best), a.suf + b.pre);
+    r.len = a.len + b.len;
+    return r;
+}
+
+__device__ __forceinline__ RunSummary summarize_word(uint32_t w) {
+    RunSummary s;
+    s.len = 32;
+    if (w == 0u) {
+        s.pre = s.suf = s.best = 0;
+    } else if (w == 0xFFFFFFFFu) {
+        s.pre = s.suf = s.best = 32;
+    } else {
+        s.pre = __ffs(~w) - 1;
+        s.suf = __clz(~w);
+        int k = 0;
+        for (uint32_t t = w; t; t &= t << 1) ++k;
+        s.best = k;
+    }
+    return s;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+n_features_kernel(const uint8_t *__restrict__ codes, int code_pitch, const int32_t *__restrict__ rows, int64_t n_rows,
+                  int n_loci, int words, int32_t *__restrict__ n_count, int32_t *__restrict__ n_maxrun) {
+    extern __shared__ uint32_t smem_bits[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = words + 2;
+    uint32_t *bits = smem_bits + warp * stride;
+    const int64_t n_warps = (int64_t)gridDim.x * kScanWarps;
+    for (int64_t t = (int64_t)blockIdx.x * kScanWarps + warp; t < n_rows; t += n_warps) {
+        const int64_t r = rows ? (int64_t)__ldg(rows + t) : t;
+        const uint32_t any = build_bits<kClassN, kClassN>(codes + r * (int64_t)code_pitch, code_pitch, n_loci, words,
+                                                          bits, stride, lane);
+        int count = 0, best = 0;
+        if (any) {
+            __syncwarp();
+            RunSummary acc = {0, 0, 0, 0};
+            for (int k0 = 0; k0 < words; k0 += 32) {
+                const uint32_t w = k0 + lane < words ? bits[k0 + lane] : 0u;
+                count += __popc(w);
+                RunSummary s = summarize_word(w);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {  // ordered reduction: lane i holds lanes i .. i + 2d - 1
+                    RunSummary o;
+                    o.pre = __shfl_down_sync(0xffffffffu, s.pre, d);
+                    o.suf = __shfl_down_sync(0xffffffffu, s.suf, d);
+                    o.best = __shfl_down_sync(0xffffffffu, s.best, d);
+                    o.len = __shfl_down_sync(0xffffffffu, s.len, d);
+                    if (lane + d < 32) s = combine(s, o);
+                }
+                acc = combine(acc, s);  // lane 0's value is the block's; the others are not used
+            }
+            count = __reduce_add_sync(0xffffffffu, count);
+            best = __shfl_sync(0xffffffffu, acc.best, 0);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            n_count[t] = count;
+            n_maxrun[t] = best;
+        }
+    }
+}
+
+__device__ __forceinline__ void emit_record(int32_t *records, uint32_t *n_records, uint32_t capacity, int type,
+                                            int read, int start, int size) {
+    const uint32_t slot = atomicAdd(n_records, 1u);
+    if (slot < capacity) {
+        int32_t *p = records + (size_t)slot * 4;
+        p[0] = type;
+        p[1] = read;
+        p[2] = start;
+        p[3] = size;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+sv_scan_kernel(const uint8_t *__restrict__ codes, int code_pitch, const int32_t *__restrict__ rows, int64_t n_rows,
+               int n_loci, int words, const uint32_t *__restrict__ del_loci, const uint32_t *__restrict__ ins_loci,
+               int min_size, DjTextRef text, int32_t *__restrict__ records, uint32_t *__restrict__ n_records,
+               uint32_t capacity) {
+    extern __shared__ uint32_t smem_bits[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = words + 2;
+    uint32_t *bits = smem_bits + warp * kClasses * stride;
+    for (int c = kClassDel; c <= kClassIns; ++c)
+        if (lane < 2) bits[c * stride + words + lane] = 0u;
+    const int64_t n_warps = (int64_t)gridDim.x * kScanWarps;
+    for (int64_t t = (int64_t)blockIdx.x * kScanWarps + warp; t < n_rows; t += n_warps) {
+        const int64_t r = rows ? (int64_t)__ldg(rows + t) : t;
+        const uint8_t *row = codes + r * (int64_t)code_pitch;
+        const uint32_t any = build_bits<kClassDel, kClassIns>(row, code_pitch, n_loci, words, bits, stride, lane);
+        if (any == 0) continue;
+        __syncwarp();
+        // deletions only count on loci whose mutation_loci holds '-' (sv_detector.py:67)
+        if (any & (1u << kClassDel))
+            for (int k = lane; k < words; k += 32) bits[kClassDel * stride + k] &= __ldg(del_loci + k);
+        __syncwarp();
+#pragma unroll 1
+        for (int c = kClassDel; c <= kClassLower; ++c) {  // runs of at least min_size tokens (:65-74, :80-82)
+            if (!(any & (1u << c))) continue;
+            const uint32_t *b = bits + c * stride;
+            for (int k = lane; k < words; k += 32) {
+                const uint32_t lo = b[k];
+                if (lo == 0u) continue;
+                // starts of runs inside this word: a set bit whose predecessor is clear
+                const uint32_t prev = k > 0 ? b[k - 1] >> 31 : 0u;
+                uint32_t starts = lo & ~((lo << 1) | prev);
+                while (starts) {
+                    const int bit = __ffs(starts) - 1;
+                    starts &= starts - 1;
+                    int len = 0, kk = k, bb = bit;  // length of the run that starts here
+                    for (;;) {
+                        const uint32_t w = ~(b[kk] >> bb);  // zero word behind the row ends every run
+                        const int ones = w ? __ffs(w) - 1 : 32;
+                        const int room = 32 - bb;
+                        if (ones < room) {
+                            len += ones;
+                            break;
+                        }
+                        len += room;
+                        ++kk;
+                        bb = 0;
+                    }
+                    if (len >= min_size) emit_record(records, n_records, capacity, c == kClassDel ? 0 : 1, (int)t,
+                                                     k * 32 + bit, len);
+                }
+            }
+        }
+        if (any & (1u << kClassIns)) {  // insertions on loci whose mutation_loci holds '+' (:76-78)
+            for (int k = lane; k < words; k += 32) {
+                uint32_t cand = bits[kClassIns * stride + k] & __ldg(ins_loci + k);
+                while (cand) {
+                    const int locus = k * 32 + __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    int off, len;
+                    if (!dj_find_token(text, r, locus, &off, &len)) continue;
+                    const int anchor = row[locus] & 0x7F;
+                    const int n_ins = (len - (anchor < 20 ? 2 : 3)) / 3;  // every inserted base is "+B|"
+                    if (n_ins >= min_size) emit_record(records, n_records, capacity, 2, (int)t, locus, n_ins);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+int scan_geometry(const char *who, int32_t code_pitch, int32_t n_loci, int classes, int *words, size_t *smem) {
+    if (n_loci <= 0 || code_pitch < n_loci || (code_pitch & 15) != 0) {
+        dj_set_error("%s: code_pitch %d must be a multiple of 16 and >= n_loci %d > 0", who, code_pitch, n_loci);
+        return 1;
+    }
+    *words = ((n_loci + 511) / 512) * 16;  // whole 512-token trips
+    *smem = (size_t)kScanWarps * classes * (*words + 2) * sizeof(uint32_t);
+    if (*smem > 200 * 1024) {
+        dj_set_error("%s: n_loci %d is beyond the %d loci the shared-memory bit strings hold", who, n_loci,
+                     (int)(200 * 1024 / (kScanWarps * classes * 4) - 2) * 32);
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int dj_read_n_features(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, int64_t n_rows,
+                                  int32_t n_loci, int32_t *n_count, int32_t *n_maxrun, void *stream) {
+    if (n_rows <= 0) return 0;
+    int words = 0;
+    size_t smem = 0;
+    if (scan_geometry("dj_read_n_features", code_pitch, n_loci, 1, &words, &smem)) return 1;
+    if (((uintptr_t)codes & 15) != 0) {
+        dj_set_error("dj_read_n_features: the code matrix must be 16-byte aligned");
+        return 1;
+    }
+    const int sms = dj_sm_count();
+    if (sms <= 0) return 1;
+    static size_t configured = 0;
+    if (configured < smem) {
+        DJ_CUDA_CHECK(cudaFuncSetAttribute(n_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int64_t ctas = (n_rows + kScanWarps - 1) / kScanWarps;
+    if (ctas > (int64_t)sms * 8) ctas = (int64_t)sms * 8;
+    n_features_kernel<<<(unsigned)ctas, kScanThreads, smem, (cudaStream_t)stream>>>(codes, code_pitch, rows, n_rows,
+                                                                                  n_loci, words, n_count, n_maxrun);
+    DJ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int dj_sv_scan(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, int64_t n_rows,
+                          int32_t n_loci, const uint8_t *text, const int64_t *row_off, const int32_t *row_len,
+                          const uint32_t *ckpt, int32_t ckpt_pitch, const uint32_t *del_loci, const uint32_t *ins_loci,
+                          int32_t min_size, int32_t *records, uint32_t capacity, uint32_t *n_records, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    DJ_CUDA_CHECK(cudaMemsetAsync(n_records, 0, sizeof(uint32_t), st));
+    if (n_rows <= 0) return 0;
+    int words = 0;
+    size_t smem = 0;
+    if (scan_geometry("dj_sv_scan", code_pitch, n_loci, kClasses, &words, &smem)) return 1;
+    if (((uintptr_t)codes & 15) != 0) {
+        dj_set_error("dj_sv_scan: the code matrix must be 16-byte aligned");
+        return 1;
+    }
+    const int sms = dj_sm_count();
+    if (sms <= 0) return 1;
+    static size_t configured = 0;
+    if (configured < smem) {
+        DJ_CUDA_CHECK(cudaFuncSetAttribute(sv_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int64_t ctas = (n_rows + kScanWarps - 1) / kScanWarps;
+    if (ctas > (int64_t)sms * 8) ctas = (int64_t)sms * 8;
+    DjTextRef tr{text, row_off, row_len, ckpt, ckpt_pitch};
+    sv_scan_kernel<<<(unsigned)ctas, kScanThreads, smem, st>>>(codes, code_pitch, rows, n_rows, n_loci, words, del_loci,
+                                                              ins_loci, min_size, tr, records, n_records, capacity);
+    DJ_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int32_t dj_loci_words(int32_t n_loci) { return ((n_loci + 511) / 512) * 16; }

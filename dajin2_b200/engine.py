@@ -8,6 +8,7 @@ CUDA device or without the built library these functions raise.
 from __future__ import annotations
 
 import ctypes
+import os
 import re
 from dataclasses import dataclass, field
 from itertools import groupby
@@ -80,10 +81,12 @@ class EncodedReads:
     """One MIDSV file on the device: text, row index, read x locus code matrix and per-read scalars."""
 
     def __init__(self, host: HostReads, n_loci: int, validate: bool = True, encode: bool = True,
-                 sequence: str | None = None):
-        """``sequence`` (the allele the reads were aligned to, when the caller has it) lets the encoder verify plain
-        stretches against the rendered reference instead of translating them (``dj_encode_ref``); the codes are the
-        same with or without it."""
+                 sequence: str | None = None, assisted: bool | None = None):
+        """``sequence`` (the allele the reads were aligned to, when the caller has it) with ``assisted`` lets the
+        encoder verify plain stretches against the rendered reference instead of translating them
+        (``dj_encode_ref``); the codes are the same with or without it.  Measured on B200 the assisted kernel is
+        4 % slower than the generic one, so it is off unless ``assisted`` or
+        ``DAJIN2_B200_ENCODE_REF=1`` asks for it."""
         dev = require_cuda()
         self.n_reads = host.n_reads
         self.n_loci = int(n_loci)
@@ -107,7 +110,9 @@ class EncodedReads:
         self.flags = torch.zeros(n, dtype=torch.int32, device=dev)
         self.ckpt = torch.empty((n, self.ckpt_pitch), dtype=torch.int32, device=dev)
         self.ref = None
-        if sequence is not None and len(sequence) == self.n_loci:
+        if assisted is None:
+            assisted = os.environ.get("DAJIN2_B200_ENCODE_REF", "0") == "1"
+        if assisted and sequence is not None and len(sequence) == self.n_loci:
             self.ref = torch.from_numpy(np.frombuffer(sequence.encode("ascii", "replace"), dtype=np.uint8).copy()).to(dev)
         if encode:
             self.encode()
@@ -153,6 +158,43 @@ class EncodedReads:
 
     def histogram(self, rows: torch.Tensor | None = None) -> np.ndarray:
         return self.histogram_device(rows).cpu().numpy()
+
+    def n_features(self, rows: torch.Tensor | None = None) -> tuple[np.ndarray, np.ndarray]:
+        """(N count, longest N run) of every read: the features of ``extract_n_features`` before the division by the
+        token count (reference ``error_correction/sequence_error_handler.py:26-41``)."""
+        n = self.n_reads if rows is None else int(rows.shape[0])
+        dev = self.codes.device
+        n_count = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        n_maxrun = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+        _cabi.call("dj_read_n_features", _p(self.codes), self.pitch, _p(rows), n, self.n_loci, _p(n_count),
+                   _p(n_maxrun), _stream())
+        return n_count[:n].cpu().numpy(), n_maxrun[:n].cpu().numpy()
+
+    def sv_records(self, mutation_loci: list[set[str]], min_size: int = 10) -> np.ndarray:
+        """int32[K, 4] rows (type, read, start, size), sorted: every structural-variant feature
+        ``get_index_and_sv_size`` finds in the file, for the three SV types at once (type 0 deletion, 1 inversion,
+        2 insertion; reference ``structural_variants/sv_detector.py:53-97``)."""
+        dev = self.codes.device
+        words = _cabi.call("dj_loci_words", self.n_loci)
+        bits = np.zeros((2, words * 32), dtype=bool)
+        for i, muts in enumerate(mutation_loci[: self.n_loci]):
+            bits[0, i] = "-" in muts
+            bits[1, i] = "+" in muts
+        packed = np.packbits(bits, axis=1, bitorder="little").view(np.uint32)
+        del_d = torch.as_tensor(packed[0].copy(), device=dev)
+        ins_d = torch.as_tensor(packed[1].copy(), device=dev)
+        capacity = 1 << 16
+        while True:
+            rec = torch.empty((capacity, 4), dtype=torch.int32, device=dev)
+            n_rec = torch.zeros(1, dtype=torch.int32, device=dev)
+            _cabi.call("dj_sv_scan", _p(self.codes), self.pitch, _p(None), self.n_reads, self.n_loci, _p(self.text),
+                       _p(self.row_off), _p(self.row_len), _p(self.ckpt), self.ckpt_pitch, _p(del_d), _p(ins_d),
+                       min_size, _p(rec), capacity, _p(n_rec), _stream())
+            found = int(n_rec.item())
+            if found <= capacity:
+                out = rec[:found].cpu().numpy()
+                return out[np.lexsort((out[:, 2], out[:, 1], out[:, 0]))] if found else out.reshape(0, 4)
+            capacity = 1 << int(found - 1).bit_length()
 
     def fetch_tokens(self, reads, loci) -> list[str]:
         """Raw text of token ``loci[k]`` of read ``reads[k]`` (used to print raw insertion tokens)."""

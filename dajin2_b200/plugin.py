@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import importlib
 
-from . import classification, clustering, preprocess
+from . import classification, clustering, preprocess, sequence_error, structural_variants
 
 _PATCHES = [
     # (module, attribute, replacement)
@@ -43,6 +43,22 @@ _PATCHES = [
     ("DAJIN2.core.clustering.label_extractor", "extract_labels", clustering.extract_labels),
     ("DAJIN2.core.clustering", "extract_labels", clustering.extract_labels),
     ("DAJIN2.core.preprocess.structural_variants.sv_detector", "optimize_labels", clustering.optimize_labels),
+    # SV features and the sequence-error read filter
+    ("DAJIN2.core.preprocess.structural_variants.sv_detector", "process_sv_indices",
+     structural_variants.process_sv_indices),
+    ("DAJIN2.core.preprocess.structural_variants.sv_detector", "extract_sv_features",
+     structural_variants.extract_sv_features),
+    ("DAJIN2.core.preprocess.error_correction.sequence_error_handler", "detect_sequence_error_reads_in_control",
+     sequence_error.detect_sequence_error_reads_in_control),
+    ("DAJIN2.core.preprocess.error_correction.sequence_error_handler", "detect_sequence_error_reads_in_sample",
+     sequence_error.detect_sequence_error_reads_in_sample),
+    ("DAJIN2.core.preprocess.error_correction.sequence_error_handler", "detect_sequence_error_reads",
+     sequence_error.detect_sequence_error_reads),
+    ("DAJIN2.core.preprocess.error_correction.sequence_error_handler", "replace_midsv_without_sequence_errors",
+     sequence_error.replace_midsv_without_sequence_errors),
+    ("DAJIN2.core.preprocess", "detect_sequence_error_reads", sequence_error.detect_sequence_error_reads),
+    ("DAJIN2.core.preprocess", "replace_midsv_without_sequence_errors",
+     sequence_error.replace_midsv_without_sequence_errors),
 ]
 
 _saved: list[tuple] = []

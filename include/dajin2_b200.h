@@ -219,6 +219,36 @@ int dj_member_locate(const int32_t *slot_of_row, int64_t n_rows, const int32_t *
 int dj_gather_labels(const int32_t *slot_of_row, int64_t n_rows, const int32_t *label_of_slot,
                      int32_t *labels, void *stream);
 
+/*
+ * Per-read N features of the sequence-error read filter: n_count[t] = number of tokens of read rows[t] for which
+ * is_n_tag holds (utils/midsv_handler.py:8-14), n_maxrun[t] = the longest run of such tokens.  Replaces the pass
+ * convert_nm_tag + extract_n_features make over every token of the control and sample files
+ * (preprocess/error_correction/sequence_error_handler.py:26-41, :48-53, :104-107) and the N count of the consensus
+ * stage's control filter (consensus/consensus_mutation_analyzer.py:85-88).  rows == NULL: all n_rows reads in order.
+ */
+int dj_read_n_features(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, int64_t n_rows,
+                       int32_t n_loci, int32_t *n_count, int32_t *n_maxrun, void *stream);
+
+/* Words of a per-locus bit string (bit b of word k = locus 32 * k + b) as dj_sv_scan expects them. */
+int32_t dj_loci_words(int32_t n_loci);
+
+/*
+ * Structural-variant features of every read (get_index_and_sv_size, preprocess/structural_variants/
+ * sv_detector.py:53-97), all three SV types in one scan of the code matrix:
+ *   type 0  deletion   a maximal run of >= min_size tokens that start with '-' on loci set in del_loci
+ *                      ('-' in mutation_loci[i], :67): start = first locus of the run, size = its length
+ *   type 1  inversion  a maximal run of >= min_size lowercase tokens (:70-73)
+ *   type 2  insertion  a token that starts with '+' on a locus set in ins_loci with >= min_size inserted bases
+ *                      (tags[i].count("|"), :76-78): start = the locus, size = the number of inserted bases
+ * records[k] = {type, t, start, size} (int32 x 4, t = position in `rows`), in no particular order; *n_records
+ * (device) receives the number of records found, which may exceed `capacity` (only `capacity` are stored).
+ * del_loci / ins_loci: dj_loci_words(n_loci) words each.
+ */
+int dj_sv_scan(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, int64_t n_rows, int32_t n_loci,
+               const uint8_t *text, const int64_t *row_off, const int32_t *row_len, const uint32_t *ckpt,
+               int32_t ckpt_pitch, const uint32_t *del_loci, const uint32_t *ins_loci, int32_t min_size,
+               int32_t *records, uint32_t capacity, uint32_t *n_records, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

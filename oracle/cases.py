@@ -105,6 +105,26 @@ def single_like_case(n_sample: int = 900, n_control: int = 500, profile: str = "
     return out
 
 
+def sv_like_case(n_sample: int = 1200, n_control: int = 600, profile: str = "r10") -> dict:
+    """one FASTA allele; the sample mixes wild type with a 120-nt deletion, an 80-nt inversion
+    and a 30-nt insertion allele; 8 % of the reads of both files end in long '=N' tails (the sequence-error reads the
+    read filter is there to find)."""
+    base = synth.random_reference(1500)
+    D, I, V = synth.DEL, synth.INS, synth.INV  # noqa: E741
+    # starts and sizes jitter the way nanopore alignments of one SV do (grouped within 5 nt by the reference); an 8-nt
+    # deletion stays below the size threshold and a 15-nt one at 2 % below the coverage threshold
+    alleles = [[], [(D, 400, 120)], [(D, 402, 118)], [(D, 397, 125)], [(V, 700, 80)], [(V, 703, 75)], [(I, 1100, 30)],
+               [(I, 1101, 28)], [(D, 900, 8)], [(D, 1300, 15)]]
+    ps = synth.Population(base, alleles, [0.17, 0.20, 0.06, 0.04, 0.18, 0.05, 0.18, 0.05, 0.05, 0.02], profile,
+                          trunc_prob=0.08)
+    pc = synth.Population(base, [[]], [1.0], profile, trunc_prob=0.08)
+    return {"sequence": base, "sample": _pack(synth.generate(ps, n_sample, seed=synth.SEED + 1)),
+            "control": _pack(synth.generate(pc, n_control, seed=synth.SEED + 99)), "knockin": None, "kind": "sv",
+            # the reference's loci selection misses the insertion on this input (its MLP step is chaotic, DESIGN.md §3);
+            # the SV features are taken with '+' added at the two insertion loci so that all three SV types are covered
+            "force_plus": [1100, 1101]}
+
+
 def kat_case() -> dict:
     """SURVEY.md §8c extra known-answer case (quirk ii: '@,@,@' is a scored k-mer)."""
     sample = ["=A,=C,-G,+T|+T|=T,=A,=C"] * 3 + ["=A,=C,-G,+A|=T,=A,=C"] * 2 + ["=A,=C,=G,=T,=A,=C"] * 5
@@ -130,6 +150,7 @@ RECIPES = {
     "flox_like": (flox_like_case, dict()),
     "single_like": (single_like_case, dict()),
     "kat": (kat_case, dict()),
+    "sv_like": (sv_like_case, dict()),
 }
 
 

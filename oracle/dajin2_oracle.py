@@ -533,3 +533,129 @@ def cluster_allele_group(rows_sample, strands_sample, rows_control, loci_t, knoc
     xc = list(annotate_score(rows_control, score, loci_t, is_control=True))
     labels = return_labels(xs, xc, strands_sample, strand_all)
     return {"score": score, "rows_sample": xs, "rows_control": xc, "labels": relabel_consecutive(labels)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY.md §8(f) rank 3 : sequence-error read filter and structural-variant features
+# ---------------------------------------------------------------------------------------------------------
+
+
+def n_features(rows) -> np.ndarray:
+    """error_correction/sequence_error_handler.py:26-41 — per read [N ratio, longest N run] over its tokens
+    (``convert_nm_tag``: 'N' where ``is_n_tag`` holds, 'M' elsewhere; ``extract_n_features``)."""
+    feats = []
+    for row in rows:
+        flags = [is_n_token(t) for t in row.split(",")]
+        n = sum(flags)
+        best = run = 0
+        for f in flags:
+            run = run + 1 if f else 0
+            best = max(best, run)
+        feats.append([n / len(flags) if flags else 0, best])
+    return np.array(feats)
+
+
+def match_counts(rows) -> list[int]:
+    """sequence_error_handler.py:57-59 — number of 'M' characters of the NM string of every read."""
+    return [sum(0 if is_n_token(t) else 1 for t in row.split(",")) for row in rows]
+
+
+def sequence_error_control(rows, qnames):
+    """sequence_error_handler.py:44-79 — KMeans(2) on the N features; the cluster with the smaller median match
+    count is the sequence-error cluster.  Returns (qnames without error, error fraction)."""
+    from sklearn.cluster import KMeans
+
+    X = n_features(rows)
+    labels = KMeans(n_clusters=2, random_state=1).fit_predict(X)
+    per_label = {0: [], 1: []}
+    for m, lab in zip(match_counts(rows), labels):
+        per_label[int(lab)].append(m)
+    error_label = 0 if np.median(per_label[0]) < np.median(per_label[1]) else 1
+    with_error = [q for q, lab in zip(qnames, labels) if lab == error_label]
+    without_error = [q for q, lab in zip(qnames, labels) if lab != error_label]
+    return without_error, len(with_error) / len(qnames)
+
+
+def sequence_error_sample(rows_control, qnames_control, control_without_error, rows_sample, qnames_sample):
+    """sequence_error_handler.py:89-122 — logistic regression trained on the control's two groups (clean reads first,
+    then error reads, each in file order), applied to the sample's features; label 0 = no sequence error."""
+    from sklearn.linear_model import LogisticRegression
+
+    clean = set(control_without_error)
+    feats = n_features(rows_control)
+    keep = np.array([q in clean for q in qnames_control], dtype=bool)
+    X = np.vstack([feats[keep].reshape(-1, 2), feats[~keep].reshape(-1, 2)])
+    y = np.array([0] * int(keep.sum()) + [1] * int((~keep).sum()))
+    clf = LogisticRegression(random_state=0).fit(X, y)
+    labels = clf.predict(n_features(rows_sample))
+    return [q for q, lab in zip(qnames_sample, labels) if lab == 0]
+
+
+def index_and_sv_size(row: str, sv_type: str, loci_t, converter=None, min_size: int = 10) -> dict[int, int]:
+    """structural_variants/sv_detector.py:53-97 — {start index: size} of the read's SV features: maximal runs of
+    tokens starting with '-' on loci holding '-', maximal runs of lowercase tokens, insertion tokens on loci holding
+    '+' (size = number of '|'); only sizes >= 10; with a converter only the indices it knows, renamed."""
+    toks = row.split(",")
+    found = []
+    if sv_type == "insertion":
+        found = [(i, t.count("|")) for i, t in enumerate(toks) if t.startswith("+") and "+" in loci_t[i]]
+    else:
+        if sv_type == "deletion":
+            hit = [t.startswith("-") and "-" in loci_t[i] for i, t in enumerate(toks)]
+        else:
+            hit = [t.islower() for t in toks]
+        i = 0
+        while i < len(hit):
+            if not hit[i]:
+                i += 1
+                continue
+            j = i
+            while j < len(hit) and hit[j]:
+                j += 1
+            found.append((i, j - i))
+            i = j
+    out = {}
+    for start, size in found:
+        if size < min_size:
+            continue
+        if converter is None:
+            out[start] = size
+        elif start in converter:
+            out[converter[start]] = size
+    return out
+
+
+def group_similar_indices(indices, distance: int = 5, min_coverage: float = 5.0) -> list[list[int]]:
+    """sv_detector.py:26-43 — sorted start indices chained while neighbours are <= distance apart; groups of more
+    than min_coverage members survive."""
+    groups, cur = [], []
+    for v in sorted(indices):
+        if cur and v - cur[-1] > distance:
+            groups.append(cur)
+            cur = []
+        cur.append(v)
+    if cur:
+        groups.append(cur)
+    return [g for g in groups if len(g) > min_coverage]
+
+
+def index_converter(groups) -> dict[int, int]:
+    """sv_detector.py:46-51 — every index of a group -> the group's most frequent index (first of the ties in the
+    sorted group, i.e. the smallest)."""
+    conv = {}
+    for g in groups:
+        rep = Counter(g).most_common()[0][0]
+        conv.update(dict.fromkeys(g, rep))
+    return conv
+
+
+def process_sv_indices(rows, sv_type: str, loci_t, coverage: int) -> dict[int, int]:
+    """sv_detector.py:131-140."""
+    starts = [k for row in rows for k in index_and_sv_size(row, sv_type, loci_t)]
+    return index_converter(group_similar_indices(starts, 5, max(5, coverage * 0.05)))
+
+
+def sv_feature_matrix(records: list[dict[int, int]], all_indices) -> np.ndarray:
+    """sv_detector.py:100-109 — reads x sorted SV indices, the SV size or 0."""
+    cols = sorted(set(all_indices) | {k for r in records for k in r})
+    return np.array([[r.get(c, 0) for c in cols] for r in records])

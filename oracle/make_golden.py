@@ -154,6 +154,71 @@ def run_reference(alleles: dict, given_loci=None) -> dict:
     return out
 
 
+def _sparse_dicts(records) -> dict:
+    return {str(i): {str(k): int(v) for k, v in d.items()} for i, d in enumerate(records) if d}
+
+
+def run_reference_sv(case: dict) -> dict:
+    """Sequence-error read filter and SV features of the real reference on one FASTA allele ("control")."""
+    from DAJIN2.core.clustering.clustering import optimize_labels
+    from DAJIN2.core.preprocess.error_correction import sequence_error_handler as seh
+    from DAJIN2.core.preprocess.structural_variants import sv_detector as svd
+
+    g = {"sha_sample": cases.digest(case["sample"]), "sha_control": cases.digest(case["control"])}
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = Path(tmp)
+        sname, cname = "sample", "ctrl"
+        key = to_allele_key("control")
+        p_s = tmp / sname / "midsv" / key / f"{sname}_midsv.jsonl"
+        p_c = tmp / cname / "midsv" / key / f"{cname}_midsv.jsonl"
+        write_jsonl(p_s, case["sample"], "control")
+        write_jsonl(p_c, case["control"], "control")
+        args = SimpleNamespace(tempdir=tmp, sample_name=sname, control_name=cname,
+                               fasta_alleles={"control": case["sequence"]})
+        for name, part in (("sample", case["sample"]), ("control", case["control"])):
+            feats = seh.extract_n_features([seh.convert_nm_tag(r.split(",")) for r in part["rows"]])
+            g[f"n_features_{name}"] = [[float(a).hex(), int(b)] for a, b in feats]
+        seh.detect_sequence_error_reads(args, is_control=True)
+        seh.detect_sequence_error_reads(args, is_control=False)
+        g["control_without_error"] = (tmp / cname / "sequence_error" / "qnames_without_error.txt").read_text().splitlines()
+        g["error_fraction"] = (tmp / cname / "sequence_error" / "error_fraction.txt").read_text().strip()
+        g["sample_without_error"] = (tmp / sname / "sequence_error" / "qnames_without_error.txt").read_text().splitlines()
+        seh.replace_midsv_without_sequence_errors(args)
+        g["sha_sample_filtered_file"] = __import__("hashlib").sha256(p_s.read_bytes()).hexdigest()
+        # the rest of the flow runs on the filtered sample file, as core.py:153-185 does
+        preprocess.cache_mutation_loci(args, is_control=True)
+        preprocess.cache_mutation_loci(args, is_control=False)
+        loci = pickle.loads((tmp / sname / "mutation_loci" / key / "mutation_loci.pickle").read_bytes())
+        for i in case.get("force_plus", []):
+            loci[i] = set(loci[i]) | {"+"}
+        g["mutation_loci"] = ["".join(sorted(s)) for s in loci]
+        n_s, n_c = fileio_count(p_s), fileio_count(p_c)
+        g["coverage"] = [n_s, n_c]
+        g["sv"] = {}
+        for sv_type in ("deletion", "inversion", "insertion"):
+            raw_s = svd.extract_sv_features(p_s, sv_type, loci, None)
+            conv_s = svd.process_sv_indices(p_s, sv_type, loci, n_s)
+            conv_c = svd.process_sv_indices(p_c, sv_type, loci, n_c)
+            feat_s = svd.extract_sv_features(p_s, sv_type, loci, conv_s)
+            feat_c = svd.extract_sv_features(p_c, sv_type, loci, conv_c)
+            e = {"raw_sample": _sparse_dicts(raw_s), "converter_sample": {str(k): int(v) for k, v in conv_s.items()},
+                 "converter_control": {str(k): int(v) for k, v in conv_c.items()},
+                 "features_sample": _sparse_dicts(feat_s), "features_control": _sparse_dicts(feat_c)}
+            all_idx = {k for r in feat_s + feat_c for k in r}
+            if all_idx:
+                X = __import__("numpy").vstack([svd.extract_features(feat_s, all_idx), svd.extract_features(feat_c, all_idx)])
+                e["X_shape"] = list(X.shape)
+                e["labels"] = [int(x) for x in optimize_labels(X, n_s, n_c)]
+            g["sv"][sv_type] = e
+    return {"alleles": {"control": g}}
+
+
+def fileio_count(path: Path) -> int:
+    from DAJIN2.utils import fileio
+
+    return fileio.count_newlines(path)
+
+
 def main(names) -> None:
     for name in names:
         if name == "fixture_flox100":
@@ -162,7 +227,9 @@ def main(names) -> None:
             payload["inputs"] = {"control": {**case, "knockin": None}}
         else:
             case = cases.build_case(name)
-            if "alleles" in case:
+            if case.get("kind") == "sv":
+                payload = run_reference_sv(case)
+            elif "alleles" in case:
                 payload = run_reference(case["alleles"])
             elif "loci" in case:
                 payload = run_reference({"control": case}, given_loci=case["loci"])

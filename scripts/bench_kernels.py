@@ -51,7 +51,7 @@ def timeit(fn, nbytes, name):
 
 
 timeit(enc.encode, text_bytes + args.reads * (args.loci + 16), "encode")
-enc_ref = engine.EncodedReads(hs, args.loci, validate=True, encode=True, sequence=pop.reference)
+enc_ref = engine.EncodedReads(hs, args.loci, validate=True, encode=True, sequence=pop.reference, assisted=True)
 timeit(enc_ref.encode, text_bytes + args.reads * (args.loci + 16), "encode_ref")
 for name in ("codes", "match_score", "n_tokens", "flags"):
     a, b = getattr(enc, name), getattr(enc_ref, name)

@@ -206,7 +206,7 @@ def test_encode_ref_equals_generic(name):
             shuffled = seq[7:] + seq[:7]
             odd = "".join("NnRa"[i % 4] if i % 5 == 0 else ch for i, ch in enumerate(seq))
             for ref in (seq, shuffled, odd):
-                got = engine.EncodedReads(host, L, sequence=ref)
+                got = engine.EncodedReads(host, L, sequence=ref, assisted=True)
                 assert got.ref is not None
                 assert torch.equal(got.codes[:, :L], want.codes[:, :L])
                 assert torch.equal(got.match_score, want.match_score)
@@ -236,14 +236,14 @@ def test_encode_ref_edge_cases():
         variants.append(",".join("=" + c.lower() for c in seq))      # an inverted read
         host = pack_rows(variants)
         want = engine.EncodedReads(host, L)
-        got = engine.EncodedReads(host, L, sequence=seq)
+        got = engine.EncodedReads(host, L, sequence=seq, assisted=True)
         assert torch.equal(got.codes[:, :L], want.codes[:, :L]), L
         assert torch.equal(got.match_score, want.match_score), L
         assert torch.equal(got.n_tokens, want.n_tokens) and torch.equal(got.flags, want.flags)
     # rows with a wrong token count / a bad token are flagged the same way
     host = pack_rows(["=A,=C,=G", "=A,=C", "=A,=R,=G", "=A,=C,=G,=T"])
     a = engine.EncodedReads(host, 3, validate=False)
-    b = engine.EncodedReads(host, 3, validate=False, sequence="ACG")
+    b = engine.EncodedReads(host, 3, validate=False, sequence="ACG", assisted=True)
     assert torch.equal(a.flags, b.flags) and torch.equal(a.n_tokens, b.n_tokens)
 
 
@@ -390,3 +390,153 @@ def test_sharded_equals_unsharded(name, n_shards):
         labels[r.gpos_sorted.cpu().numpy()] = lab.cpu().numpy()
         assert info["cluster_sizes"] == full.cluster_sizes
     assert labels.tolist() == full.labels.tolist()
+
+
+# --- sequence-error read filter, structural-variant features ------------------------
+
+
+@pytest.mark.parametrize("name", SINGLE_CASES + ["sv_like"])
+def test_n_features_match_oracle(name):
+    """dj_read_n_features: N count and longest N run of every read (sequence_error_handler.py:26-41)."""
+    from dajin2_b200 import sequence_error
+    from oracle import dajin2_oracle as orc
+
+    alleles, golden = load_case(name)
+    for aname, a in alleles.items():
+        L = len(a["sequence"])
+        for part in ("sample", "control"):
+            enc = _enc(a[part], L)
+            feats, matches = sequence_error.n_features_of(enc)
+            want = orc.n_features(a[part]["rows"])
+            assert [[float(x).hex(), int(y)] for x, y in feats] == [[float(x).hex(), int(y)] for x, y in want]
+            assert matches.tolist() == orc.match_counts(a[part]["rows"])
+            key = f"n_features_{part}"
+            if key in golden["alleles"][aname]:
+                assert [[float(x).hex(), int(y)] for x, y in feats] == golden["alleles"][aname][key]
+
+
+def test_n_features_edge_cases():
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+    from oracle import dajin2_oracle as orc
+
+    rng = np.random.default_rng(5)
+    for L in (1, 15, 16, 17, 31, 32, 33, 511, 512, 513, 1025, 5000):
+        rows = [",".join(["=N"] * L), ",".join(["=A"] * L)]
+        for _ in range(10):
+            toks = ["=A"] * L
+            for _ in range(int(rng.integers(1, 6))):
+                s = int(rng.integers(0, L))
+                e = min(L, s + int(rng.integers(1, max(2, L // 2))))
+                for i in range(s, e):
+                    toks[i] = ["=N", "=n", "+A|+C|=N", "+a|=n"][int(rng.integers(0, 4))]
+            for i in rng.integers(0, L, max(1, L // 50)):
+                toks[int(i)] = ["-N", "*NA", "=a", "+N|=A", "-n"][int(rng.integers(0, 5))]  # none of these is an N tag
+            rows.append(",".join(toks))
+        enc = engine.EncodedReads(pack_rows(rows), L)
+        n_count, n_maxrun = enc.n_features()
+        want = orc.n_features(rows)
+        assert n_count.tolist() == [round(x * L) for x in want[:, 0]], L
+        assert n_maxrun.tolist() == want[:, 1].astype(int).tolist(), L
+        sub = torch.as_tensor(np.array([len(rows) - 1, 0, 3], dtype=np.int32), device="cuda")
+        c2, r2 = enc.n_features(sub)
+        assert c2.tolist() == n_count[[len(rows) - 1, 0, 3]].tolist() and r2.tolist() == n_maxrun[[len(rows) - 1, 0, 3]].tolist()
+
+
+def test_sequence_error_filter_on_files(tmp_path):
+    """detect_sequence_error_reads (control, then sample) and replace_midsv_without_sequence_errors through the drop-in
+    functions: the files the real reference wrote for the same input (core.py:64,153-155)."""
+    import hashlib
+
+    from dajin2_b200 import cache, sequence_error
+    from dajin2_b200.preprocess import _allele_key
+
+    cache.clear()
+    alleles, golden = load_case("sv_like")
+    g = golden["alleles"]["control"]
+    args = _write_tree(tmp_path, alleles)
+    sequence_error.detect_sequence_error_reads(args, is_control=True)
+    sequence_error.detect_sequence_error_reads(args, is_control=False)
+    out_c, out_s = tmp_path / "ctrl" / "sequence_error", tmp_path / "sample" / "sequence_error"
+    assert (out_c / "qnames_without_error.txt").read_text().splitlines() == g["control_without_error"]
+    assert (out_c / "error_fraction.txt").read_text().strip() == g["error_fraction"]
+    assert (out_s / "qnames_without_error.txt").read_text().splitlines() == g["sample_without_error"]
+    sequence_error.replace_midsv_without_sequence_errors(args)
+    p_s = tmp_path / "sample" / "midsv" / _allele_key("control") / "sample_midsv.jsonl"
+    assert hashlib.sha256(p_s.read_bytes()).hexdigest() == g["sha_sample_filtered_file"]
+
+
+def test_sv_features_on_files(tmp_path):
+    """process_sv_indices / extract_sv_features (sv_detector.py:131-148) from one dj_sv_scan per file, and the dense
+    optimize_labels call of detect_sv_alleles (:299-302), against the real reference's outputs."""
+    from dajin2_b200 import cache, clustering, structural_variants as sv
+    from dajin2_b200.preprocess import _allele_key
+    from oracle import dajin2_oracle as orc
+
+    cache.clear()
+    alleles, golden = load_case("sv_like")
+    a, g = alleles["control"], golden["alleles"]["control"]
+    clean = set(g["sample_without_error"])
+    keep = [i for i, q in enumerate(a["sample"]["qnames"]) if q in clean]
+    filtered = {"control": {**a, "sample": {k: [v[i] for i in keep] for k, v in a["sample"].items()}}}
+    args = _write_tree(tmp_path, filtered)
+    key = _allele_key("control")
+    p_s = tmp_path / "sample" / "midsv" / key / "sample_midsv.jsonl"
+    p_c = tmp_path / "ctrl" / "midsv" / key / "ctrl_midsv.jsonl"
+    loci = golden_loci(g)
+    n_s, n_c = g["coverage"]
+    sparse = lambda recs: {str(i): {str(k): v for k, v in d.items()} for i, d in enumerate(recs) if d}  # noqa: E731
+    for sv_type, e in g["sv"].items():
+        assert sparse(sv.extract_sv_features(p_s, sv_type, loci, None)) == e["raw_sample"]
+        conv_s = sv.process_sv_indices(p_s, sv_type, loci, n_s)
+        conv_c = sv.process_sv_indices(p_c, sv_type, loci, n_c)
+        assert {str(k): v for k, v in conv_s.items()} == e["converter_sample"]
+        assert {str(k): v for k, v in conv_c.items()} == e["converter_control"]
+        feat_s = sv.extract_sv_features(p_s, sv_type, loci, conv_s)
+        feat_c = sv.extract_sv_features(p_c, sv_type, loci, conv_c)
+        assert len(feat_s) == n_s and len(feat_c) == n_c
+        assert sparse(feat_s) == e["features_sample"] and sparse(feat_c) == e["features_control"]
+        all_idx = {k for r in feat_s + feat_c for k in r}
+        X = np.vstack([orc.sv_feature_matrix(feat_s, all_idx), orc.sv_feature_matrix(feat_c, all_idx)])
+        labels = clustering.optimize_labels(X, n_s, n_c)
+        assert _ari(e["labels"], labels) >= 0.99 and _percent_gap(e["labels"], labels) <= 0.5
+    assert args.sample_name == "sample"
+
+
+def test_sv_scan_edge_cases():
+    """Runs across 32-token words and 512-token trips, at both row ends, cut by mutation_loci; insertion sizes around
+    the threshold; every read against the oracle's restatement of get_index_and_sv_size."""
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+    from oracle import dajin2_oracle as orc
+
+    rng = np.random.default_rng(9)
+    for L in (9, 10, 11, 31, 32, 33, 64, 500, 512, 530, 1100):
+        loci = [set() for _ in range(L)]
+        for i in range(L):
+            if rng.random() < 0.9:
+                loci[i].add("-")
+            if rng.random() < 0.5:
+                loci[i].add("+")
+        rows = [",".join(["-A"] * L), ",".join(["=a"] * L), ",".join(["=A"] * L)]
+        for _ in range(24):
+            toks = ["=A"] * L
+            for _ in range(int(rng.integers(1, 5))):
+                s = int(rng.integers(0, L))
+                e = min(L, s + int(rng.integers(1, 40)))
+                kind = int(rng.integers(0, 3))
+                for i in range(s, e):
+                    toks[i] = ["-C", "=c", "-g"][kind]
+            for i in rng.integers(0, L, 3):
+                k = int(rng.integers(8, 13))
+                # an insertion takes the case of its anchor (include/dajin2_b200.h)
+                toks[int(i)] = [("+A|", "=T"), ("+C|", "*GA"), ("+G|", "-C"), ("+a|", "=t")][int(rng.integers(0, 4))]
+                toks[int(i)] = toks[int(i)][0] * k + toks[int(i)][1]
+            rows.append(",".join(toks))
+        enc = engine.EncodedReads(pack_rows(rows), L)
+        rec = enc.sv_records(loci)
+        for t, name in enumerate(("deletion", "inversion", "insertion")):
+            got = [dict() for _ in rows]
+            for _, read, start, size in rec[rec[:, 0] == t].tolist():
+                got[read][start] = size
+            assert got == [orc.index_and_sv_size(r, name, loci) for r in rows], (L, name)

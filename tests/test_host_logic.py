@@ -169,3 +169,21 @@ def test_jsonl_tokenizer_matches_json_loads(tmp_path):
         host.text[o : o + n].tobytes().decode() for o, n in zip(host.row_off, host.row_len)]
     assert host.qnames.tolist() == [r["QNAME"].encode() for r in host.records]
     assert host.strand.tobytes().decode() == "".join(r["STRAND"] for r in host.records)
+
+
+def test_sv_index_grouping_matches_oracle():
+    """group_similar_indices / define_index_converter of the product (numpy) against the oracle's restatement of
+    sv_detector.py:26-51, ties and thresholds included."""
+    from dajin2_b200 import structural_variants as sv
+    from oracle import dajin2_oracle as orc
+
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        n = int(rng.integers(0, 60))
+        idx = rng.integers(0, 80, n).tolist()
+        cov = float(rng.integers(0, 8))
+        dist = int(rng.integers(1, 7))
+        groups = sv.group_similar_indices(list(idx), dist, cov)
+        assert groups == orc.group_similar_indices(list(idx), dist, cov)
+        assert sv.define_index_converter(groups) == orc.index_converter(groups)
+    assert sv.group_similar_indices([]) == []

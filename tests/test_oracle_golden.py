@@ -146,3 +146,66 @@ def test_kat_cosine_and_dissimilar():  # tests/.../test_anomaly_detector.py
     c = np.zeros(13)
     assert orc.is_dissimilar_loci(s, c, 0)
     assert not orc.is_dissimilar_loci(c, c, 3)
+
+
+# --- sequence-error read filter, structural-variant features ------------------------
+
+
+def _sv_case():
+    alleles, golden = load_case("sv_like")
+    return alleles["control"], golden["alleles"]["control"]
+
+
+def _filtered_sample(a, g):
+    clean = set(g["sample_without_error"])
+    return [r for r, q in zip(a["sample"]["rows"], a["sample"]["qnames"]) if q in clean]
+
+
+def test_sequence_error_filter_matches_reference():
+    a, g = _sv_case()
+    for part in ("sample", "control"):
+        feats = orc.n_features(a[part]["rows"])
+        assert [[float(x).hex(), int(y)] for x, y in feats] == g[f"n_features_{part}"]
+    clean, fraction = orc.sequence_error_control(a["control"]["rows"], a["control"]["qnames"])
+    assert clean == g["control_without_error"] and str(fraction) == g["error_fraction"]
+    got = orc.sequence_error_sample(a["control"]["rows"], a["control"]["qnames"], clean, a["sample"]["rows"],
+                                    a["sample"]["qnames"])
+    assert got == g["sample_without_error"]
+
+
+@pytest.mark.parametrize("sv_type", ["deletion", "inversion", "insertion"])
+def test_sv_features_match_reference(sv_type):
+    a, g = _sv_case()
+    loci = golden_loci(g)
+    rows_s, rows_c = _filtered_sample(a, g), a["control"]["rows"]
+    assert [len(rows_s), len(rows_c)] == g["coverage"]
+    e = g["sv"][sv_type]
+    sparse = lambda recs: {str(i): {str(k): v for k, v in d.items()} for i, d in enumerate(recs) if d}  # noqa: E731
+    assert sparse([orc.index_and_sv_size(r, sv_type, loci) for r in rows_s]) == e["raw_sample"]
+    conv_s = orc.process_sv_indices(rows_s, sv_type, loci, len(rows_s))
+    conv_c = orc.process_sv_indices(rows_c, sv_type, loci, len(rows_c))
+    assert {str(k): v for k, v in conv_s.items()} == e["converter_sample"]
+    assert {str(k): v for k, v in conv_c.items()} == e["converter_control"]
+    feat_s = [orc.index_and_sv_size(r, sv_type, loci, conv_s) for r in rows_s]
+    feat_c = [orc.index_and_sv_size(r, sv_type, loci, conv_c) for r in rows_c]
+    assert sparse(feat_s) == e["features_sample"] and sparse(feat_c) == e["features_control"]
+    all_idx = {k for r in feat_s + feat_c for k in r}
+    X = np.vstack([orc.sv_feature_matrix(feat_s, all_idx), orc.sv_feature_matrix(feat_c, all_idx)])
+    assert list(X.shape) == e["X_shape"]
+    assert orc.optimize_labels(X, len(rows_s), len(rows_c)) == e["labels"]
+
+
+def test_kat_sv_index_and_size():  # the loop of sv_detector.py:53-97 on hand-made reads
+    loci = [{"-"}] * 30 + [set()] * 20
+    row = ",".join(["=A"] * 3 + ["-A"] * 12 + ["=C"] + ["-A"] * 5 + ["=a"] * 11 + ["+A|" * 10 + "=C"])
+    assert orc.index_and_sv_size(row, "deletion", loci) == {3: 12}
+    assert orc.index_and_sv_size(row, "inversion", loci) == {21: 11}
+    assert orc.index_and_sv_size(row, "insertion", [{"+"}] * 50) == {32: 10}
+    assert orc.index_and_sv_size(row, "insertion", loci) == {}
+    assert orc.index_and_sv_size(row, "deletion", loci, {3: 5}) == {5: 12}
+    assert orc.index_and_sv_size(row, "deletion", loci, {4: 5}) == {}
+    broken = [{"-"}] * 9 + [set()] + [{"-"}] * 40  # a run is cut where '-' is not in mutation_loci
+    assert orc.index_and_sv_size(row, "deletion", broken) == {}
+    assert orc.group_similar_indices([1, 2, 3, 4, 5, 6, 20, 40, 41, 42, 43, 44, 45, 46]) == [
+        [1, 2, 3, 4, 5, 6], [40, 41, 42, 43, 44, 45, 46]]
+    assert orc.index_converter([[7, 7, 8, 8, 9]]) == {7: 7, 8: 7, 9: 7}
