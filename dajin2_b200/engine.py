@@ -108,7 +108,7 @@ class EncodedReads:
         self.match_score = torch.empty(n, dtype=torch.int32, device=dev)
         self.n_tokens = torch.empty(n, dtype=torch.int32, device=dev)
         self.flags = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.ckpt = torch.empty((n, self.ckpt_pitch), dtype=torch.int32, device=dev)
+        self.ckpt = torch.zeros((n, self.ckpt_pitch), dtype=torch.int32, device=dev)  # entries past a row's end stay 0
         self.ref = None
         if assisted is None:
             assisted = os.environ.get("DAJIN2_B200_ENCODE_REF", "0") == "1"
