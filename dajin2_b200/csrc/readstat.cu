@@ -12,9 +12,9 @@
 //                        over the two files for this (three SV types x {collect indices, extract features} x
 //                        {sample, control}); the records of ONE scan serve all of them.
 //
-// Both kernels are one warp per read: the row is turned into bit strings in shared memory (one bit per locus and
-// token class, found sixteen code bytes at a time with byte-parallel range tests), and runs are then found with
-// word-parallel shifts -- no per-token loop anywhere.  Reads are independent; HBM traffic is the code matrix once
+// Both kernels are one warp per read, four 512-token trips in flight: token classes are found sixteen code bytes at a
+// time with byte-parallel range tests, rows become bit strings in shared memory (one bit per locus and class) only
+// where a class occurs, and runs are found on the words of those bit strings -- no per-token loop anywhere.  Reads are independent; HBM traffic is the code matrix once
 // (algorithmic bytes per read: code_pitch).
 #include "dj_common.cuh"
 
@@ -36,7 +36,7 @@ __device__ __forceinline__ uint32_t bytes_in_range(uint32_t y) {
 // bit j = bit 7 of byte j
 __device__ __forceinline__ uint32_t movemask4(uint32_t z) { return ((z >> 7) * 0x01020408u) >> 24; }
 
-enum { kClassN = 0, kClassDel = 1, kClassLower = 2, kClassIns = 3, kClasses = 4 };
+enum { kClassN = 0, kClassDel = 1, kClassLower = 2, kClassIns = 3 };
 
 // bit 7 of each byte: the token class tests on four code bytes
 __device__ __forceinline__ uint32_t class_flags(uint32_t w, int cls) {
@@ -53,32 +53,64 @@ __device__ __forceinline__ uint32_t class_flags(uint32_t w, int cls) {
     }
 }
 
-__device__ __forceinline__ uint32_t class_mask16(const uint4 &v, int cls) {
-    return movemask4(class_flags(v.x, cls)) | (movemask4(class_flags(v.y, cls)) << 4) |
-           (movemask4(class_flags(v.z, cls)) << 8) | (movemask4(class_flags(v.w, cls)) << 12);
+__device__ __forceinline__ uint4 class_flags4(const uint4 &v, int cls) {
+    return make_uint4(class_flags(v.x, cls), class_flags(v.y, cls), class_flags(v.z, cls), class_flags(v.w, cls));
 }
 
-// Bit strings of one row: bits[c][k] bit b = token 32 * k + b belongs to class c.  `words` words per class plus two
+__device__ __forceinline__ uint32_t movemask16(const uint4 &f) {
+    return movemask4(f.x) | (movemask4(f.y) << 4) | (movemask4(f.z) << 8) | (movemask4(f.w) << 12);
+}
+
+// 0x80 in every byte of w that is not a plain match (code byte >= 4)
+__device__ __forceinline__ uint32_t nonplain_flags(uint32_t w) {
+    return (((w | kHigh) - 0x04040404u) | w) & kHigh;
+}
+
+// Bit strings of one row: bits[c - kFirst][k] bit b = token 32 * k + b belongs to class c.  `words` words per class plus two
 // zero words behind them.  Returns, per class, whether any bit is set (warp-uniform).
 template <int kFirst, int kLast>
 __device__ __forceinline__ uint32_t build_bits(const uint8_t *__restrict__ row, int code_pitch, int n_loci, int words,
                                                uint32_t *bits, int stride, int lane) {
+    constexpr int kInFlight = 4;  // 512-token trips loaded before the first is looked at (2 KB per warp in flight)
     uint32_t any = 0;
-    for (int base = 0; base < words * 32; base += 512) {
-        const int pos = base + lane * 16;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (pos < code_pitch) v = __ldg(reinterpret_cast<const uint4 *>(row + pos));
-        // tokens past n_loci (row padding) never count
-        uint32_t valid = 0xFFFFu;
-        if (pos + 16 > n_loci) valid = pos >= n_loci ? 0u : (0xFFFFu >> (pos + 16 - n_loci));
+    const int n_tokens = words * 32;
+    for (int base0 = 0; base0 < n_tokens; base0 += 512 * kInFlight) {
+        uint4 v[kInFlight];
 #pragma unroll
-        for (int c = kFirst; c <= kLast; ++c) {
-            uint32_t m = 0;
-            if (((v.x | v.y | v.z | v.w) & 0xFCFCFCFCu) != 0) m = class_mask16(v, c) & valid;  // plain matches: no class
-            const uint32_t hi = __shfl_down_sync(0xffffffffu, m, 1);
+        for (int u = 0; u < kInFlight; ++u) {
+            const int pos = base0 + u * 512 + lane * 16;
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (pos < code_pitch) v[u] = __ldg(reinterpret_cast<const uint4 *>(row + pos));
+        }
+#pragma unroll
+        for (int u = 0; u < kInFlight; ++u) {
+            const int base = base0 + u * 512;
+            if (base >= n_tokens) break;
+            const int pos = base + lane * 16;
+            // tokens past n_loci (row padding) never count
+            uint32_t valid = 0xFFFFu;
+            if (pos + 16 > n_loci) valid = pos >= n_loci ? 0u : (0xFFFFu >> (pos + 16 - n_loci));
+            const bool plain = ((v[u].x | v[u].y | v[u].z | v[u].w) & 0xFCFCFCFCu) == 0;  // plain matches: no class
             const int k = (base >> 5) + (lane >> 1);
-            if ((lane & 1) == 0 && k < words) bits[c * stride + k] = m | (hi << 16);
-            any |= (__ballot_sync(0xffffffffu, m != 0) != 0 ? 1u : 0u) << c;
+            if (__ballot_sync(0xffffffffu, !plain) == 0) {  // nothing but plain matches in these 512 tokens
+#pragma unroll
+                for (int c = kFirst; c <= kLast; ++c)
+                    if ((lane & 1) == 0) bits[(c - kFirst) * stride + k] = 0u;
+                continue;
+            }
+#pragma unroll
+            for (int c = kFirst; c <= kLast; ++c) {
+                uint4 f = make_uint4(0, 0, 0, 0);
+                if (!plain) f = class_flags4(v[u], c);
+                if (__ballot_sync(0xffffffffu, (f.x | f.y | f.z | f.w) != 0) == 0) {  // no token of this class here
+                    if ((lane & 1) == 0) bits[(c - kFirst) * stride + k] = 0u;
+                    continue;
+                }
+                const uint32_t m = movemask16(f) & valid;
+                const uint32_t hi = __shfl_down_sync(0xffffffffu, m, 1);
+                if ((lane & 1) == 0) bits[(c - kFirst) * stride + k] = m | (hi << 16);
+                any |= (__ballot_sync(0xffffffffu, m != 0) != 0 ? 1u : 0u) << c;
+            }
         }
     }
     return any;
@@ -156,6 +188,71 @@ n_features_kernel(const uint8_t *__restrict__ codes, int code_pitch, const int32
     }
 }
 
+// Length in bytes of token `idx` of read r, found by the whole warp (every lane passes the same arguments): the
+// checkpoint table gives the 1 KB segment the token starts in, its commas are located 32 bytes per lane.  The serial
+// dj_find_token costs one DRAM round trip per 32-byte sector; this costs two per token.  Returns -1 if absent.
+__device__ int warp_token_length(const DjTextRef &tr, int64_t r, int idx, int lane) {
+    const int64_t off = __ldg(tr.row_off + r);
+    const int len = __ldg(tr.row_len + r);
+    const int head = (int)(off & 15);
+    const int n_iter = (head + len + DJ_ENC_CHUNK - 1) / DJ_ENC_CHUNK;
+    const uint32_t *ck = tr.ckpt + r * (int64_t)tr.ckpt_pitch;
+    int lo = 0;  // the last segment whose checkpoint is <= idx (checkpoints do not decrease)
+    for (int j0 = 0; j0 < n_iter; j0 += 32) {
+        const int j = j0 + lane;
+        const uint32_t le = __ballot_sync(0xffffffffu, j < n_iter && (int)__ldg(ck + j) <= idx);
+        if (le == 0u) break;
+        lo = j0 + 31 - __clz(le);
+        if (le != 0xffffffffu) break;
+    }
+    const int first = max(lo * DJ_ENC_CHUNK - head, 0);  // row-relative byte the search starts at
+    const uint8_t *row = tr.text + off;
+    // a token starts at `first` when the byte in front of it is a comma (or `first` is the row start)
+    const int starts_here = (first == 0 || __ldg(row + first - 1) == ',') ? 1 : 0;
+    // commas at positions >= first are numbered 0, 1, ...; the token ends at comma number `end_no` and starts behind
+    // comma number end_no - 1 (at `first` itself when end_no == 0, which requires starts_here)
+    const int end_no = idx - (int)__ldg(ck + lo) - starts_here + 1;
+    if (end_no < 0 || (end_no == 0 && !starts_here)) return -1;
+    int start = end_no == 0 ? first : -1, seen = 0;
+    const uint8_t *aligned = row - head;  // 16-byte aligned
+    for (int w0 = (first + head) & ~15; w0 < head + len; w0 += 1024) {  // offsets relative to `aligned`
+        uint32_t commas = 0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int p = w0 + lane * 32 + h * 16;  // this lane's sixteen bytes
+            if (p >= head + len) continue;
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(aligned + p));
+            const uint32_t word[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t x = word[k] ^ 0x2C2C2C2Cu;
+                const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & kHigh;  // 0x80 where the byte is ','
+                commas |= movemask4(z) << (h * 16 + k * 4);
+            }
+        }
+        // only bytes of the row from `first` on count
+        const int lane0 = w0 + lane * 32 - head;  // row-relative position of this lane's first byte
+        if (lane0 < first) commas &= first - lane0 >= 32 ? 0u : 0xFFFFFFFFu << (first - lane0);
+        if (lane0 + 32 > len) commas &= lane0 >= len ? 0u : 0xFFFFFFFFu >> (lane0 + 32 - len);
+        const int mine = __popc(commas);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const int before = seen + incl - mine;  // number of the first comma of this lane
+        int found_start = -1, found_end = -1;
+        if (end_no - 1 >= before && end_no - 1 < before + mine) found_start = lane0 + (int)__fns(commas, 0, end_no - before) + 1;
+        if (end_no >= before && end_no < before + mine) found_end = lane0 + (int)__fns(commas, 0, end_no - before + 1);
+        const uint32_t vs = __ballot_sync(0xffffffffu, found_start >= 0), ve = __ballot_sync(0xffffffffu, found_end >= 0);
+        if (vs) start = __shfl_sync(0xffffffffu, found_start, __ffs(vs) - 1);
+        if (ve) return __shfl_sync(0xffffffffu, found_end, __ffs(ve) - 1) - start;
+        seen += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    return start >= 0 ? len - start : -1;  // the last token of the row has no closing comma
+}
+
 __device__ __forceinline__ void emit_record(int32_t *records, uint32_t *n_records, uint32_t capacity, int type,
                                             int read, int start, int size) {
     const uint32_t slot = atomicAdd(n_records, 1u);
@@ -176,24 +273,63 @@ sv_scan_kernel(const uint8_t *__restrict__ codes, int code_pitch, const int32_t 
     extern __shared__ uint32_t smem_bits[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stride = words + 2;
-    uint32_t *bits = smem_bits + warp * kClasses * stride;
-    for (int c = kClassDel; c <= kClassIns; ++c)
-        if (lane < 2) bits[c * stride + words + lane] = 0u;
+    uint32_t *bits = smem_bits + warp * 2 * stride;  // deletion and lowercase classes
+    if (lane < 4) bits[(lane >> 1) * stride + words + (lane & 1)] = 0u;  // the zero words behind both bit strings
     const int64_t n_warps = (int64_t)gridDim.x * kScanWarps;
     for (int64_t t = (int64_t)blockIdx.x * kScanWarps + warp; t < n_rows; t += n_warps) {
         const int64_t r = rows ? (int64_t)__ldg(rows + t) : t;
         const uint8_t *row = codes + r * (int64_t)code_pitch;
-        const uint32_t any = build_bits<kClassDel, kClassIns>(row, code_pitch, n_loci, words, bits, stride, lane);
+        // Pass A, every read: (i) insertion tokens on loci that hold '+' (:76-78) are looked up at once; (ii) a run of
+        // seven or more deletions / lowercase tokens covers an aligned group of four code bytes none of which is a
+        // plain match, so reads without such a group (all but the SV-carrying and N-tailed ones) are finished here.
+        bool has_full = min_size < 7;
+        constexpr int kInFlight = 4;
+        for (int base0 = 0; base0 < words * 32; base0 += 512 * kInFlight) {
+            uint4 v[kInFlight];
+#pragma unroll
+            for (int u = 0; u < kInFlight; ++u) {
+                const int pos = base0 + u * 512 + lane * 16;
+                v[u] = make_uint4(0, 0, 0, 0);
+                if (pos < code_pitch) v[u] = __ldg(reinterpret_cast<const uint4 *>(row + pos));
+            }
+#pragma unroll
+            for (int u = 0; u < kInFlight; ++u) {
+                const int pos = base0 + u * 512 + lane * 16;
+                if (base0 + u * 512 >= words * 32) break;
+                const bool full = nonplain_flags(v[u].x) == kHigh || nonplain_flags(v[u].y) == kHigh ||
+                                  nonplain_flags(v[u].z) == kHigh || nonplain_flags(v[u].w) == kHigh;
+                uint32_t cand = 0;
+                if (((v[u].x | v[u].y | v[u].z | v[u].w) & kHigh) != 0)
+                    cand = (__ldg(ins_loci + (pos >> 5)) >> (pos & 31)) & 0xFFFFu;  // loci past n_loci are never set
+                const uint32_t votes = __ballot_sync(0xffffffffu, full);
+                has_full = has_full || votes != 0;
+                if (cand) cand &= movemask16(make_uint4(v[u].x & kHigh, v[u].y & kHigh, v[u].z & kHigh, v[u].w & kHigh));
+                // candidates are rare: the warp looks each one up together
+                for (uint32_t busy = __ballot_sync(0xffffffffu, cand != 0); busy; busy = __ballot_sync(0xffffffffu, cand != 0)) {
+                    const int src = __ffs(busy) - 1;
+                    const int locus = __shfl_sync(0xffffffffu, pos + __ffs(cand) - 1, src);
+                    if (lane == src) cand &= cand - 1;
+                    const int len = warp_token_length(text, r, locus, lane);
+                    if (len < 0 || lane != src) continue;
+                    const int anchor = row[locus] & 0x7F;
+                    const int n_ins = (len - (anchor < 20 ? 2 : 3)) / 3;  // every inserted base is "+B|"
+                    if (n_ins >= min_size) emit_record(records, n_records, capacity, 2, (int)t, locus, n_ins);
+                }
+            }
+        }
+        if (!has_full) continue;
+        // Pass B, the few reads left: bit strings of the deletion and lowercase classes, then their runs.
+        const uint32_t any = build_bits<kClassDel, kClassLower>(row, code_pitch, n_loci, words, bits, stride, lane);
         if (any == 0) continue;
         __syncwarp();
         // deletions only count on loci whose mutation_loci holds '-' (sv_detector.py:67)
         if (any & (1u << kClassDel))
-            for (int k = lane; k < words; k += 32) bits[kClassDel * stride + k] &= __ldg(del_loci + k);
+            for (int k = lane; k < words; k += 32) bits[k] &= __ldg(del_loci + k);
         __syncwarp();
 #pragma unroll 1
         for (int c = kClassDel; c <= kClassLower; ++c) {  // runs of at least min_size tokens (:65-74, :80-82)
             if (!(any & (1u << c))) continue;
-            const uint32_t *b = bits + c * stride;
+            const uint32_t *b = bits + (c - kClassDel) * stride;
             for (int k = lane; k < words; k += 32) {
                 const uint32_t lo = b[k];
                 if (lo == 0u) continue;
@@ -218,20 +354,6 @@ sv_scan_kernel(const uint8_t *__restrict__ codes, int code_pitch, const int32_t 
                     }
                     if (len >= min_size) emit_record(records, n_records, capacity, c == kClassDel ? 0 : 1, (int)t,
                                                      k * 32 + bit, len);
-                }
-            }
-        }
-        if (any & (1u << kClassIns)) {  // insertions on loci whose mutation_loci holds '+' (:76-78)
-            for (int k = lane; k < words; k += 32) {
-                uint32_t cand = bits[kClassIns * stride + k] & __ldg(ins_loci + k);
-                while (cand) {
-                    const int locus = k * 32 + __ffs(cand) - 1;
-                    cand &= cand - 1;
-                    int off, len;
-                    if (!dj_find_token(text, r, locus, &off, &len)) continue;
-                    const int anchor = row[locus] & 0x7F;
-                    const int n_ins = (len - (anchor < 20 ? 2 : 3)) / 3;  // every inserted base is "+B|"
-                    if (n_ins >= min_size) emit_record(records, n_records, capacity, 2, (int)t, locus, n_ins);
                 }
             }
         }
@@ -290,7 +412,7 @@ extern "C" int dj_sv_scan(const uint8_t *codes, int32_t code_pitch, const int32_
     if (n_rows <= 0) return 0;
     int words = 0;
     size_t smem = 0;
-    if (scan_geometry("dj_sv_scan", code_pitch, n_loci, kClasses, &words, &smem)) return 1;
+    if (scan_geometry("dj_sv_scan", code_pitch, n_loci, 2, &words, &smem)) return 1;
     if (((uintptr_t)codes & 15) != 0) {
         dj_set_error("dj_sv_scan: the code matrix must be 16-byte aligned");
         return 1;

@@ -62,6 +62,18 @@ del enc_ref
 hist = torch.empty((_cabi.HIST_ROWS, args.loci), dtype=torch.int32, device="cuda")
 timeit(lambda: _cabi.call("dj_hist", engine._p(enc.codes), enc.pitch, engine._p(enc.strand), engine._p(None), enc.n_reads,
                           enc.n_loci, engine._p(hist), engine._stream()), args.reads * (args.loci + 1), "hist")
+# the rank-3 scans of the code matrix: N features and structural-variant records
+nc = torch.zeros(args.reads, dtype=torch.int32, device="cuda"); nr = torch.zeros(args.reads, dtype=torch.int32, device="cuda")
+timeit(lambda: _cabi.call("dj_read_n_features", engine._p(enc.codes), enc.pitch, engine._p(None), enc.n_reads, enc.n_loci,
+                          engine._p(nc), engine._p(nr), engine._stream()), args.reads * enc.pitch, "n_features")
+words = _cabi.call("dj_loci_words", args.loci)
+lm = torch.zeros(words, dtype=torch.int32, device="cuda"); lm[40:47] = -1; lm[75] = 0xFFFF  # 240 loci hold '-' / '+'
+rec = torch.empty((1 << 20, 4), dtype=torch.int32, device="cuda"); nrec = torch.zeros(1, dtype=torch.int32, device="cuda")
+timeit(lambda: _cabi.call("dj_sv_scan", engine._p(enc.codes), enc.pitch, engine._p(None), enc.n_reads, enc.n_loci,
+                          engine._p(enc.text), engine._p(enc.row_off), engine._p(enc.row_len), engine._p(enc.ckpt),
+                          enc.ckpt_pitch, engine._p(lm), engine._p(lm), 10, engine._p(rec), 1 << 20, engine._p(nrec),
+                          engine._stream()), args.reads * enc.pitch, "sv_scan")
+print("sv records", int(nrec.item()), "reads with N", int((nc > 0).sum().item()))
 out = {"codes": enc.codes[:, : args.loci].cpu().numpy(), "match": enc.match_scores(), "ntok": enc.n_tokens.cpu().numpy(),
        "ckpt": enc.ckpt.cpu().numpy(), "hist": hist.cpu().numpy()}
 if args.save:
