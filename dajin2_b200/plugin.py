@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import importlib
 
-from . import classification, clustering, preprocess, sequence_error, structural_variants
+from . import classification, clustering, consensus, preprocess, sequence_error, structural_variants
 
 _PATCHES = [
     # (module, attribute, replacement)
@@ -59,6 +59,12 @@ _PATCHES = [
     ("DAJIN2.core.preprocess", "detect_sequence_error_reads", sequence_error.detect_sequence_error_reads),
     ("DAJIN2.core.preprocess", "replace_midsv_without_sequence_errors",
      sequence_error.replace_midsv_without_sequence_errors),
+    # the consensus stage re-uses the histogram / strand / N-count kernels
+    ("DAJIN2.core.consensus.consensus_mutation_analyzer", "summarize_indels", preprocess.summarize_indels),
+    ("DAJIN2.core.consensus.consensus_mutation_analyzer", "extract_sequence_errors_in_strand_biased_loci",
+     preprocess.extract_sequence_errors_in_strand_biased_loci),
+    ("DAJIN2.core.consensus.consensus_mutation_analyzer", "extract_path_n_filtered_control",
+     consensus.extract_path_n_filtered_control),
 ]
 
 _saved: list[tuple] = []

@@ -591,6 +591,16 @@ def sequence_error_sample(rows_control, qnames_control, control_without_error, r
     return [q for q, lab in zip(qnames_sample, labels) if lab == 0]
 
 
+def n_filtered_control(rows) -> list[bool]:
+    """consensus/consensus_mutation_analyzer.py:85-94 — keep the control reads whose N-token count is at most the mean
+    of the two MiniBatchKMeans centres."""
+    from sklearn.cluster import MiniBatchKMeans
+
+    n_counts = np.array([sum(1 if is_n_token(t) else 0 for t in row.split(",")) for row in rows])
+    kmeans = MiniBatchKMeans(n_clusters=2, random_state=0).fit(n_counts.reshape(-1, 1))
+    return (n_counts <= kmeans.cluster_centers_.mean()).tolist()
+
+
 def index_and_sv_size(row: str, sv_type: str, loci_t, converter=None, min_size: int = 10) -> dict[int, int]:
     """structural_variants/sv_detector.py:53-97 — {start index: size} of the read's SV features: maximal runs of
     tokens starting with '-' on loci holding '-', maximal runs of lowercase tokens, insertion tokens on loci holding

@@ -183,6 +183,11 @@ def run_reference_sv(case: dict) -> dict:
         g["control_without_error"] = (tmp / cname / "sequence_error" / "qnames_without_error.txt").read_text().splitlines()
         g["error_fraction"] = (tmp / cname / "sequence_error" / "error_fraction.txt").read_text().strip()
         g["sample_without_error"] = (tmp / sname / "sequence_error" / "qnames_without_error.txt").read_text().splitlines()
+        from DAJIN2.core.consensus import consensus_mutation_analyzer as cma
+
+        p_nf = cma.extract_path_n_filtered_control(tmp, cname, sname, p_c, "control")  # consensus stage's N filter
+        g["sha_control_n_filtered_file"] = __import__("hashlib").sha256(p_nf.read_bytes()).hexdigest()
+        g["control_n_filtered_reads"] = fileio_count(p_nf)
         seh.replace_midsv_without_sequence_errors(args)
         g["sha_sample_filtered_file"] = __import__("hashlib").sha256(p_s.read_bytes()).hexdigest()
         # the rest of the flow runs on the filtered sample file, as core.py:153-185 does

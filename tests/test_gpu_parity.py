@@ -540,3 +540,21 @@ def test_sv_scan_edge_cases():
             for _, read, start, size in rec[rec[:, 0] == t].tolist():
                 got[read][start] = size
             assert got == [orc.index_and_sv_size(r, name, loci) for r in rows], (L, name)
+
+
+def test_consensus_n_filter_on_files(tmp_path):
+    """extract_path_n_filtered_control (consensus_mutation_analyzer.py:75-102): the file the real reference wrote."""
+    import hashlib
+
+    from dajin2_b200 import cache, consensus
+    from dajin2_b200.preprocess import _allele_key
+
+    cache.clear()
+    alleles, golden = load_case("sv_like")
+    g = golden["alleles"]["control"]
+    _write_tree(tmp_path, alleles)
+    p_c = tmp_path / "ctrl" / "midsv" / _allele_key("control") / "ctrl_midsv.jsonl"
+    out = consensus.extract_path_n_filtered_control(tmp_path, "ctrl", "sample", p_c, "control")
+    assert out == tmp_path / "ctrl" / "consensus" / _allele_key("control") / "sample_n_filtered.jsonl"
+    assert hashlib.sha256(out.read_bytes()).hexdigest() == g["sha_control_n_filtered_file"]
+    assert consensus.extract_path_n_filtered_control(tmp_path, "ctrl", "sample", p_c, "control") == out  # cached file

@@ -209,3 +209,15 @@ def test_kat_sv_index_and_size():  # the loop of sv_detector.py:53-97 on hand-ma
     assert orc.group_similar_indices([1, 2, 3, 4, 5, 6, 20, 40, 41, 42, 43, 44, 45, 46]) == [
         [1, 2, 3, 4, 5, 6], [40, 41, 42, 43, 44, 45, 46]]
     assert orc.index_converter([[7, 7, 8, 8, 9]]) == {7: 7, 8: 7, 9: 7}
+
+
+def test_consensus_n_filter_matches_reference():  # consensus_mutation_analyzer.py:75-102 on the sv_like control
+    import hashlib
+    import json
+
+    a, g = _sv_case()
+    keep = orc.n_filtered_control(a["control"]["rows"])
+    assert sum(keep) == g["control_n_filtered_reads"]
+    text = "".join(json.dumps({"QNAME": q, "RNAME": "control", "MIDSV": r, "STRAND": s, "PRESET": "map-ont"}) + "\n"
+                   for q, r, s, k in zip(a["control"]["qnames"], a["control"]["rows"], a["control"]["strands"], keep) if k)
+    assert hashlib.sha256(text.encode()).hexdigest() == g["sha_control_n_filtered_file"]
