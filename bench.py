@@ -369,6 +369,7 @@ def run_ours(args):
     text_bytes = int(hs.row_len.astype(np.int64).sum())
     enc_bytes = text_bytes + hs.n_reads * (len(sequence) + 16)
     enc_pitch = int(enc_s.pitch)
+    enc_kernel = "encode_ref_kernel" if enc_s.ref is not None else "encode_kernel"
 
     def device_step():
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -471,7 +472,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(r2.timings.get("h2d_bytes", 0)),
                 "d2h_bytes_per_step": int(r2.timings.get("d2h_bytes", 0))},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "encode_ref_kernel" if enc_s.ref is not None else "encode_kernel", "bound": "hbm",
+        "roofline": {"kernel": enc_kernel, "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes_per_launch": enc_bytes, "ms_per_launch": enc_ms},
