@@ -267,8 +267,20 @@ def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, g
 
     from .pipeline import HotPathResult, global_positions
 
+    import time
+
+    phase_ms: dict = {}
+    clock = [time.perf_counter()]
+
+    def mark(name):  # host time of each phase of this rank (the phases end in host-visible results anyway)
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        phase_ms[name] = phase_ms.get(name, 0.0) + (now - clock[0]) * 1e3
+        clock[0] = now
+
     run = ShardRun(sample, control, sequence, knockin, gpos)
     reduced = comm.allreduce_sum(run.histogram_and_strands())
+    mark("hist_allreduce_ms")
 
     def positions():
         if gpos is None:
@@ -279,21 +291,27 @@ def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, g
         loci_mask = ["".join(sorted(m)) for m in run.select_loci(reduced, while_waiting=positions)]
     else:
         positions()
+        mark("order_ms")
     loci_t = [set(m) for m in comm.broadcast_object(loci_mask)]
+    mark("loci_ms")
     order = run.rows.cpu().numpy()
     n_total = int(reduced[-1].item())
     if all(not m for m in loci_t) or n_total < 5:
         labels = np.ones(sample.n_reads, dtype=np.int32) if fetch_labels else None
         return HotPathResult(labels, order, [n_total], [100.0], loci_t, None, {"collectives": comm.collectives})
     kmers = comm.allgather_object(run.count_kmers(reduced, loci_t))
+    mark("kmers_ms")
     points = comm.allgather_object(run.score_rows(kmers))
+    mark("score_rows_ms")
     gpos_d, point_d = run.points_of_reads(points, comm.rank)
     sizes = [int(p[1].sum()) for p in points]
     gpos_all = comm.allgather_rows(gpos_d, sizes)
     point_all = comm.allgather_rows(point_d, sizes)
+    mark("points_allgather_ms")
     labels_d, info = run.cluster(gpos_all, point_all)
+    mark("cluster_ms")
     labels = labels_d.cpu().numpy() if fetch_labels else None
     sizes_c = info["cluster_sizes"]
     pct = [round(s / n_total * 100, 3) for s in sizes_c]
-    timings = {"n_points": info["n_points"], "n_cols": run.model.n_cols, "collectives": comm.collectives}
+    timings = {"n_points": info["n_points"], "n_cols": run.model.n_cols, "collectives": comm.collectives, **phase_ms}
     return HotPathResult(labels, order, sizes_c, pct, loci_t, run.model, timings)
