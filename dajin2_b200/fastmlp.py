@@ -56,6 +56,18 @@ def build(force: bool = False) -> Path:
     return LIB
 
 
+def default_threads() -> int:
+    """Threads of the element-wise passes of one fit (``DAJIN2_B200_MLP_THREADS`` overrides).  Three fits run at a time
+    (one per mutation type) and, in a multi-GPU run, on rank 0 only, so each gets a third of the cores left after one
+    per local rank: 4 on a 16-core box, up to 8 on larger ones.  The thread count cannot change a bit of the result."""
+    raw = os.environ.get("DAJIN2_B200_MLP_THREADS")
+    if raw:
+        return max(1, int(raw))
+    cores = os.cpu_count() or 8
+    ranks = int(os.environ.get("LOCAL_WORLD_SIZE") or 1)
+    return max(2, min(8, (cores - ranks - 2) // 3))
+
+
 def load_host_lib():
     global _lib
     if _lib is None:
@@ -78,7 +90,7 @@ def load_host_lib():
         lib.dj_jsonl_index.restype = i64
         lib.dj_gather_fixed.argtypes = [vp, vp, vp, i64, ctypes.c_int32, vp, ci]
         lib.dj_gather_fixed.restype = None
-        lib.fm_set_threads(max(1, int(os.environ.get("DAJIN2_B200_MLP_THREADS", "4"))))
+        lib.fm_set_threads(default_threads())
         lib.fm_pairwise_sum.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         lib.fm_pairwise_sum.restype = ctypes.c_double
         _lib = lib

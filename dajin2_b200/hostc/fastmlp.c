@@ -177,7 +177,7 @@ static inline __attribute__((always_inline)) void reduce_product(int64_t n, cons
         for (int j = 0; j < h; j++) g[k * h + j] = acc[(k - k0) * h + j];
 }
 
-/* one of the four reduction tasks; called with literal sizes for the reference's model */
+/* one of the four reduction tasks (generic layer sizes) */
 static inline __attribute__((always_inline)) void reduce_task(
     const int task, const double *X, int64_t xs_row, int64_t xs_col, int64_t n, const int n_in, const int half,
     const double *a1, const int h1, const int h2, const double *d2, const double *d1, double *cs2, double *g2,
@@ -186,6 +186,45 @@ static inline __attribute__((always_inline)) void reduce_task(
     else if (task == 1) reduce_product(n, X, xs_row, xs_col, 0, half, d1, h1, g1);
     else if (task == 2) reduce_product(n, X, xs_row, xs_col, half, n_in, d1, h1, g1);
     else reduce_colsums(n, h1, h2, d2, d1, cs2, cs1);
+}
+
+/* The same four tasks for the reference's model (2 inputs, hidden layers of 5 and 2) with every chain in a register:
+ * the generic loops above keep their accumulators in memory, which puts a store-to-load round trip into each step of
+ * each chain (4x slower).  The operations and their order per chain are the same. */
+static void reduce_task_252(const int task, const double *X, int64_t xs_row, int64_t xs_col, int64_t n, const double *a1,
+                            const double *d2, const double *d1, double *cs2, double *g2, double *cs1, double *g1) {
+    if (task == 0) { /* g2[k][j] = sum_i a1[i][k] * d2[i][j] */
+        double c00 = 0, c01 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c30 = 0, c31 = 0, c40 = 0, c41 = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const double *x = a1 + i * 5, y0 = d2[i * 2], y1 = d2[i * 2 + 1];
+            c00 = fma(x[0], y0, c00); c01 = fma(x[0], y1, c01);
+            c10 = fma(x[1], y0, c10); c11 = fma(x[1], y1, c11);
+            c20 = fma(x[2], y0, c20); c21 = fma(x[2], y1, c21);
+            c30 = fma(x[3], y0, c30); c31 = fma(x[3], y1, c31);
+            c40 = fma(x[4], y0, c40); c41 = fma(x[4], y1, c41);
+        }
+        g2[0] = c00; g2[1] = c01; g2[2] = c10; g2[3] = c11; g2[4] = c20; g2[5] = c21; g2[6] = c30; g2[7] = c31;
+        g2[8] = c40; g2[9] = c41;
+    } else if (task == 1 || task == 2) { /* g1[k][j] = sum_i X[i][k] * d1[i][j] for k = task - 1 */
+        const int k = task - 1;
+        double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const double x = X[i * xs_row + k * xs_col], *y = d1 + i * 5;
+            c0 = fma(x, y[0], c0); c1 = fma(x, y[1], c1); c2 = fma(x, y[2], c2); c3 = fma(x, y[3], c3);
+            c4 = fma(x, y[4], c4);
+        }
+        double *o = g1 + k * 5;
+        o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3; o[4] = c4;
+    } else { /* column sums of d2 and d1 */
+        double s0 = 0, s1 = 0, t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const double *p = d2 + i * 2, *q = d1 + i * 5;
+            s0 += p[0]; s1 += p[1];
+            t0 += q[0]; t1 += q[1]; t2 += q[2]; t3 += q[3]; t4 += q[4];
+        }
+        cs2[0] = s0; cs2[1] = s1;
+        cs1[0] = t0; cs1[1] = t1; cs1[2] = t2; cs1[3] = t3; cs1[4] = t4;
+    }
 }
 
 int fm_backward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n_in, const double *a1, int h1,
@@ -200,12 +239,8 @@ int fm_backward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int 
             for (int c = 0; c < FM_CHUNKS; c++)
                 backward_rows(c * step, (c + 1) * step < n ? (c + 1) * step : n, a1, 5, a2, 2, W2, W3, d3, d2, d1);
 #pragma omp for schedule(dynamic, 1)
-            for (int task = 0; task < 4; task++) {
-                if (task == 0) reduce_task(0, X, xs_row, xs_col, n, 2, 1, a1, 5, 2, d2, d1, cs2, g2, cs1, g1);
-                else if (task == 1) reduce_task(1, X, xs_row, xs_col, n, 2, 1, a1, 5, 2, d2, d1, cs2, g2, cs1, g1);
-                else if (task == 2) reduce_task(2, X, xs_row, xs_col, n, 2, 1, a1, 5, 2, d2, d1, cs2, g2, cs1, g1);
-                else reduce_task(3, X, xs_row, xs_col, n, 2, 1, a1, 5, 2, d2, d1, cs2, g2, cs1, g1);
-            }
+            for (int task = 0; task < 4; task++)
+                reduce_task_252(task, X, xs_row, xs_col, n, a1, d2, d1, cs2, g2, cs1, g1);
         }
     } else {
         const int half = (n_in + 1) / 2;
