@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=1_000_000, help="sample reads per GPU")
     ap.add_argument("--loci", type=int, default=5000)
     ap.add_argument("--profile", default="r10")
-    ap.add_argument("--cpu-sample", type=int, default=600, help="sample reads of the cpu_baseline leg")
+    ap.add_argument("--cpu-sample", type=int, default=3000, help="sample reads of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
