@@ -35,3 +35,22 @@ def extract_path_n_filtered_control(tempdir: Path, control_name: str, sample_nam
         raise RuntimeError(f"{path_control}: {len(lines)} lines but {enc.n_reads} records")
     path_output.write_bytes(b"".join(ln + b"\n" for ln, k in zip(lines, keep) if k))
     return path_output
+
+
+def get_thresholds(path_indels_normalized_sample, path_indels_normalized_control) -> dict[str, float]:
+    """consensus_mutation_analyzer.py:40-56 — per mutation type the mean of the two MiniBatchKMeans centres of
+    ``sample - min(control, sample)``, at least 10 (host arithmetic on 3 x L values, scikit-learn as the reference)."""
+    import pickle
+
+    from sklearn.cluster import MiniBatchKMeans
+
+    with open(path_indels_normalized_sample, "rb") as f:
+        norm_sample = pickle.load(f)
+    with open(path_indels_normalized_control, "rb") as f:
+        norm_control = pickle.load(f)
+    thresholds = {}
+    for mut in {"+", "-", "*"}:
+        diff = norm_sample[mut] - np.minimum(norm_control[mut], norm_sample[mut])
+        kmeans = MiniBatchKMeans(n_clusters=2, random_state=0).fit(diff.reshape(-1, 1))
+        thresholds[mut] = max(kmeans.cluster_centers_.mean(), 10)
+    return thresholds

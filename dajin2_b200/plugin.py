@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import importlib
 
-from . import classification, clustering, consensus, preprocess, sequence_error, structural_variants
+from . import classification, clustering, consensus, engine, preprocess, sequence_error, structural_variants
 
 _PATCHES = [
     # (module, attribute, replacement)
@@ -65,6 +65,11 @@ _PATCHES = [
      preprocess.extract_sequence_errors_in_strand_biased_loci),
     ("DAJIN2.core.consensus.consensus_mutation_analyzer", "extract_path_n_filtered_control",
      consensus.extract_path_n_filtered_control),
+    # the candidate-loci step with its three concurrent, bit-identical MLP fits (anomaly_detector.py:99-109), for the
+    # consensus stage (one call per cluster, is_consensus=True) and for anyone else who imported it by value
+    ("DAJIN2.core.consensus.consensus_mutation_analyzer", "extract_anomal_loci", engine.extract_anomal_loci),
+    ("DAJIN2.core.preprocess.mutation_processing.anomaly_detector", "extract_anomal_loci", engine.extract_anomal_loci),
+    ("DAJIN2.core.preprocess.mutation_processing.mutation_extractor", "extract_anomal_loci", engine.extract_anomal_loci),
 ]
 
 _saved: list[tuple] = []

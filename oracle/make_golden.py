@@ -194,6 +194,29 @@ def run_reference_sv(case: dict) -> dict:
         preprocess.cache_mutation_loci(args, is_control=True)
         preprocess.cache_mutation_loci(args, is_control=False)
         loci = pickle.loads((tmp / sname / "mutation_loci" / key / "mutation_loci.pickle").read_bytes())
+        # the consensus stage's candidate loci (consensus_mutation_analyzer.py:40-56,145-153): data-driven thresholds
+        # and the is_consensus branch of is_dissimilar_loci, here on the whole sample standing in for one cluster
+        from DAJIN2.core.preprocess.mutation_processing.anomaly_detector import extract_anomal_loci
+        from DAJIN2.core.preprocess.mutation_processing.indel_counter import minimize_mutation_counts
+
+        from DAJIN2.core.preprocess.mutation_processing.indel_counter import summarize_indels
+
+        recs = [json.loads(line) for line in p_s.read_text().splitlines()]
+        members = [i for i, r in enumerate(recs) if r["MIDSV"].split(",")[450].startswith("-")]  # the deletion allele
+        p_cluster = tmp / sname / "consensus" / key / "1" / f"{sname}_sample.jsonl"
+        p_cluster.parent.mkdir(parents=True, exist_ok=True)
+        p_cluster.write_text("".join(json.dumps(recs[i]) + "\n" for i in members))
+        _, norm_s = summarize_indels(p_cluster, case["sequence"])
+        _, norm_c_raw = summarize_indels(p_c, case["sequence"])
+        p_ns, p_nc = p_cluster.parent / "normalized_sample.pickle", p_cluster.parent / "normalized_control.pickle"
+        p_ns.write_bytes(pickle.dumps(norm_s))
+        p_nc.write_bytes(pickle.dumps(norm_c_raw))
+        thresholds = cma.get_thresholds(p_ns, p_nc)
+        g["consensus_cluster_reads"] = members
+        g["consensus_thresholds"] = {k: float(v).hex() for k, v in thresholds.items()}
+        norm_c = minimize_mutation_counts(norm_c_raw, norm_s)
+        anomal = extract_anomal_loci(norm_s, norm_c, thresholds, is_consensus=True)
+        g["consensus_anomal_loci"] = {k: sorted(int(i) for i in v) for k, v in anomal.items()}
         for i in case.get("force_plus", []):
             loci[i] = set(loci[i]) | {"+"}
         g["mutation_loci"] = ["".join(sorted(s)) for s in loci]

@@ -558,3 +558,31 @@ def test_consensus_n_filter_on_files(tmp_path):
     assert out == tmp_path / "ctrl" / "consensus" / _allele_key("control") / "sample_n_filtered.jsonl"
     assert hashlib.sha256(out.read_bytes()).hexdigest() == g["sha_control_n_filtered_file"]
     assert consensus.extract_path_n_filtered_control(tmp_path, "ctrl", "sample", p_c, "control") == out  # cached file
+
+
+def test_consensus_anomal_loci(tmp_path):
+    """The consensus stage's candidate loci for one cluster (consensus_mutation_analyzer.py:119-153): per-cluster
+    summarize_indels, get_thresholds and extract_anomal_loci(is_consensus=True) through the drop-in functions."""
+    from dajin2_b200 import cache, consensus, engine, preprocess
+    from dajin2_b200.preprocess import _allele_key
+
+    cache.clear()
+    alleles, golden = load_case("sv_like")
+    a, g = alleles["control"], golden["alleles"]["control"]
+    clean = set(g["sample_without_error"])
+    keep = [i for i, q in enumerate(a["sample"]["qnames"]) if q in clean]
+    members = [keep[i] for i in g["consensus_cluster_reads"]]
+    cluster = {"control": {**a, "sample": {k: [v[i] for i in members] for k, v in a["sample"].items()}}}
+    _write_tree(tmp_path, cluster)
+    key = _allele_key("control")
+    p_s = tmp_path / "sample" / "midsv" / key / "sample_midsv.jsonl"
+    p_c = tmp_path / "ctrl" / "midsv" / key / "ctrl_midsv.jsonl"
+    _, norm_s = preprocess.summarize_indels(p_s, a["sequence"])
+    _, norm_c = preprocess.summarize_indels(p_c, a["sequence"])
+    (tmp_path / "ns.pickle").write_bytes(pickle.dumps(norm_s))
+    (tmp_path / "nc.pickle").write_bytes(pickle.dumps(norm_c))
+    thresholds = consensus.get_thresholds(tmp_path / "ns.pickle", tmp_path / "nc.pickle")
+    assert {k: float(v).hex() for k, v in thresholds.items()} == g["consensus_thresholds"]
+    got = engine.extract_anomal_loci(norm_s, preprocess.minimize_mutation_counts(norm_c, norm_s), thresholds,
+                                     is_consensus=True)
+    assert {k: sorted(v) for k, v in got.items()} == g["consensus_anomal_loci"]

@@ -221,3 +221,17 @@ def test_consensus_n_filter_matches_reference():  # consensus_mutation_analyzer.
     text = "".join(json.dumps({"QNAME": q, "RNAME": "control", "MIDSV": r, "STRAND": s, "PRESET": "map-ont"}) + "\n"
                    for q, r, s, k in zip(a["control"]["qnames"], a["control"]["rows"], a["control"]["strands"], keep) if k)
     assert hashlib.sha256(text.encode()).hexdigest() == g["sha_control_n_filtered_file"]
+
+
+def test_consensus_anomal_loci_match_reference():
+    """extract_anomal_loci(..., is_consensus=True) with the consensus stage's data-driven thresholds
+    (consensus_mutation_analyzer.py:40-56,145-153) on the deletion-allele reads of sv_like standing in for a cluster."""
+    a, g = _sv_case()
+    rows = _filtered_sample(a, g)
+    cluster = [rows[i] for i in g["consensus_cluster_reads"]]
+    L = len(a["sequence"])
+    norm_s = orc.normalize_indels(orc.count_indels(cluster, L))
+    norm_c = orc.minimize_mutation_counts(orc.normalize_indels(orc.count_indels(a["control"]["rows"], L)), norm_s)
+    thresholds = {k: float.fromhex(v) for k, v in g["consensus_thresholds"].items()}
+    got = orc.extract_anomal_loci(norm_s, norm_c, thresholds, is_consensus=True)
+    assert {k: sorted(v) for k, v in got.items()} == g["consensus_anomal_loci"]
