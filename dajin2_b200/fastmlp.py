@@ -15,7 +15,12 @@ one loss/gradient evaluation (``_loss_grad_lbfgs``) by the same arithmetic fused
     unit (dgemv: another order) are still made by numpy, exactly as scikit-learn's ``safe_sparse_dot`` makes them;
   * sums are numpy's pairwise summation or row-by-row accumulation, whichever numpy uses for that shape;
   * ``expit`` / ``xlogy`` are libm's ``exp`` / ``log`` as in scipy.special; these two take most of the time left and
-    run on ``DAJIN2_B200_MLP_THREADS`` threads (element-wise, so the thread count cannot change a bit).
+    run on ``DAJIN2_B200_MLP_THREADS`` threads (element-wise, so the thread count cannot change a bit), each thread
+    also summing the leaves of numpy's pairwise sums that lie in its rows;
+  * the hidden layers' forward pass and the whole backward pass (deltas and all 27 reduction chains in one sweep) run on
+    one thread with AVX2 + FMA, vector lanes being different output elements, never a split sum: spread over threads
+    these passes were bounded by their arrays travelling between cores (``scripts/mlp_breakdown.py``,
+    ``scripts/mlp_concurrency.py``: the longest of three concurrent fits 246 -> 195 ms on the 16-core B200 host).
 
 Trust, but verify: every fit evaluates scikit-learn's original ``_loss_grad_lbfgs`` at the first and at the last
 iterate and compares loss and gradient bit for bit; on any difference (another numpy / scipy / libm than the ones
@@ -42,13 +47,16 @@ _c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
 def build(force: bool = False) -> Path:
-    """gcc -O2 without fast-math and without FMA contraction: the C code must round exactly like numpy does."""
+    """gcc -O3 without fast-math and without FMA contraction: the C code must round exactly like numpy does."""
     if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime for src in SOURCES):
         tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
-        flags = ["-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp"]
+        flags = ["-O3", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp"]
         try:
-            if " fma " in Path("/proc/cpuinfo").read_text():
+            cpu = Path("/proc/cpuinfo").read_text()
+            if " fma " in cpu:
                 flags.append("-mfma")  # fma() inlines to vfmadd; without it libm's (exact, slow) fma is called
+            if " avx2 " in cpu:
+                flags.append("-mavx2")  # the loops over rows vectorise (rows are independent: same bits)
         except OSError:
             pass
         subprocess.run(["gcc", *flags, "-o", str(tmp), *map(str, SOURCES), "-lm"], check=True)
@@ -71,8 +79,10 @@ def default_threads() -> int:
 def load_host_lib():
     global _lib
     if _lib is None:
-        build()
-        lib = ctypes.CDLL(str(LIB))
+        alt = os.environ.get("DAJIN2_B200_HOSTLIB")  # an alternative build of the same helper (experiments under scripts/)
+        if not alt:
+            build()
+        lib = ctypes.CDLL(alt or str(LIB))
         vp, i64, ci, cd = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
         lib.fm_set_threads.argtypes = [ci]
         lib.fm_set_threads.restype = None

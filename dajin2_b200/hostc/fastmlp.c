@@ -17,10 +17,12 @@
  *   - expit and xlogy are scipy.special's: 1 / (1 + exp(-x)) and x * log(y) with libm's exp / log.
  * None of this is taken on trust: dajin2_b200/fastmlp.py compares loss and gradient with scikit-learn's own function
  * at the first and the last iterate of every fit and falls back to scikit-learn on any difference.
- * Compile WITHOUT -ffast-math, with -ffp-contract=off (and -mfma where the CPU has it).
+ * Compile WITHOUT -ffast-math, with -ffp-contract=off (and -mfma -mavx2 where the CPU has them: the one-thread
+ * vector passes of the reference's 2-5-2 model below need both; without them the generic threaded passes run).
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #ifdef _OPENMP
 #include <omp.h>
@@ -82,12 +84,115 @@ static inline __attribute__((always_inline)) void forward_rows(
     }
 }
 
+/* ---- the reference's model (2 inputs, hidden layers of 5 and 2) on ONE thread with AVX2 + FMA: the lanes of a vector
+ * are different output elements (the units of a layer, the chains of a reduction), never a split of one sum, so every
+ * element sees the scalar code's operations in the scalar code's order.  Measured on the 16-core host of a B200 box:
+ * spreading these two passes over threads makes the arrays they share (a1, a2 and the deltas) travel from core to
+ * core every evaluation, and that traffic, not the arithmetic, bounded them (scripts/mlp_breakdown.py). ---- */
+#if defined(__AVX2__) && defined(__FMA__)
+#include <immintrin.h>
+#define FM_HAVE_252_AVX2 1
+
+static inline __m256d relu4(__m256d v) { /* v unless v < 0 (NaN and -0.0 pass through) */
+    return _mm256_blendv_pd(v, _mm256_setzero_pd(), _mm256_cmp_pd(v, _mm256_setzero_pd(), _CMP_LT_OQ));
+}
+
+static void forward_252(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, const double *W1, const double *b1,
+                        const double *W2, const double *b2, double *a1, double *a2) {
+    const __m256d w0 = _mm256_loadu_pd(W1), w1 = _mm256_loadu_pd(W1 + 5), bb = _mm256_loadu_pd(b1);
+    const double w04 = W1[4], w14 = W1[9], b4 = b1[4];
+    const __m128d b2v = _mm_loadu_pd(b2);
+    __m128d w2[5];
+    for (int k = 0; k < 5; k++) w2[k] = _mm_loadu_pd(W2 + 2 * k);
+    const __m256d zero = _mm256_setzero_pd();
+    for (int64_t i = 0; i < n; i++) {
+        const double x0 = X[i * xs_row], x1 = X[i * xs_row + xs_col];
+        /* a1[i][j] = relu((0 + x0 W1[0][j]) + x1 W1[1][j] ... as one fma chain over the inputs, + b1[j]) */
+        const __m256d acc = _mm256_fmadd_pd(_mm256_set1_pd(x1), w1, _mm256_fmadd_pd(_mm256_set1_pd(x0), w0, zero));
+        const __m256d h = relu4(_mm256_add_pd(acc, bb));
+        const double h4 = relu(fma(x1, w14, fma(x0, w04, 0.0)) + b4);
+        _mm256_storeu_pd(a1 + i * 5, h);
+        a1[i * 5 + 4] = h4;
+        /* a2[i][j]: fma chain over the five hidden units, both outputs side by side */
+        double hh[4];
+        _mm256_storeu_pd(hh, h);
+        __m128d o = _mm_fmadd_pd(_mm_set1_pd(hh[0]), w2[0], _mm_setzero_pd());
+        o = _mm_fmadd_pd(_mm_set1_pd(hh[1]), w2[1], o);
+        o = _mm_fmadd_pd(_mm_set1_pd(hh[2]), w2[2], o);
+        o = _mm_fmadd_pd(_mm_set1_pd(hh[3]), w2[3], o);
+        o = _mm_fmadd_pd(_mm_set1_pd(h4), w2[4], o);
+        o = _mm_add_pd(o, b2v);
+        o = _mm_blendv_pd(o, _mm_setzero_pd(), _mm_cmplt_pd(o, _mm_setzero_pd()));
+        _mm_storeu_pd(a2 + i * 2, o);
+    }
+}
+
+/* Backward pass and all 27 reduction chains in one sweep: d2 = d3 W3^T masked by a2 and d1 = d2 W2^T masked by a1 are
+ * formed per row in registers and feed g2 = a1^T d2, g1 = X^T d1 and the column sums of d2 and d1 directly. */
+static void backward_252(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, const double *a1, const double *a2,
+                         const double *W2, const double *W3, const double *d3, double *cs2, double *g2, double *cs1,
+                         double *g1) {
+    const __m256d zero = _mm256_setzero_pd();
+    const __m256d wa = _mm256_set_pd(W2[6], W2[4], W2[2], W2[0]), wb = _mm256_set_pd(W2[7], W2[5], W2[3], W2[1]);
+    const double wa4 = W2[8], wb4 = W2[9], w30 = W3[0], w31 = W3[1];
+    __m256d c0 = zero, c1 = zero, p0 = zero, p1 = zero, t = zero; /* chains of units 0..3 */
+    double c40 = 0, c41 = 0, p04 = 0, p14 = 0, t4 = 0, s0 = 0, s1 = 0; /* unit 4 and the two sums of d2 */
+    for (int64_t i = 0; i < n; i++) {
+        const double g = d3[i];
+        const double e0 = a2[2 * i] == 0.0 ? 0.0 : 0.0 + g * w30;
+        const double e1 = a2[2 * i + 1] == 0.0 ? 0.0 : 0.0 + g * w31;
+        const __m256d e0v = _mm256_set1_pd(e0), e1v = _mm256_set1_pd(e1);
+        const __m256d a = _mm256_loadu_pd(a1 + i * 5);
+        const double a4 = a1[i * 5 + 4];
+        __m256d d = _mm256_fmadd_pd(e1v, wb, _mm256_fmadd_pd(e0v, wa, zero));
+        d = _mm256_blendv_pd(d, zero, _mm256_cmp_pd(a, zero, _CMP_EQ_OQ));
+        const double d4 = a4 == 0.0 ? 0.0 : fma(e1, wb4, fma(e0, wa4, 0.0));
+        const double x0 = X[i * xs_row], x1 = X[i * xs_row + xs_col];
+        c0 = _mm256_fmadd_pd(a, e0v, c0);
+        c1 = _mm256_fmadd_pd(a, e1v, c1);
+        c40 = fma(a4, e0, c40);
+        c41 = fma(a4, e1, c41);
+        p0 = _mm256_fmadd_pd(_mm256_set1_pd(x0), d, p0);
+        p1 = _mm256_fmadd_pd(_mm256_set1_pd(x1), d, p1);
+        p04 = fma(x0, d4, p04);
+        p14 = fma(x1, d4, p14);
+        s0 += e0;
+        s1 += e1;
+        t = _mm256_add_pd(t, d);
+        t4 += d4;
+    }
+    double v0[4], v1[4];
+    _mm256_storeu_pd(v0, c0);
+    _mm256_storeu_pd(v1, c1);
+    for (int k = 0; k < 4; k++) {
+        g2[2 * k] = v0[k];
+        g2[2 * k + 1] = v1[k];
+    }
+    g2[8] = c40;
+    g2[9] = c41;
+    _mm256_storeu_pd(g1, p0);
+    g1[4] = p04;
+    _mm256_storeu_pd(g1 + 5, p1);
+    g1[9] = p14;
+    cs2[0] = s0;
+    cs2[1] = s1;
+    _mm256_storeu_pd(cs1, t);
+    cs1[4] = t4;
+}
+#endif
+
 #define FM_CHUNKS 64
 
 int fm_forward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n_in, const double *W1, const double *b1,
                int h1, const double *W2, const double *b2, int h2, double *a1, double *a2) {
     if (h1 > FM_MAX_H || h2 > FM_MAX_H || n_in > FM_MAX_H) return 1;
     const int64_t step = (n + FM_CHUNKS - 1) / FM_CHUNKS;
+#ifdef FM_HAVE_252_AVX2
+    if (n_in == 2 && h1 == 5 && h2 == 2) {
+        forward_252(X, xs_row, xs_col, n, W1, b1, W2, b2, a1, a2);
+        return 0;
+    }
+#endif
     if (n_in == 2 && h1 == 5 && h2 == 2) {
 #pragma omp parallel for num_threads(g_threads) schedule(static)
         for (int c = 0; c < FM_CHUNKS; c++)
@@ -104,25 +209,72 @@ int fm_forward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n
 /* Output unit: a = expit(z + b); binary_log_loss(y, a); delta = a - y.
  * Returns -mean(xlogy(y, p) + xlogy(1 - y, 1 - p)) with p = clip(a, eps, 1 - eps); *sum_delta = np.sum(delta, axis=0).
  * z is overwritten with a; `terms` is scratch of n doubles. */
+/* numpy's pairwise sum splits a long array in halves (the first rounded down to a multiple of 8) until at most 128
+ * elements are left: the leaves are independent sums, only their combination is a fixed tree.  So the leaves are
+ * summed by the threads that produced their elements, and one thread adds the leaf sums in numpy's order. */
+static int64_t leaves_of(int64_t lo, int64_t n, int64_t *off, int64_t *len, int64_t k) {
+    if (n <= 128) {
+        off[k] = lo;
+        len[k] = n;
+        return k + 1;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    k = leaves_of(lo, n2, off, len, k);
+    return leaves_of(lo + n2, n - n2, off, len, k);
+}
+
+static double combine_leaves(const double *leaf, int64_t n, int64_t *cursor) {
+    if (n <= 128) return leaf[(*cursor)++];
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    const double left = combine_leaves(leaf, n2, cursor);
+    return left + combine_leaves(leaf, n - n2, cursor);
+}
+
+static int64_t g_leaf_n = -1, g_n_leaves = 0, *g_leaf_off = 0, *g_leaf_len = 0;
+static double *g_leaf_a = 0, *g_leaf_b = 0;
+
 double fm_output(double *z, double b, const double *y, int64_t n, double *delta, double *terms, double *sum_delta) {
     const double eps = 2.220446049250313e-16;
     const double hi = 1.0 - eps;
-#pragma omp parallel for num_threads(g_threads) schedule(static)
-    for (int64_t i = 0; i < n; i++) {
-        double v = z[i] + b;
-        double a = 1.0 / (1.0 + exp(-v));
-        z[i] = a;
-        double p = a < eps ? eps : (a > hi ? hi : a);
-        double yi = y[i], t1, t2;
-        /* scipy.special.xlogy: 0 when x == 0 and y is not NaN, else x * log(y) */
-        t1 = (yi == 0.0 && p == p) ? 0.0 : yi * log(p);
-        double q = 1.0 - p, w = 1.0 - yi;
-        t2 = (w == 0.0 && q == q) ? 0.0 : w * log(q);
-        terms[i] = t1 + t2;
-        delta[i] = a - yi;
+    if (n != g_leaf_n) { /* the leaf table of this length (one training-set size per fit) */
+        const int64_t cap = n / 32 + 4;
+        free(g_leaf_off); free(g_leaf_len); free(g_leaf_a); free(g_leaf_b);
+        g_leaf_off = (int64_t *)malloc(sizeof(int64_t) * cap);
+        g_leaf_len = (int64_t *)malloc(sizeof(int64_t) * cap);
+        g_leaf_a = (double *)malloc(sizeof(double) * cap);
+        g_leaf_b = (double *)malloc(sizeof(double) * cap);
+        g_n_leaves = n > 0 ? leaves_of(0, n, g_leaf_off, g_leaf_len, 0) : 0;
+        g_leaf_n = n;
     }
-    *sum_delta = pairwise_sum(delta, n);
-    return -(pairwise_sum(terms, n) / (double)n);
+#pragma omp parallel for num_threads(g_threads) schedule(static)
+    for (int64_t l = 0; l < g_n_leaves; l++) {
+        const int64_t lo = g_leaf_off[l], m = g_leaf_len[l];
+        for (int64_t i = lo; i < lo + m; i++) {
+            double v = z[i] + b;
+            double a = 1.0 / (1.0 + exp(-v));
+            z[i] = a;
+            double p = a < eps ? eps : (a > hi ? hi : a);
+            double yi = y[i], t1, t2;
+            /* scipy.special.xlogy: 0 when x == 0 and y is not NaN, else x * log(y) */
+            t1 = (yi == 0.0 && p == p) ? 0.0 : yi * log(p);
+            double q = 1.0 - p, w = 1.0 - yi;
+            t2 = (w == 0.0 && q == q) ? 0.0 : w * log(q);
+            terms[i] = t1 + t2;
+            delta[i] = a - yi;
+        }
+        g_leaf_a[l] = pairwise_sum(delta + lo, m);
+        g_leaf_b[l] = pairwise_sum(terms + lo, m);
+    }
+    if (n <= 0) {
+        *sum_delta = 0.0;
+        return -(0.0 / (double)n);
+    }
+    int64_t cursor = 0;
+    *sum_delta = combine_leaves(g_leaf_a, n, &cursor);
+    cursor = 0;
+    return -(combine_leaves(g_leaf_b, n, &cursor) / (double)n);
 }
 
 /* Backward pass below the output unit (d3 = delta of the output unit, n x 1; W3 = h2 weights of the output unit):
@@ -232,6 +384,12 @@ int fm_backward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int 
                 double *cs2, double *g2, double *cs1, double *g1) {
     if (h1 > FM_MAX_H || h2 > FM_MAX_H || n_in > FM_MAX_H) return 1;
     const int64_t step = (n + FM_CHUNKS - 1) / FM_CHUNKS;
+#ifdef FM_HAVE_252_AVX2
+    if (n_in == 2 && h1 == 5 && h2 == 2) {
+        backward_252(X, xs_row, xs_col, n, a1, a2, W2, W3, d3, cs2, g2, cs1, g1);
+        return 0;
+    }
+#endif
     if (n_in == 2 && h1 == 5 && h2 == 2) {
 #pragma omp parallel num_threads(g_threads)
         {
