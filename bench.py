@@ -396,6 +396,8 @@ def run_ours(args):
         for k, v in last.timings.items():
             if isinstance(v, float):
                 stage[k] = stage.get(k, 0.0) + v
+        if rank == 0 and os.environ.get("DAJIN2_B200_BENCH_TRACE"):
+            print("step", {k: round(v, 2) for k, v in last.timings.items() if isinstance(v, float)}, file=sys.stderr)
     end.record()
     barrier()
     clocks = sampler.stop() if sampler else None
