@@ -378,14 +378,21 @@ def kmer_percentages(rows, loci_t) -> list[dict[str, float]]:
     return [{k: round(v / coverage * 100, 3) for k, v in c.items()} for c in counts]
 
 
-def make_score(rows_sample, rows_control, loci_t, knockin: set[int]) -> list[dict[str, float]]:
-    """score_handler.py:115-127."""
-    ps = kmer_percentages(rows_sample, loci_t)
-    pc = kmer_percentages(rows_control, loci_t)
-    # :24-31 Counter subtraction keeps strictly positive differences; knock-in loci keep the sample dict
-    diff = [dict(s) if i in knockin else dict(Counter(s) - Counter(c)) for i, (s, c) in enumerate(zip(ps, pc))]
-    kept = [{k: v for k, v in d.items() if v > 0.5} for d in diff]  # :34-35
-    # :60-107 every '+'-centred k-mer inside a run of consecutive '+' loci takes the run's maximum
+def subtract_percentage(percent_sample, percent_control, knockin: set[int]) -> list[dict[str, float]]:
+    """score_handler.py:24-31 — Counter subtraction keeps strictly positive differences; knock-in loci keep the sample
+    dict."""
+    return [dict(s) if i in knockin else dict(Counter(s) - Counter(c))
+            for i, (s, c) in enumerate(zip(percent_sample, percent_control))]
+
+
+def discard_common_error(percent_subtracted, threshold: float = 0.5) -> list[dict[str, float]]:
+    """score_handler.py:34-35."""
+    return [{k: v for k, v in d.items() if v > threshold} for d in percent_subtracted]
+
+
+def update_insertion_score(percent_discarded, loci_t) -> list[dict[str, float]]:
+    """score_handler.py:60-107 — every '+'-centred k-mer inside a run of consecutive '+' loci takes the run's maximum."""
+    kept = [dict(d) for d in percent_discarded]
     plus_idx = sorted(i for i, m in enumerate(loci_t) if "+" in m)
     for _, grp in groupby(enumerate(plus_idx), lambda t: t[0] - t[1]):
         run = [i for _, i in grp]
@@ -398,8 +405,20 @@ def make_score(rows_sample, rows_control, loci_t, knockin: set[int]) -> list[dic
             for k in kept[i]:
                 if k.split(",")[1].startswith("+"):
                     kept[i][k] = top
-    # :38-52 drop '='-centred k-mers
-    return [{k: v for k, v in d.items() if not k.split(",")[1].startswith("=")} for d in kept]
+    return kept
+
+
+def discard_matches_and_ns(percent_discarded) -> list[dict[str, float]]:
+    """score_handler.py:38-52 — drop the k-mers whose centre token starts with '='."""
+    return [{k: v for k, v in d.items() if not k.split(",")[1].startswith("=")} for d in percent_discarded]
+
+
+def make_score(rows_sample, rows_control, loci_t, knockin: set[int]) -> list[dict[str, float]]:
+    """score_handler.py:115-127."""
+    ps = kmer_percentages(rows_sample, loci_t)
+    pc = kmer_percentages(rows_control, loci_t)
+    kept = discard_common_error(subtract_percentage(ps, pc, knockin))
+    return discard_matches_and_ns(update_insertion_score(kept, loci_t))
 
 
 def annotate_score(rows, score: list[dict[str, float]], loci_t, is_control: bool = False):

@@ -235,3 +235,94 @@ def test_consensus_anomal_loci_match_reference():
     thresholds = {k: float.fromhex(v) for k, v in g["consensus_thresholds"].items()}
     got = orc.extract_anomal_loci(norm_s, norm_c, thresholds, is_consensus=True)
     assert {k: sorted(v) for k, v in got.items()} == g["consensus_anomal_loci"]
+
+
+# --- further known-answer vectors restated from the reference's own test-suite ---------------
+
+
+@pytest.mark.parametrize("midsv, sv_type, loci, converter, expected", [  # tests/src/preprocess/test_sv_detector.py:6-71
+    ("=G,-T,-T,-T,-T,-T,-T,-T,-T,-T,-T,=G", "deletion", [set()] + [{"+", "-", "*"}] * 10 + [set()], None, {1: 10}),
+    ("=G,-T,-T,-T,-T,-T,-T,-T,-T,-T,=G", "deletion", [set()] + [{"+", "-", "*"}] * 9 + [set()], None, {}),
+    ("=G,=t,=t,=t,=t,=t,=t,=t,=t,=t,=t,=G", "inversion", [set()] * 12, None, {1: 10}),
+    ("=G,=t,=t,=t,=t,=t,=t,=t,=t,=t,=G", "inversion", [set()] * 11, None, {}),
+    ("=G,+T|+T|+T|+T|+T|+T|+T|+T|+T|+T|,+T,=G", "insertion", [set(), {"+", "-"}, set(), set()], None, {1: 10}),
+    ("=G,+T|+T|+T|+T|+T|,+T,=G", "insertion", [set(), {"+", "-"}, set(), set()], None, {}),
+    ("=G,-T,-T,-T,-T,-T,-T,-T,-T,-T,-T,=G", "deletion", [set()] + [{"+", "-", "*"}] * 10 + [set()], {1: 100}, {100: 10}),
+])
+def test_kat_get_index_and_sv_size(midsv, sv_type, loci, converter, expected):
+    assert orc.index_and_sv_size(midsv, sv_type, loci, converter) == expected
+
+
+def test_kat_strand_counts_and_biases():  # tests/src/clustering/test_strand_bias_handler.py:11-46
+    assert orc.strand_counts_by_label(["+", "-", "+", "+"], [1, 2, 1, 3]) == {
+        1: {"+": 2, "-": 0}, 2: {"+": 0, "-": 1}, 3: {"+": 1, "-": 0}}
+    assert orc.strand_counts_by_label(["+", "+"], [0, 0]) == {0: {"+": 2, "-": 0}}
+    assert orc.strand_counts_by_label(["-", "-"], [1, 1]) == {1: {"+": 0, "-": 2}}
+    assert orc.strand_counts_by_label([], []) == {}
+    all_s = {"+": 100, "-": 100}
+    assert orc.strand_biases({1: {"+": 100, "-": 100}}, all_s) == {1: False}
+    assert orc.strand_biases({1: {"+": 100, "-": 1}}, all_s) == {1: True}
+    assert orc.strand_biases({1: {"+": 50, "-": 150}}, {"+": 150, "-": 50}) == {1: False}
+
+
+def test_kat_normalize_and_minimize():  # tests/.../test_indel_counter.py:71-141
+    norm = orc.normalize_indels({"=": [0, 0, 0], "+": [5, 0, 0], "-": [0, 7, 0], "*": [0, 0, 9]})
+    assert norm["+"][0] == 100.0 and norm["-"][1] == 100.0 and norm["*"][2] == 100.0
+    control = {"+": np.array([10.0, 20.0, 5.0]), "-": np.array([15.0, 5.0, 25.0]), "*": np.array([8.0, 12.0, 3.0])}
+    sample = {"+": np.array([8.0, 25.0, 10.0]), "-": np.array([20.0, 3.0, 15.0]), "*": np.array([10.0, 8.0, 5.0])}
+    got = orc.minimize_mutation_counts(control, sample)
+    assert got["+"].tolist() == [8.0, 20.0, 5.0] and got["-"].tolist() == [15.0, 3.0, 15.0]
+    assert got["*"].tolist() == [8.0, 8.0, 3.0]
+
+
+def test_kat_homopolymer_regions():  # tests/src/preprocess/test_homopolymer_handler.py:19-70 through the error filter
+    """Regions of >= 4 equal bases; a region is exempt only when BOTH start-1 and end+1 are candidate loci; loci
+    start..end inclusive are reported when the sample and control profiles are similar inside the region."""
+    seq = "ACGTAAAACCCCTTTTTGGGGAAAA"
+    L = len(seq)
+    flat = {op: np.full(L, 1.0) for op in "+-*"}
+    none = {op: set() for op in "+-*"}
+    got = orc.homopolymer_errors(seq, flat, flat, none)
+    want = set(range(4, 9)) | set(range(8, 13)) | set(range(12, 18)) | set(range(17, 22)) | set(range(21, 26))
+    assert got["+"] == want and got["-"] == want and got["*"] == want
+    exempt = {"+": {3, 9}, "-": set(), "*": set()}  # AAAA at 4..8: start-1 = 3 and end+1 = 9 are both candidates
+    got = orc.homopolymer_errors(seq, flat, flat, exempt)
+    assert 4 not in got["+"] and 5 not in got["+"] and 4 in got["-"]
+    assert orc.homopolymer_errors("ACGTACGTACGT", {op: np.ones(12) for op in "+-*"}, {op: np.ones(12) for op in "+-*"},
+                                  none) == {"+": set(), "-": set(), "*": set()}
+
+
+def test_kat_merge_minor_alleles():  # tests/src/classification/test_allele_merger.py:25-47
+    scores = [
+        {"QNAME": "read3", "MIDSV": "=A", "SCORE": 0, "ALLELE": "minor"},
+        {"QNAME": "read1", "MIDSV": "=A", "SCORE": 0, "ALLELE": "major"},
+        {"QNAME": "read2", "MIDSV": "=A", "SCORE": 0, "ALLELE": "major"},
+        {"QNAME": "read3", "MIDSV": "=A", "SCORE": -1, "ALLELE": "major"},
+        {"QNAME": "read1", "MIDSV": "=A", "SCORE": -1, "ALLELE": "minor"},
+        {"QNAME": "read2", "MIDSV": "=A", "SCORE": -1, "ALLELE": "minor"},
+    ]
+    result = orc.merge_minor_alleles(scores, threshold=2)
+    read3 = [s for s in result if s["QNAME"] == "read3"]
+    assert len(result) == len(scores) and len(read3) == 2
+    assert {s["ALLELE"] for s in read3} == {"major"}
+    assert max(read3, key=lambda s: s["SCORE"])["ALLELE"] == "major"
+    assert scores[0]["ALLELE"] == "minor" and scores[0]["SCORE"] == 0
+
+
+def test_kat_score_handler_steps():  # tests/src/clustering/test_score_handler.py:30-120
+    got = orc.subtract_percentage([{"A": 40, "T": 60}, {"C": 40, "G": 60}, {"A": 30, "T": 70}],
+                                  [{"A": 30, "T": 50}, {"C": 30, "G": 70}, {"A": 20, "T": 80}], {1})
+    assert got == [{"A": 10, "T": 10}, {"C": 40, "G": 60}, {"A": 10}]
+    got = orc.discard_common_error([{"A": 0.4, "T": 99.6}, {"C": 0.5, "G": 99.5}, {"A": 0.6, "T": 99.4}], 0.5)
+    assert got == [{"T": 99.6}, {"G": 99.5}, {"A": 0.6, "T": 99.4}]
+    got = orc.discard_matches_and_ns([{"=A,=A,=A": 10, "=A,+I,=A": 20}, {"=C,=C,=C": 15, "=C,+I,=C": 25},
+                                      {"=A,=N,=A": 10, "=A,+I,=A": 10}, {"=A,=A,=A": 10, "=A,=N,=A": 40}, {}])
+    assert got == [{"=A,+I,=A": 20}, {"=C,+I,=C": 25}, {"=A,+I,=A": 10}, {}, {}]
+    percent = [{"=A,=A,=A": 10, "=A,+I,=A": 20}, {"=C,=C,=C": 15, "=C,+I,=C": 25}, {"=A,=A,=A": 10, "=A,+I,=A": 10},
+               {"=A,=A,=A": 10, "=A,+I,=A": 40}]
+    got = orc.update_insertion_score(percent, [set("+"), set(), set("+"), set("+")])
+    assert got == [{"=A,=A,=A": 10, "=A,+I,=A": 20}, {"=C,=C,=C": 15, "=C,+I,=C": 25},
+                   {"=A,=A,=A": 10, "=A,+I,=A": 40}, {"=A,=A,=A": 10, "=A,+I,=A": 40}]
+    # call_count + call_percent (:4-28) through the oracle's k-mer route: every locus selected, so tokens stand alone
+    counts = [dict(__import__("collections").Counter(col)) for col in zip(["=A", "*ag", "-gg", "=T"], ["=A", "-a", "-gg", "*ag"])]
+    assert counts == [{"=A": 2}, {"*ag": 1, "-a": 1}, {"-gg": 2}, {"=T": 1, "*ag": 1}]
