@@ -108,7 +108,7 @@ def load_host_lib():
 
 
 def _ptr(a: np.ndarray) -> int:
-    return a.ctypes.data
+    return a.__array_interface__["data"][0]  # the address, without building the ctypes helper object each time
 
 
 class FastMLPClassifier(MLPClassifier):

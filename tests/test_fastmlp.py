@@ -89,3 +89,22 @@ def test_fallback_when_the_fused_path_does_not_apply():
 def test_fast_path_is_taken_here():
     X, y, _ = training_set(300, 5)
     assert _fit(fastmlp.FastMLPClassifier, X, y).fast_path_used_
+
+
+def test_fit_predict_equals_the_reference_call():
+    """mlp_pool.fit_predict (labels as an array, fused evaluation) proposes exactly the candidate loci of the reference's
+    own call sequence (anomaly_detector.py:61-94, restated in the oracle with scikit-learn's MLPClassifier)."""
+    import numpy as np
+
+    from dajin2_b200 import mlp_pool
+    from oracle import dajin2_oracle as orc
+
+    rng = np.random.default_rng(12)
+    for L, thr in ((700, 0.1), (1500, 10.0)):
+        control = np.abs(rng.normal(0.8, 0.15, L))
+        sample = control + rng.normal(0, 0.05, L)
+        sample[[L // 5, L // 3, L // 2]] += [25, 15, 60]
+        sample = np.clip(sample, 0, 100)
+        control = np.minimum(control, sample)
+        got = mlp_pool.fit_predict(sample, control, thr)
+        assert set(np.flatnonzero(got).tolist()) == set(orc.mlp_candidates(sample, control, thr))
