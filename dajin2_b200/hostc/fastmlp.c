@@ -105,15 +105,55 @@ static void forward_252(const double *X, int64_t xs_row, int64_t xs_col, int64_t
     __m128d w2[5];
     for (int k = 0; k < 5; k++) w2[k] = _mm_loadu_pd(W2 + 2 * k);
     const __m256d zero = _mm256_setzero_pd();
-    for (int64_t i = 0; i < n; i++) {
+    int64_t i = 0;
+    /* four rows at a time, one row per lane (each lane = the scalar code on its row), results transposed back into the
+     * row-major a1 / a2 the backward pass and numpy read */
+    for (; i + 4 <= n; i += 4) {
+        __m256d x0v, x1v;
+        if (xs_row == 2 && xs_col == 1) { /* row-major X, as scikit-learn hands it over */
+            const __m256d p = _mm256_loadu_pd(X + 2 * i), q = _mm256_loadu_pd(X + 2 * i + 4);
+            x0v = _mm256_permute4x64_pd(_mm256_unpacklo_pd(p, q), 0xD8);
+            x1v = _mm256_permute4x64_pd(_mm256_unpackhi_pd(p, q), 0xD8);
+        } else {
+            x0v = _mm256_set_pd(X[(i + 3) * xs_row], X[(i + 2) * xs_row], X[(i + 1) * xs_row], X[i * xs_row]);
+            x1v = _mm256_set_pd(X[(i + 3) * xs_row + xs_col], X[(i + 2) * xs_row + xs_col], X[(i + 1) * xs_row + xs_col],
+                                X[i * xs_row + xs_col]);
+        }
+        __m256d h[5];
+        for (int j = 0; j < 5; j++)
+            h[j] = relu4(_mm256_add_pd(_mm256_fmadd_pd(x1v, _mm256_set1_pd(W1[5 + j]),
+                                                       _mm256_fmadd_pd(x0v, _mm256_set1_pd(W1[j]), zero)),
+                                       _mm256_set1_pd(b1[j])));
+        __m256d o0 = zero, o1 = zero;
+        for (int k = 0; k < 5; k++) {
+            o0 = _mm256_fmadd_pd(h[k], _mm256_set1_pd(W2[2 * k]), o0);
+            o1 = _mm256_fmadd_pd(h[k], _mm256_set1_pd(W2[2 * k + 1]), o1);
+        }
+        o0 = relu4(_mm256_add_pd(o0, _mm256_set1_pd(b2[0])));
+        o1 = relu4(_mm256_add_pd(o1, _mm256_set1_pd(b2[1])));
+        const __m256d t0 = _mm256_unpacklo_pd(h[0], h[1]), t1 = _mm256_unpackhi_pd(h[0], h[1]);
+        const __m256d t2 = _mm256_unpacklo_pd(h[2], h[3]), t3 = _mm256_unpackhi_pd(h[2], h[3]);
+        _mm256_storeu_pd(a1 + 5 * i, _mm256_permute2f128_pd(t0, t2, 0x20));
+        _mm256_storeu_pd(a1 + 5 * i + 5, _mm256_permute2f128_pd(t1, t3, 0x20));
+        _mm256_storeu_pd(a1 + 5 * i + 10, _mm256_permute2f128_pd(t0, t2, 0x31));
+        _mm256_storeu_pd(a1 + 5 * i + 15, _mm256_permute2f128_pd(t1, t3, 0x31));
+        double h4[4];
+        _mm256_storeu_pd(h4, h[4]);
+        a1[5 * i + 4] = h4[0];
+        a1[5 * i + 9] = h4[1];
+        a1[5 * i + 14] = h4[2];
+        a1[5 * i + 19] = h4[3];
+        const __m256d lo = _mm256_unpacklo_pd(o0, o1), hi = _mm256_unpackhi_pd(o0, o1);
+        _mm256_storeu_pd(a2 + 2 * i, _mm256_permute2f128_pd(lo, hi, 0x20));
+        _mm256_storeu_pd(a2 + 2 * i + 4, _mm256_permute2f128_pd(lo, hi, 0x31));
+    }
+    for (; i < n; i++) { /* the last rows, one at a time with the units of a layer in the lanes */
         const double x0 = X[i * xs_row], x1 = X[i * xs_row + xs_col];
-        /* a1[i][j] = relu((0 + x0 W1[0][j]) + x1 W1[1][j] ... as one fma chain over the inputs, + b1[j]) */
         const __m256d acc = _mm256_fmadd_pd(_mm256_set1_pd(x1), w1, _mm256_fmadd_pd(_mm256_set1_pd(x0), w0, zero));
         const __m256d h = relu4(_mm256_add_pd(acc, bb));
         const double h4 = relu(fma(x1, w14, fma(x0, w04, 0.0)) + b4);
         _mm256_storeu_pd(a1 + i * 5, h);
         a1[i * 5 + 4] = h4;
-        /* a2[i][j]: fma chain over the five hidden units, both outputs side by side */
         double hh[4];
         _mm256_storeu_pd(hh, h);
         __m128d o = _mm_fmadd_pd(_mm_set1_pd(hh[0]), w2[0], _mm_setzero_pd());
