@@ -54,3 +54,81 @@ def get_thresholds(path_indels_normalized_sample, path_indels_normalized_control
         kmeans = MiniBatchKMeans(n_clusters=2, random_state=0).fit(diff.reshape(-1, 1))
         thresholds[mut] = max(kmeans.cluster_centers_.mean(), 10)
     return thresholds
+
+
+# ---------------------------------------------------------------------------------------------------------
+# functions of the consensus stage that are views of the code matrix (<= 1000 reads per cluster, core.py:250):
+# the token loops of the reference become array operations on the uint8 matrix the encoder already produced
+# ---------------------------------------------------------------------------------------------------------
+
+
+def _encoded(records) -> tuple:
+    """(EncodedReads, code matrix uint8[N, L] on the host) of in-memory MIDSV records."""
+    from . import engine
+    from .ingest import pack_rows
+
+    recs = list(records)
+    n_loci = recs[0]["MIDSV"].count(",") + 1
+    enc = engine.EncodedReads(pack_rows([r["MIDSV"] for r in recs], [r.get("STRAND", "+") for r in recs]), n_loci)
+    return enc, enc.codes[: enc.n_reads, :n_loci].cpu().numpy()
+
+
+def _op_classes(codes_host: np.ndarray) -> dict[str, np.ndarray]:
+    anchor = codes_host & 0x7F
+    ins = (codes_host & 0x80) != 0
+    return {"+": ins, "-": ~ins & (anchor >= 10) & (anchor < 20), "*": ~ins & (anchor >= 20) & (anchor < 70)}
+
+
+def onehot_by_mutations(midsv_sample) -> dict[str, np.ndarray]:
+    """similarity_searcher.py:18-25 — per mutation type the reads x loci 0/1 matrix of ``token.startswith(mut)``: three
+    comparisons on the code matrix."""
+    _, codes_host = _encoded(midsv_sample)
+    return {mut: m.astype(np.int64) for mut, m in _op_classes(codes_host).items()}
+
+
+def call_percentage(midsv_tags: list[list[str]], mutation_loci: list[set[str]], sequence: str) -> list[dict[str, float]]:
+    """consensus/consensus.py:19-75 (convert_to_percentage, remove_all_n, adjust_to_100_percent) — the position weight
+    matrix of a cluster.  Token identities come from the code matrix (the raw text is fetched only for insertions);
+    the percentages are the reference's own float operations: ``1 / coverage * 100`` added once per read, in read
+    order, so a token seen k times holds the k-fold repeated sum, and dict order is first appearance."""
+    from . import codes as codemod
+
+    enc, cm = _encoded({"MIDSV": ",".join(tags)} for tags in midsv_tags)
+    n, n_loci = cm.shape
+    step = 1 / n * 100
+    repeated = np.zeros(n + 1, dtype=np.float64)  # repeated[k] = 0.0 + step + step + ... (k times), as count_cs[cs] += step
+    acc = 0.0
+    for k in range(1, n + 1):
+        acc += step
+        repeated[k] = acc
+    masked = np.zeros((n_loci,), dtype=np.uint8)
+    for i, muts in enumerate(mutation_loci[:n_loci]):
+        masked[i] = ("+" in muts) | (("-" in muts) << 1) | (("*" in muts) << 2)
+    classes = _op_classes(cm)
+    # tokens whose operator is not a mutation of the locus read as the reference base (:33-36)
+    as_ref = (classes["+"] & ((masked & 1) == 0)) | (classes["-"] & ((masked & 2) == 0)) | (classes["*"] & ((masked & 4) == 0))
+    ins_kept = classes["+"] & ~as_ref
+    rr, ll = np.nonzero(ins_kept)
+    raw = dict(zip(zip(rr.tolist(), ll.tolist()), enc.fetch_tokens(rr.astype(np.int32), ll.astype(np.int32)))) if rr.size else {}
+    out = []
+    for i in range(n_loci):
+        col, ref_col = cm[:, i], as_ref[:, i]
+        ref_tok = "=" + sequence[i].upper()
+        counts: dict[str, int] = {}
+        if not ins_kept[:, i].any() and not ref_col.any():  # the usual locus: a handful of distinct codes
+            values, first, cnt = np.unique(col, return_index=True, return_counts=True)
+            for j in np.argsort(first, kind="stable"):
+                counts[codemod.anchor_str(int(values[j]) & 0x7F)] = int(cnt[j])
+        else:
+            for r in range(n):
+                tok = ref_tok if ref_col[r] else (raw[(r, i)] if ins_kept[r, i] else codemod.anchor_str(int(col[r]) & 0x7F))
+                counts[tok] = counts.get(tok, 0) + 1
+        cons = {tok: float(repeated[k]) for tok, k in counts.items()}
+        # remove_all_n (:44-52): '=N' / '=n' go unless the locus holds nothing else
+        if not (len(cons) == 1 and ("=N" in cons or "=n" in cons)):
+            cons.pop("=N", None)
+            cons.pop("=n", None)
+        total = sum(cons.values())  # adjust_to_100_percent (:55-66)
+        factor = 100 / total
+        out.append({tok: v * factor for tok, v in cons.items()})
+    return out

@@ -688,3 +688,34 @@ def sv_feature_matrix(records: list[dict[int, int]], all_indices) -> np.ndarray:
     """sv_detector.py:100-109 — reads x sorted SV indices, the SV size or 0."""
     cols = sorted(set(all_indices) | {k for r in records for k in r})
     return np.array([[r.get(c, 0) for c in cols] for r in records])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY.md §8(f) rank 2 : views of the token matrix used by the consensus stage
+# ---------------------------------------------------------------------------------------------------------
+
+
+def onehot_by_mutations(rows) -> dict[str, np.ndarray]:
+    """consensus/similarity_searcher.py:18-25."""
+    toks = [r.split(",") for r in rows]
+    return {mut: np.array([[1 if t.startswith(mut) else 0 for t in row] for row in toks]) for mut in MUTS}
+
+
+def call_percentage(rows, loci_t, sequence: str) -> list[dict[str, float]]:
+    """consensus/consensus.py:19-75 — convert_to_percentage, remove_all_n, adjust_to_100_percent."""
+    columns = list(zip(*(r.split(",") for r in rows)))
+    coverage = len(rows)
+    out = []
+    for col, muts, base in zip(columns, loci_t, sequence):
+        cons: dict[str, float] = defaultdict(float)
+        for tok in col:
+            if tok[0] in "+-*" and tok[0] not in muts:
+                tok = "=" + base.upper()
+            cons[tok] += 1 / coverage * 100
+        cons = dict(cons)
+        if not (len(cons) == 1 and ("=N" in cons or "=n" in cons)):
+            cons.pop("=N", None)
+            cons.pop("=n", None)
+        factor = 100 / sum(cons.values())
+        out.append({k: v * factor for k, v in cons.items()})
+    return out

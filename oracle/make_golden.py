@@ -217,6 +217,28 @@ def run_reference_sv(case: dict) -> dict:
         norm_c = minimize_mutation_counts(norm_c_raw, norm_s)
         anomal = extract_anomal_loci(norm_s, norm_c, thresholds, is_consensus=True)
         g["consensus_anomal_loci"] = {k: sorted(int(i) for i in v) for k, v in anomal.items()}
+        # views of the cluster's token matrix used by the consensus stage: one-hot matrices
+        # (similarity_searcher.py:18-25) and the position weight matrix (consensus.py:19-75)
+        import hashlib
+
+        from DAJIN2.core.consensus.consensus import call_percentage
+        from DAJIN2.core.consensus.similarity_searcher import onehot_by_mutations
+
+        cluster_recs = [recs[i] for i in members]
+        onehot = onehot_by_mutations(iter(cluster_recs))
+        g["consensus_onehot_sha"] = {k: hashlib.sha256(__import__("numpy").ascontiguousarray(v, dtype="int64").tobytes()).hexdigest()
+                                     for k, v in onehot.items()}
+        g["consensus_onehot_sum"] = {k: int(v.sum()) for k, v in onehot.items()}
+        cons_loci = [set(s) for s in loci]
+        for i in anomal["-"]:
+            cons_loci[i] = set(cons_loci[i]) | {"-"}
+        cons_loci[1100] = set(cons_loci[1100]) | {"+"}  # a kept insertion locus, so that raw insertion tokens appear
+        pwm = call_percentage([r["MIDSV"].split(",") for r in cluster_recs], cons_loci, case["sequence"])
+        g["consensus_loci"] = ["".join(sorted(s)) for s in cons_loci]
+        g["consensus_percentage_sha"] = hashlib.sha256(json.dumps(
+            [[[k, float(v).hex()] for k, v in d.items()] for d in pwm]).encode()).hexdigest()
+        g["consensus_percentage_sparse"] = {str(i): [[k, float(v).hex()] for k, v in d.items()]
+                                            for i, d in enumerate(pwm) if len(d) > 1 or i % 250 == 0}
         for i in case.get("force_plus", []):
             loci[i] = set(loci[i]) | {"+"}
         g["mutation_loci"] = ["".join(sorted(s)) for s in loci]

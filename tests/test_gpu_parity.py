@@ -586,3 +586,26 @@ def test_consensus_anomal_loci(tmp_path):
     got = engine.extract_anomal_loci(norm_s, preprocess.minimize_mutation_counts(norm_c, norm_s), thresholds,
                                      is_consensus=True)
     assert {k: sorted(v) for k, v in got.items()} == g["consensus_anomal_loci"]
+
+
+def test_consensus_views_of_the_code_matrix():
+    """onehot_by_mutations (similarity_searcher.py:18-25) and call_percentage (consensus.py:19-75) computed from the
+    device-encoded code matrix: the real reference's arrays and position weight matrix, bit for bit, dict order included."""
+    import hashlib
+
+    from dajin2_b200 import consensus
+
+    alleles, golden = load_case("sv_like")
+    a, g = alleles["control"], golden["alleles"]["control"]
+    clean = set(g["sample_without_error"])
+    rows = [r for r, q in zip(a["sample"]["rows"], a["sample"]["qnames"]) if q in clean]
+    cluster = [rows[i] for i in g["consensus_cluster_reads"]]
+    onehot = consensus.onehot_by_mutations({"MIDSV": r} for r in cluster)
+    assert {k: int(v.sum()) for k, v in onehot.items()} == g["consensus_onehot_sum"]
+    assert {k: hashlib.sha256(np.ascontiguousarray(v, dtype="int64").tobytes()).hexdigest() for k, v in onehot.items()} \
+        == g["consensus_onehot_sha"]
+    pwm = consensus.call_percentage([r.split(",") for r in cluster], [set(s) for s in g["consensus_loci"]], a["sequence"])
+    for i, want in g["consensus_percentage_sparse"].items():
+        assert [[k, float(v).hex()] for k, v in pwm[int(i)].items()] == want, i
+    digest = hashlib.sha256(json.dumps([[[k, float(v).hex()] for k, v in d.items()] for d in pwm]).encode()).hexdigest()
+    assert digest == g["consensus_percentage_sha"]

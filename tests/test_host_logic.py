@@ -187,3 +187,38 @@ def test_sv_index_grouping_matches_oracle():
         assert groups == orc.group_similar_indices(list(idx), dist, cov)
         assert sv.define_index_converter(groups) == orc.index_converter(groups)
     assert sv.group_similar_indices([]) == []
+
+
+def test_consensus_views_host_logic(monkeypatch):
+    """The array logic of consensus.onehot_by_mutations / call_percentage on a code matrix built on the host
+    (tests/helpers.encode_rows stands in for the encoder): the real reference's outputs for the sv_like cluster."""
+    import hashlib
+    import json
+
+    from dajin2_b200 import consensus
+    from tests.helpers import encode_rows, load_case
+
+    alleles, golden = load_case("sv_like")
+    a, g = alleles["control"], golden["alleles"]["control"]
+    clean = set(g["sample_without_error"])
+    rows = [r for r, q in zip(a["sample"]["rows"], a["sample"]["qnames"]) if q in clean]
+    cluster = [rows[i] for i in g["consensus_cluster_reads"]]
+
+    class FakeEncoded:
+        def __init__(self, recs):
+            self.toks = [r["MIDSV"].split(",") for r in recs]
+
+        def fetch_tokens(self, reads, loci):
+            return [self.toks[int(r)][int(i)] for r, i in zip(reads, loci)]
+
+    def fake_encoded(records):
+        recs = list(records)
+        return FakeEncoded(recs), encode_rows([r["MIDSV"] for r in recs])
+
+    monkeypatch.setattr(consensus, "_encoded", fake_encoded)
+    onehot = consensus.onehot_by_mutations({"MIDSV": r} for r in cluster)
+    assert {k: hashlib.sha256(np.ascontiguousarray(v, dtype="int64").tobytes()).hexdigest() for k, v in onehot.items()} \
+        == g["consensus_onehot_sha"]
+    pwm = consensus.call_percentage([r.split(",") for r in cluster], [set(s) for s in g["consensus_loci"]], a["sequence"])
+    digest = hashlib.sha256(json.dumps([[[k, float(v).hex()] for k, v in d.items()] for d in pwm]).encode()).hexdigest()
+    assert digest == g["consensus_percentage_sha"]

@@ -326,3 +326,30 @@ def test_kat_score_handler_steps():  # tests/src/clustering/test_score_handler.p
     # call_count + call_percent (:4-28) through the oracle's k-mer route: every locus selected, so tokens stand alone
     counts = [dict(__import__("collections").Counter(col)) for col in zip(["=A", "*ag", "-gg", "=T"], ["=A", "-a", "-gg", "*ag"])]
     assert counts == [{"=A": 2}, {"*ag": 1, "-a": 1}, {"-gg": 2}, {"=T": 1, "*ag": 1}]
+
+
+def _consensus_cluster():
+    a, g = _sv_case()
+    rows = _filtered_sample(a, g)
+    return [rows[i] for i in g["consensus_cluster_reads"]], a, g
+
+
+def _pwm_digest(pwm):
+    import hashlib
+    import json
+
+    return hashlib.sha256(json.dumps([[[k, float(v).hex()] for k, v in d.items()] for d in pwm]).encode()).hexdigest()
+
+
+def test_consensus_views_match_reference():
+    """onehot_by_mutations (similarity_searcher.py:18-25) and call_percentage (consensus.py:19-75) on a cluster."""
+    import hashlib
+
+    cluster, a, g = _consensus_cluster()
+    onehot = orc.onehot_by_mutations(cluster)
+    assert {k: hashlib.sha256(np.ascontiguousarray(v, dtype="int64").tobytes()).hexdigest() for k, v in onehot.items()} \
+        == g["consensus_onehot_sha"]
+    pwm = orc.call_percentage(cluster, [set(s) for s in g["consensus_loci"]], a["sequence"])
+    assert _pwm_digest(pwm) == g["consensus_percentage_sha"]
+    for i, want in g["consensus_percentage_sparse"].items():
+        assert [[k, float(v).hex()] for k, v in pwm[int(i)].items()] == want
