@@ -78,13 +78,13 @@ def dedup_rows(ids: torch.Tensor, strand: torch.Tensor, rows: torch.Tensor | Non
 
 def uniform_choice2(rng: np.random.RandomState, n: int) -> np.ndarray:
     """``rng.choice(n, size=2, replace=False, p=np.ones(n) / np.ones(n).sum())`` -- the draw scikit-learn makes to seed
-    a bisection (``sklearn/cluster/_kmeans.py:1030-1037`` with unit sample weights) -- without numpy's O(n)
-    temporaries: same generator state afterwards, same indices (``hostc/choice.c`` restates the cumulative-sum
-    search; ``tests/test_host_logic.py`` compares them).  Falls back to numpy for n > 4M and when the two draws
-    coincide (numpy then redraws)."""
+    a bisection (``sklearn/cluster/_kmeans.py:1030-1037`` with unit sample weights) -- in O(log n) instead of numpy's
+    O(n) time and memory: same generator state afterwards, same indices (``hostc/choice.c`` restates numpy's sequential
+    cumulative sum as exact arithmetic progressions per binade; ``tests/test_host_logic.py`` compares terms and draws).
+    Falls back to numpy when the two draws coincide (numpy then redraws; probability 1/n)."""
     from .fastmlp import load_host_lib
 
-    if n < 2 or n > 4_000_000:
+    if n < 2:
         return rng.choice(n, size=2, replace=False, p=np.ones(n) / np.ones(n).sum())
     state = rng.get_state()
     x = rng.random_sample(2)

@@ -94,6 +94,8 @@ def load_host_lib():
         lib.fm_backward_packed.restype = ci
         lib.fm_uniform_choice.argtypes = [i64, vp, ci, vp]
         lib.fm_uniform_choice.restype = ci
+        lib.fm_uniform_cumsum_term.argtypes = [i64, i64]
+        lib.fm_uniform_cumsum_term.restype = cd
         lib.dj_jsonl_count_lines.argtypes = [vp, i64, ci]
         lib.dj_jsonl_count_lines.restype = i64
         lib.dj_jsonl_index.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, ci]

@@ -132,13 +132,27 @@ def test_uniform_choice_matches_numpy_legacy_choice():
     """clusterer.uniform_choice2 == RandomState.choice(n, 2, replace=False, p=uniform): indices and generator state."""
     from dajin2_b200.clusterer import uniform_choice2
 
-    for n in (2, 3, 7, 100, 4095, 4096, 4097, 10_000, 99_999, 433_328, 1_000_000):
-        for seed in range(3):
+    for n in (2, 3, 7, 100, 4095, 4096, 4097, 10_000, 99_999, 433_328, 1_000_000, 1_048_576, 4_001_000, 8_000_123):
+        for seed in range(3 if n <= 1_048_576 else 1):
             r1, r2 = np.random.RandomState(seed), np.random.RandomState(seed)
             for _ in range(3):
                 want = r1.choice(n, size=2, replace=False, p=np.ones(n) / np.ones(n).sum())
                 assert uniform_choice2(r2, n).tolist() == want.tolist()
             assert r1.random_sample() == r2.random_sample()
+
+
+def test_uniform_cumsum_terms_are_numpys():
+    """hostc/choice.c: the k-th term of np.cumsum(np.full(n, 1 / n)) from the per-binade arithmetic progressions, for
+    every k of small n and a stride of k for large n (the draws above are binary searches over these terms)."""
+    from dajin2_b200.fastmlp import load_host_lib
+
+    lib = load_host_lib()
+    rng = np.random.default_rng(4)
+    for n in list(range(1, 300)) + [int(v) for v in rng.integers(300, 300_000, 40)] + [2 ** 20, 3_000_007, 6_000_001]:
+        ref = np.cumsum(np.full(n, 1.0 / n))
+        ks = np.arange(1, n + 1) if n < 2000 else np.unique(np.concatenate([rng.integers(1, n + 1, 1500), [1, 2, n - 1, n]]))
+        got = np.array([lib.fm_uniform_cumsum_term(n, int(k)) for k in ks])
+        assert np.array_equal(got, ref[ks - 1]), n
 
 
 def test_jsonl_tokenizer_irregular_lines(tmp_path):
