@@ -35,39 +35,51 @@ def _control_path(ARGS) -> Path:
     return Path(ARGS.tempdir, ARGS.control_name, "midsv", _allele_key("control"), f"{ARGS.control_name}_midsv.jsonl")
 
 
-def detect_sequence_error_reads_in_control(ARGS) -> None:
-    """sequence_error_handler.py:44-79."""
+def split_control_reads(X: np.ndarray, matches: np.ndarray, qnames: list[str]) -> tuple[list[str], float]:
+    """sequence_error_handler.py:54-68 on the N x 2 feature matrix: (QNAMEs without sequence error, error fraction).
+    KMeans(2) as the reference calls it; the cluster whose reads match less (median) holds the sequence errors."""
     from sklearn.cluster import KMeans
 
-    X, matches, qnames = extract_n_features_file(_control_path(ARGS))
     labels = KMeans(n_clusters=2, random_state=1).fit_predict(X)
-    # the cluster whose reads match less (median) holds the sequence errors (:57-61)
     error_label = 0 if np.median(matches[labels == 0]) < np.median(matches[labels == 1]) else 1
     with_error = labels == error_label
+    return [q for q, e in zip(qnames, with_error) if not e], int(with_error.sum()) / len(qnames)
+
+
+def classify_sample_reads(X_control: np.ndarray, qnames_control: list[str], clean_control: set[str],
+                          X_sample: np.ndarray, qnames_sample: list[str]) -> list[str]:
+    """sequence_error_handler.py:95-113 on the feature matrices: QNAMEs of the sample reads without sequence error.
+    Logistic regression trained on the control's clean reads (label 0) followed by its error reads (label 1)."""
+    from sklearn.linear_model import LogisticRegression
+
+    keep = np.fromiter((q in clean_control for q in qnames_control), dtype=bool, count=len(qnames_control))
+    X = np.vstack([X_control[keep], X_control[~keep]])
+    y = np.array([0] * int(keep.sum()) + [1] * int((~keep).sum()))
+    labels = LogisticRegression(random_state=0).fit(X, y).predict(X_sample)
+    return [q for q, lab in zip(qnames_sample, labels) if lab == 0]
+
+
+def detect_sequence_error_reads_in_control(ARGS) -> None:
+    """sequence_error_handler.py:44-79."""
+    X, matches, qnames = extract_n_features_file(_control_path(ARGS))
+    clean, fraction = split_control_reads(X, matches, qnames)
     out = Path(ARGS.tempdir, ARGS.control_name, "sequence_error")
     out.mkdir(parents=True, exist_ok=True)
-    Path(out, "qnames_without_error.txt").write_text("\n".join(q for q, e in zip(qnames, with_error) if not e) + "\n")
-    Path(out, "error_fraction.txt").write_text(str(int(with_error.sum()) / len(qnames)) + "\n")
+    Path(out, "qnames_without_error.txt").write_text("\n".join(clean) + "\n")
+    Path(out, "error_fraction.txt").write_text(str(fraction) + "\n")
 
 
 def detect_sequence_error_reads_in_sample(ARGS) -> None:
     """sequence_error_handler.py:89-122."""
-    from sklearn.linear_model import LogisticRegression
-
     clean = set(Path(ARGS.tempdir, ARGS.control_name, "sequence_error", "qnames_without_error.txt")
                 .read_text().splitlines())
     Xc, _, qn_c = extract_n_features_file(_control_path(ARGS))
-    keep = np.fromiter((q in clean for q in qn_c), dtype=bool, count=len(qn_c))
-    X = np.vstack([Xc[keep], Xc[~keep]])  # clean reads first, then the error reads, each in file order (:95-105)
-    y = np.array([0] * int(keep.sum()) + [1] * int((~keep).sum()))
-    clf = LogisticRegression(random_state=0).fit(X, y)
     path_sample = Path(ARGS.tempdir, ARGS.sample_name, "midsv", _allele_key("control"),
                        f"{ARGS.sample_name}_midsv.jsonl")
     Xs, _, qn_s = extract_n_features_file(path_sample)
-    labels = clf.predict(Xs)
     out = Path(ARGS.tempdir, ARGS.sample_name, "sequence_error")
     out.mkdir(parents=True, exist_ok=True)
-    Path(out, "qnames_without_error.txt").write_text("\n".join(q for q, lab in zip(qn_s, labels) if lab == 0) + "\n")
+    Path(out, "qnames_without_error.txt").write_text("\n".join(classify_sample_reads(Xc, qn_c, clean, Xs, qn_s)) + "\n")
 
 
 def detect_sequence_error_reads(ARGS, is_control: bool = False) -> None:

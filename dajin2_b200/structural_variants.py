@@ -57,9 +57,10 @@ def process_sv_indices(path_midsv, sv_type, mutation_loci, coverage) -> dict[int
     return define_index_converter(group_similar_indices(starts.tolist(), distance=5, min_coverage=max(5, coverage * 0.05)))
 
 
-def extract_sv_features(midsv_path, sv_type, mutation_loci, index_converter) -> list[dict[int, int]]:
-    """sv_detector.py:143-148 — per read (file order) the dict ``get_index_and_sv_size`` returns (:53-97)."""
-    rec, n_reads = sv_records(midsv_path, mutation_loci)
+def features_from_records(rec: np.ndarray, n_reads: int, sv_type: str, index_converter) -> list[dict[int, int]]:
+    """Per read (file order) the dict ``get_index_and_sv_size`` returns (sv_detector.py:53-97) from the records of one
+    scan: with a converter only the start indices it knows, renamed; a later feature of a read overwrites an earlier
+    one that was renamed to the same index (``result |= {start_index: sv_size}``)."""
     out: list[dict[int, int]] = [{} for _ in range(n_reads)]
     for _, read, start, size in rec[rec[:, 0] == SV_TYPE_ID[sv_type]].tolist():  # ascending start within a read
         if index_converter is None:
@@ -67,3 +68,9 @@ def extract_sv_features(midsv_path, sv_type, mutation_loci, index_converter) -> 
         elif start in index_converter:
             out[read][index_converter[start]] = size
     return out
+
+
+def extract_sv_features(midsv_path, sv_type, mutation_loci, index_converter) -> list[dict[int, int]]:
+    """sv_detector.py:143-148."""
+    rec, n_reads = sv_records(midsv_path, mutation_loci)
+    return features_from_records(rec, n_reads, sv_type, index_converter)

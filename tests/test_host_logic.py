@@ -236,3 +236,52 @@ def test_consensus_views_host_logic(monkeypatch):
     pwm = consensus.call_percentage([r.split(",") for r in cluster], [set(s) for s in g["consensus_loci"]], a["sequence"])
     digest = hashlib.sha256(json.dumps([[[k, float(v).hex()] for k, v in d.items()] for d in pwm]).encode()).hexdigest()
     assert digest == g["consensus_percentage_sha"]
+
+
+def test_sequence_error_split_host_logic():
+    """sequence_error.split_control_reads / classify_sample_reads on feature matrices == the oracle's restatement of
+    sequence_error_handler.py:44-122 on the same reads (features here come from the oracle; on the GPU they come from
+    dj_read_n_features, tests/test_gpu_parity.py)."""
+    from dajin2_b200 import sequence_error as se
+    from oracle import dajin2_oracle as orc
+    from tests.helpers import load_case
+
+    alleles, golden = load_case("sv_like")
+    a, g = alleles["control"], golden["alleles"]["control"]
+    Xc, Xs = orc.n_features(a["control"]["rows"]), orc.n_features(a["sample"]["rows"])
+    mc = np.array(orc.match_counts(a["control"]["rows"]))
+    clean, fraction = se.split_control_reads(Xc, mc, a["control"]["qnames"])
+    assert clean == g["control_without_error"] and str(fraction) == g["error_fraction"]
+    got = se.classify_sample_reads(Xc, a["control"]["qnames"], set(clean), Xs, a["sample"]["qnames"])
+    assert got == g["sample_without_error"]
+    # no N anywhere: one empty cluster, the median of nothing is NaN, nothing is called an error (as the reference does)
+    flat = np.zeros((50, 2))
+    clean, fraction = se.split_control_reads(flat, np.full(50, 100), [f"r{i}" for i in range(50)])
+    want_clean, want_fraction = orc.sequence_error_control(["=A,=C,=G"] * 50, [f"r{i}" for i in range(50)])
+    assert clean == want_clean and fraction == want_fraction == 0.0
+
+
+def test_sv_features_from_records_host_logic():
+    """structural_variants.features_from_records / process_sv_indices' host half on records of the kind dj_sv_scan
+    returns (here produced by the oracle): the dicts of the oracle's get_index_and_sv_size, converter included."""
+    from dajin2_b200 import structural_variants as sv
+    from oracle import dajin2_oracle as orc
+    from tests.helpers import golden_loci, load_case
+
+    alleles, golden = load_case("sv_like")
+    a, g = alleles["control"], golden["alleles"]["control"]
+    clean = set(g["sample_without_error"])
+    rows = [r for r, q in zip(a["sample"]["rows"], a["sample"]["qnames"]) if q in clean]
+    loci = golden_loci(g)
+    rec = []
+    for t, name in enumerate(("deletion", "inversion", "insertion")):
+        for r, row in enumerate(rows):
+            rec += [(t, r, s, n) for s, n in sorted(orc.index_and_sv_size(row, name, loci).items())]
+    rec = np.array(rec, dtype=np.int32).reshape(-1, 4)
+    sparse = lambda recs: {str(i): {str(k): v for k, v in d.items()} for i, d in enumerate(recs) if d}  # noqa: E731
+    for name, e in g["sv"].items():
+        starts = rec[rec[:, 0] == sv.SV_TYPE_ID[name], 2].tolist()
+        conv = sv.define_index_converter(sv.group_similar_indices(starts, 5, max(5, len(rows) * 0.05)))
+        assert {str(k): v for k, v in conv.items()} == e["converter_sample"]
+        assert sparse(sv.features_from_records(rec, len(rows), name, None)) == e["raw_sample"]
+        assert sparse(sv.features_from_records(rec, len(rows), name, conv)) == e["features_sample"]
