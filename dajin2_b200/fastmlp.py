@@ -119,6 +119,24 @@ class FastMLPClassifier(MLPClassifier):
 
     fast_path_used_: bool = False
 
+    def _validate_input(self, X, y, incremental, reset):
+        """scikit-learn's input validation spends several ms per fit in the generic label machinery (sparse label
+        binarisation of 2 x (10 000 + L) labels).  For the one shape the reference feeds it -- a finite float64
+        matrix and 1-D integer labels that are exactly {0, 1} -- the same attributes and the same (n, 1) boolean target
+        are produced directly; anything else goes through scikit-learn's own method."""
+        from sklearn.preprocessing import LabelBinarizer
+
+        if (not incremental and reset and not self.warm_start and isinstance(X, np.ndarray) and X.ndim == 2
+                and X.dtype == np.float64 and X.flags.c_contiguous and isinstance(y, np.ndarray) and y.ndim == 1
+                and y.dtype.kind == "i" and y.shape[0] == X.shape[0] and X.shape[0] > 1):
+            ones = y == 1
+            if (ones | (y == 0)).all() and ones.any() and not ones.all() and np.isfinite(X).all():
+                self.n_features_in_ = X.shape[1]
+                self._label_binarizer = LabelBinarizer().fit(np.array([0, 1], dtype=y.dtype))
+                self.classes_ = self._label_binarizer.classes_
+                return X, ones.reshape(-1, 1)
+        return super()._validate_input(X, y, incremental, reset)
+
     def _fast_applicable(self, X, y, sample_weight) -> bool:
         return (sample_weight is None and self.activation == "relu" and self.out_activation_ == "logistic"
                 and self.n_layers_ == 4 and self.n_outputs_ == 1 and isinstance(X, np.ndarray)

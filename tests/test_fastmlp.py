@@ -108,3 +108,38 @@ def test_fit_predict_equals_the_reference_call():
         control = np.minimum(control, sample)
         got = mlp_pool.fit_predict(sample, control, thr)
         assert set(np.flatnonzero(got).tolist()) == set(orc.mlp_candidates(sample, control, thr))
+
+
+def test_fast_validation_leaves_the_same_estimator():
+    """FastMLPClassifier fitted on array labels (short-cut input validation) == MLPClassifier fitted on the reference's
+    list labels: parameters, iteration count, loss, classes, predictions and probabilities."""
+    import sys
+    import warnings
+    from pathlib import Path
+
+    import numpy as np
+    from sklearn.neural_network import MLPClassifier
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "scripts"))
+    from mlp_case import case
+
+    from dajin2_b200.fastmlp import FastMLPClassifier
+
+    X, y = case(900, 4)
+    kw = dict(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = MLPClassifier(**kw).fit(X, y)
+        got = FastMLPClassifier(**kw).fit(X, np.array(y))
+    assert got.fast_path_used_
+    assert all(np.array_equal(a, b) for a, b in zip(ref.coefs_ + ref.intercepts_, got.coefs_ + got.intercepts_))
+    assert (ref.n_iter_, ref.loss_, ref.n_features_in_, ref.n_outputs_) == (got.n_iter_, got.loss_, got.n_features_in_, got.n_outputs_)
+    assert ref.classes_.tolist() == got.classes_.tolist() == [0, 1]
+    probe = np.random.default_rng(0).uniform(0, 100, (3000, 2))
+    assert np.array_equal(ref.predict(probe), got.predict(probe))
+    assert np.array_equal(ref.predict_proba(probe), got.predict_proba(probe))
+    # labels outside {0, 1} or non-finite inputs take scikit-learn's own validation
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        other = FastMLPClassifier(**kw).fit(X, np.array(y) + 3)
+    assert other.classes_.tolist() == [3, 4]
