@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
     tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
-    subprocess.run([nvcc, "-shared", "--cudart", "shared", "-o", str(tmp), *objs], check=True)
+    subprocess.run([nvcc, "-shared", "--cudart", "shared", "-Wno-deprecated-gpu-targets", "-o", str(tmp), *objs], check=True)
     os.replace(tmp, LIB)
     return LIB
 
