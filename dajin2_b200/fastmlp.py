@@ -40,6 +40,7 @@ from sklearn.neural_network import MLPClassifier
 
 HERE = Path(__file__).resolve().parent
 SOURCES = [HERE / "hostc" / "fastmlp.c", HERE / "hostc" / "choice.c", HERE / "hostc" / "ingest.c"]  # one small host library
+VMATH = HERE / "hostc" / "vmath.c"
 LIB = HERE / "hostc" / "libdjhost.so"
 
 _lib = None
@@ -47,10 +48,12 @@ _c_double_p = ctypes.POINTER(ctypes.c_double)
 
 
 def build(force: bool = False) -> Path:
-    """gcc -O3 without fast-math and without FMA contraction: the C code must round exactly like numpy does."""
-    if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime for src in SOURCES):
+    """gcc -O3 without fast-math and without FMA contraction: the C code must round exactly like numpy does.  Only
+    ``vmath.c`` (exp / log that return libm's bits) is compiled with ``-ffp-contract=fast``, as glibc itself is."""
+    sources = SOURCES + [VMATH]
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime for src in sources):
         tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
-        flags = ["-O3", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-fopenmp"]
+        flags = ["-O3", "-fPIC", "-fno-fast-math", "-fopenmp"]
         try:
             cpu = Path("/proc/cpuinfo").read_text()
             if " fma " in cpu:
@@ -59,9 +62,60 @@ def build(force: bool = False) -> Path:
                 flags.append("-mavx2")  # the loops over rows vectorise (rows are independent: same bits)
         except OSError:
             pass
-        subprocess.run(["gcc", *flags, "-o", str(tmp), *map(str, SOURCES), "-lm"], check=True)
+        objs = []
+        for src in sources:
+            obj = LIB.parent / (src.name + ".%d.o" % os.getpid())
+            contract = "-ffp-contract=fast" if src == VMATH else "-ffp-contract=off"
+            subprocess.run(["gcc", *flags, contract, "-c", "-o", str(obj), str(src)], check=True)
+            objs.append(obj)
+        try:
+            subprocess.run(["gcc", "-shared", "-fopenmp", "-o", str(tmp), *map(str, objs), "-lm"], check=True)
+        finally:
+            for obj in objs:
+                obj.unlink(missing_ok=True)
         tmp.replace(LIB)
     return LIB
+
+
+def _libm_tables():
+    """(exp header, exp table, log header, log table) of the libm loaded in this process, read from the library file:
+    glibc's ``__exp_data`` / ``__log_data`` (sysdeps/ieee754/dbl-64/e_exp_data.c, e_log_data.c).  They are found by
+    their leading constants; ``fm_vmath_init`` then checks the vector routines built on them against libm itself, so
+    a layout this does not know simply leaves the vector pass switched off."""
+    import struct
+
+    path = None
+    try:
+        ctypes.CDLL("libm.so.6")
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "/libm.so" in line or "/libm-" in line:
+                    path = line.split()[-1]
+                    break
+        data = Path(path).read_bytes()
+    except (OSError, TypeError):
+        return None
+    fh = float.fromhex
+    e = data.find(struct.pack("<dd", fh("0x1.71547652b82fep+7"), fh("0x1.8p52")))  # N / ln2, shift
+    if e < 0:
+        return None
+    t = data.find(struct.pack("<QQ", 0, 0x3FF0000000000000), e, e + 4096)  # 2^(0/128): tail 0, scale 1.0
+    if t < 0:
+        return None
+    pat = struct.pack("<dd", fh("0x1.62e42fefa3800p-1"), fh("0x1.ef35793c76730p-45"))  # ln2 hi, lo
+    pos, found = data.find(pat), -1
+    while pos >= 0:
+        head = np.frombuffer(data, dtype=np.float64, count=18, offset=pos)
+        if head[7] == -0.5 and abs(head[2] + 0.5) < 1e-9 and abs(head[8] - 1 / 3) < 1e-9:  # B[0], A[0], B[1]
+            found = pos
+            break
+        pos = data.find(pat, pos + 8)
+    if found < 0 or t + 2048 > len(data) or found + 144 + 2048 > len(data):
+        return None
+    return (np.frombuffer(data, dtype=np.float64, count=8, offset=e).copy(),
+            np.frombuffer(data, dtype=np.uint64, count=256, offset=t).copy(),
+            np.frombuffer(data, dtype=np.float64, count=18, offset=found).copy(),
+            np.frombuffer(data, dtype=np.float64, count=256, offset=found + 144).copy())
 
 
 def default_threads() -> int:
@@ -88,8 +142,12 @@ def load_host_lib():
         lib.fm_set_threads.restype = None
         lib.fm_forward_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, vp, vp, vp]
         lib.fm_forward_packed.restype = ci
-        lib.fm_output.argtypes = [vp, cd, vp, i64, vp, vp, vp]
+        lib.fm_output.argtypes = [vp, cd, vp, i64, vp, vp, vp, ci]
         lib.fm_output.restype = cd
+        lib.fm_vmath_init.argtypes = [vp, vp, vp, vp, i64]
+        lib.fm_vmath_init.restype = i64
+        lib.fm_vmath_ready.argtypes = []
+        lib.fm_vmath_ready.restype = ci
         lib.fm_backward_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, cd, cd, vp]
         lib.fm_backward_packed.restype = ci
         lib.fm_uniform_choice.argtypes = [i64, vp, ci, vp]
@@ -103,6 +161,10 @@ def load_host_lib():
         lib.dj_gather_fixed.argtypes = [vp, vp, vp, i64, ctypes.c_int32, vp, ci]
         lib.dj_gather_fixed.restype = None
         lib.fm_set_threads(default_threads())
+        if os.environ.get("DAJIN2_B200_MLP_VMATH", "1") != "0":
+            tables = _libm_tables()
+            if tables is not None:  # 0 differences in the self test switches the four-wide exp / log pass on
+                lib.fm_vmath_init(*(t.ctypes.data for t in tables), 250_000)
         lib.fm_pairwise_sum.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         lib.fm_pairwise_sum.restype = ctypes.c_double
         _lib = lib
@@ -154,6 +216,8 @@ class FastMLPClassifier(MLPClassifier):
             "o_w3": n_in * h1 + h1 * h2, "o_b3": n_in * h1 + h1 * h2 + h2 + h1 + h2,
             "n_par": n_in * h1 + h1 * h2 + h2 + h1 + h2 + 1,
         }
+        yy = fm["y"]
+        fm["vec"] = int(bool(fm["lib"].fm_vmath_ready()) and bool(((yy == 0.0) | (yy == 1.0)).all()))
         fm["a2T"] = fm["a2"].T
         fm["ptr"] = {k: _ptr(fm[k]) for k in ("a1", "a2", "d3", "d2", "d1", "terms", "sum3", "y", "X")}
         self._fm = fm
@@ -171,7 +235,8 @@ class FastMLPClassifier(MLPClassifier):
             raise RuntimeError("layer too wide for the fused evaluation")
         W3 = packed[o_w3:o_w3 + h2].reshape(h2, 1)  # the view _unpack makes of the output unit's weights
         a3 = fm["a2"] @ W3  # (n, h2) @ (h2, 1): numpy -> dgemv, as safe_sparse_dot does
-        loss = np.float64(lib.fm_output(_ptr(a3), float(packed[o_b3]), ptr["y"], n, ptr["d3"], ptr["terms"], ptr["sum3"]))
+        loss = np.float64(lib.fm_output(_ptr(a3), float(packed[o_b3]), ptr["y"], n, ptr["d3"], ptr["terms"], ptr["sum3"],
+                                      fm["vec"]))
         values = 0
         lo = 0
         for size in (n_in * h1, h1 * h2, h2):  # for s in self.coefs_: values += np.dot(s.ravel(), s.ravel())
@@ -196,6 +261,9 @@ class FastMLPClassifier(MLPClassifier):
                                                coef_grads, intercept_grads)
                 try:
                     got = self._fast_loss_grad(packed_coef_inter, X)
+                    if not _same_bits(ref, got) and self._fm["vec"]:
+                        self._fm["vec"] = 0  # the four-wide exp / log pass is not libm's here: libm's own calls
+                        got = self._fast_loss_grad(packed_coef_inter, X)
                     if _same_bits(ref, got):
                         mode = "fast"
                 except Exception:  # noqa: BLE001 - anything unexpected: scikit-learn's own evaluation is always right

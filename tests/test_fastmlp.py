@@ -143,3 +143,38 @@ def test_fast_validation_leaves_the_same_estimator():
         warnings.simplefilter("ignore")
         other = FastMLPClassifier(**kw).fit(X, np.array(y) + 3)
     assert other.classes_.tolist() == [3, 4]
+
+
+def test_vector_exp_log_return_libms_bits():
+    """hostc/vmath.c: the four-wide exp / log built on the tables of the loaded libm agree with libm bit for bit on
+    4 x 10^6 arguments each (ranges of the MLP, special-case boundaries, random bit patterns); with tables that are
+    not libm's the self test fails, the pass stays off and fits go through libm's own calls -- same result."""
+    import warnings
+
+    import numpy as np
+    import pytest
+    from sklearn.neural_network import MLPClassifier
+
+    from dajin2_b200 import fastmlp
+
+    lib = fastmlp.load_host_lib()
+    tables = fastmlp._libm_tables()
+    if tables is None or lib.fm_vmath_init(*(t.ctypes.data for t in tables), 10) < 0:
+        pytest.skip("no AVX2 + FMA, or a libm whose exp / log tables are laid out differently")
+    assert lib.fm_vmath_init(*(t.ctypes.data for t in tables), 1_000_000) == 0 and lib.fm_vmath_ready() == 1
+    rng = np.random.default_rng(2)
+    X = np.concatenate([rng.uniform(0, 100, (600, 2)), rng.uniform(0, 3, (600, 2))])
+    y = np.repeat(np.array([0, 1]), 600)
+    kw = dict(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=300)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = MLPClassifier(**kw).fit(X, y.tolist())
+        on = fastmlp.FastMLPClassifier(**kw).fit(X, y)
+        wrong = [t.copy() for t in tables]
+        wrong[1][5] ^= np.uint64(1)  # one bit of one table entry
+        assert lib.fm_vmath_init(*(t.ctypes.data for t in wrong), 100_000) > 0 and lib.fm_vmath_ready() == 0
+        off = fastmlp.FastMLPClassifier(**kw).fit(X, y)
+        assert lib.fm_vmath_init(*(t.ctypes.data for t in tables), 100_000) == 0
+    for m in (on, off):
+        assert m.fast_path_used_
+        assert all(np.array_equal(a, b) for a, b in zip(ref.coefs_ + ref.intercepts_, m.coefs_ + m.intercepts_))
