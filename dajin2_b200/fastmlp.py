@@ -39,7 +39,7 @@ import numpy as np
 from sklearn.neural_network import MLPClassifier
 
 HERE = Path(__file__).resolve().parent
-SOURCES = [HERE / "hostc" / "fastmlp.c", HERE / "hostc" / "choice.c", HERE / "hostc" / "ingest.c"]  # one small host library
+SOURCES = [HERE / "hostc" / name for name in ("fastmlp.c", "choice.c", "ingest.c", "midsvfix.c")]  # one small host library
 VMATH = HERE / "hostc" / "vmath.c"
 LIB = HERE / "hostc" / "libdjhost.so"
 
@@ -160,6 +160,8 @@ def load_host_lib():
         lib.dj_jsonl_index.restype = i64
         lib.dj_gather_fixed.argtypes = [vp, vp, vp, i64, ctypes.c_int32, vp, ci]
         lib.dj_gather_fixed.restype = None
+        lib.dj_midsv_postfix.argtypes = [vp, vp, vp, i64, vp, i64, ctypes.c_int32, cd, vp, vp, vp, ci]
+        lib.dj_midsv_postfix.restype = i64
         lib.fm_set_threads(default_threads())
         if os.environ.get("DAJIN2_B200_MLP_VMATH", "1") != "0":
             tables = _libm_tables()

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import importlib
 
-from . import classification, clustering, consensus, engine, preprocess, sequence_error, structural_variants
+from . import alignment, classification, clustering, consensus, engine, preprocess, sequence_error, structural_variants
 
 _PATCHES = [
     # (module, attribute, replacement)
@@ -72,6 +72,14 @@ _PATCHES = [
     ("DAJIN2.core.consensus.consensus_mutation_analyzer", "extract_anomal_loci", engine.extract_anomal_loci),
     ("DAJIN2.core.preprocess.mutation_processing.anomaly_detector", "extract_anomal_loci", engine.extract_anomal_loci),
     ("DAJIN2.core.preprocess.mutation_processing.mutation_extractor", "extract_anomal_loci", engine.extract_anomal_loci),
+    # SURVEY.md §8f rank 4 (pinned part): the post-fixes generate_midsv chains after midsv.transform, reached through
+    # the defining module's globals only (midsv_caller.py:267-272)
+    ("DAJIN2.core.preprocess.alignment.midsv_caller", "replace_internal_n_to_d", alignment.replace_internal_n_to_d),
+    ("DAJIN2.core.preprocess.alignment.midsv_caller", "filter_samples_by_n_proportion",
+     alignment.filter_samples_by_n_proportion),
+    ("DAJIN2.core.preprocess.alignment.midsv_caller", "convert_consecutive_indels_to_match",
+     alignment.convert_consecutive_indels_to_match),
+    ("DAJIN2.core.preprocess.alignment.midsv_caller", "convert_consecutive_indels", alignment.convert_consecutive_indels),
 ]
 
 _saved: list[tuple] = []

@@ -135,6 +135,67 @@ def kat_case() -> dict:
             "loci": ["", "", "-", "+", "*", ""]}
 
 
+def raw_midsv_case(length: int = 400, n_reads: int = 300, seed: int = 7) -> dict:
+    """MIDSV strings as ``midsv.transform`` leaves them, before the post-fixes of ``midsv_caller.py:108-202``:
+    synthetic reads with injected internal '=N' runs (plain, lowercase, N-anchored insertions), leading / trailing N
+    runs on both sides of the 95 % filter threshold, and '-X..,+X..|anchor' artefacts (exact repeats, near misses,
+    runs that only become deletions through the N replacement, an insertion with too few tokens before it)."""
+    import numpy as np
+
+    pop = synth.throughput_population(length, "r9")
+    batch = synth.generate(pop, n_reads, seed=synth.SEED + 5)
+    seq = pop.reference
+    rng = np.random.default_rng(seed)
+    rows, flags = [], []
+    for r in range(n_reads):
+        toks = batch.midsv(r).split(",")
+        mode = r % 10
+        if mode in (1, 2, 3):  # internal N runs
+            for _ in range(int(rng.integers(1, 4))):
+                a = int(rng.integers(5, length - 40))
+                for j in range(a, a + int(rng.integers(1, 30))):
+                    pick = int(rng.integers(0, 10))
+                    toks[j] = "=n" if pick == 0 else ("+A|+c|=N" if pick == 1 else ("+G|=n" if pick == 2 else "=N"))
+        if mode in (2, 4, 5):  # N tails; every fifth such read sits at the threshold
+            n_tail = int(rng.integers(1, length // 3))
+            if r % 50 in (2, 4):
+                n_tail = length * 95 // 100 - (1 if r % 50 == 4 else 0)
+            lead = int(rng.integers(0, n_tail + 1)) if mode != 5 else 0
+            for j in list(range(lead)) + list(range(length - (n_tail - lead), length)):
+                toks[j] = "=N"
+        if mode in (3, 6, 7, 8):  # consecutive-indel artefacts
+            for _ in range(int(rng.integers(1, 5))):
+                k = int(rng.integers(1, 4))
+                p = int(rng.integers(k + 1, length - 1))
+                if any(t.startswith("+") or t in ("=N", "=n") for t in toks[p - k:p + 1]):
+                    continue
+                lower = mode == 8 and bool(rng.integers(0, 2))
+                bases = [seq[q].lower() if lower else seq[q] for q in range(p - k, p)]
+                kind = int(rng.integers(0, 6))
+                ins = list(bases)
+                if kind == 1:  # one inserted base differs
+                    ins[-1] = "A" if ins[-1] not in ("A", "a") else "C"
+                if kind == 2:  # case differs
+                    ins[0] = ins[0].swapcase()
+                for q, b in zip(range(p - k, p), bases):
+                    toks[q] = "-" + b
+                if kind == 3:  # one of the tokens before is not a deletion
+                    toks[p - k] = "=" + seq[p - k]
+                if kind == 4 and mode == 3:  # deletions that only exist after the N replacement
+                    for q in range(p - k, p):
+                        toks[q] = "=N"
+                toks[p] = "|".join("+" + b for b in ins) + "|" + toks[p]
+        if mode == 9:
+            toks[0] = "+" + seq[0] + "|+" + seq[1] + "|" + toks[0]  # more elements than tokens before it
+            toks[3] = "+T"  # an insertion token without an anchor
+        rows.append(",".join(toks))
+        flags.append(int(rng.choice([0, 16, 2048, 2064])))
+    rows += ["", "=N", "=N,=N,=N", "-A,+A|=N", "=N,-C,+C|=T,=N,=A,=N", "-A,-C,+A|+C|-G,+G|=T"]
+    flags += [0, 16, 0, 16, 0, 16]
+    qnames = [f"raw{i:05d}" for i in range(len(rows))]
+    return {"kind": "raw_midsv", "sequence": seq, "rows": rows, "flags": flags, "qnames": qnames}
+
+
 RECIPES = {
     # name: (builder, kwargs)
     "tp_L1000_N2000_r10": (synthetic_case, dict(length=1000, n_sample=2000, n_control=1000, profile="r10")),
@@ -151,6 +212,7 @@ RECIPES = {
     "single_like": (single_like_case, dict()),
     "kat": (kat_case, dict()),
     "sv_like": (sv_like_case, dict()),
+    "raw_midsv": (raw_midsv_case, dict()),
 }
 
 

@@ -719,3 +719,68 @@ def call_percentage(rows, loci_t, sequence: str) -> list[dict[str, float]]:
         factor = 100 / sum(cons.values())
         out.append({k: v * factor for k, v in cons.items()})
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# §8f rank 4 (pinned part): post-fixes of freshly transformed MIDSV strings, preprocess/alignment/midsv_caller.py
+# ---------------------------------------------------------------------------------------------------------
+
+
+def n_boundaries(toks: list[str]) -> tuple[int, int]:
+    """midsv_caller.py:88-105 — (index of the last leading N token, index of the first trailing N token)."""
+    left = 0
+    while left < len(toks) and is_n_token(toks[left]):
+        left += 1
+    right = len(toks) - 1
+    while right >= 0 and is_n_token(toks[right]):
+        right -= 1
+    return left - 1, right + 1
+
+
+def replace_internal_n_to_d(row: str, sequence: str) -> str:
+    """midsv_caller.py:108-126 — N tokens strictly inside the boundaries become '-<reference base>'; positions past
+    the end of ``sequence`` are left alone (the reference zips tokens with the sequence)."""
+    toks = row.split(",")
+    left, right = n_boundaries(toks)
+    for j in range(min(len(toks), len(sequence))):
+        if left < j < right and is_n_token(toks[j]):
+            toks[j] = "-" + sequence[j]
+    return ",".join(toks)
+
+
+def keeps_n_proportion(row: str, threshold: float = 95) -> bool:
+    """midsv_caller.py:145-155 — a read stays when its share of N tokens is below ``threshold`` percent."""
+    toks = row.split(",")
+    return sum(1 for t in toks if is_n_token(t)) / len(toks) * 100 < threshold
+
+
+def convert_consecutive_indels_to_match(row: str) -> str:
+    """midsv_caller.py:163-202 — an insertion whose elements repeat the deletions right before it is reverted to
+    matches ('-C,-G,+C|+G|=T' -> '=C,=G,=T').  Restated on the forward list: element e of the k inserted ones must
+    equal the deletion k - e tokens before the insertion, all k of those tokens must be deletions."""
+    toks = row.split(",")
+    out = list(toks)
+    for p, tok in enumerate(toks):
+        if not tok.startswith("+"):
+            continue
+        pieces = tok.split("|")
+        inserted = [x.lstrip("+") for x in pieces[:-1]]
+        k = len(inserted)
+        if k == 0 or p - k < 0:
+            continue
+        before = toks[p - k:p]
+        if all(t.startswith("-") for t in before) and [t.lstrip("-") for t in before] == inserted:
+            out[p] = pieces[-1]
+            for q in range(p - k, p):
+                out[q] = toks[q].replace("-", "=")
+    return ",".join(out)
+
+
+def postprocess_midsv(rows: list[str], sequence: str, threshold: float = 95) -> tuple[list[str], list[bool]]:
+    """The order of midsv_caller.py:267-272: N replacement, N-proportion filter, consecutive-indel repair."""
+    fixed, keep = [], []
+    for row in rows:
+        row = replace_internal_n_to_d(row, sequence)
+        keep.append(keeps_n_proportion(row, threshold))
+        fixed.append(convert_consecutive_indels_to_match(row))
+    return fixed, keep

@@ -263,6 +263,28 @@ def run_reference_sv(case: dict) -> dict:
     return {"alleles": {"control": g}}
 
 
+def run_reference_postfix(case: dict) -> dict:
+    """The reference's own post-fix generators (``midsv_caller.py:108-220``) on the raw-MIDSV case, step by step and
+    as the chain ``generate_midsv`` builds (:267-272)."""
+    from DAJIN2.core.preprocess.alignment import midsv_caller as mc
+
+    seq = case["sequence"]
+    mk = lambda: [{"QNAME": q, "RNAME": "control", "MIDSV": row, "FLAG": f}  # noqa: E731
+                  for q, row, f in zip(case["qnames"], case["rows"], case["flags"])]
+    replaced = [d["MIDSV"] for d in mc.replace_internal_n_to_d(iter(mk()), seq)]
+    kept = {d["QNAME"] for d in mc.filter_samples_by_n_proportion(iter(mk()))}
+    consecutive = [mc.convert_consecutive_indels_to_match(row) for row in case["rows"]]
+    best_preset = {q: ("map-ont" if i % 3 else "splice") for i, q in enumerate(case["qnames"]) if i % 7}
+    chain = mc.replace_internal_n_to_d(iter(mk()), seq)
+    chain = mc.convert_flag_to_strand(chain)
+    chain = mc.filter_samples_by_n_proportion(chain)
+    chain = mc.convert_consecutive_indels(chain)
+    chain = mc.append_best_preset(chain, best_preset)
+    return {"inputs": case, "replace_internal_n_to_d": replaced,
+            "filter_keeps": [q in kept for q in case["qnames"]], "consecutive_indels": consecutive,
+            "best_preset": best_preset, "chain": list(chain)}
+
+
 def fileio_count(path: Path) -> int:
     from DAJIN2.utils import fileio
 
@@ -279,6 +301,8 @@ def main(names) -> None:
             case = cases.build_case(name)
             if case.get("kind") == "sv":
                 payload = run_reference_sv(case)
+            elif case.get("kind") == "raw_midsv":
+                payload = run_reference_postfix(case)
             elif "alleles" in case:
                 payload = run_reference(case["alleles"])
             elif "loci" in case:

@@ -285,3 +285,111 @@ def test_sv_features_from_records_host_logic():
         assert {str(k): v for k, v in conv.items()} == e["converter_sample"]
         assert sparse(sv.features_from_records(rec, len(rows), name, None)) == e["raw_sample"]
         assert sparse(sv.features_from_records(rec, len(rows), name, conv)) == e["features_sample"]
+
+
+# ---- §8f rank 4 (pinned part): the post-fixes of generate_midsv in one native pass (hostc/midsvfix.c) ----
+
+
+def _raw_records(g):
+    c = g["inputs"]
+    return [{"QNAME": q, "RNAME": "control", "MIDSV": r, "FLAG": f} for q, r, f in zip(c["qnames"], c["rows"], c["flags"])]
+
+
+def test_midsv_postfix_reference_vectors():
+    """The vectors of the reference's tests/src/preprocess/test_midsv_caller.py through the drop-in functions."""
+    from dajin2_b200 import alignment as al
+
+    seq = "XYZABCDEF"
+    for row, want in [("=N,=N,A,B,=N,=N", "=N,=N,A,B,=N,=N"), ("A,B,=N,=N,C,D", "A,B,-Z,-A,C,D"),
+                      ("A,=N,B,=N,C", "A,-Y,B,-A,C"), ("A,B,=N,=N,C,=N,=N,D", "A,B,-Z,-A,C,-C,-D,D")]:
+        assert list(al.replace_internal_n_to_d([{"MIDSV": row}], seq)) == [{"MIDSV": want}]
+    two = [{"MIDSV": "=N,=N,=N,=A,=N,=C,=N,=N"}, {"MIDSV": "=N,=N,=A,=N,=N,=C,=C,=N"}]
+    assert list(al.replace_internal_n_to_d(two, "GCAACCCC")) == [{"MIDSV": "=N,=N,=N,=A,-C,=C,=N,=N"},
+                                                                 {"MIDSV": "=N,=N,=A,-A,-C,=C,=C,=N"}]
+    for row, want in [("=A,-C,-G,-T,+T|=A", "=A,-C,-G,=T,=A"), ("=A,-C,-G,-T,+G|+T|=A", "=A,-C,=G,=T,=A"),
+                      ("=A,-C,-G,-T,+C|+G|+T|=A", "=A,=C,=G,=T,=A"), ("=A,=C,=G,=T,=A", "=A,=C,=G,=T,=A"), ("", "")]:
+        assert al.convert_consecutive_indels_to_match(row) == want
+    got = list(al.convert_flag_to_strand(iter([{"FLAG": 16}, {"FLAG": 2064}, {"FLAG": 32}])))
+    assert got == [{"STRAND": "-"}, {"STRAND": "-"}, {"STRAND": "+"}]
+    assert list(al.replace_internal_n_to_d([], seq)) == [] and list(al.filter_samples_by_n_proportion([])) == []
+
+
+def test_midsv_postfix_equals_the_reference():
+    """Each drop-in generator, their chain, and the fused pass against the outputs of the real reference."""
+    from dajin2_b200 import alignment as al
+    from oracle import cases
+
+    g = cases.load_golden("raw_midsv")
+    seq = g["inputs"]["sequence"]
+    recs = _raw_records(g)
+    out = list(al.replace_internal_n_to_d(iter(recs), seq))
+    assert all(a is b for a, b in zip(out, recs))  # the same dicts, mutated in place, as the reference yields them
+    assert [d["MIDSV"] for d in out] == g["replace_internal_n_to_d"]
+    kept = {d["QNAME"] for d in al.filter_samples_by_n_proportion(iter(_raw_records(g)))}
+    assert [q in kept for q in g["inputs"]["qnames"]] == g["filter_keeps"]
+    assert [d["MIDSV"] for d in al.convert_consecutive_indels(iter(_raw_records(g)))] == g["consecutive_indels"]
+    chain = al.replace_internal_n_to_d(iter(_raw_records(g)), seq)
+    chain = al.convert_flag_to_strand(chain)
+    chain = al.filter_samples_by_n_proportion(chain)
+    chain = list(al.convert_consecutive_indels(chain))
+    for d in chain:
+        if d["QNAME"] in g["best_preset"]:
+            d["PRESET"] = g["best_preset"][d["QNAME"]]
+    assert chain == g["chain"]
+    assert list(al.postprocess_midsv(_raw_records(g), seq, g["best_preset"])) == g["chain"]
+
+
+def test_midsv_postfix_token_soup_equals_the_oracle():
+    """Random token lists outside the grammar as well (stacked signs, empty tokens, missing anchors, non-ASCII)."""
+    import random
+
+    from dajin2_b200 import alignment as al
+
+    rnd = random.Random(5)
+    alphabet = ["=A", "=C", "=N", "=n", "-A", "-C", "-c", "--C", "+A|=T", "+A|+C|=T", "+A|+C|-G", "++A|=T", "+|=A", "+A",
+                "", "|", "+A|", "+A|=N", "+c|=n", "*AG", "-", "+", "+-A|=C", "N", "-N", "+A|+A|+A|=A", "-a", "+a|=T",
+                "é", "+é|=T", "-é"]
+    rows = [",".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 14))) for _ in range(4000)]
+    seq = "".join(rnd.choice("ACGT-") for _ in range(11))  # shorter than some rows: zip() stops at the sequence's end
+    want_fixed, want_keep = orc.postprocess_midsv(rows, seq, 60)
+    fixed, keep = al.fix_rows(rows, seq, 7, 60)
+    assert fixed == want_fixed and keep.tolist() == want_keep
+    assert al.fix_rows(rows, seq, 1)[0] == [orc.replace_internal_n_to_d(r, seq) for r in rows]
+    assert al.fix_rows(rows, None, 2, 60)[1].tolist() == [orc.keeps_n_proportion(r, 60) for r in rows]
+    assert al.fix_rows(rows, None, 4)[0] == [orc.convert_consecutive_indels_to_match(r) for r in rows]
+
+
+def test_plugin_rebinds_every_seam_of_the_reference():
+    """Build container only (the GPU box has no /root/reference): ``install(strict=True)`` finds every module and
+    attribute it names in the real reference, the rebound post-fix seams pass the reference's own vectors through
+    the reference's module, and ``uninstall()`` puts the originals back."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import pytest
+
+    if not Path("/root/reference/src/DAJIN2").is_dir():
+        pytest.skip("no reference checkout on this machine")
+    root = Path(__file__).resolve().parent.parent
+    code = f"""
+import sys
+sys.path[:0] = [{str(root / 'oracle' / 'ref_stubs')!r}, '/root/reference/src', {str(root)!r}]
+from dajin2_b200 import plugin
+from DAJIN2.core.preprocess.alignment import midsv_caller as mc
+originals = {{(m, a): getattr(__import__(m, fromlist=[a]), a, None) for m, a, _ in plugin._PATCHES}}
+done = plugin.install(strict=True)
+assert len(done) == len(plugin._PATCHES)
+for m, a, repl in plugin._PATCHES:
+    assert getattr(sys.modules[m], a) is repl, (m, a)
+assert list(mc.replace_internal_n_to_d([{{"MIDSV": "A,B,=N,=N,C,=N,=N,D"}}], "XYZABCDEF")) == [{{"MIDSV": "A,B,-Z,-A,C,-C,-D,D"}}]
+assert mc.convert_consecutive_indels_to_match("=A,-C,-G,-T,+G|+T|=A") == "=A,-C,=G,=T,=A"
+assert list(mc.convert_consecutive_indels([{{"MIDSV": "-C,+C|=T"}}])) == [{{"MIDSV": "=C,=T"}}]
+assert list(mc.filter_samples_by_n_proportion([{{"MIDSV": "=N,=N"}}, {{"MIDSV": "=N,=A"}}])) == [{{"MIDSV": "=N,=A"}}]
+plugin.uninstall()
+for (m, a), old in originals.items():
+    assert getattr(sys.modules[m], a, None) is old, (m, a)
+print("ok")
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stderr[-2000:]

@@ -353,3 +353,39 @@ def test_consensus_views_match_reference():
     assert _pwm_digest(pwm) == g["consensus_percentage_sha"]
     for i, want in g["consensus_percentage_sparse"].items():
         assert [[k, float(v).hex()] for k, v in pwm[int(i)].items()] == want
+
+
+# ---- §8f rank 4 (pinned part): post-fixes of freshly transformed MIDSV strings (midsv_caller.py:88-202) ----
+
+
+def test_midsv_postfix_known_answers():
+    """The vectors of the reference's tests/src/preprocess/test_midsv_caller.py, restated."""
+    assert orc.n_boundaries(["=N", "=N", "A", "B", "=N", "=N"]) == (1, 4)
+    assert orc.n_boundaries(["=N", "=N", "A", "B", "A", "B"]) == (1, 6)
+    assert orc.n_boundaries(["A", "B", "A", "B", "=N", "=N"]) == (-1, 4)
+    assert orc.n_boundaries(["A", "B", "A", "B", "A", "B"]) == (-1, 6)
+    seq = "XYZABCDEF"
+    for row, want in [("=N,=N,A,B,=N,=N", "=N,=N,A,B,=N,=N"), ("A,B,=N,=N,C,D", "A,B,-Z,-A,C,D"),
+                      ("A,=N,B,=N,C", "A,-Y,B,-A,C"), ("=N,=N,=N,A,B,C,=N,=N", "=N,=N,=N,A,B,C,=N,=N"),
+                      ("A,B,=N,=N,C,=N,=N,D", "A,B,-Z,-A,C,-C,-D,D"), ("A,B,=N,C,D", "A,B,-Z,C,D"),
+                      ("A,B,C,D,E", "A,B,C,D,E")]:
+        assert orc.replace_internal_n_to_d(row, seq) == want
+    assert orc.replace_internal_n_to_d("=N,=N,=N,=A,=N,=C,=N,=N", "GCAACCCC") == "=N,=N,=N,=A,-C,=C,=N,=N"
+    assert orc.replace_internal_n_to_d("=N,=N,=A,=N,=N,=C,=C,=N", "GCAACCCC") == "=N,=N,=A,-A,-C,=C,=C,=N"
+    assert orc.replace_internal_n_to_d("=N,=N,=N,=N,=N,=N,=C,=N,=A", "GCAACCCCA") == "=N,=N,=N,=N,=N,=N,=C,-C,=A"
+    for row, want in [("=A,-C,-G,-T,+T|=A", "=A,-C,-G,=T,=A"), ("=A,-C,-G,-T,+G|+T|=A", "=A,-C,=G,=T,=A"),
+                      ("=A,-C,-G,-T,+C|+G|+T|=A", "=A,=C,=G,=T,=A"), ("=A,=C,=G,=T,=A", "=A,=C,=G,=T,=A"), ("", "")]:
+        assert orc.convert_consecutive_indels_to_match(row) == want
+
+
+def test_midsv_postfix_against_the_reference():
+    from oracle import cases
+
+    g = cases.load_golden("raw_midsv")
+    rows, seq = g["inputs"]["rows"], g["inputs"]["sequence"]
+    assert [orc.replace_internal_n_to_d(r, seq) for r in rows] == g["replace_internal_n_to_d"]
+    assert [orc.keeps_n_proportion(r) for r in rows] == g["filter_keeps"]
+    assert [orc.convert_consecutive_indels_to_match(r) for r in rows] == g["consecutive_indels"]
+    fixed, keep = orc.postprocess_midsv(rows, seq)
+    assert [f for f, k in zip(fixed, keep) if k] == [d["MIDSV"] for d in g["chain"]]
+    assert keep.count(False) >= 4 and sum(a != b for a, b in zip(fixed, rows)) >= 90  # the case exercises the fixes
