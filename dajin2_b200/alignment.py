@@ -15,6 +15,7 @@ from collections.abc import Iterable, Iterator
 import numpy as np
 
 MODE_REPLACE_N, MODE_FILTER_N, MODE_CONSECUTIVE_INDELS = 1, 2, 4
+BATCH_ROWS = 1 << 15  # rows packed per native call
 
 
 def _threads() -> int:
@@ -30,6 +31,13 @@ def fix_rows(rows: list[str], sequence: str | None, mode: int, threshold: float 
         return [], np.zeros(0, dtype=bool)
     if mode & MODE_REPLACE_N and (sequence is None or not sequence.isascii()):
         raise ValueError("replace_internal_n_to_d needs an ASCII allele sequence")
+    if n > BATCH_ROWS:  # bounded transient memory: the packed text and its fixed copy exist for one batch at a time
+        fixed, keep = [], []
+        for lo in range(0, n, BATCH_ROWS):
+            f, k = fix_rows(rows[lo : lo + BATCH_ROWS], sequence, mode, threshold)
+            fixed += f
+            keep.append(k)
+        return fixed, np.concatenate(keep)
     blob = "\n".join(rows).encode("utf-8")  # ',', '|', '+', '-', '=' never occur inside a multi-byte character
     if len(blob) == sum(map(len, rows)) + n - 1:
         lens = np.fromiter(map(len, rows), dtype=np.int64, count=n)
