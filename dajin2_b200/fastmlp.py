@@ -32,6 +32,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import platform
 import subprocess
 from pathlib import Path
 
@@ -41,6 +42,7 @@ from sklearn.neural_network import MLPClassifier
 HERE = Path(__file__).resolve().parent
 SOURCES = [HERE / "hostc" / name for name in ("fastmlp.c", "choice.c", "ingest.c", "midsvfix.c")]  # one small host library
 VMATH = HERE / "hostc" / "vmath.c"
+AVX512 = HERE / "hostc" / "fastmlp512.c"  # compiled for AVX-512 on any x86-64 build machine, entered after a run-time check
 LIB = HERE / "hostc" / "libdjhost.so"
 
 _lib = None
@@ -50,7 +52,7 @@ _c_double_p = ctypes.POINTER(ctypes.c_double)
 def build(force: bool = False) -> Path:
     """gcc -O3 without fast-math and without FMA contraction: the C code must round exactly like numpy does.  Only
     ``vmath.c`` (exp / log that return libm's bits) is compiled with ``-ffp-contract=fast``, as glibc itself is."""
-    sources = SOURCES + [VMATH]
+    sources = SOURCES + [VMATH, AVX512]
     if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime for src in sources):
         tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
         flags = ["-O3", "-fPIC", "-fno-fast-math", "-fopenmp"]
@@ -65,8 +67,10 @@ def build(force: bool = False) -> Path:
         objs = []
         for src in sources:
             obj = LIB.parent / (src.name + ".%d.o" % os.getpid())
-            contract = "-ffp-contract=fast" if src == VMATH else "-ffp-contract=off"
-            subprocess.run(["gcc", *flags, contract, "-c", "-o", str(obj), str(src)], check=True)
+            extra = ["-ffp-contract=fast" if src == VMATH else "-ffp-contract=off"]
+            if src == AVX512 and platform.machine() in ("x86_64", "AMD64"):
+                extra += ["-mavx512f", "-mavx512dq", "-mavx512vl", "-mavx2", "-mfma"]
+            subprocess.run(["gcc", *flags, *extra, "-c", "-o", str(obj), str(src)], check=True)
             objs.append(obj)
         try:
             subprocess.run(["gcc", "-shared", "-fopenmp", "-o", str(tmp), *map(str, objs), "-lm"], check=True)
@@ -148,6 +152,11 @@ def load_host_lib():
         lib.fm_vmath_init.restype = i64
         lib.fm_vmath_ready.argtypes = []
         lib.fm_vmath_ready.restype = ci
+        lib.fm_set_avx512.argtypes = [ci]
+        lib.fm_set_avx512.restype = None
+        lib.fm_get_avx512.argtypes = []
+        lib.fm_get_avx512.restype = ci
+        lib.fm_set_avx512(int(os.environ.get("DAJIN2_B200_MLP_AVX512", "1") != "0"))
         lib.fm_backward_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, cd, cd, vp]
         lib.fm_backward_packed.restype = ci
         lib.fm_uniform_choice.argtypes = [i64, vp, ci, vp]

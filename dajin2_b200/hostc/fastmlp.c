@@ -31,6 +31,20 @@
 static int g_threads = 1;
 void fm_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 
+/* fastmlp512.c: the one-thread passes of the 2-5-2 model on AVX-512, entered only when the running CPU has it */
+int fm512_supported(void);
+void fm512_forward_252(const double *X, int64_t xs_row, int64_t xs_col, int64_t n8, const double *W1, const double *b1,
+                       const double *W2, const double *b2, double *a1, double *a2);
+void fm512_backward_252(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, const double *a1, const double *a2,
+                        const double *W2, const double *W3, const double *d3, double *cs2, double *g2, double *cs1,
+                        double *g1);
+static int g_avx512 = -1; /* -1: not asked yet */
+void fm_set_avx512(int on) { g_avx512 = (on && fm512_supported()) ? 1 : 0; }
+int fm_get_avx512(void) {
+    if (g_avx512 < 0) g_avx512 = fm512_supported() ? 1 : 0;
+    return g_avx512;
+}
+
 /* numpy/_core/src/umath/loops_utils.h.src: @TYPE@_pairwise_sum */
 static double pairwise_sum(const double *a, int64_t n) {
     if (n < 8) {
@@ -229,7 +243,12 @@ int fm_forward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n
     const int64_t step = (n + FM_CHUNKS - 1) / FM_CHUNKS;
 #ifdef FM_HAVE_252_AVX2
     if (n_in == 2 && h1 == 5 && h2 == 2) {
-        forward_252(X, xs_row, xs_col, n, W1, b1, W2, b2, a1, a2);
+        int64_t done = 0;
+        if (fm_get_avx512()) { /* eight rows per trip; the last n % 8 rows go through the four-row form */
+            done = n - n % 8;
+            fm512_forward_252(X, xs_row, xs_col, done, W1, b1, W2, b2, a1, a2);
+        }
+        if (done < n) forward_252(X + done * xs_row, xs_row, xs_col, n - done, W1, b1, W2, b2, a1 + 5 * done, a2 + 2 * done);
         return 0;
     }
 #endif
@@ -433,7 +452,8 @@ int fm_backward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int 
     const int64_t step = (n + FM_CHUNKS - 1) / FM_CHUNKS;
 #ifdef FM_HAVE_252_AVX2
     if (n_in == 2 && h1 == 5 && h2 == 2) {
-        backward_252(X, xs_row, xs_col, n, a1, a2, W2, W3, d3, cs2, g2, cs1, g1);
+        if (fm_get_avx512()) fm512_backward_252(X, xs_row, xs_col, n, a1, a2, W2, W3, d3, cs2, g2, cs1, g1);
+        else backward_252(X, xs_row, xs_col, n, a1, a2, W2, W3, d3, cs2, g2, cs1, g1);
         return 0;
     }
 #endif

@@ -178,3 +178,47 @@ def test_vector_exp_log_return_libms_bits():
     for m in (on, off):
         assert m.fast_path_used_
         assert all(np.array_equal(a, b) for a, b in zip(ref.coefs_ + ref.intercepts_, m.coefs_ + m.intercepts_))
+
+
+def test_avx512_passes_return_the_avx2_bits():
+    """hostc/fastmlp512.c: forward activations and the packed gradient of the 2-5-2 model, AVX-512 form against the
+    AVX2 form, bit for bit -- row counts around the eight-row trips, column-major X, dead units (zeros and negative
+    zeros behind the relu masks)."""
+    import numpy as np
+    import pytest
+
+    from dajin2_b200 import fastmlp
+
+    lib = fastmlp.load_host_lib()
+    P = fastmlp._ptr
+    lib.fm_set_avx512(1)
+    if not lib.fm_get_avx512():
+        pytest.skip("no AVX-512 on this machine")
+
+    def run(on, X, packed, d3):
+        n = X.shape[0]
+        lib.fm_set_avx512(on)
+        a1, a2 = np.full((n, 5), np.nan), np.full((n, 2), np.nan)
+        sr, sc = X.strides[0] // 8, X.strides[1] // 8
+        assert lib.fm_forward_packed(P(X), sr, sc, n, 2, 5, 2, P(packed), P(a1), P(a2)) == 0
+        d2, d1, g3, grad = np.empty((n, 2)), np.empty((n, 5)), a2.T @ d3, np.empty(packed.shape[0])
+        assert lib.fm_backward_packed(P(X), sr, sc, n, 2, 5, 2, P(packed), P(a1), P(a2), P(d3), P(d2), P(d1), P(g3), 0.5,
+                                      1e-5, P(grad)) == 0
+        return a1, a2, grad
+
+    rng = np.random.default_rng(0)
+    try:
+        for n in (1, 7, 8, 9, 16, 17, 33, 1001, 30003):
+            for trial in range(3):
+                X = rng.uniform(0, 100, (n, 2))
+                if trial == 2:
+                    X = np.asfortranarray(X)
+                packed = rng.normal(0, 0.7, 2 * 5 + 5 * 2 + 2 + 5 + 2 + 1)
+                if trial == 1:
+                    packed[10:12] = 0.0
+                    packed[:5] = -np.abs(packed[:5])
+                d3 = rng.normal(0, 1, (n, 1))
+                for a, b in zip(run(0, X, packed, d3), run(1, X, packed, d3)):
+                    assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (n, trial)
+    finally:
+        lib.fm_set_avx512(1)
