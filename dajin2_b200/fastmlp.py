@@ -43,6 +43,8 @@ HERE = Path(__file__).resolve().parent
 SOURCES = [HERE / "hostc" / name for name in ("fastmlp.c", "choice.c", "ingest.c", "midsvfix.c")]  # one small host library
 VMATH = HERE / "hostc" / "vmath.c"
 AVX512 = HERE / "hostc" / "fastmlp512.c"  # compiled for AVX-512 on any x86-64 build machine, entered after a run-time check
+VMATH512 = HERE / "hostc" / "vmath512.c"
+HEADERS = [HERE / "hostc" / "vmath_lanes.h"]
 LIB = HERE / "hostc" / "libdjhost.so"
 
 _lib = None
@@ -52,8 +54,8 @@ _c_double_p = ctypes.POINTER(ctypes.c_double)
 def build(force: bool = False) -> Path:
     """gcc -O3 without fast-math and without FMA contraction: the C code must round exactly like numpy does.  Only
     ``vmath.c`` (exp / log that return libm's bits) is compiled with ``-ffp-contract=fast``, as glibc itself is."""
-    sources = SOURCES + [VMATH, AVX512]
-    if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime for src in sources):
+    sources = SOURCES + [VMATH, AVX512, VMATH512]
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(src.stat().st_mtime for src in sources + HEADERS):
         tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
         flags = ["-O3", "-fPIC", "-fno-fast-math", "-fopenmp"]
         try:
@@ -67,8 +69,8 @@ def build(force: bool = False) -> Path:
         objs = []
         for src in sources:
             obj = LIB.parent / (src.name + ".%d.o" % os.getpid())
-            extra = ["-ffp-contract=fast" if src == VMATH else "-ffp-contract=off"]
-            if src == AVX512 and platform.machine() in ("x86_64", "AMD64"):
+            extra = ["-ffp-contract=fast" if src in (VMATH, VMATH512) else "-ffp-contract=off"]
+            if src in (AVX512, VMATH512) and platform.machine() in ("x86_64", "AMD64"):
                 extra += ["-mavx512f", "-mavx512dq", "-mavx512vl", "-mavx2", "-mfma"]
             subprocess.run(["gcc", *flags, *extra, "-c", "-o", str(obj), str(src)], check=True)
             objs.append(obj)
@@ -152,6 +154,10 @@ def load_host_lib():
         lib.fm_vmath_init.restype = i64
         lib.fm_vmath_ready.argtypes = []
         lib.fm_vmath_ready.restype = ci
+        lib.fm512_vmath_init.argtypes = [vp, vp, vp, vp, i64]
+        lib.fm512_vmath_init.restype = i64
+        lib.fm512_vmath_ready.argtypes = []
+        lib.fm512_vmath_ready.restype = ci
         lib.fm_set_avx512.argtypes = [ci]
         lib.fm_set_avx512.restype = None
         lib.fm_get_avx512.argtypes = []
@@ -176,6 +182,8 @@ def load_host_lib():
             tables = _libm_tables()
             if tables is not None:  # 0 differences in the self test switches the four-wide exp / log pass on
                 lib.fm_vmath_init(*(t.ctypes.data for t in tables), 250_000)
+                if lib.fm_get_avx512():  # and the eight-wide one, on the same terms
+                    lib.fm512_vmath_init(*(t.ctypes.data for t in tables), 125_000)
         lib.fm_pairwise_sum.argtypes = [ctypes.c_void_p, ctypes.c_int64]
         lib.fm_pairwise_sum.restype = ctypes.c_double
         _lib = lib
@@ -228,7 +236,10 @@ class FastMLPClassifier(MLPClassifier):
             "n_par": n_in * h1 + h1 * h2 + h2 + h1 + h2 + 1,
         }
         yy = fm["y"]
-        fm["vec"] = int(bool(fm["lib"].fm_vmath_ready()) and bool(((yy == 0.0) | (yy == 1.0)).all()))
+        fm["vec"] = 0
+        if bool(((yy == 0.0) | (yy == 1.0)).all()):  # 2: eight rows at a time (AVX-512), 1: four, 0: libm's own calls
+            lib = fm["lib"]
+            fm["vec"] = 2 if (lib.fm_get_avx512() and lib.fm512_vmath_ready()) else int(bool(lib.fm_vmath_ready()))
         fm["a2T"] = fm["a2"].T
         fm["ptr"] = {k: _ptr(fm[k]) for k in ("a1", "a2", "d3", "d2", "d1", "terms", "sum3", "y", "X")}
         self._fm = fm

@@ -297,12 +297,15 @@ static double *g_leaf_a = 0, *g_leaf_b = 0;
 /* vmath.c: the same element-wise arithmetic four rows at a time, with exp / log that return libm's bits */
 int fm_vmath_ready(void);
 void fm_output_rows_vec(double *z, double b, const double *y, double *delta, double *terms, int64_t lo, int64_t m);
+int fm512_vmath_ready(void); /* vmath512.c: eight rows at a time */
+void fm512_output_rows_vec(double *z, double b, const double *y, double *delta, double *terms, int64_t lo, int64_t m);
 
 double fm_output(double *z, double b, const double *y, int64_t n, double *delta, double *terms, double *sum_delta,
                  int use_vec) {
     const double eps = 2.220446049250313e-16;
     const double hi = 1.0 - eps;
-    const int vec = use_vec && fm_vmath_ready(); /* the caller asks for it only when every label is exactly 0 or 1 */
+    /* the caller asks for it only when every label is exactly 0 or 1; 2 = the eight-wide form */
+    const int vec = !use_vec ? 0 : (use_vec == 2 && fm_get_avx512() && fm512_vmath_ready()) ? 2 : fm_vmath_ready();
     if (n != g_leaf_n) { /* the leaf table of this length (one training-set size per fit) */
         const int64_t cap = n / 32 + 4;
         free(g_leaf_off); free(g_leaf_len); free(g_leaf_a); free(g_leaf_b);
@@ -316,7 +319,8 @@ double fm_output(double *z, double b, const double *y, int64_t n, double *delta,
 #pragma omp parallel for num_threads(g_threads) schedule(static)
     for (int64_t l = 0; l < g_n_leaves; l++) {
         const int64_t lo = g_leaf_off[l], m = g_leaf_len[l];
-        if (vec) fm_output_rows_vec(z, b, y, delta, terms, lo, m);
+        if (vec == 2) fm512_output_rows_vec(z, b, y, delta, terms, lo, m);
+        else if (vec) fm_output_rows_vec(z, b, y, delta, terms, lo, m);
         else for (int64_t i = lo; i < lo + m; i++) {
             double v = z[i] + b;
             double a = 1.0 / (1.0 + exp(-v));

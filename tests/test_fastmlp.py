@@ -162,6 +162,8 @@ def test_vector_exp_log_return_libms_bits():
     if tables is None or lib.fm_vmath_init(*(t.ctypes.data for t in tables), 10) < 0:
         pytest.skip("no AVX2 + FMA, or a libm whose exp / log tables are laid out differently")
     assert lib.fm_vmath_init(*(t.ctypes.data for t in tables), 1_000_000) == 0 and lib.fm_vmath_ready() == 1
+    if lib.fm_get_avx512():  # the eight-wide form (vmath512.c) on the same terms
+        assert lib.fm512_vmath_init(*(t.ctypes.data for t in tables), 500_000) == 0 and lib.fm512_vmath_ready() == 1
     rng = np.random.default_rng(2)
     X = np.concatenate([rng.uniform(0, 100, (600, 2)), rng.uniform(0, 3, (600, 2))])
     y = np.repeat(np.array([0, 1]), 600)
@@ -173,8 +175,19 @@ def test_vector_exp_log_return_libms_bits():
         wrong = [t.copy() for t in tables]
         wrong[1][5] ^= np.uint64(1)  # one bit of one table entry
         assert lib.fm_vmath_init(*(t.ctypes.data for t in wrong), 100_000) > 0 and lib.fm_vmath_ready() == 0
+        if lib.fm_get_avx512():
+            four = fastmlp.FastMLPClassifier(**kw).fit(X, y)  # eight-wide pass still on, four-wide one off
+            assert lib.fm512_vmath_init(*(t.ctypes.data for t in wrong), 100_000) > 0 and lib.fm512_vmath_ready() == 0
         off = fastmlp.FastMLPClassifier(**kw).fit(X, y)
         assert lib.fm_vmath_init(*(t.ctypes.data for t in tables), 100_000) == 0
+        if lib.fm_get_avx512():
+            assert lib.fm512_vmath_init(*(t.ctypes.data for t in tables), 100_000) == 0
+            lib.fm_set_avx512(0)
+            narrow = fastmlp.FastMLPClassifier(**kw).fit(X, y)  # AVX-512 off altogether: the four-wide pass
+            lib.fm_set_avx512(1)
+            for m in (four, narrow):
+                assert m.fast_path_used_
+                assert all(np.array_equal(a, b) for a, b in zip(ref.coefs_ + ref.intercepts_, m.coefs_ + m.intercepts_))
     for m in (on, off):
         assert m.fast_path_used_
         assert all(np.array_equal(a, b) for a, b in zip(ref.coefs_ + ref.intercepts_, m.coefs_ + m.intercepts_))
