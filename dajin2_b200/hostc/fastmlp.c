@@ -128,6 +128,9 @@ static void forward_252(const double *X, int64_t xs_row, int64_t xs_col, int64_t
             const __m256d p = _mm256_loadu_pd(X + 2 * i), q = _mm256_loadu_pd(X + 2 * i + 4);
             x0v = _mm256_permute4x64_pd(_mm256_unpacklo_pd(p, q), 0xD8);
             x1v = _mm256_permute4x64_pd(_mm256_unpackhi_pd(p, q), 0xD8);
+        } else if (xs_row == 1) { /* column-major X: what numpy builds from the reference's concatenation of .T views */
+            x0v = _mm256_loadu_pd(X + i);
+            x1v = _mm256_loadu_pd(X + i + xs_col);
         } else {
             x0v = _mm256_set_pd(X[(i + 3) * xs_row], X[(i + 2) * xs_row], X[(i + 1) * xs_row], X[i * xs_row]);
             x1v = _mm256_set_pd(X[(i + 3) * xs_row + xs_col], X[(i + 2) * xs_row + xs_col], X[(i + 1) * xs_row + xs_col],

@@ -22,7 +22,8 @@ static inline __m512d relu8(__m512d v) { /* v unless v < 0 (NaN and -0.0 pass th
     return _mm512_maskz_mov_pd(_mm512_cmp_pd_mask(v, _mm512_setzero_pd(), _CMP_NLT_UQ), v);
 }
 
-/* rows [0, n8) with n8 a multiple of 8; X row-major with two columns (xs_row == 2, xs_col == 1) or any element strides */
+/* rows [0, n8) with n8 a multiple of 8; X row-major with two columns (xs_row == 2, xs_col == 1), column-major
+ * (xs_row == 1) or any other element strides */
 void fm512_forward_252(const double *X, int64_t xs_row, int64_t xs_col, int64_t n8, const double *W1, const double *b1,
                        const double *W2, const double *b2, double *a1, double *a2) {
     const __m512d zero = _mm512_setzero_pd();
@@ -55,6 +56,9 @@ void fm512_forward_252(const double *X, int64_t xs_row, int64_t xs_col, int64_t 
             const __m512d p = _mm512_loadu_pd(X + 2 * i), q = _mm512_loadu_pd(X + 2 * i + 8);
             x0v = _mm512_permutex2var_pd(p, even, q);
             x1v = _mm512_permutex2var_pd(p, odd, q);
+        } else if (xs_row == 1) { /* column-major X: what numpy builds from the reference's concatenation of .T views */
+            x0v = _mm512_loadu_pd(X + i);
+            x1v = _mm512_loadu_pd(X + i + xs_col);
         } else {
             double t0[8], t1[8];
             for (int r = 0; r < 8; r++) {

@@ -131,8 +131,11 @@ def test_fast_validation_leaves_the_same_estimator():
         warnings.simplefilter("ignore")
         ref = MLPClassifier(**kw).fit(X, y)
         got = FastMLPClassifier(**kw).fit(X, np.array(y))
-    assert got.fast_path_used_
-    assert all(np.array_equal(a, b) for a, b in zip(ref.coefs_ + ref.intercepts_, got.coefs_ + got.intercepts_))
+        row_major = FastMLPClassifier(**kw).fit(np.ascontiguousarray(X), np.array(y))
+    assert X.flags.f_contiguous and not X.flags.c_contiguous  # what the reference's construction yields
+    for m in (got, row_major):
+        assert m.fast_path_used_ and m.fast_validation_used_
+        assert all(np.array_equal(a, b) for a, b in zip(ref.coefs_ + ref.intercepts_, m.coefs_ + m.intercepts_))
     assert (ref.n_iter_, ref.loss_, ref.n_features_in_, ref.n_outputs_) == (got.n_iter_, got.loss_, got.n_features_in_, got.n_outputs_)
     assert ref.classes_.tolist() == got.classes_.tolist() == [0, 1]
     probe = np.random.default_rng(0).uniform(0, 100, (3000, 2))
@@ -142,7 +145,7 @@ def test_fast_validation_leaves_the_same_estimator():
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         other = FastMLPClassifier(**kw).fit(X, np.array(y) + 3)
-    assert other.classes_.tolist() == [3, 4]
+    assert other.classes_.tolist() == [3, 4] and not other.fast_validation_used_
 
 
 def test_vector_exp_log_return_libms_bits():
