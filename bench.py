@@ -11,9 +11,9 @@ combined across ranks, so the job classifies N x reads reads.
   e2e        the same through ``dajin2_b200.pipeline.run_host``: pinned host buffers -> H2D -> path -> labels D2H
   roofline   the encoder (dominant kernel): algorithmic bytes (text + codes + scalars) / CUDA-event time, against
              the measured HBM copy bandwidth in MEASURED_PEAKS.json
-  cpu_baseline  the oracle port of the reference's Python path on one host core, on a bounded sample
+  cpu_baseline  the reference's own Python path (unmodified, oracle/_ref) on one host core, on a bounded sample
 
-``--impl reference`` times the oracle port of the reference's CPU path with every host core on bounded samples.
+``--impl reference`` times the reference's own code with every host core: one bounded sample per core per step.
 """
 
 from __future__ import annotations
@@ -172,8 +172,30 @@ def oracle_pass(rows_s, strands_s, qn_s, rows_c, sequence) -> dict:
 
 
 def cpu_baseline(args, hs, hc, sequence) -> dict:
+    """One core, one process, BLAS threads = 1 — how the reference runs a sample (``main.py:5-9``) — on a bounded
+    sample of the same workload.  The code timed is the reference's own (``oracle/_ref``, kind "reference"); the
+    oracle port only stands in when that copy is absent (kind "port")."""
+    from oracle import build_ref
+
     n_s = min(args.cpu_sample, hs.n_reads)
     n_c = min(max(n_s // 2, 50), hc.n_reads)
+    if build_ref.available():
+        import shutil
+
+        from oracle import ref_runner
+
+        tmp = Path(tempfile.mkdtemp(prefix="dj_ref_"))
+        try:
+            dt, parts, res = ref_runner.time_sample(ref_runner.hostreads_part(hs, n_s),
+                                                    ref_runner.hostreads_part(hc, n_c), sequence, tmp)
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+        return {"value": n_s / dt, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"{n_s} sample + {n_c} control reads of the same workload through the reference's own "
+                          f"cache_mutation_loci -> classify_alleles -> extract_labels (DAJIN2 {build_ref.version()}, "
+                          f"unmodified, from oracle/_ref), 1 process, BLAS threads = 1, {dt:.1f} s",
+                "seconds": dt, "stage_seconds": {k: round(v, 3) for k, v in parts.items()},
+                "n_clusters": len(set(res["labels"]))}
     rows_s, rows_c = rows_of(hs, n_s), rows_of(hc, n_c)
     strands = [chr(x) for x in hs.strand[:n_s]]
     qn = [q.decode() for q in hs.qnames[:n_s]]
@@ -182,140 +204,70 @@ def cpu_baseline(args, hs, hc, sequence) -> dict:
     dt = time.perf_counter() - t0
     return {"value": n_s / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{n_s} sample + {n_c} control reads of the same workload, oracle port of the reference's "
-                      f"Python path, 1 process, BLAS threads = 1 (as the reference runs a sample), {dt:.1f} s",
+                      f"Python path (oracle/_ref absent), 1 process, BLAS threads = 1, {dt:.1f} s",
             "seconds": dt, "stage_seconds": {k: round(v, 3) for k, v in parts.items() if k != "n_clusters"}}
 
 
-def _ref_worker(job):
-    """Linear passes of the reference path on one shard of reads (process-pool worker)."""
-    from oracle import dajin2_oracle as orc
-
-    kind, payload = job
-    if kind == "count":
-        rows, L = payload
-        return orc.count_indels(rows, L), [orc.calc_match(r) for r in rows]
-    if kind == "strand":
-        rows, strands, loci_t = payload
-        return orc.count_strand_of_indels(rows, strands, loci_t)
-    if kind == "kmers":
-        rows, loci_t = payload
-        from collections import Counter
-
-        return [Counter(col) for col in zip(*orc.mutation_kmers(rows, loci_t))]
-    if kind == "annotate":
-        rows, score, loci_t, is_control = payload
-        return list(orc.annotate_score(rows, score, loci_t, is_control))
-    raise ValueError(kind)
-
-
 def run_reference_arm(args):
-    """The reference's CPU path (oracle port) with every host core: read-parallel passes in a process pool,
-    per-locus reductions and clustering in the parent, on bounded samples of the workload."""
+    """The reference's own CPU implementation of the path with every host core.  The reference's parallelism is one
+    process per sample (``utils/multiprocess.py:117-150``, BLAS threads = 1 inside each): a step runs one bounded
+    sample of the workload per core, each through the unmodified reference code of ``oracle/_ref``; reads/s = reads
+    of all samples / wall time of the step."""
     import multiprocessing as mp
-    from collections import Counter
+    import shutil
 
-    import numpy as np
-
-    from oracle import dajin2_oracle as orc
+    from oracle import build_ref
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     workers = max(1, min(cores, 64))
-    n_s = max(200, 120 * workers)
-    n_c = max(100, n_s // 4)
-    small = argparse.Namespace(**{**vars(args), "reads": n_s})
-    pop, hs, hc, _ = make_workload(small, 0, 1, pinned=False)
-    sequence = pop.reference
-    L = len(sequence)
-    rows_s, rows_c = rows_of(hs, n_s), rows_of(hc, n_c)
-    strands = [chr(x) for x in hs.strand[:n_s]]
-    qn = [q.decode() for q in hs.qnames[:n_s]]
+    # bounded sample: the whole --steps/--warmup run should end within a few minutes (~11 ms per read and ~4 s fixed
+    # per sample on one core at L = 5000)
+    per_step = 220.0 / max(1, args.steps + args.warmup)
+    n_s = int(min(2000, max(200, (per_step - 4.0) / 0.011)))
+    n_c = max(100, n_s // 2)
+    if not build_ref.available():
+        line = {"impl": "reference", "unavailable": "oracle/_ref is absent (run python oracle/build_ref.py where "
+                                                    "/root/reference exists)"}
+        print(json.dumps(line), flush=True)
+        return
+    from oracle import ref_runner
 
-    def shards(seq, k):
-        step = (len(seq) + k - 1) // k
-        return [seq[i : i + step] for i in range(0, len(seq), step)]
-
+    base = tempfile.mkdtemp(prefix="dj_refarm_")
     ctx = mp.get_context("fork")
-    with ctx.Pool(workers) as pool:
-        def step():
-            res = pool.map(_ref_worker, [("count", (sh, L)) for sh in shards(rows_s, workers)])
-            cs = {op: np.sum([r[0][op] for r in res], axis=0).tolist() for op in "=+-*"}
-            resc = pool.map(_ref_worker, [("count", (sh, L)) for sh in shards(rows_c, workers)])
-            cc = {op: np.sum([r[0][op] for r in resc], axis=0).tolist() for op in "=+-*"}
-            ns, nc = orc.normalize_indels(cs), orc.normalize_indels(cc)
-            ncm = orc.minimize_mutation_counts(nc, ns)
-            loci = orc.extract_anomal_loci(ns, ncm, {"*": 0.1, "-": 0.1, "+": 0.1})
-            homo = orc.homopolymer_errors(sequence, ns, ncm, loci)
-            loci_t = orc.transpose_loci(loci, L)
-            # strand pass, sharded (the Fisher tests stay in the parent)
-            from scipy.stats import fisher_exact
+    try:
+        with ctx.Pool(workers) as pool:
+            pool.map(ref_runner.pool_init_slot, [(base, k, workers, n_s, n_c, args.loci, args.profile)
+                                                 for k in range(workers)], chunksize=1)
 
-            tabs = pool.map(_ref_worker, [("strand", (sh, st, loci_t)) for sh, st in
-                                          zip(shards(rows_s, workers), shards(strands, workers))])
-            merged: dict = {}
-            for tab in tabs:
-                for i, per in tab.items():
-                    for op, c in per.items():
-                        cell = merged.setdefault(i, {}).setdefault(op, {"+": 0, "-": 0})
-                        cell["+"] += c["+"]
-                        cell["-"] += c["-"]
-            n_plus = strands.count("+")
-            bias = {op: set() for op in "+-*"}
-            for i, per in merged.items():
-                for op, c in per.items():
-                    ratio = c["+"] / (c["+"] + c["-"])
-                    if not (0.2 < ratio < 0.8) and fisher_exact([[c["+"], c["-"]], [n_plus, n_s - n_plus]]).pvalue < 0.01:
-                        bias[op].add(i)
-            loci = orc.discard_errors(orc.discard_errors(loci, homo), bias)
-            loci_t = orc.transpose_loci(orc.merge_consecutive_indels(loci), L)
-            order = sorted(range(n_s), key=lambda i: qn[i])
-            rows_sorted = [rows_s[i] for i in order]
-            # make_score with sharded k-mer counting; the percentage arithmetic is the oracle's
-            ks = pool.map(_ref_worker, [("kmers", (sh, loci_t)) for sh in shards(rows_sorted, workers)])
-            kc = pool.map(_ref_worker, [("kmers", (sh, loci_t)) for sh in shards(rows_c, workers)])
+            def step():
+                return pool.map(ref_runner.pool_run_slot, [(base, k) for k in range(workers)], chunksize=1)
 
-            def pct(parts, total):
-                out = []
-                for cols in zip(*parts):
-                    c = Counter()
-                    for x in cols:
-                        c.update(x)
-                    out.append({k: round(v / total * 100, 3) for k, v in c.items()})
-                return out
-
-            ps, pc = pct(ks, n_s), pct(kc, n_c)
-            saved = orc.kmer_percentages
-            try:
-                it = iter([ps, pc])
-                orc.kmer_percentages = lambda rows, lt: next(it)
-                score = orc.make_score(rows_sorted, rows_c, loci_t, set())
-            finally:
-                orc.kmer_percentages = saved
-            xs = [r for part in pool.map(_ref_worker, [("annotate", (sh, score, loci_t, False))
-                                                        for sh in shards(rows_sorted, workers)]) for r in part]
-            xc = [r for part in pool.map(_ref_worker, [("annotate", (sh, score, loci_t, True))
-                                                        for sh in shards(rows_c, workers)]) for r in part]
-            st = [strands[i] for i in order]
-            if any(loci_t):
-                orc.return_labels(xs, xc, st, {"+": st.count("+"), "-": st.count("-")})
-
-        for _ in range(args.warmup):
-            step()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            step()
-        dt = time.perf_counter() - t0
-    value = n_s * args.steps / dt
+            for _ in range(args.warmup):
+                step()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                last = step()
+            dt = time.perf_counter() - t0
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+    value = n_s * workers * args.steps / dt
+    slowest = max(last, key=lambda r: r[0])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample_per_step": f"{n_s} sample + {n_c} control reads"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port",
-                         "sample": f"{n_s} sample + {n_c} control reads per step; read-parallel passes of the oracle "
-                                   f"port in a {workers}-process pool, reductions + sklearn clustering in the parent"},
+        "config": {"workload": workload_name(args),
+                   "sample_per_step": f"{workers} samples x ({n_s} sample + {n_c} control reads), one per core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "reference",
+                         "sample": f"per step {workers} samples of {n_s} sample + {n_c} control reads of the workload, "
+                                   f"one process per sample (the reference's own batch parallelism), each through the "
+                                   f"unmodified DAJIN2 {build_ref.version()} functions cache_mutation_loci -> "
+                                   f"classify_alleles -> extract_labels (oracle/_ref), BLAS threads = 1",
+                         "slowest_sample_seconds": round(slowest[0], 2),
+                         "stage_seconds": {k: round(v, 3) for k, v in slowest[1].items()}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)

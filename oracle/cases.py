@@ -36,6 +36,18 @@ def digest(part: dict) -> str:
     return h.hexdigest()
 
 
+def digest_batch(batch, strands=None) -> str:
+    """``digest`` of a generated batch straight from its buffers (no Python strings: the 10^5-read cases)."""
+    h = hashlib.sha256()
+    text = batch.text
+    st = batch.strand if strands is None else strands
+    for r in range(batch.n_reads):
+        o, n = int(batch.row_off[r]), int(batch.row_len[r])
+        h.update(text[o: o + n].tobytes())
+        h.update(bytes([int(st[r])]))
+    return h.hexdigest()
+
+
 def synthetic_case(length: int, n_sample: int, n_control: int, profile: str, kind: str = "throughput",
                    fraction: float = 0.1) -> dict:
     if kind == "throughput":
@@ -50,6 +62,85 @@ def synthetic_case(length: int, n_sample: int, n_control: int, profile: str, kin
     sample = synth.generate(pop, n_sample, seed=synth.SEED + 1)
     control = synth.generate(ctrl, n_control, seed=synth.SEED + 99)
     return {"sequence": pop.reference, "sample": _pack(sample), "control": _pack(control), "knockin": None}
+
+
+def bench_batches(length: int, n_sample: int, n_control: int, profile: str = "r10"):
+    """The bench.py workload as generator batches: (population, sample batch, control batch)."""
+    pop = synth.throughput_population(length, profile)
+    sample = synth.generate(pop, n_sample, seed=synth.SEED + 1)
+    control = synth.generate(synth.control_population(length, profile, reference=pop.reference), n_control,
+                             seed=synth.SEED + 99)
+    return pop, sample, control
+
+
+def strand_biased_case(length: int = 1200, n_sample: int = 3000, n_control: int = 1000, profile: str = "r10",
+                       x: int = 400, y: int = 700, fractions=(0.38, 0.25, 0.25, 0.12)) -> dict:
+    """A sample whose loci are strand-balanced but one of whose CLUSTERS is not: alleles A (sub@x) and D (sub@y) on
+    both strands, allele C (sub@x + sub@y) on the '+' strand only.  The locus-level filter
+    (error_correction/strand_bias_handler.py:36-60) keeps x and y (plus-ratio 0.66 at both), the cluster-level one
+    (clustering/strand_bias_handler.py:109-134) finds cluster C biased and runs its DecisionTree re-allocation."""
+    ref = synth.random_reference(length)
+    S = synth.SUB
+    pop = synth.Population(ref, [[], [(S, x, 1)], [(S, y, 1)], [(S, x, 1), (S, y, 1)]], list(fractions), profile)
+    sample = synth.generate(pop, n_sample, seed=synth.SEED + 1)
+    control = synth.generate(synth.control_population(length, profile, reference=ref), n_control, seed=synth.SEED + 99)
+    part = _pack(sample)
+    part["strands"] = ["+" if a == 3 else s for a, s in zip(sample.allele.tolist(), part["strands"])]
+    return {"sequence": ref, "sample": part, "control": _pack(control), "knockin": None}
+
+
+def flox_full_case(n_sample: int = 1000, n_control: int = 1000, profile: str = "r10") -> dict:
+    """BASELINE.json configs[1] stand-in at the sizes of SURVEY.md §8(d): FASTA alleles control (2724 nt) and flox
+    (2832 nt = control + knock-ins of 46 and 62 nt; knock-in loci 1732-1777 and 2427-2488 of the flox allele, 108
+    loci), FOUR samples of 1000 reads sharing one control of 1000 reads: flox; flox + 1-nt deletion; flox + 1-nt
+    substitution; flox + 1-nt insertion (the variant alleles at 1:1 with plain flox)."""
+    base = synth.random_reference(2724)
+    ins_a = synth.random_reference(46, seed=7)
+    ins_b = synth.random_reference(62, seed=8)
+    pa, pb = 1732, 2427 - 46  # positions in the control allele
+    flox = base[:pa] + ins_a + base[pa:pb] + ins_b + base[pb:]
+    assert len(flox) == 2832
+    knockin = set(range(1732, 1778)) | set(range(2427, 2489))
+    assert len(knockin) == 108
+    S, D, I = synth.SUB, synth.DEL, synth.INS  # noqa: E741
+    kin = [(I, pa, 46), (I, pb, 62)]
+    v = 900  # variant position in control coordinates (before both knock-ins)
+    variants = {"flox": None, "flox_del": (D, v, 1), "flox_sub": (S, v, 1), "flox_ins": (I, v, 1)}
+    ctrl_vs_control = synth.Population(base, [[]], [1.0], profile, rname="control")
+    ctrl_vs_flox = synth.Population(flox, [[(D, 1732, 46), (D, 2427, 62)]], [1.0], profile, rname="flox")
+    control = {"control": _pack(synth.generate(ctrl_vs_control, n_control, seed=synth.SEED + 99)),
+               "flox": _pack(synth.generate(ctrl_vs_flox, n_control, seed=synth.SEED + 99))}
+    out = {"samples": {}}
+    for k, (sname, var) in enumerate(variants.items()):
+        if var is None:
+            al_c, al_f, fr = [kin], [[]], [1.0]
+        else:
+            al_c, al_f, fr = [kin, kin + [var]], [[], [var]], [0.5, 0.5]
+        vs_control = synth.Population(base, al_c, fr, profile, rname="control")
+        vs_flox = synth.Population(flox, al_f, fr, profile, rname="flox")
+        out["samples"][sname] = {"alleles": {
+            "control": {"sequence": base, "sample": _pack(synth.generate(vs_control, n_sample, seed=synth.SEED + 1 + k)),
+                        "control": control["control"], "knockin": None},
+            "flox": {"sequence": flox, "sample": _pack(synth.generate(vs_flox, n_sample, seed=synth.SEED + 1 + k)),
+                     "control": control["flox"], "knockin": knockin},
+        }}
+    return out
+
+
+def batch_full_case(length: int = 2845, n_sample: int = 5000, n_control: int = 5000, profile: str = "r10") -> dict:
+    """BASELINE.json configs[3] stand-in at the sizes of SURVEY.md §8(d): three samples (point mutation at 1 %, 10 %,
+    50 %) of 5000 reads sharing ONE control of 5000 reads — the control's counts are cached by the first sample and
+    found by the others (mutation_extractor.py:113-114)."""
+    ref = synth.random_reference(length)
+    control = _pack(synth.generate(synth.control_population(length, profile, reference=ref), n_control,
+                                   seed=synth.SEED + 99))
+    out = {"samples": {}}
+    for k, (sname, fr) in enumerate((("tyr_01", 0.01), ("tyr_10", 0.10), ("tyr_50", 0.50))):
+        pop = synth.Population(ref, [[], [(synth.SUB, length // 2, 1)]], [1 - fr, fr], profile)
+        out["samples"][sname] = {"alleles": {"control": {
+            "sequence": ref, "sample": _pack(synth.generate(pop, n_sample, seed=synth.SEED + 1 + k)),
+            "control": control, "knockin": None}}}
+    return out
 
 
 def flox_like_case(n_sample: int = 400, n_control: int = 300, profile: str = "r10") -> dict:
@@ -79,18 +170,23 @@ def flox_like_case(n_sample: int = 400, n_control: int = 300, profile: str = "r1
     return out
 
 
-def single_like_case(n_sample: int = 900, n_control: int = 500, profile: str = "r10") -> dict:
+def single_like_case(n_sample: int = 900, n_control: int = 500, profile: str = "r10", length: int = 1000,
+                     del_at: int = 300, del_len: int = 150, inv_at: int = 600, inv_len: int = 200,
+                     sub_at: int = 500) -> dict:
     """Three FASTA alleles as in examples/example_single (control, large deletion, inversion); the sample is a 1:1:1
     mixture of a point mutant of the control, the deletion allele and the inversion allele, every read expressed
-    against each FASTA allele (BASELINE.json configs[0] stand-in: exercises classify_alleles over three alleles)."""
-    base = synth.random_reference(1000)
-    deletion = base[:300] + base[450:]
+    against each FASTA allele (BASELINE.json configs[0] stand-in: exercises classify_alleles over three alleles).
+    ``single_full`` runs it at the sizes of SURVEY.md §8(d): L = 4309 / 3582 / 4309, N = 1500 sample, 2000 control."""
+    base = synth.random_reference(length)
+    deletion = base[:del_at] + base[del_at + del_len:]
     S, D, I, V = synth.SUB, synth.DEL, synth.INS, synth.INV  # noqa: E741
     fr = [1 / 3, 1 / 3, 1 / 3]
+    da, dl, va, vl, sa = del_at, del_len, inv_at, inv_len, sub_at
+    assert da + dl <= sa < va, "geometry: deletion, then the point mutation, then the inversion"
     truth = {  # true allele (point mutant, deletion, inversion) against each FASTA allele
-        "control": (base, [[(S, 500, 1)], [(D, 300, 150)], [(V, 600, 200)]], [[]]),
-        "deletion": (deletion, [[(I, 300, 150), (S, 350, 1)], [], [(I, 300, 150), (V, 450, 200)]], [[(I, 300, 150)]]),
-        "inversion": (base, [[(V, 600, 200), (S, 500, 1)], [(D, 300, 150), (V, 600, 200)], []], [[(V, 600, 200)]]),
+        "control": (base, [[(S, sa, 1)], [(D, da, dl)], [(V, va, vl)]], [[]]),
+        "deletion": (deletion, [[(I, da, dl), (S, sa - dl, 1)], [], [(I, da, dl), (V, va - dl, vl)]], [[(I, da, dl)]]),
+        "inversion": (base, [[(V, va, vl), (S, sa, 1)], [(D, da, dl), (V, va, vl)], []], [[(V, va, vl)]]),
     }
     out = {"alleles": {}}
     for name, (seq, sample_alleles, control_alleles) in truth.items():
@@ -211,9 +307,29 @@ RECIPES = {
     "flox_like": (flox_like_case, dict()),
     "single_like": (single_like_case, dict()),
     "kat": (kat_case, dict()),
+    # --- round 2: the sizes SURVEY.md §8(d) specifies, and the bench generator at the reference's own scale ------
+    "single_full": (single_like_case, dict(n_sample=1500, n_control=2000, length=4309, del_at=1200, del_len=727,
+                                           inv_at=2600, inv_len=800, sub_at=2200)),
+    "flox_full": (flox_full_case, dict()),
+    "batch_full": (batch_full_case, dict()),
+    "inv_full": (synthetic_case, dict(length=2724, n_sample=1000, n_control=1000, profile="r10", kind="inversion")),
+    "strand_biased": (strand_biased_case, dict()),
+    "tp_L5000_N20000_r10": (synthetic_case, dict(length=5000, n_sample=20000, n_control=10000, profile="r10")),
+    "tp_L5000_N5000_r9": (synthetic_case, dict(length=5000, n_sample=5000, n_control=5000, profile="r9")),
     "sv_like": (sv_like_case, dict()),
     "raw_midsv": (raw_midsv_case, dict()),
 }
+
+
+#: the bench.py generator at the reference's scale, run through the reference's whole flow with recording hooks
+#: (oracle/make_golden.py:run_reference_bench); inputs are never materialised as Python strings
+BENCH_RECIPES = {
+    "bench_L5000_N100000": dict(length=5000, n_sample=100_000, n_control=10_000, profile="r10"),
+}
+
+#: single-sample cases recorded through the whole flow with hooks (silhouette trace, labels before the strand-bias
+#: re-allocation, DecisionTree fits) instead of the stage-by-stage payload of the round-1 cases
+FLOW_RECIPES = {"strand_biased", "tp_L5000_N20000_r10", "tp_L5000_N5000_r9", "single_full", "inv_full"}
 
 
 def build_case(name: str) -> dict:

@@ -154,6 +154,187 @@ def run_reference(alleles: dict, given_loci=None) -> dict:
     return out
 
 
+class _Hooks:
+    """Recording wrappers around reference functions that other reference modules imported BY VALUE (the reference's
+    code is not modified: the wrappers call the original and note what went in and came out)."""
+
+    def __init__(self, compact: bool):
+        from DAJIN2.core.clustering import label_extractor
+        from DAJIN2.core.clustering import strand_bias_handler as clu_strand
+
+        self.compact = compact
+        self.records = []  # one dict per clustered allele group, in extract_labels order
+        self._saved = []
+        cur = {}
+
+        def patch(mod, name, fn):
+            self._saved.append((mod, name, getattr(mod, name)))
+            setattr(mod, name, fn)
+
+        real_make_score = label_extractor.make_score
+        real_return_labels = label_extractor.return_labels
+        real_silhouette = ref_clustering.silhouette_score
+        real_optimize = ref_clustering.optimize_labels
+        real_remove = ref_clustering.remove_biased_clusters
+        real_train = clu_strand.train_decision_tree
+
+        def make_score(path_sample, path_control, loci, knockin):
+            out = real_make_score(path_sample, path_control, loci, knockin)
+            cur.clear()
+            cur["make_score"] = {str(i): {k: float(v).hex() for k, v in d.items()} for i, d in enumerate(out) if d}
+            return out
+
+        def silhouette(X, labels, **kw):
+            v = real_silhouette(X, labels, **kw)
+            cur.setdefault("silhouette_trace", []).append([int(len(set(labels))), float(v).hex()])
+            return v
+
+        def optimize(X, n_s, n_c):
+            out = real_optimize(X, n_s, n_c)
+            cur["optimize_labels"] = [int(x) for x in out]
+            cur["x_shape"] = [int(X.shape[0]), int(X.shape[1])]
+            return out
+
+        def train(train_data, train_labels):
+            cur["decision_tree_fits"] = cur.get("decision_tree_fits", 0) + 1
+            cur.setdefault("decision_tree_train_rows", []).append(len(train_labels))
+            return real_train(train_data, train_labels)
+
+        def remove(path_sample, path_score_sample, labels, strand_sample):
+            before = list(labels)
+            out = real_remove(path_sample, path_score_sample, labels, strand_sample)
+            cur["labels_before_strand_bias"] = [int(x) for x in before]
+            return out
+
+        def return_labels(path_score_sample, path_score_control, path_sample, strand_sample):
+            xs = [json.loads(line) for line in open(path_score_sample)]
+            xc = [json.loads(line) for line in open(path_score_control)]
+            cur["rows_sample"] = unique_rows(xs)
+            cur["rows_control"] = unique_rows(xc)
+            cur["strand_sample"] = dict(strand_sample)
+            del xs, xc
+            out = real_return_labels(path_score_sample, path_score_control, path_sample, strand_sample)
+            cur["return_labels"] = [int(x) for x in out]
+            cur["group_qnames_sha"] = __import__("hashlib").sha256(
+                "\n".join(json.loads(line)["QNAME"] for line in open(path_sample)).encode()).hexdigest()
+            self.records.append(dict(cur))
+            return out
+
+        patch(label_extractor, "make_score", make_score)
+        patch(label_extractor, "return_labels", return_labels)
+        patch(ref_clustering, "silhouette_score", silhouette)
+        patch(ref_clustering, "optimize_labels", optimize)
+        patch(ref_clustering, "remove_biased_clusters", remove)
+        patch(clu_strand, "train_decision_tree", train)
+
+    def close(self):
+        for mod, name, fn in reversed(self._saved):
+            setattr(mod, name, fn)
+
+
+def _sha_lines(lines) -> str:
+    import hashlib
+
+    return hashlib.sha256("\n".join(lines).encode()).hexdigest()
+
+
+def run_reference_samples(samples: dict, write_sample=None, write_control=None) -> dict:
+    """The reference's batch flow (main.py:152-235): the control once, then every sample against it in one temp dir
+    (so that later samples find the control's cached counts, mutation_extractor.py:113-114); per sample the call
+    sequence of core.execute_sample (core.py:161,217-233) with recording hooks.  ``samples``: {sample name: {"alleles":
+    FASTA-ordered {allele: case dict}}}; the control parts of the first sample are the shared control."""
+    import hashlib
+
+    import numpy as np
+
+    out = {"samples": {}}
+    cname = "ctrl"
+    with tempfile.TemporaryDirectory() as tmp:
+        tmp = Path(tmp)
+        first = next(iter(samples.values()))["alleles"]
+        for name, a in first.items():
+            key = to_allele_key(name)
+            if write_control is not None:
+                write_control(tmp / cname / "midsv" / key / f"{cname}_midsv.jsonl", name)
+            else:
+                write_jsonl(tmp / cname / "midsv" / key / f"{cname}_midsv.jsonl", a["control"], name)
+        for sname, entry in samples.items():
+            alleles = entry["alleles"]
+            fasta = {name: a["sequence"] for name, a in alleles.items()}
+            for name, a in alleles.items():
+                key = to_allele_key(name)
+                if write_sample is not None:
+                    write_sample(tmp / sname / "midsv" / key / f"{sname}_midsv.jsonl", name)
+                else:
+                    write_jsonl(tmp / sname / "midsv" / key / f"{sname}_midsv.jsonl", a["sample"], name)
+                if a.get("knockin") is not None:
+                    p = tmp / sname / "knockin_loci" / key / "knockin.pickle"
+                    p.parent.mkdir(parents=True, exist_ok=True)
+                    p.write_bytes(pickle.dumps(set(a["knockin"])))
+            (tmp / sname / "clustering").mkdir(parents=True, exist_ok=True)
+            args = SimpleNamespace(tempdir=tmp, sample_name=sname, control_name=cname, fasta_alleles=fasta)
+            stamp = {}
+            for name in alleles:
+                pc = tmp / cname / "mutation_loci" / to_allele_key(name) / f"{cname}_count.pickle"
+                stamp[name] = pc.stat().st_mtime_ns if pc.exists() else None
+            preprocess.cache_mutation_loci(args, is_control=True)   # execute_control (core.py:95)
+            preprocess.cache_mutation_loci(args, is_control=False)  # execute_sample (core.py:161)
+            g_s = {"alleles": {}, "control_counts_reused": {}}
+            for name, a in alleles.items():
+                key = to_allele_key(name)
+                pc = tmp / cname / "mutation_loci" / key / f"{cname}_count.pickle"
+                g_s["control_counts_reused"][name] = stamp[name] is not None and pc.stat().st_mtime_ns == stamp[name]
+                d = tmp / sname / "mutation_loci" / key
+                g = {}
+                if "sample" in a:
+                    g["sha_sample"], g["sha_control"] = cases.digest(a["sample"]), cases.digest(a["control"])
+                else:
+                    g["sha_sample"], g["sha_control"] = a["sha_sample"], a["sha_control"]
+                g["count_sample"] = pickle.loads((d / f"{sname}_count.pickle").read_bytes())
+                norm = pickle.loads((d / f"{sname}_normalized.pickle").read_bytes())
+                g["norm_sample"] = {k: [float(x).hex() for x in v] for k, v in norm.items()}
+                g["count_control"] = pickle.loads(pc.read_bytes())
+                loci = pickle.loads((d / "mutation_loci.pickle").read_bytes())
+                g["mutation_loci"] = ["".join(sorted(s)) for s in loci]
+                p_s = tmp / sname / "midsv" / key / f"{sname}_midsv.jsonl"
+                g["strand_counts"] = {str(i): v for i, v in ref_strand.count_strandless_of_indels(p_s, loci).items()}
+                cm = np.array([classifier.calc_match(json.loads(line)["MIDSV"]) for line in open(p_s)], dtype="<i4")
+                g["calc_match_sha"] = hashlib.sha256(cm.tobytes()).hexdigest()
+                g["calc_match_sum"] = int(cm.sum())
+                g_s["alleles"][name] = g
+            hooks = _Hooks(compact=True)
+            try:
+                classif = classification.classify_alleles(tmp, fasta, sname)
+                g_s["classify_sha"] = _sha_lines(c["QNAME"] + "\t" + c["ALLELE"] for c in classif)
+                g_s["classify_counts"] = {k: int(v) for k, v in __import__("collections").Counter(
+                    c["ALLELE"] for c in classif).items()}
+                labels = clustering.extract_labels(classif, tmp, sname, cname)
+            finally:
+                hooks.close()
+            g_s["extract_labels_order_sha"] = _sha_lines(c["QNAME"] for c in classif)
+            g_s["extract_labels_alleles"] = [c["ALLELE"] for c in classif] if len(fasta) > 1 else None
+            g_s["extract_labels"] = [int(x) for x in labels]
+            clust = clustering.update_labels(clustering.add_percent(clustering.add_readnum(
+                clustering.add_labels(classif, labels))))
+            g_s["final_labels"] = [int(c["LABEL"]) for c in clust]
+            g_s["final_percent"] = sorted({(int(c["LABEL"]), c["ALLELE"], int(c["READNUM"]), c["PERCENT"]) for c in clust})
+            g_s["groups"] = hooks.records
+            out["samples"][sname] = g_s
+    return out
+
+
+def run_reference_bench(length: int, n_sample: int, n_control: int, profile: str) -> dict:
+    """The bench.py generator at the reference's own scale (up to its 100 000-read cap): files are written straight
+    from the generator's buffers, inputs are pinned by their digest."""
+    pop, bs, bc = cases.bench_batches(length, n_sample, n_control, profile)
+    entry = {"alleles": {"control": {"sequence": pop.reference, "knockin": None,
+                                     "sha_sample": cases.digest_batch(bs), "sha_control": cases.digest_batch(bc)}}}
+    payload = run_reference_samples({"sample": entry}, write_sample=lambda p, name: bs.write_jsonl(p),
+                                    write_control=lambda p, name: bc.write_jsonl(p))
+    payload["bench"] = {"length": length, "n_sample": n_sample, "n_control": n_control, "profile": profile}
+    return payload
+
+
 def _sparse_dicts(records) -> dict:
     return {str(i): {str(k): int(v) for k, v in d.items()} for i, d in enumerate(records) if d}
 
@@ -297,12 +478,20 @@ def main(names) -> None:
             case = fixture_case()
             payload = run_reference({"control": case})
             payload["inputs"] = {"control": {**case, "knockin": None}}
+        elif name in cases.BENCH_RECIPES:
+            payload = run_reference_bench(**cases.BENCH_RECIPES[name])
+        elif name in cases.FLOW_RECIPES:
+            case = cases.build_case(name)
+            alleles = case["alleles"] if "alleles" in case else {"control": case}
+            payload = run_reference_samples({"sample": {"alleles": alleles}})
         else:
             case = cases.build_case(name)
             if case.get("kind") == "sv":
                 payload = run_reference_sv(case)
             elif case.get("kind") == "raw_midsv":
                 payload = run_reference_postfix(case)
+            elif "samples" in case:
+                payload = run_reference_samples(case["samples"])
             elif "alleles" in case:
                 payload = run_reference(case["alleles"])
             elif "loci" in case:
