@@ -19,7 +19,7 @@ CODE_INVALID = 0x7F
 CODE_INS = 0x80
 FLAG_TOKEN_COUNT = 1
 FLAG_BAD_TOKEN = 2
-ENC_CHUNK = 1024
+ENC_CHUNK = 1536
 HIST_ROWS = 10
 MASK_INS, MASK_DEL, MASK_SUB = 1, 2, 4
 KMER_AT, KMER_RAW = 256, 257
@@ -57,6 +57,8 @@ SIGNATURES = {
     "dj_ckpt_pitch": (c_int32, [c_int32]),
     "dj_encode": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                             c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dj_encode_v1": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p]),
     "dj_encode_ref": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dj_encode_ref_smem_bytes": (c_int64, [c_int32, c_int32]),
@@ -96,7 +98,7 @@ _NO_STATUS = {"dj_abi_version", "dj_last_error", "dj_code_pitch", "dj_ckpt_pitch
 
 # kernels launched per call (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    "dj_encode": 1, "dj_encode_ref": 1, "dj_hist": 2, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
+    "dj_encode": 1, "dj_encode_v1": 1, "dj_encode_ref": 1, "dj_hist": 2, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
     "dj_fetch_tokens": 1, "dj_dedup_rows": 1, "dj_dedup_export": 1, "dj_bisect": 1, "dj_assign_rows": 1,
     "dj_silhouette": 2, "dj_member_counts": 1, "dj_member_locate": 1, "dj_gather_labels": 1,
     "dj_read_n_features": 1, "dj_sv_scan": 1,

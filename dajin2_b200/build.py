@@ -14,7 +14,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libdajin2_b200.so"
-SOURCES = ["cabi.cu", "encode.cu", "hist.cu", "kmer.cu", "cluster.cu", "readstat.cu"]
+SOURCES = ["cabi.cu", "encode.cu", "encode_v1.cu", "hist.cu", "kmer.cu", "cluster.cu", "readstat.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
@@ -33,7 +33,7 @@ def needs_build() -> bool:
     if not LIB.exists():
         return True
     stamp = LIB.stat().st_mtime
-    deps = [CSRC / s for s in SOURCES] + [CSRC / "dj_common.cuh", HERE.parent / "include" / "dajin2_b200.h"]
+    deps = [CSRC / s for s in SOURCES] + sorted(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "dajin2_b200.h"]
     return any(d.stat().st_mtime > stamp for d in deps)
 
 

@@ -82,11 +82,10 @@ class EncodedReads:
 
     def __init__(self, host: HostReads, n_loci: int, validate: bool = True, encode: bool = True,
                  sequence: str | None = None, assisted: bool | None = None):
-        """``sequence`` (the allele the reads were aligned to, when the caller has it) with ``assisted`` lets the
-        encoder verify plain stretches against the rendered reference instead of translating them
-        (``dj_encode_ref``); the codes are the same with or without it.  Measured on B200 the assisted kernel is
-        4 % slower than the generic one, so it is off unless ``assisted`` or
-        ``DAJIN2_B200_ENCODE_REF=1`` asks for it."""
+        """``sequence`` / ``assisted`` select the ``dj_encode_ref`` entry point (round 1: plain stretches verified
+        against the rendered reference).  The unit encoder behind ``dj_encode`` verifies plain stretches against
+        their own periodic structure and needs no sequence; ``dj_encode_ref`` now forwards to it, the arguments are
+        kept for callers of round 1 (same codes with or without them)."""
         dev = require_cuda()
         self.n_reads = host.n_reads
         self.n_loci = int(n_loci)
@@ -128,6 +127,18 @@ class EncodedReads:
         _cabi.call("dj_encode", _p(self.text), _p(self.row_off), _p(self.row_len), self.n_reads, self.n_loci,
                    self.pitch, self.ckpt_pitch, _p(self.codes), _p(self.match_score), _p(self.n_tokens),
                    _p(self.flags), _p(self.ckpt), _stream())
+
+    def encode_v1(self):
+        """The round-1 generic kernel on the same text (cross-check of the unit encoder): codes, match_score,
+        n_tokens, flags as new tensors."""
+        n = max(self.n_reads, 1)
+        codes = torch.empty((n, self.pitch), dtype=torch.uint8, device=self.codes.device)
+        ms = torch.empty(n, dtype=torch.int32, device=self.codes.device)
+        nt = torch.empty(n, dtype=torch.int32, device=self.codes.device)
+        fl = torch.zeros(n, dtype=torch.int32, device=self.codes.device)
+        _cabi.call("dj_encode_v1", _p(self.text), _p(self.row_off), _p(self.row_len), self.n_reads, self.n_loci,
+                   self.pitch, _p(codes), _p(ms), _p(nt), _p(fl), _stream())
+        return codes, ms, nt, fl
 
     def validate(self) -> None:
         if self.n_reads == 0:

@@ -44,7 +44,7 @@ extern "C" {
 #define DJ_FLAG_BAD_TOKEN 2u   /* a token outside the supported grammar */
 
 /* bytes of text one trip of the encoder's main loop covers; checkpoint granularity of the token index */
-#define DJ_ENC_CHUNK 1024
+#define DJ_ENC_CHUNK 1536
 
 /* rows of dj_hist output: counts[DJ_HIST_ROWS][n_loci] (int32) */
 #define DJ_HIST_MATCH 0   /* '=' with the N / lowercase skip rule   (indel_counter.py:15-31)            */
@@ -107,6 +107,12 @@ int32_t dj_ckpt_pitch(int32_t max_row_len);
 int dj_encode(const uint8_t *text, const int64_t *row_off, const int32_t *row_len, int64_t n_reads,
               int32_t n_loci, int32_t code_pitch, int32_t ckpt_pitch, uint8_t *codes, int32_t *match_score,
               int32_t *n_tokens, uint32_t *flags, uint32_t *ckpt, void *stream);
+
+/* The round-1 generic encoder (every 16-byte chunk through the comma slots, no checkpoints), kept as an on-device
+ * cross-check of dj_encode: same codes, match_score, n_tokens and flags for any input. */
+int dj_encode_v1(const uint8_t *text, const int64_t *row_off, const int32_t *row_len, int64_t n_reads,
+                 int32_t n_loci, int32_t code_pitch, uint8_t *codes, int32_t *match_score, int32_t *n_tokens,
+                 uint32_t *flags, void *stream);
 
 /* dj_encode with the allele sequence as an accelerator: ref_seq[n_loci] (device, ASCII bases).  Stretches of plain
  * matches are verified against the reference rendered as "=X,=X,..." instead of being translated token by token;
