@@ -29,30 +29,38 @@
 #include "encode_unit.cuh"
 
 #ifndef DJ_ENC_WARPS
-#define DJ_ENC_WARPS 24  // warps per CTA, one CTA per SM
+#define DJ_ENC_WARPS 16  // warps per CTA, one CTA per SM
 #endif
 #ifndef DJ_ENC_STAGES
 #define DJ_ENC_STAGES 3  // slots of the per-warp text ring
 #endif
+#ifndef DJ_ENC_UNITS
+#define DJ_ENC_UNITS 2   // units per lane and trip
+#endif
 
-static_assert(DJ_ENC_CHUNK == dju::kTripBytes, "the checkpoint grid is the trip of the unit encoder");
+static_assert(DJ_ENC_CHUNK == dju::kTripBytes, "the checkpoint grid is one unit per lane of the unit encoder");
 
 namespace {
 
 constexpr int kWarps = DJ_ENC_WARPS;
 constexpr int kStages = DJ_ENC_STAGES;
-constexpr int kTrip = dju::kTripBytes;             // 1536
+constexpr int kU = DJ_ENC_UNITS;
+constexpr int kHalf = dju::kTripBytes;             // 1536 bytes: one unit per lane (the checkpoint grid)
+constexpr int kTrip = kU * kHalf;                  // bytes of text per trip of the main loop
 constexpr int kSlotBytes = 16 + kTrip;             // 16 bytes in front of the text: the word before the trip lives there
-constexpr int kMaxTokensPerTrip = 544;             // a valid trip closes at most 513 tokens
-constexpr int kStageBytes = 640;                   // 31 carried bytes + kMaxTokensPerTrip + one rotated spill word
-constexpr int kListBytes = 32;
-constexpr int kWarpBytes = kStages * kSlotBytes + kStageBytes + kListBytes;
-constexpr int kPatOffset = kLutSize * 4;           // four uint4: pattern f0, f1, shift bits of phases 0..2, impossible
+constexpr int kMaxTokensPerTrip = kU * 544;        // a valid trip closes at most kU * 512 + 1 tokens
+constexpr int kStageBytes = 64 + kMaxTokensPerTrip;  // 31 carried bytes + the trip's codes + one rotated spill word
+constexpr int kListBytes = kU * 32;                // unit ids of the slow path, compacted
+constexpr int kCntBytes = kU * 32 * 4;             // per unit: commas of its three chunks (one byte each)
+constexpr int kExclBytes = kU * 32 * 2;            // per unit: rank of its first token inside the trip
+constexpr int kWarpBytes = kStages * kSlotBytes + kStageBytes + kListBytes + kCntBytes + kExclBytes;
+constexpr int kPatOffset = kLutSize * 4;           // four phase entries (uint4)
 constexpr int kBarOffset = kPatOffset + 64;
 constexpr int kWarpOffset = (kBarOffset + kWarps * kStages * 8 + 127) & ~127;
 constexpr int kSmemBytes = kWarpOffset + kWarps * kWarpBytes;
-static_assert(kWarpBytes % 16 == 0 && kSlotBytes % 16 == 0, "16-byte alignment of the ring slots");
+static_assert(kWarpBytes % 16 == 0 && kSlotBytes % 16 == 0 && kStageBytes % 16 == 0, "16-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory of the unit encoder");
+static_assert(kU >= 1 && kU <= 2, "units per lane");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -87,6 +95,15 @@ __device__ __forceinline__ uint32_t chunk_commas_exact(const uint4 &c, uint32_t 
            (dju::comma_flags_exact(c.w) >> 3);
 }
 
+// inclusive warp scan, one shuffle and one predicated add per step
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t x) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile("{\n .reg .pred p;\n .reg .u32 t;\n shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n @p add.u32 %0, %0, t;\n}\n"
+                     : "+r"(x) : "r"(d));
+    return x;
+}
+
 struct RowGeom {
     const uint8_t *base;  // 16-byte aligned start of the row's span
     int head;             // bytes of the span in front of the row
@@ -113,10 +130,8 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     uint4 *pat = reinterpret_cast<uint4 *>(smem + kPatOffset);
     build_token_lut(lut);
     if (threadIdx.x < 4) {
-        const int c0 = (int)threadIdx.x;
-        const dju::UnitMap m = dju::plain_pattern(c0 < 3 ? c0 : 0);
-        pat[c0] = c0 < 3 ? make_uint4(m.f0, m.f1, dju::phase_shift_bits(c0), 0u)
-                         : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 16u, 0u);
+        const dju::Phase ph = dju::phase_entry(threadIdx.x);
+        pat[threadIdx.x] = make_uint4(ph.shift, ph.trail, ph.bad, 0u);
     }
 
     const int lane = threadIdx.x & 31;
@@ -124,6 +139,8 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     uint8_t *wbase = smem + kWarpOffset + wid * kWarpBytes;
     uint8_t *stage = wbase + kStages * kSlotBytes;
     uint8_t *list = stage + kStageBytes;
+    uint8_t *cntbuf = list + kListBytes;
+    uint16_t *exclbuf = reinterpret_cast<uint16_t *>(cntbuf + kCntBytes);
     const uint32_t ring_s = smem_u32(wbase);
     const uint32_t stage_s = smem_u32(stage);
     const uint32_t lut_s = smem_u32(lut);
@@ -199,71 +216,119 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
         for (int t = 0; t < geom.n_trips; ++t) {
             produce();  // refills the slot the previous trip read (all of its reads are behind a __syncwarp)
             mbar_wait(bar_s + 8u * c_slot, (c_phase >> c_slot) & 1u);
-            const uint8_t *sb = wbase + c_slot * kSlotBytes;
+            uint8_t *sb = wbase + c_slot * kSlotBytes;
             c_phase ^= 1u << c_slot;
             c_slot = c_slot + 1 == kStages ? 0 : c_slot + 1;
             if (broken) {
                 __syncwarp();
                 continue;
             }
-
-            uint32_t w[12];
-            {
-                const uint4 *up = reinterpret_cast<const uint4 *>(sb + 16 + dju::kUnitBytes * lane);
-                const uint4 q0 = up[0], q1 = up[1], q2 = up[2];
-                w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
-                w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
-                w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
-            }
-            const int g = t * kTrip + dju::kUnitBytes * lane;  // span offset of this lane's unit
-            const bool dead = g > nbytes;                      // past the virtual closing comma
-            const bool edge_trip = (t == 0 && head > 0) || (t + 1) * kTrip > nbytes;
+            const int g0 = t * kTrip;
+            const bool edge_trip = (t == 0 && head > 0) || g0 + kTrip > nbytes;
+            if (lane == 0) *reinterpret_cast<uint32_t *>(sb + 12) = carry_w;
             if (edge_trip) {
-                // units that hold bytes outside the row: ' ' in front of the row and behind it, ONE ',' at `nbytes`;
-                // the padded words go back to the ring, the slow path reads them there
-                if (!dead && (g < head || g + dju::kUnitBytes > nbytes)) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) w[j] = pad_word(w[j], g + 4 * j, head, nbytes);
-                    uint4 *up = reinterpret_cast<uint4 *>(const_cast<uint8_t *>(sb) + 16 + dju::kUnitBytes * lane);
-                    up[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    up[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                    up[2] = make_uint4(w[8], w[9], w[10], w[11]);
-                }
-                if (dead) {
-#pragma unroll
-                    for (int j = 0; j < 12; ++j) w[j] = kFill;
+                // bytes of the trip that lie outside the row: ' ' in front of the row, ONE ',' at `nbytes` (it closes
+                // the last token) and ' ' behind it up to the end of its unit; units further back are dead
+                if (t == 0 && lane < head) sb[16 + lane] = ' ';
+                const int rel = nbytes - g0;  // >= 0; inside this trip <=> this is the row's last trip
+                if (rel < kTrip) {
+                    const int unit_end = (rel / dju::kUnitBytes + 1) * dju::kUnitBytes;
+                    if (rel + lane < unit_end) sb[16 + rel + lane] = lane == 0 ? ',' : ' ';
+                    if (rel + 32 + lane < unit_end) sb[16 + rel + 32 + lane] = ' ';
                 }
             }
-            uint32_t wprev = __shfl_up_sync(0xffffffffu, w[11], 1);
-            const uint32_t next_carry = __shfl_sync(0xffffffffu, w[11], 31);
-            if (lane == 0) {
-                wprev = carry_w;
-                // checkpoint: tokens that START before this trip's first byte (dj_find_token resumes from it)
-                ck[t] = t == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
-                *reinterpret_cast<uint32_t *>(const_cast<uint8_t *>(sb) + 12) = carry_w;
-            }
+            __syncwarp();
 
-            // ---- every lane: comma bitmap, phase, sixteen codes if the unit is plain ---------------------------
-            const dju::UnitMap fm = dju::comma_bitmap(w);
-            const uint32_t pc0 = dju::popc(fm.f0);
-            const uint32_t cnt = dead ? 0u : pc0 + dju::popc(fm.f1);
-            const uint4 pe = pat[dju::phase_index(fm.f0)];
-            const dju::UnitOut uo = dju::decode_unit(wprev, w, pe.z);
-            bool plain = !dead && fm.f0 == pe.x && fm.f1 == pe.y && uo.bad == 0;
-            // a unit that closes fewer than four tokens (the inside of a long insertion) does not cover the words it
-            // shares with its neighbours: such a trip goes through the slow path as a whole
-            if (__any_sync(0xffffffffu, !dead && !plain && cnt < 4u)) plain = false;
-            const uint32_t plain_mask = __ballot_sync(0xffffffffu, plain);
-            const uint32_t slow_mask = __ballot_sync(0xffffffffu, !plain && !dead);
-
-            uint32_t incl = cnt;
+            // ---- every lane: its units; sixteen codes each if the unit is plain ---------------------------------
+            uint32_t cw[kU][4];
+            uint32_t n_del[kU];
+            bool plain[kU], dead[kU];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
+            for (int h = 0; h < kU; ++h) {
+                const uint8_t *up = sb + 16 + h * kHalf + dju::kUnitBytes * lane;
+                uint32_t w[12];
+                {
+                    const uint4 q0 = reinterpret_cast<const uint4 *>(up)[0], q1 = reinterpret_cast<const uint4 *>(up)[1],
+                                q2 = reinterpret_cast<const uint4 *>(up)[2];
+                    w[0] = q0.x; w[1] = q0.y; w[2] = q0.z; w[3] = q0.w;
+                    w[4] = q1.x; w[5] = q1.y; w[6] = q1.z; w[7] = q1.w;
+                    w[8] = q2.x; w[9] = q2.y; w[10] = q2.z; w[11] = q2.w;
+                }
+                const uint32_t wprev = *reinterpret_cast<const uint32_t *>(up - 4);
+                const uint4 pe = pat[dju::phase_index(w[0])];
+                dju::Phase ph;
+                ph.shift = pe.x; ph.trail = pe.y; ph.bad = pe.z; ph.pad = 0;
+                const dju::UnitOut uo = dju::decode_unit(wprev, w, ph);
+                dead[h] = g0 + h * kHalf + dju::kUnitBytes * lane > nbytes;  // past the virtual closing comma
+                plain[h] = !dead[h] && uo.bad == 0;
+                n_del[h] = uo.n_del;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cw[h][q] = uo.c[q];
             }
-            const int total = (int)__shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t excl = incl - cnt;
+
+            // ---- ranks: a plain unit closes sixteen tokens; the chunks of the other units are compacted over the
+            //      lanes and counted (the same compaction translates them further down) ------------------------------
+            uint32_t plain_mask[kU], slow_mask[kU], cnt[kU];
+            uint32_t zz_first = 0;
+            int n_chunks = 0;
+            bool force = false;
+#pragma unroll 1
+            for (;;) {
+                int n_slow = 0;
+#pragma unroll
+                for (int h = 0; h < kU; ++h) {
+                    const bool p = plain[h] && !force;
+                    plain_mask[h] = __ballot_sync(0xffffffffu, p);
+                    slow_mask[h] = __ballot_sync(0xffffffffu, !p && !dead[h]);
+                    if (!p && !dead[h]) list[n_slow + __popc(slow_mask[h] & lanes_below)] = (uint8_t)(h * 32 + lane);
+                    n_slow += __popc(slow_mask[h]);
+                }
+                n_chunks = 3 * n_slow;
+                if (n_slow > 0) {
+                    __syncwarp();
+#pragma unroll 1
+                    for (int j0 = 0; j0 < n_chunks; j0 += 32) {
+                        const int j = j0 + lane;
+                        if (j < n_chunks) {
+                            const int ui = (j * 171) >> 9;  // j / 3 for j < 192
+                            const int c = j - 3 * ui;
+                            const int u = list[ui];
+                            const uint4 ch = *reinterpret_cast<const uint4 *>(sb + 16 + dju::kUnitBytes * u + 16 * c);
+                            const uint32_t zz = chunk_commas_exact(ch, high);
+                            cntbuf[4 * u + c] = (uint8_t)__popc(zz);
+                            if (j0 == 0) zz_first = zz;
+                        }
+                    }
+                    __syncwarp();
+                }
+                bool small = false;
+#pragma unroll
+                for (int h = 0; h < kU; ++h) {
+                    const bool p = plain[h] && !force;
+                    const uint32_t cb = reinterpret_cast<const uint32_t *>(cntbuf)[h * 32 + lane];
+                    const uint32_t slow_cnt = (cb & 0xFFu) + ((cb >> 8) & 0xFFu) + ((cb >> 16) & 0xFFu);
+                    cnt[h] = dead[h] ? 0u : (p ? 16u : slow_cnt);
+                    small = small || (!dead[h] && !p && slow_cnt < 4u);
+                }
+                // a unit that closes fewer than four tokens (the inside of a long insertion) does not cover the words
+                // it shares with its neighbours: such a trip goes through the slow path as a whole
+                if (force || !__any_sync(0xffffffffu, small)) break;
+                bool any_plain = false;
+#pragma unroll
+                for (int h = 0; h < kU; ++h) any_plain = any_plain || plain_mask[h] != 0u;
+                if (!any_plain) break;
+                force = true;
+            }
+
+            uint32_t packed = cnt[0];
+            if (kU == 2) packed |= cnt[kU - 1] << 16;
+            const uint32_t incl = warp_scan_incl(packed);
+            const uint32_t totals = __shfl_sync(0xffffffffu, incl, 31);
+            const int total0 = (int)(totals & 0xFFFFu);
+            const int total = total0 + (kU == 2 ? (int)(totals >> 16) : 0);
+            uint32_t excl[kU];
+            excl[0] = (incl & 0xFFFFu) - cnt[0];
+            if (kU == 2) excl[kU - 1] = (uint32_t)total0 + (incl >> 16) - cnt[kU - 1];
             // not MIDSV: more commas than a trip of tokens can hold, or more tokens than the row has room for (tested
             // BEFORE anything is staged or stored: a row never writes past its own row of the code matrix)
             if (total > kMaxTokensPerTrip || tokbase + total > code_pitch) {
@@ -273,61 +338,75 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                 __syncwarp();
                 continue;
             }
+            if (lane == 0) {
+                // checkpoints: tokens that START before byte j * DJ_ENC_CHUNK of the span (dj_find_token resumes there)
+                ck[kU * t] = t == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
+                if (kU == 2 && g0 + kHalf <= nbytes)
+                    ck[kU * t + 1] = (uint32_t)(tokbase + total0) + (sb[16 + kHalf - 1] == ',' ? 0u : 1u);
+            }
             const uint32_t t0 = (uint32_t)tokbase & 31u;  // stage[0] holds locus (tokbase & ~31) of the row
 
-            // ---- plain lanes: sixteen code bytes as whole words ------------------------------------------------
-            {
-                const uint32_t o = t0 + excl;
+            // ---- plain units: sixteen code bytes as whole words (the word shared with a plain neighbour is merged
+            //      through a shuffle; a word shared with another unit is overwritten by the slow path afterwards) -------
+            uint32_t last_spill = 0;
+            bool last_plain = false;
+#pragma unroll
+            for (int h = 0; h < kU; ++h) {
+                const bool p = plain[h] && !force;
+                const uint32_t o = t0 + excl[h];
                 uint32_t rot[5];
-                dju::rotate_codes(uo.c, o & 3u, rot);
+                dju::rotate_codes(cw[h], o & 3u, rot);
                 const uint32_t spill = __shfl_up_sync(0xffffffffu, rot[4], 1);
-                const uint32_t carried = *reinterpret_cast<const uint32_t *>(stage + (t0 & ~3u));
-                if (lane == 0) rot[0] |= carried & ((1u << (8u * (t0 & 3u))) - 1u);
-                else if ((plain_mask >> (lane - 1)) & 1u) rot[0] |= spill;
-                if (plain) {
+                if (lane == 0) {
+                    if (h == 0) rot[0] |= *reinterpret_cast<const uint32_t *>(stage + (t0 & ~3u)) & ((1u << (8u * (t0 & 3u))) - 1u);
+                    else if (last_plain) rot[0] |= last_spill;
+                } else if ((plain_mask[h] >> (lane - 1)) & 1u) {
+                    rot[0] |= spill;
+                }
+                const bool next_plain = lane < 31 ? ((plain_mask[h] >> (lane + 1)) & 1u) != 0u
+                                                  : (h + 1 < kU ? (plain_mask[(h + 1) % kU] & 1u) != 0u : false);
+                if (p) {
                     uint32_t *dst = reinterpret_cast<uint32_t *>(stage + (o & ~3u));
                     dst[0] = rot[0];
                     dst[1] = rot[1];
                     dst[2] = rot[2];
                     dst[3] = rot[3];
-                    if (lane == 31 || !((plain_mask >> (lane + 1)) & 1u)) dst[4] = rot[4];
-                    mism += uo.n_del;
+                    if (!next_plain) dst[4] = rot[4];
+                    mism += n_del[h];
+                } else if (!dead[h]) {
+                    exclbuf[h * 32 + lane] = (uint16_t)excl[h];
+                }
+                if (h + 1 < kU) {
+                    last_spill = __shfl_sync(0xffffffffu, rot[4], 31);
+                    last_plain = (plain_mask[h] >> 31) != 0u;
                 }
             }
             __syncwarp();
 
-            // ---- slow path: the 16-byte chunks of the other units, compacted over the lanes --------------------
-            if (slow_mask != 0u) {
-                if (!plain && !dead) list[__popc(slow_mask & lanes_below)] = (uint8_t)lane;
-                const uint32_t pack = excl | (dju::popc(fm.f0 & 0x0F0F0F0Fu) << 16) | (pc0 << 24);
-                __syncwarp();
-                const int n_chunks = 3 * __popc(slow_mask);
+            // ---- slow path: the 16-byte chunks of the other units go through the generic comma slots ------------
 #pragma unroll 1
-                for (int j0 = 0; j0 < n_chunks; j0 += 32) {
-                    const int j = j0 + lane;
-                    const bool active = j < n_chunks;
-                    const int ju = active ? j : 0;
-                    const int ui = (ju * 43) >> 7;  // ju / 3 for ju < 96
-                    const int c = ju - 3 * ui;
+            for (int j0 = 0; j0 < n_chunks; j0 += 32) {
+                const int j = j0 + lane;
+                if (j < n_chunks) {
+                    const int ui = (j * 171) >> 9;
+                    const int c = j - 3 * ui;
                     const int u = list[ui];
-                    const uint32_t info = __shfl_sync(0xffffffffu, pack, u);
-                    if (active) {
-                        const uint8_t *cp = sb + 16 + dju::kUnitBytes * u + 16 * c;
-                        const uint4 ch = *reinterpret_cast<const uint4 *>(cp);
-                        const uint32_t wp = *reinterpret_cast<const uint32_t *>(cp - 4);
-                        const uint32_t zz = chunk_commas_exact(ch, high);
-                        const uint32_t rel = (info & 0xFFFFu) + (c == 0 ? 0u : (c == 1 ? (info >> 16) & 0xFFu : info >> 24));
-                        uint32_t acc = 0;
-                        const uint32_t wrote = emit_chunk(acc, stage_s + t0 + rel, lut_s, wp, ch, zz, c_four, c_shift);
-                        // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV: bits
-                        // 0..3; the table's "special" counter: bits 8..12
-                        sticky |= (wrote ^ (uint32_t)__popc(zz)) | ((acc >> 15) & 0x1F00u);
-                        mism += (acc >> kStatShift) & 0x3Fu;
-                        n_sub += (acc >> 18) & 0x1Fu;
-                    }
+                    const uint8_t *cp = sb + 16 + dju::kUnitBytes * u + 16 * c;
+                    const uint4 ch = *reinterpret_cast<const uint4 *>(cp);
+                    const uint32_t wp = *reinterpret_cast<const uint32_t *>(cp - 4);
+                    const uint32_t zz = j0 == 0 ? zz_first : chunk_commas_exact(ch, high);
+                    const uint32_t cb = reinterpret_cast<const uint32_t *>(cntbuf)[u];
+                    const uint32_t rel = exclbuf[u] + (c == 0 ? 0u : (c == 1 ? cb & 0xFFu : (cb & 0xFFu) + ((cb >> 8) & 0xFFu)));
+                    uint32_t acc = 0;
+                    const uint32_t wrote = emit_chunk(acc, stage_s + t0 + rel, lut_s, wp, ch, zz, c_four, c_shift);
+                    // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV: bits
+                    // 0..3; the table's "special" counter: bits 8..12
+                    sticky |= (wrote ^ (uint32_t)__popc(zz)) | ((acc >> 15) & 0x1F00u);
+                    mism += (acc >> kStatShift) & 0x3Fu;
+                    n_sub += (acc >> 18) & 0x1Fu;
                 }
-                __syncwarp();
             }
+            __syncwarp();
 
             // ---- complete 32-byte sectors leave; the incomplete one moves to the front of the staging buffer ---
             const int staged = (int)t0 + total;
@@ -336,11 +415,11 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             for (int fb = lane * 16; fb < flush_bytes; fb += 512)
                 *reinterpret_cast<uint4 *>(outp + (fb - lane * 16)) = *reinterpret_cast<const uint4 *>(stage + fb);
             const uint8_t b = stage[flush_bytes + lane];  // lanes past the tail read stale bytes, never stored
+            carry_w = *reinterpret_cast<const uint32_t *>(sb + 16 + kTrip - 4);
             __syncwarp();
             if (lane < staged - flush_bytes) stage[lane] = b;
             tokbase += total;
             outp += flush_bytes;
-            carry_w = next_carry;
             if (edge_trip) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // padded words were written
             __syncwarp();
         }

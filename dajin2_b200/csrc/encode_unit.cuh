@@ -5,18 +5,19 @@
 // 16, so in a stretch of plain tokens ("=X," or "-X,", three bytes each) every unit of the stretch sees the same
 // phase, holds exactly sixteen closing commas and therefore sixteen tokens.
 //
-//   comma bitmap   every byte of the unit is compared with ',' (exact for any byte value); the 48 flags are packed
-//                  into two words: bit 8*b + (k & 7) of F[k >> 3] <=> byte b of word k is a comma.  popc = tokens the
-//                  unit closes, for ANY unit; equality with the periodic pattern of phase c0 <=> the commas sit at
-//                  bytes c0, c0+3, ..., c0+45 and nowhere else.
+//   phase          the first comma of a plain unit is byte 0, 1 or 2 (c0); a four-entry table keyed on the comma
+//                  flags of bytes 0 and 1 gives the shift that aligns the byte stream and the mask of the unit's
+//                  trailing bytes (behind the last token the window closes), which must not hold a comma.
 //   alignment      the byte stream is shifted so that a window starts two bytes in front of the first comma: the
 //                  twelve aligned words are four GROUPS "=X,=" "X,=X" ",=X,".
-//   group          two byte-permutes gather the four bases, two the four operators; a base is translated through a
-//                  byte-permute look-up keyed on bits 1..3 of the letter (A C G T N -> 0 1 3 2 7) and verified by
-//                  translating the code back to the letter; the operator must be '=' or '-' ('-' adds 10 to the code).
-//   unit is PLAIN  <=> bitmap == pattern, every operator / base verified, and the byte in front of the window is ','
-//                  (the first token is not the anchor of an insertion that began in the previous unit).  Its sixteen code bytes are exactly what
-//                  the generic comma-slot path (encode_common.cuh) produces for the same text.
+//   group          two byte-permutes each gather the four bases, the four operators and the four commas; a base is
+//                  translated through a byte-permute look-up keyed on its low three bits (A C G T N -> 1 3 7 4 6) and
+//                  verified by translating the look-up index back to the letter; the operator must be '=' or '-' ('-'
+//                  adds 10 to the code), the commas must be commas.
+//   unit is PLAIN  <=> every group verified, no comma in the trailing bytes, and the byte in front of the window is
+//                  ',' (the first token is not the anchor of an insertion that began in the previous unit).  Then the
+//                  unit closes exactly sixteen tokens and its sixteen code bytes are exactly what the generic
+//                  comma-slot path (encode_common.cuh) produces for the same text.
 #pragma once
 #include <stdint.h>
 
@@ -83,72 +84,76 @@ DJU_HD uint32_t comma_flags_exact(uint32_t w) {
     return ~(y | w) & 0x80808080u;
 }
 
-// acc + (f >> n): the flags of one word land in their slot of the bitmap
-DJU_HD uint32_t add_shifted(uint32_t acc, uint32_t f, int n) { return acc + (f >> n); }
-
-struct UnitMap {
-    uint32_t f0, f1;  // comma bitmap (see the header comment)
+// Phase table entry for the comma flags of bytes 0 and 1 of the unit (index = [byte 0 is ','] + 2 * [byte 1 is ',']):
+//   .shift   bits the byte stream is shifted right by so that the window starts two bytes in front of the first comma
+//   .trail   comma flags (0x80 per byte) of the unit's last word that must be clear: the bytes behind the window
+//   .bad     != 0: no plain unit starts like this
+struct Phase {
+    uint32_t shift, trail, bad, pad;
 };
 
-DJU_HD UnitMap comma_bitmap(const uint32_t *w) {
-    UnitMap m;
-    m.f0 = comma_flags_exact(w[7]);
-    m.f1 = 0;
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int k = 0; k < 7; ++k) m.f0 = add_shifted(m.f0, comma_flags_exact(w[k]), 7 - k);
-#ifdef __CUDA_ARCH__
-#pragma unroll
-#endif
-    for (int k = 8; k < 12; ++k) m.f1 = add_shifted(m.f1, comma_flags_exact(w[k]), 15 - k);
-    return m;
-}
-
-// bit of the bitmap that stands for byte p (0..47) of the unit: word index in .x, mask in .y
-DJU_HD uint32_t bitmap_word(int p) { return (uint32_t)(p >> 5); }
-DJU_HD uint32_t bitmap_mask(int p) { return 1u << (8 * (p & 3) + ((p >> 2) & 7)); }
-
-// the bitmap of a plain unit whose first comma is byte c0 (0..2)
-DJU_HD UnitMap plain_pattern(int c0) {
-    UnitMap m;
-    m.f0 = 0;
-    m.f1 = 0;
-    for (int p = c0; p < kUnitBytes; p += 3) {
-        if (bitmap_word(p)) m.f1 |= bitmap_mask(p); else m.f0 |= bitmap_mask(p);
+DJU_HD Phase phase_entry(uint32_t index) {
+    Phase p;
+    p.pad = 0;
+    p.bad = 0;
+    if (index == 0) {  // neither: the first comma can only be byte 2 (the window starts at byte 0)
+        p.shift = 32; p.trail = 0;
+    } else if (index == 1) {  // byte 0: the window starts two bytes in front of the unit; bytes 46, 47 trail
+        p.shift = 16; p.trail = 0x80800000u;
+    } else if (index == 2) {  // byte 1: byte 47 trails
+        p.shift = 24; p.trail = 0x80000000u;
+    } else {  // ",," is not MIDSV
+        p.shift = 16; p.trail = 0; p.bad = 1;
     }
-    return m;
+    return p;
 }
 
-// index (0..3) into the pattern table from the comma flags of bytes 0..2 of the unit: one comma at byte c0 -> c0;
-// anything else -> an index whose pattern cannot match the bitmap (3 holds an impossible pattern)
-DJU_HD uint32_t phase_index(uint32_t f0) {
-    const uint32_t m = f0 & 0x00010101u;
-    return ((m >> 8) | (m >> 15)) & 3u;
+DJU_HD uint32_t phase_index(uint32_t w0) {
+    const uint32_t f = comma_flags_exact(w0);
+    return ((f >> 7) | (f >> 14)) & 3u;
 }
 
-// bits the byte stream is shifted right by so that the window starts two bytes in front of the first comma
-DJU_HD uint32_t phase_shift_bits(int c0) { return 8u * (uint32_t)(c0 + 2); }
+// idx + (idx >> 4): byte 0 = i0 | i1 << 4, byte 2 = i2 | i3 << 4 (a multiply-add, off the ALU pipe on the device)
+DJU_HD uint32_t fold_nibbles(uint32_t idx) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, 0x10000000, %1;" : "=r"(r) : "r"(idx));
+    return r;
+#else
+    return idx + (idx >> 4);
+#endif
+}
+
+// byte permute without the selector masking of __byte_perm (the selectors built here never set bit 3 of a nibble)
+DJU_HD uint32_t prmt_raw(uint32_t a, uint32_t b, uint32_t s) {
+#ifdef __CUDA_ARCH__
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+#else
+    return prmt(a, b, s);
+#endif
+}
 
 struct GroupOut {
-    uint32_t codes;  // four code bytes (valid when the unit turns out plain)
-    uint32_t bad;    // != 0: an operator is not '=' / '-', or a base is not one of A C G T N
+    uint32_t codes;  // four code bytes (valid when bad == 0)
+    uint32_t bad;    // != 0: a comma is missing, an operator is not '=' / '-', or a base is not one of A C G T N
     uint32_t dels;   // 0x10 in every byte whose operator is '-'
 };
 
-// one aligned group: v0 = "=X,=", v1 = "X,=X", v2 = ",=X,"  (commas are vouched for by the bitmap)
+// one aligned group: v0 = "=X,=", v1 = "X,=X", v2 = ",=X,"
 DJU_HD GroupOut decode_group(uint32_t v0, uint32_t v1, uint32_t v2) {
     GroupOut g;
-    const uint32_t x = prmt(prmt(v0, v1, 0x0741u), v2, 0x6210u);   // bases: v0.b1 v1.b0 v1.b3 v2.b2
-    const uint32_t op = prmt(prmt(v0, v1, 0x0630u), v2, 0x5210u);  // operators: v0.b0 v0.b3 v1.b2 v2.b1
-    const uint32_t idx = (x >> 1) & 0x07070707u;                   // A 0, C 1, T 2, G 3, N 7
-    const uint32_t nib = idx + (idx >> 4);                         // byte 0 = i0 | i1 << 4, byte 2 = i2 | i3 << 4
-    const uint32_t sel = prmt(nib, 0u, 0x4420u);
-    const uint32_t code = prmt(0x02030100u, 0x04FFFFFFu, sel);
-    const uint32_t back = prmt(0x47544341u, 0x4E000000u, sel);     // "ACTG", 'N' at 7
-    g.dels = ~op & 0x10101010u;                                    // '-' = 0x2D, '=' = 0x3D
-    g.bad = ((op | 0x10101010u) ^ 0x3D3D3D3Du) | (back ^ x);
-    g.codes = code + ((g.dels * 10u) >> 4);                        // "-X" = 10 + base
+    const uint32_t x = prmt_raw(prmt_raw(v0, v1, 0x0741u), v2, 0x6210u);   // bases: v0.b1 v1.b0 v1.b3 v2.b2
+    const uint32_t op = prmt_raw(prmt_raw(v0, v1, 0x0630u), v2, 0x5210u);  // operators: v0.b0 v0.b3 v1.b2 v2.b1
+    const uint32_t cm = prmt_raw(prmt_raw(v0, v1, 0x0052u), v2, 0x7410u);  // commas: v0.b2 v1.b1 v2.b0 v2.b3
+    const uint32_t idx = x & 0x07070707u;                                   // A 1, C 3, T 4, N 6, G 7
+    const uint32_t sel = prmt_raw(fold_nibbles(idx), 0u, 0x4420u);
+    const uint32_t code = prmt_raw(0x01FF00FFu, 0x0204FF03u, sel);          // index -> code, 0xFF for 0 / 2 / 5
+    const uint32_t back = prmt_raw(0x43004100u, 0x474E0054u, sel);          // index -> letter
+    g.dels = ~op & 0x10101010u;                                             // '-' = 0x2D, '=' = 0x3D
+    g.bad = (cm ^ 0x2C2C2C2Cu) | ((op | 0x10101010u) ^ 0x3D3D3D3Du) | (back ^ x);
+    g.codes = code + ((g.dels * 10u) >> 4);                                 // "-X" = 10 + base
     return g;
 }
 
@@ -158,8 +163,9 @@ struct UnitOut {
     uint32_t n_del;  // deletions among the sixteen tokens (calc_match counts one per deletion)
 };
 
-// w[-1] is the word in front of the unit (prev); shift = phase_shift_bits(c0)
-DJU_HD UnitOut decode_unit(uint32_t prev, const uint32_t *w, uint32_t shift) {
+// prev is the word in front of the unit; ph = phase_entry(phase_index(w[0]))
+DJU_HD UnitOut decode_unit(uint32_t prev, const uint32_t *w, const Phase &ph) {
+    const uint32_t shift = ph.shift;
     uint32_t v[12];
     v[0] = shr_pair(prev, w[0], shift);
 #ifdef __CUDA_ARCH__
@@ -167,9 +173,9 @@ DJU_HD UnitOut decode_unit(uint32_t prev, const uint32_t *w, uint32_t shift) {
 #endif
     for (int j = 1; j < 12; ++j) v[j] = shr_pair(w[j - 1], w[j], shift);
     UnitOut u;
-    // the byte in front of the window separates the first token from its predecessor: ',' or the token is an
+    // the byte in front of the window separates the first token from its predecessor: ',' -- or the token is an
     // insertion whose anchor alone lies in the window ('|'), or the first token of the row (filler)
-    u.bad = ((prev >> (shift - 8u)) & 0xFFu) ^ 0x2Cu;
+    u.bad = ph.bad | (((prev >> (shift - 8u)) & 0xFFu) ^ 0x2Cu) | (comma_flags_exact(w[11]) & ph.trail);
     uint32_t dsum = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll

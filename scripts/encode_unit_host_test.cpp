@@ -33,10 +33,6 @@ int main() {
                            "+T|+G|*CA", "*ag", "+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|=T", "=R", "==", "A"};
     const int n_vocab = sizeof(vocab) / sizeof(vocab[0]);
     long units = 0, plain_units = 0, missed = 0;
-    // pattern table
-    dju::UnitMap pat[4];
-    for (int c = 0; c < 3; ++c) pat[c] = dju::plain_pattern(c);
-    pat[3].f0 = pat[3].f1 = 0xFFFFFFFFu;
     for (int iter = 0; iter < 4000; ++iter) {
         const int rare = 1 + (int)(rng() % 60);  // one token in `rare` is not a plain match
         std::string row;
@@ -63,23 +59,11 @@ int main() {
             uint32_t w[12], prev;
             memcpy(w, buf.data() + start, 48);
             memcpy(&prev, buf.data() + start - 4, 4);
-            const dju::UnitMap m = dju::comma_bitmap(w);
             int n_commas = 0;
-            for (int p = 0; p < 48; ++p) {
-                const bool is = buf[start + p] == ',';
-                n_commas += is;
-                const uint32_t word = dju::bitmap_word(p) ? m.f1 : m.f0;
-                if (((word & dju::bitmap_mask(p)) != 0) != is) { printf("bitmap mismatch\n"); return 1; }
-            }
-            if ((int)(dju::popc(m.f0) + dju::popc(m.f1)) != n_commas) { printf("popc mismatch\n"); return 1; }
-            const uint32_t ci = dju::phase_index(m.f0);
-            const bool periodic = m.f0 == pat[ci].f0 && m.f1 == pat[ci].f1;
-            bool plain = false;
-            dju::UnitOut u{};
-            if (periodic) {
-                u = dju::decode_unit(prev, w, dju::phase_shift_bits((int)ci));
-                plain = u.bad == 0;
-            }
+            for (int p = 0; p < 48; ++p) n_commas += buf[start + p] == ',';
+            const dju::Phase ph = dju::phase_entry(dju::phase_index(w[0]));
+            const dju::UnitOut u = dju::decode_unit(prev, w, ph);
+            const bool plain = u.bad == 0;
             // truth: the tokens closed by the unit's commas
             const int first = rank[start];
             bool truth_plain = n_commas == 16;
