@@ -29,10 +29,10 @@
 #include "encode_unit.cuh"
 
 #ifndef DJ_ENC_WARPS
-#define DJ_ENC_WARPS 16  // warps per CTA, one CTA per SM
+#define DJ_ENC_WARPS 24  // warps per CTA, one CTA per SM (80 registers)
 #endif
 #ifndef DJ_ENC_STAGES
-#define DJ_ENC_STAGES 3  // slots of the per-warp text ring
+#define DJ_ENC_STAGES 2  // slots of the per-warp text ring (one trip in flight while one is translated)
 #endif
 #ifndef DJ_ENC_UNITS
 #define DJ_ENC_UNITS 2   // units per lane and trip
@@ -79,12 +79,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 
-// one lane: arm the barrier with the byte count and start the bulk copy global -> shared
+// the whole warp calls (warp-uniform arguments); one elected lane arms the barrier with the byte count and starts the
+// bulk copy global -> shared
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        " elect.sync _|p, 0xffffffff;\n"
+        " @p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n"
+        " @p cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n}\n" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
 }
 
 // comma flags of one 16-byte chunk in the layout emit_chunk expects (bit 7-k of byte j <=> byte j of word k), exact
@@ -131,7 +135,7 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     build_token_lut(lut);
     if (threadIdx.x < 4) {
         const dju::Phase ph = dju::phase_entry(threadIdx.x);
-        pat[threadIdx.x] = make_uint4(ph.shift, ph.trail, ph.bad, 0u);
+        pat[threadIdx.x] = make_uint4(ph.shift, ph.trail, ph.bad, ph.n0);
     }
 
     const int lane = threadIdx.x & 31;
@@ -158,36 +162,33 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
 
     // ---- producer: the sequence of (row, trip) this warp will consume, issued kStages - 1 trips ahead -------------
     int64_t p_row = warp;
-    RowGeom p_geom = {text, 0, 0, 0};
-    int p_trip = 0, p_slot = 0;
+    const uint8_t *p_src = text;  // next 16-byte aligned piece of the producer's row
+    int p_left = 0;               // bytes of the row's span (rounded up to 16) from p_src on; may run below 16
+    int p_trips = 0;              // trips of the producer's row still to issue; 0: no row left
+    int p_slot = 0;
     int64_t p_next_off = 0;
     int p_next_len = 0;
-    if (p_row < n_reads) {
-        p_geom = row_geom(text, row_off[p_row], row_len[p_row]);
+    auto p_open = [&](int64_t off, int len) {
+        const RowGeom g = row_geom(text, off, len);
+        p_src = g.base;
+        p_left = (g.nbytes + 15) & ~15;
+        p_trips = g.n_trips;
         if (p_row + n_warps < n_reads) {
             p_next_off = row_off[p_row + n_warps];
             p_next_len = row_len[p_row + n_warps];
         }
-    }
+    };
+    if (p_row < n_reads) p_open(row_off[p_row], row_len[p_row]);
     auto produce = [&]() {
-        if (p_row >= n_reads) return;
-        const int span = (p_geom.nbytes + 15) & ~15;
-        int bytes = span - p_trip * kTrip;
-        bytes = bytes > kTrip ? kTrip : (bytes < 16 ? 16 : bytes);
-        if (lane == 0)
-            bulk_load(ring_s + (uint32_t)(p_slot * kSlotBytes + 16), p_geom.base + (int64_t)p_trip * kTrip, (uint32_t)bytes,
-                      bar_s + 8u * p_slot);
+        if (p_trips == 0) return;
+        const int bytes = p_left > kTrip ? kTrip : (p_left < 16 ? 16 : p_left);
+        bulk_load(ring_s + (uint32_t)(p_slot * kSlotBytes + 16), p_src, (uint32_t)bytes, bar_s + 8u * p_slot);
         p_slot = p_slot + 1 == kStages ? 0 : p_slot + 1;
-        if (++p_trip == p_geom.n_trips) {
+        p_src += kTrip;
+        p_left -= kTrip;
+        if (--p_trips == 0) {
             p_row += n_warps;
-            p_trip = 0;
-            if (p_row < n_reads) {
-                p_geom = row_geom(text, p_next_off, p_next_len);
-                if (p_row + n_warps < n_reads) {
-                    p_next_off = row_off[p_row + n_warps];
-                    p_next_len = row_len[p_row + n_warps];
-                }
-            }
+            if (p_row < n_reads) p_open(p_next_off, p_next_len);
         }
     };
 #pragma unroll 1
@@ -243,6 +244,7 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             uint32_t cw[kU][4];
             uint32_t n_del[kU];
             bool plain[kU], dead[kU];
+            bool tail[kU];  // the unit holds the row's end: nothing is stored behind it
 #pragma unroll
             for (int h = 0; h < kU; ++h) {
                 const uint8_t *up = sb + 16 + h * kHalf + dju::kUnitBytes * lane;
@@ -257,9 +259,11 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                 const uint32_t wprev = *reinterpret_cast<const uint32_t *>(up - 4);
                 const uint4 pe = pat[dju::phase_index(w[0])];
                 dju::Phase ph;
-                ph.shift = pe.x; ph.trail = pe.y; ph.bad = pe.z; ph.pad = 0;
+                ph.shift = pe.x; ph.trail = pe.y; ph.bad = pe.z; ph.n0 = pe.w;
                 const dju::UnitOut uo = dju::decode_unit(wprev, w, ph);
-                dead[h] = g0 + h * kHalf + dju::kUnitBytes * lane > nbytes;  // past the virtual closing comma
+                const int g = g0 + h * kHalf + dju::kUnitBytes * lane;
+                dead[h] = g > nbytes;  // past the virtual closing comma
+                tail[h] = g + dju::kUnitBytes > nbytes;
                 plain[h] = !dead[h] && uo.bad == 0;
                 n_del[h] = uo.n_del;
 #pragma unroll
@@ -308,10 +312,11 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                     const uint32_t cb = reinterpret_cast<const uint32_t *>(cntbuf)[h * 32 + lane];
                     const uint32_t slow_cnt = (cb & 0xFFu) + ((cb >> 8) & 0xFFu) + ((cb >> 16) & 0xFFu);
                     cnt[h] = dead[h] ? 0u : (p ? 16u : slow_cnt);
-                    small = small || (!dead[h] && !p && slow_cnt < 4u);
+                    small = small || (!tail[h] && !p && slow_cnt < 4u);
                 }
                 // a unit that closes fewer than four tokens (the inside of a long insertion) does not cover the words
-                // it shares with its neighbours: such a trip goes through the slow path as a whole
+                // it shares with its neighbours: such a trip goes through the slow path as a whole (the unit that holds
+                // the row's end has no neighbour behind it)
                 if (force || !__any_sync(0xffffffffu, small)) break;
                 bool any_plain = false;
 #pragma unroll
@@ -340,10 +345,11 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             }
             if (lane == 0) {
                 // checkpoints: tokens that START before byte j * DJ_ENC_CHUNK of the span (dj_find_token resumes there)
-                ck[kU * t] = t == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
+                ck[0] = t == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
                 if (kU == 2 && g0 + kHalf <= nbytes)
-                    ck[kU * t + 1] = (uint32_t)(tokbase + total0) + (sb[16 + kHalf - 1] == ',' ? 0u : 1u);
+                    ck[1] = (uint32_t)(tokbase + total0) + (sb[16 + kHalf - 1] == ',' ? 0u : 1u);
             }
+            ck += kU;
             const uint32_t t0 = (uint32_t)tokbase & 31u;  // stage[0] holds locus (tokbase & ~31) of the row
 
             // ---- plain units: sixteen code bytes as whole words (the word shared with a plain neighbour is merged

@@ -88,13 +88,14 @@ DJU_HD uint32_t comma_flags_exact(uint32_t w) {
 //   .shift   bits the byte stream is shifted right by so that the window starts two bytes in front of the first comma
 //   .trail   comma flags (0x80 per byte) of the unit's last word that must be clear: the bytes behind the window
 //   .bad     != 0: no plain unit starts like this
+//   .n0      commas a plain stretch of this phase has among the first 16 bytes of the unit (tokens its first chunk closes)
 struct Phase {
-    uint32_t shift, trail, bad, pad;
+    uint32_t shift, trail, bad, n0;
 };
 
 DJU_HD Phase phase_entry(uint32_t index) {
     Phase p;
-    p.pad = 0;
+    p.n0 = index == 1 ? 6u : 5u;  // commas at bytes 0,3,..,15 / 1,..,13 / 2,..,14
     p.bad = 0;
     if (index == 0) {  // neither: the first comma can only be byte 2 (the window starts at byte 0)
         p.shift = 32; p.trail = 0;
@@ -158,9 +159,11 @@ DJU_HD GroupOut decode_group(uint32_t v0, uint32_t v1, uint32_t v2) {
 }
 
 struct UnitOut {
-    uint32_t c[4];   // sixteen code bytes
-    uint32_t bad;    // != 0: not plain
-    uint32_t n_del;  // deletions among the sixteen tokens (calc_match counts one per deletion)
+    uint32_t c[4];        // sixteen code bytes
+    uint32_t bad;         // != 0: not plain
+    uint32_t bad_head;    // != 0: the first two groups (eight tokens, bytes 0..21+ of the unit) are not plain either
+    uint32_t n_del;       // deletions among the sixteen tokens (calc_match counts one per deletion)
+    uint32_t n_del_head;  // deletions among the first ph.n0 tokens (those the unit's first 16-byte chunk closes)
 };
 
 // prev is the word in front of the unit; ph = phase_entry(phase_index(w[0]))
@@ -175,18 +178,23 @@ DJU_HD UnitOut decode_unit(uint32_t prev, const uint32_t *w, const Phase &ph) {
     UnitOut u;
     // the byte in front of the window separates the first token from its predecessor: ',' -- or the token is an
     // insertion whose anchor alone lies in the window ('|'), or the first token of the row (filler)
-    u.bad = ph.bad | (((prev >> (shift - 8u)) & 0xFFu) ^ 0x2Cu) | (comma_flags_exact(w[11]) & ph.trail);
-    uint32_t dsum = 0;
+    u.bad_head = ph.bad | (((prev >> (shift - 8u)) & 0xFFu) ^ 0x2Cu);
+    u.bad = comma_flags_exact(w[11]) & ph.trail;
+    uint32_t dsum = 0, dhead = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
     for (int g = 0; g < 4; ++g) {
         const GroupOut o = decode_group(v[3 * g], v[3 * g + 1], v[3 * g + 2]);
         u.c[g] = o.codes;
-        u.bad |= o.bad;
+        if (g < 2) u.bad_head |= o.bad; else u.bad |= o.bad;
         dsum += o.dels << g;  // 0x10, 0x20, 0x40, 0x80: one bit per (group, byte)
+        if (g == 0) dhead = o.dels;
+        if (g == 1) dhead += (o.dels & ((1u << (8u * (ph.n0 - 4u))) - 1u)) << 1;
     }
+    u.bad |= u.bad_head;
     u.n_del = popc(dsum);
+    u.n_del_head = popc(dhead);
     return u;
 }
 

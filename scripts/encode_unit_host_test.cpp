@@ -32,7 +32,7 @@ int main() {
     const char *vocab[] = {"=A", "=C", "=G", "=T", "=N", "-A", "-C", "-G", "-T", "-N", "*AG", "*TC", "=a", "-g", "+A|=C",
                            "+T|+G|*CA", "*ag", "+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|+G|=T", "=R", "==", "A"};
     const int n_vocab = sizeof(vocab) / sizeof(vocab[0]);
-    long units = 0, plain_units = 0, missed = 0;
+    long units = 0, plain_units = 0, missed = 0, head_units = 0;
     for (int iter = 0; iter < 4000; ++iter) {
         const int rare = 1 + (int)(rng() % 60);  // one token in `rare` is not a plain match
         std::string row;
@@ -102,10 +102,22 @@ int main() {
             } else if (truth_plain) {
                 ++missed;
             }
+            if (u.bad_head == 0) {
+                // the tokens the first 16-byte chunk closes are plain and the first eight codes are theirs (and more)
+                int n0 = 0, nd = 0;
+                for (int p = 0; p < 16; ++p) n0 += buf[start + p] == ',';
+                if (n0 != (int)ph.n0) { printf("n0 mismatch %d vs %u\n", n0, ph.n0); return 1; }
+                const uint8_t *cb = (const uint8_t *)u.c;
+                for (int j = 0; j < 8; ++j)
+                    if (cb[j] != codes[first + j]) { printf("head code mismatch\n"); return 1; }
+                for (int j = 0; j < n0; ++j) nd += codes[first + j] >= 10 && codes[first + j] < 20;
+                if (nd != (int)u.n_del_head) { printf("n_del_head mismatch %d vs %u\n", nd, u.n_del_head); return 1; }
+                ++head_units;
+            }
         }
     }
-    printf("units %ld, plain %ld (%.1f %%), truth-plain units not taken %ld\n", units, plain_units,
-           100.0 * plain_units / units, missed);
+    printf("units %ld, plain %ld (%.1f %%), head-plain %ld, truth-plain units not taken %ld\n", units, plain_units,
+           100.0 * plain_units / units, head_units, missed);
     if (missed) { printf("FAIL: a plain unit was not recognised\n"); return 1; }
     printf("OK\n");
     return 0;
