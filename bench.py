@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--profile", default="r10")
     ap.add_argument("--cpu-sample", type=int, default=3000, help="sample reads of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline-samples", type=int, default=12, help="samples of the pipelined block (0 = skip)")
+    ap.add_argument("--pipeline-depth", type=int, default=4, help="samples in flight in the pipelined block")
     return ap.parse_args()
 
 
@@ -100,6 +102,32 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------------------
+
+
+def bind_to_gpu_numa_node(local_rank: int):
+    """Best effort: run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it
+    allocates (first touch) and the H2D copies stay on that socket.  Returns (node, n_cpus) or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        node = int(Path(f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if len(cpus) < 4:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node, len(cpus)
+    except Exception:  # noqa: BLE001 - placement is an optimisation, never a requirement
+        return None
 
 
 def make_workload(args, rank: int, world: int, pinned: bool):
@@ -305,7 +333,9 @@ def run_ours(args):
     from dajin2_b200 import _cabi, engine, mlp_pool, pipeline
     from dajin2_b200 import distributed as djdist
 
-    mlp_pool.warm_up()  # the interpreter start-up of the MLP workers is not part of a step
+    bound = bind_to_gpu_numa_node(local_rank)  # pinned buffers (first touch) and worker processes next to the GPU
+    if rank == 0:  # only rank 0 selects loci: no idle worker pools on the other ranks
+        mlp_pool.warm_up()  # the interpreter start-up of the MLP workers is not part of a step
 
     pop, hs, hc, keep = make_workload(args, rank, world, pinned=True)
     sequence = pop.reference
@@ -321,7 +351,7 @@ def run_ours(args):
     text_bytes = int(hs.row_len.astype(np.int64).sum())
     enc_bytes = text_bytes + hs.n_reads * (len(sequence) + 16)
     enc_pitch = int(enc_s.pitch)
-    enc_kernel = "encode_ref_kernel" if enc_s.ref is not None else "encode_kernel"
+    enc_kernel = "encode_unit_kernel"
 
     def device_step():
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -338,6 +368,7 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _cabi.launch_count
+    del mlp_pool.STATS[:]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
     enc_events, stage = [], {}
@@ -359,6 +390,39 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     enc_ms = float(np.mean([a.elapsed_time(b) for a, b in enc_events]))
+    fits = list(mlp_pool.STATS)
+    mlp_block = {"fits": len(fits), "lbfgs_iterations": [f["n_iter"] for f in fits[-9:]],
+                 "fast_path_taken": bool(fits) and all(f["fast_path"] for f in fits),
+                 "seconds_per_fit_mean": round(float(np.mean([f["seconds"] for f in fits])), 4) if fits else None,
+                 "workers": mlp_pool.workers()}
+
+    # ---- pipelined arm (one GPU): several samples against one control, software-pipelined over the host MLP -------
+    # the reference's batch mode (utils/multiprocess.py:117-150).  Every sample does the whole path; the samples are
+    # distinct device copies (own text, code matrix, checkpoints) so nothing is re-used between samples in flight.
+    pipelined = None
+    if world == 1 and args.pipeline_samples > 0:
+        depth = args.pipeline_depth
+        copies = [enc_s] + [engine.EncodedReads(hs, len(sequence), validate=False, encode=False, sequence=sequence)
+                            for _ in range(depth - 1)]
+        n_samples = args.pipeline_samples
+
+        def stream_of_samples(n):
+            for k in range(n):
+                yield copies[k % depth]
+
+        pipeline.run_many(stream_of_samples(depth), enc_c, sequence, depth=depth, fetch_labels=False)  # warm-up
+        torch.cuda.synchronize()
+        waits = []
+        t0 = time.perf_counter()
+        n_done = pipeline.run_many(stream_of_samples(n_samples), enc_c, sequence, depth=depth, fetch_labels=False,
+                                   on_result=lambda r: waits.append(r.timings.get("loci_wait_ms", 0.0)))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        pipelined = {"value": args.reads * n_done / dt, "unit": UNIT, "samples": n_done, "depth": depth,
+                     "ms_per_sample": dt / n_done * 1e3, "loci_wait_ms_mean": round(float(np.mean(waits)), 2),
+                     "note": "samples of the same workload back to back through pipeline.run_many; text resident in HBM; "
+                             "each sample encodes, histograms, fits its three MLPs, scores and clusters"}
+        del copies
 
     # ---- end-to-end arm: pinned host buffers -> H2D -> path -> labels D2H ----------------------------------
     del enc_s, enc_c
@@ -398,7 +462,7 @@ def run_ours(args):
     tpath = ROOT / "profiles" / "ncu_traffic.json"
     if tpath.exists():
         cap = json.loads(tpath.read_text())
-        enc_cap, hist_cap = cap.get("encode_kernel"), cap.get("hist_tile_kernel")
+        enc_cap, hist_cap = cap.get(enc_kernel), cap.get("hist_tile_kernel")
         if enc_cap and enc_cap["reads_per_launch"] == args.reads and cap.get("n_loci", args.loci) == args.loci:
             traffic = enc_cap["dram_bytes_per_launch"]
         if hist_cap and hist_cap["reads_per_launch"] == args.reads and cap.get("n_loci", args.loci) == args.loci:
@@ -424,14 +488,20 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": total_reads / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                 "h2d_bytes_per_step": int(r2.timings.get("h2d_bytes", 0)),
-                "d2h_bytes_per_step": int(r2.timings.get("d2h_bytes", 0))},
+                "d2h_bytes_per_step": int(r2.timings.get("d2h_bytes", 0)),
+                "h2d_ms": round(float(r2.timings.get("h2d_ms", 0.0)), 2),
+                "h2d_GBs_rank0": round(r2.timings.get("h2d_bytes", 0) / max(r2.timings.get("h2d_ms", 1e-9), 1e-9) / 1e6, 1),
+                "numa_binding_rank0": list(bound) if bound else None},
         "gpu_launches": int(launches),
         "roofline": {"kernel": enc_kernel, "bound": "hbm",
                      "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
                      "algorithmic_bytes_per_launch": enc_bytes, "ms_per_launch": enc_ms},
         "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage.items()},
+        "mlp": mlp_block,
     }
+    if pipelined is not None:
+        line["pipelined"] = pipelined
     if hist_roofline is not None:
         line["roofline_hist"] = hist_roofline
     if not args.no_cpu_baseline:

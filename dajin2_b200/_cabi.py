@@ -14,7 +14,7 @@ import os
 # DAJIN2_B200_LIB points at an alternative build of the same library (kernel experiments under scripts/)
 LIB_PATH = Path(os.environ.get("DAJIN2_B200_LIB") or Path(__file__).resolve().parent / "libdajin2_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 CODE_INVALID = 0x7F
 CODE_INS = 0x80
 FLAG_TOKEN_COUNT = 1
@@ -79,7 +79,7 @@ SIGNATURES = {
     "dj_dedup_rows": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p,
                                 c_void_p]),
     "dj_dedup_export": (c_int32, [c_void_p, c_uint32, c_void_p, c_uint32, c_void_p, c_void_p]),
-    "dj_bisect": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_double,
+    "dj_bisect": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_double,
                             c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dj_assign_rows": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),

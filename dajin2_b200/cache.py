@@ -11,6 +11,29 @@ from .ingest import read_midsv_jsonl
 
 _CACHE: "OrderedDict[tuple, EncodedReads]" = OrderedDict()
 MAX_ENTRIES = 16
+#: resident bytes allowed (text + code matrix + checkpoints of every cached file) as a fraction of the device memory
+MAX_FRACTION = 0.45
+
+
+def _entry_bytes(enc: EncodedReads) -> int:
+    return sum(int(t.numel()) * t.element_size() for t in (enc.text, enc.codes, enc.ckpt, enc.name_keys, enc.row_off,
+                                                           enc.row_len, enc.match_score, enc.n_tokens, enc.flags))
+
+
+def _evict(incoming: int = 0) -> None:
+    """Bound the cache by entries AND bytes; forget files that no longer exist (the reference deletes its tmp_*.jsonl
+    seam files right after use, ``clustering/label_extractor.py``)."""
+    import os
+
+    import torch
+
+    for key in [k for k in _CACHE if not os.path.exists(k[0])]:
+        del _CACHE[key]
+    budget = MAX_FRACTION * torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+    total = incoming + sum(_entry_bytes(e) for e in _CACHE.values())
+    while _CACHE and (len(_CACHE) >= MAX_ENTRIES or total > budget):
+        _, old = _CACHE.popitem(last=False)
+        total -= _entry_bytes(old)
 
 
 def encoded_file(path: str | Path, n_loci: int | None = None, keep_records: bool = False,
@@ -29,10 +52,9 @@ def encoded_file(path: str | Path, n_loci: int | None = None, keep_records: bool
         else:
             o, n = int(host.row_off[0]), int(host.row_len[0])
             n_loci = int((host.text[o : o + n] == ord(",")).sum()) + 1
-    enc = EncodedReads(host, n_loci, sequence=sequence)  # the sequence only speeds the encoder up (dj_encode_ref)
+    _evict(incoming=int(host.text.nbytes) + host.n_reads * (n_loci + 64))
+    enc = EncodedReads(host, n_loci, sequence=sequence)  # (sequence: kept for round-1 callers, see EncodedReads)
     _CACHE[key] = enc
-    while len(_CACHE) > MAX_ENTRIES:
-        _CACHE.popitem(last=False)
     return enc
 
 

@@ -21,6 +21,11 @@ import torch
 from . import _cabi
 from .engine import KmerModel, _next_pow2, _p, _stream, require_cuda
 
+#: diagnostics of the most recent calls (tests compare them with the reference's own silhouette trace): one dict per
+#: optimize_labels_points call, {"silhouette": [(n_clusters, score), ...]}; remove_biased_clusters appends
+#: {"decision_tree_fits": n}.  Bounded: cleared by the caller that wants to read it.
+TRACE: list = []
+
 TOL = 1e-4  # BisectingKMeans passes its raw tol to the inner Lloyd (sklearn/cluster/_bisect_k_means.py:333-341)
 MAX_ITER = 300
 
@@ -96,15 +101,33 @@ def uniform_choice2(rng: np.random.RandomState, n: int) -> np.ndarray:
     return out
 
 
-def _bisect(X_d, w_d, leaf_host: np.ndarray, target: int, seed0: int, seed1: int):
+def last_rows_of_points(row_points: np.ndarray, n_points: int) -> np.ndarray:
+    """Last row index (position in ``row_points``) of every point, -1 for points without a row."""
+    out = np.full(n_points, -1, dtype=np.int64)
+    if len(row_points):
+        np.maximum.at(out, row_points, np.arange(len(row_points), dtype=np.int64))
+    return out
+
+
+def last_rows(rs: RowSet) -> np.ndarray:
+    """Last row (in the row order ``rs`` was built in) of every point of a device row set."""
+    dev = rs.slot_of_row.device
+    last = torch.full((int(rs.point_of_slot.shape[0]),), -1, dtype=torch.int64, device=dev)
+    if rs.n_rows:
+        last.scatter_reduce_(0, rs.slot_of_row.long(), torch.arange(rs.n_rows, dtype=torch.int64, device=dev),
+                             reduce="amax")
+    return last[torch.as_tensor(rs.slots.astype(np.int64), device=dev)].cpu().numpy()
+
+
+def _bisect(X_d, w_d, leaf_host: np.ndarray, last_row_d, target: int, seed0: int, seed1: int):
     dev = X_d.device
     n_points, n_cols = int(X_d.shape[0]), int(X_d.shape[1])
     leaf_d = torch.as_tensor(leaf_host.astype(np.int32), device=dev)
     sub = torch.zeros(n_points, dtype=torch.int8, device=dev)
     centers = torch.empty((2, n_cols), dtype=torch.float64, device=dev)
     stats = torch.zeros(8, dtype=torch.float64, device=dev)
-    _cabi.call("dj_bisect", _p(X_d), _p(w_d), n_points, n_cols, _p(leaf_d), target, seed0, seed1, TOL, MAX_ITER,
-               _p(sub), _p(centers), _p(stats), _stream())
+    _cabi.call("dj_bisect", _p(X_d), _p(w_d), n_points, n_cols, _p(leaf_d), _p(last_row_d), target, seed0, seed1, TOL,
+               MAX_ITER, _p(sub), _p(centers), _p(stats), _stream())
     return sub.cpu().numpy(), stats.cpu().numpy()
 
 
@@ -192,7 +215,9 @@ def control_subset(ids_control: torch.Tensor, strand_control: torch.Tensor, mode
     seeds = uniform_choice2(rng, n_c)
     X_d = torch.as_tensor(Xc, device=dev)
     w_d = torch.as_tensor(rs_c.count.astype(np.float64), device=dev)
-    sub, _ = _bisect(X_d, w_d, np.zeros(len(Xc), dtype=np.int32), 0, int(point_rows[seeds[0]]), int(point_rows[seeds[1]]))
+    last_d = torch.as_tensor(last_rows_of_points(point_rows, len(Xc)).astype(np.int32), device=dev)
+    sub, _ = _bisect(X_d, w_d, np.zeros(len(Xc), dtype=np.int32), last_d, 0, int(point_rows[seeds[0]]),
+                     int(point_rows[seeds[1]]))
     labels_rows = sub[point_rows].astype(np.int64)
     major = Counter(labels_rows.tolist()).most_common()[0][0]
     keep_rows = np.flatnonzero(labels_rows == major)[:limit]
@@ -216,10 +241,17 @@ def optimize_labels_points(Xs: np.ndarray, ws: np.ndarray, Xc: np.ndarray, wc: n
     w = np.concatenate([ws, wc]).astype(np.float64)
     X_d = torch.as_tensor(np.ascontiguousarray(X), device=dev)
     w_d = torch.as_tensor(w, device=dev)
+    # row order of the matrix the reference clusters: the sample rows, then the control subset (clustering.py:75-79)
+    last_s = last_rows_of_points(sample_row_points, n_s_pts) if sample_row_points is not None else last_rows(sample)
+    last_c = last_rows_of_points(control_row_points, n_c_pts) + coverage_sample
+    last_row_d = torch.as_tensor(np.concatenate([last_s, last_c]).astype(np.int32), device=dev)
     best = np.ones(n_s_pts, dtype=np.int64)
     if X.shape[1] == 0:
         return best
     prev = -1.0
+    trace = {"silhouette": []}
+    if len(TRACE) < 64:
+        TRACE.append(trace)
     rng = np.random.RandomState(1)
     tree = _Tree()
     leaf = np.zeros(n_s_pts + n_c_pts, dtype=np.int32)
@@ -248,7 +280,7 @@ def optimize_labels_points(Xs: np.ndarray, ws: np.ndarray, Xc: np.ndarray, wc: n
             else:
                 ctrl_members = np.flatnonzero(members[n_s_pts:][control_row_points])
                 seed_points.append(n_s_pts + int(control_row_points[ctrl_members[j - ns_leaf]]))
-        sub, stats = _bisect(X_d, w_d, leaf, target, seed_points[0], seed_points[1])
+        sub, stats = _bisect(X_d, w_d, leaf, last_row_d, target, seed_points[0], seed_points[1])
         a, b = tree.split(target, stats[:2])
         leaf = np.where(members, np.where(sub == 1, b, a), leaf).astype(np.int32)
         order = {node: k for k, node in enumerate(tree.leaves())}
@@ -262,6 +294,7 @@ def optimize_labels_points(Xs: np.ndarray, ws: np.ndarray, Xc: np.ndarray, wc: n
             cur = _silhouette(X_d, w_d, labels, n_clusters)
         else:
             cur = -1.0
+        trace["silhouette"].append((n_clusters, cur))
         if prev >= cur or ctrl_clusters > 1:
             break
         best, prev = lab_s.copy(), cur
@@ -300,6 +333,8 @@ def remove_biased_clusters(labels_pts: np.ndarray, rs: RowSet, X_pts_dense_fn, s
         labels[is_b] = tree.predict(X[is_b])
         biased = biases(labels)
         it += 1
+    if it and len(TRACE) < 64:
+        TRACE.append({"decision_tree_fits": it})
     return labels
 
 

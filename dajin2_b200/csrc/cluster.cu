@@ -128,7 +128,8 @@ constexpr int kBisectThreads = 512;
 // (each column sums its points in point order, so the result does not depend on the thread count).
 __global__ void __launch_bounds__(kBisectThreads)
 bisect_kernel(const double *__restrict__ X, const double *__restrict__ weight, int n_points, int n_cols,
-              const int32_t *__restrict__ leaf, int target, int seed0, int seed1, double tol, int max_iter,
+              const int32_t *__restrict__ leaf, const int32_t *__restrict__ last_row, int target, int seed0, int seed1,
+              double tol, int max_iter,
               int8_t *__restrict__ lab, int8_t *__restrict__ lab_old, double *__restrict__ dist,
               double *__restrict__ centers_out, double *__restrict__ stats) {
     extern __shared__ double smem[];
@@ -196,7 +197,10 @@ bisect_kernel(const double *__restrict__ X, const double *__restrict__ weight, i
             wsum[1] = w1;
         }
         __syncthreads();
-        // empty-cluster relocation (_k_means_common.pyx:214-272): the farthest row (weight 1) seeds the empty cluster
+        // empty-cluster relocation (_k_means_common.pyx:214-272): the farthest row (weight 1) seeds the empty cluster.
+        // scikit-learn finds it with np.argpartition(distances, -1), whose kth == n - 1 case is a linear scan that
+        // keeps the LAST of equal maxima (numpy/_core/src/npysort/selection.cpp, introselect_): among points at the
+        // same distance the one whose last row comes last in row order (last_row[]) wins
         if (wsum[0] == 0.0 || wsum[1] == 0.0) {
             const int empty = wsum[0] == 0.0 ? 0 : 1;
             double best = -1.0;
@@ -206,9 +210,9 @@ bisect_kernel(const double *__restrict__ X, const double *__restrict__ weight, i
                 const int j = lab[p];
                 const double d = euclid_sparse(X + (int64_t)p * n_cols, c_old + j * n_cols, cn[j], n_cols);
                 dist[p] = d;
-                if (d > best) { best = d; best_p = p; }
+                if (d > best || (d == best && last_row[p] > last_row[best_p])) { best = d; best_p = p; }
             }
-            // fixed-order arg-max: largest distance, smallest point index among equals
+            // fixed-order arg-max: largest distance, largest last row among equals
             scratch[tid] = best;
             s_idx[tid] = best_p;
             __syncthreads();
@@ -217,7 +221,7 @@ bisect_kernel(const double *__restrict__ X, const double *__restrict__ weight, i
                 int far = -1;
                 for (int q = 0; q < (int)blockDim.x; ++q) {
                     if (s_idx[q] < 0) continue;
-                    if (scratch[q] > m || (scratch[q] == m && s_idx[q] < far)) {
+                    if (scratch[q] > m || (scratch[q] == m && last_row[s_idx[q]] > last_row[far])) {
                         m = scratch[q];
                         far = s_idx[q];
                     }
@@ -525,8 +529,8 @@ extern "C" int dj_dedup_export(const void *table, uint32_t capacity, DjRowRecord
 }
 
 extern "C" int dj_bisect(const double *X, const double *weight, int32_t n_points, int32_t n_cols,
-                         const int32_t *leaf, int32_t target, int32_t seed0, int32_t seed1, double tol,
-                         int32_t max_iter, int8_t *sub_label, double *centers, double *stats, void *stream) {
+                         const int32_t *leaf, const int32_t *last_row, int32_t target, int32_t seed0, int32_t seed1,
+                         double tol, int32_t max_iter, int8_t *sub_label, double *centers, double *stats, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_points <= 0 || n_cols <= 0) {
         dj_set_error("dj_bisect: empty problem");
@@ -542,7 +546,7 @@ extern "C" int dj_bisect(const double *X, const double *weight, int32_t n_points
     double *dist = nullptr;
     DJ_CUDA_CHECK(cudaMallocAsync(&lab_old, (size_t)n_points, st));
     DJ_CUDA_CHECK(cudaMallocAsync(&dist, sizeof(double) * (size_t)n_points, st));
-    bisect_kernel<<<1, kBisectThreads, smem, st>>>(X, weight, n_points, n_cols, leaf, target, seed0, seed1, tol,
+    bisect_kernel<<<1, kBisectThreads, smem, st>>>(X, weight, n_points, n_cols, leaf, last_row, target, seed0, seed1, tol,
                                                    max_iter, sub_label, lab_old, dist, centers, stats);
     cudaError_t err = cudaGetLastError();
     cudaFreeAsync(lab_old, st);

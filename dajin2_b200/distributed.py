@@ -59,6 +59,12 @@ class Communicator:
         self.collectives += 1
         return box[0]
 
+    def broadcast_tensor(self, t, src: int = 0):
+        """In-place broadcast of a tensor living on ``self.device`` (same shape and dtype on every rank)."""
+        self.dist.broadcast(t, src=src)
+        self.collectives += 1
+        return t
+
     def allgather_rows(self, t, sizes: list[int]):
         """Concatenation over ranks of 1-D tensors of the given per-rank sizes (padded all-gather)."""
         import torch
@@ -286,13 +292,17 @@ def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, g
         if gpos is None:
             run.set_positions(global_positions(sample, comm))
 
-    loci_mask = None
+    # the selected loci travel as one byte per locus (DJ_MASK_* bits), not as a pickled list of strings
+    from . import engine
+
+    mask_t = torch.zeros(sample.n_loci, dtype=torch.uint8, device=comm.device)
     if comm.rank == 0:
-        loci_mask = ["".join(sorted(m)) for m in run.select_loci(reduced, while_waiting=positions)]
+        loci_sel = run.select_loci(reduced, while_waiting=positions)
+        mask_t.copy_(torch.from_numpy(engine.loci_to_mask(loci_sel)))
     else:
         positions()
         mark("order_ms")
-    loci_t = [set(m) for m in comm.broadcast_object(loci_mask)]
+    loci_t = engine.mask_to_loci(comm.broadcast_tensor(mask_t).cpu().numpy())
     mark("loci_ms")
     order = run.rows.cpu().numpy()
     n_total = int(reduced[-1].item())

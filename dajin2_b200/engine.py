@@ -303,24 +303,32 @@ def mlp_candidates(sample: np.ndarray, control: np.ndarray, threshold: float) ->
     return mlp_pool.submit(sample, control, threshold).result()
 
 
-def extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False,
-                        while_waiting=None) -> dict[str, set[int]]:
-    """``extract_anomal_loci`` (reference ``anomaly_detector.py:99-109``): the three MLP fits run concurrently in the
-    worker pool while the window distances are computed on the device (and ``while_waiting()`` is called)."""
+def submit_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False):
+    """First half of ``extract_anomal_loci`` (reference ``anomaly_detector.py:99-109``): start the three MLP fits in
+    the worker pool and compute the window distances on the device; returns a zero-argument function that waits for
+    the fits and returns the loci.  The fits of several alleles / samples can be in flight at once."""
     from . import mlp_pool
 
     pending = {}
     for op in MUTS:
         s = np.asarray(norm_sample[op], dtype=float)
         c = np.asarray(norm_control[op], dtype=float)
-        pending[op] = (s, c, mlp_pool.submit(s, c, thresholds[op]))
-    out = {}
-    masks = {op: dissimilar_mask(s, c, is_consensus) for op, (s, c, _) in pending.items()}
+        pending[op] = (mlp_pool.submit(s, c, thresholds[op]), dissimilar_mask(s, c, is_consensus))
+
+    def finish() -> dict[str, set[int]]:
+        return {op: set(np.flatnonzero(fut.result() & mask).tolist()) for op, (fut, mask) in pending.items()}
+
+    return finish
+
+
+def extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False,
+                        while_waiting=None) -> dict[str, set[int]]:
+    """``extract_anomal_loci`` (reference ``anomaly_detector.py:99-109``): the three MLP fits run concurrently in the
+    worker pool while the window distances are computed on the device (and ``while_waiting()`` is called)."""
+    finish = submit_anomal_loci(norm_sample, norm_control, thresholds, is_consensus)
     if while_waiting is not None:
         while_waiting()
-    for op, (_, _, fut) in pending.items():
-        out[op] = set(np.flatnonzero(fut.result() & masks[op]).tolist())
-    return out
+    return finish()
 
 
 def homopolymer_errors(sequence: str, norm_sample, norm_control, loci: dict[str, set[int]]) -> dict[str, set[int]]:
@@ -409,24 +417,43 @@ def transpose_loci(loci: dict[str, set[int]], n_loci: int) -> list[set[str]]:
     return out
 
 
+def begin_select_mutation_loci(hist_sample: np.ndarray, strand_host: np.ndarray, sequence: str, norm_sample,
+                               norm_control_raw, knockin: set[int] | None = None, thresholds=None,
+                               is_consensus: bool = False, insample_filter=None):
+    """``extract_mutation_loci`` (reference ``mutation_processing/mutation_extractor.py:28-87``) in two halves: this
+    call starts the MLP fits (host worker processes) and returns a zero-argument function that waits for them and
+    applies the rest of the selection.  Callers with several alleles or samples begin all of them before finishing
+    the first: the fits are independent (``mutation_extractor.py:126-168`` loops over alleles one after the other)."""
+    thresholds = thresholds or {"*": 0.1, "-": 0.1, "+": 0.1}
+    norm_control = {op: np.minimum(norm_control_raw[op], norm_sample[op]) for op in MUTS}
+    finish_anomal = submit_anomal_loci(norm_sample, norm_control, thresholds, is_consensus)
+
+    def finish() -> list[set[str]]:
+        loci = finish_anomal()
+        if knockin is not None:
+            loci = {op: loci[op] | set(knockin) for op in MUTS}
+        homo = homopolymer_errors(sequence, norm_sample, norm_control, loci)
+        bias = strand_biased_loci(hist_sample, strand_host, transpose_loci(loci, len(sequence)))
+        loci = {op: loci[op] - homo[op] for op in MUTS}
+        loci = {op: loci[op] - bias[op] for op in MUTS}
+        if is_consensus and insample_filter is not None:
+            extra = insample_filter(norm_sample)
+            loci = {op: loci[op] - extra[op] for op in MUTS}
+        return transpose_loci(merge_consecutive_indels(loci), len(sequence))
+
+    return finish
+
+
 def select_mutation_loci(hist_sample: np.ndarray, strand_host: np.ndarray, sequence: str, norm_sample, norm_control_raw,
                          knockin: set[int] | None = None, thresholds=None, is_consensus: bool = False,
                          insample_filter=None, while_waiting=None) -> list[set[str]]:
     """``extract_mutation_loci`` (reference ``mutation_processing/mutation_extractor.py:28-87``) fed by the device
     histogram of the sample file instead of two more passes over its JSONL."""
-    thresholds = thresholds or {"*": 0.1, "-": 0.1, "+": 0.1}
-    norm_control = {op: np.minimum(norm_control_raw[op], norm_sample[op]) for op in MUTS}
-    loci = extract_anomal_loci(norm_sample, norm_control, thresholds, is_consensus, while_waiting)
-    if knockin is not None:
-        loci = {op: loci[op] | set(knockin) for op in MUTS}
-    homo = homopolymer_errors(sequence, norm_sample, norm_control, loci)
-    bias = strand_biased_loci(hist_sample, strand_host, transpose_loci(loci, len(sequence)))
-    loci = {op: loci[op] - homo[op] for op in MUTS}
-    loci = {op: loci[op] - bias[op] for op in MUTS}
-    if is_consensus and insample_filter is not None:
-        extra = insample_filter(norm_sample)
-        loci = {op: loci[op] - extra[op] for op in MUTS}
-    return transpose_loci(merge_consecutive_indels(loci), len(sequence))
+    finish = begin_select_mutation_loci(hist_sample, strand_host, sequence, norm_sample, norm_control_raw, knockin,
+                                        thresholds, is_consensus, insample_filter)
+    if while_waiting is not None:
+        while_waiting()
+    return finish()
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -465,6 +492,12 @@ class KmerModel:
 
 def loci_to_mask(loci_t: list[set[str]]) -> np.ndarray:
     return np.array([sum(_MASK_BIT[m] for m in s) for s in loci_t], dtype=np.uint8)
+
+
+def mask_to_loci(mask: np.ndarray) -> list[set[str]]:
+    """Inverse of ``loci_to_mask``."""
+    table = [{m for m, bit in _MASK_BIT.items() if v & bit} for v in range(8)]
+    return [set(table[int(v) & 7]) for v in mask]
 
 
 def _count_kmers(enc: EncodedReads, rows, n_rows, mask_d, sel_d, n_sel, which, table, capacity):

@@ -41,7 +41,7 @@ int64_t dj_jsonl_count_lines(const uint8_t *buf, int64_t n, int n_threads) {
     for (int t = 0; t < n_threads; t++) {
         int64_t lo = n * t / n_threads, hi = n * (t + 1) / n_threads;
         /* lines that START in [lo, hi) */
-        if (t > 0) {
+        if (t > 0 && lo > 0) { /* lo == 0 when the file is shorter than n_threads bytes: the line starts at 0 */
             const uint8_t *q = memchr(buf + lo - 1, '\n', (size_t)(n - lo + 1));
             lo = q ? (q - buf) + 1 : n;
         }

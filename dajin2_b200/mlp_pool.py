@@ -29,8 +29,26 @@ from pathlib import Path
 
 import numpy as np
 
+#: what the most recent fits did (bench.py prints it): dicts {"n_iter", "fast_path", "seconds"}; bounded
+STATS: list = []
+
+
+def _note(stats: dict) -> None:
+    STATS.append(stats)
+    if len(STATS) > 256:
+        del STATS[:128]
+
+
 def fit_predict(sample: np.ndarray, control: np.ndarray, threshold: float) -> np.ndarray:
     """Candidate loci proposed by the reference's MLP; the training set is rebuilt exactly as the reference does."""
+    return fit_predict_stats(sample, control, threshold)[0]
+
+
+def fit_predict_stats(sample: np.ndarray, control: np.ndarray, threshold: float):
+    """``fit_predict`` plus what the fit did: (mask, {"n_iter", "fast_path", "seconds"})."""
+    import time
+
+    t0 = time.perf_counter()
     import warnings
 
     from .fastmlp import FastMLPClassifier  # scikit-learn's MLPClassifier with a fused, bit-identical loss/gradient
@@ -52,7 +70,9 @@ def fit_predict(sample: np.ndarray, control: np.ndarray, threshold: float) -> np
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")  # ConvergenceWarning, as the reference silences it (utils/config.py:79-83)
         clf.fit(X, y)
-    return clf.predict(np.array([control, sample]).T) == 1
+    mask = clf.predict(np.array([control, sample]).T) == 1
+    return mask, {"n_iter": int(getattr(clf, "n_iter_", -1)), "fast_path": bool(getattr(clf, "fast_path_used_", False)),
+                  "seconds": time.perf_counter() - t0}
 
 
 def workers() -> int:
@@ -96,7 +116,7 @@ def _worker_main() -> None:
         except EOFError:
             return
         try:
-            _send(stdout, ("ok", fit_predict(*req)))
+            _send(stdout, ("ok", fit_predict_stats(*req)))
         except BaseException as exc:  # noqa: BLE001 - reported to the parent
             _send(stdout, ("error", repr(exc)))
 
@@ -145,9 +165,11 @@ class _Pool:
     def _run(self, args):
         w = self.idle.get()
         try:
-            return w.call(args)
+            mask, stats = w.call(args)
         finally:
             self.idle.put(w)
+        _note(stats)
+        return mask
 
     def submit(self, args) -> Future:
         return self.threads.submit(self._run, args)
@@ -175,7 +197,9 @@ def submit(sample: np.ndarray, control: np.ndarray, threshold: float) -> Future:
     if n == 0:
         fut: Future = Future()
         try:
-            fut.set_result(fit_predict(sample, control, threshold))
+            mask, stats = fit_predict_stats(sample, control, threshold)
+            _note(stats)
+            fut.set_result(mask)
         except BaseException as exc:  # noqa: BLE001 - handed to the caller through the future
             fut.set_exception(exc)
         return fut

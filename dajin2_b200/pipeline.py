@@ -110,6 +110,27 @@ def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequen
             sample.validate()
             control.validate()
         return distributed.run_device_sharded(sample, control, sequence, knockin, comm, gpos, fetch_labels)
+    return _back(_front(sample, control, sequence, knockin, order, reencode), fetch_labels)
+
+
+@dataclass
+class _InFlight:
+    """A sample between the two halves of the path: its device work up to the histograms is queued, its MLP fits run in
+    the host worker pool."""
+
+    sample: engine.EncodedReads
+    control: engine.EncodedReads
+    knockin: set | None
+    order: np.ndarray | None
+    rows: torch.Tensor | None
+    finish_loci: object
+    timings: dict
+    t_submit: float
+
+
+def _front(sample, control, sequence, knockin, order, reencode) -> _InFlight:
+    """encode -> histograms -> (QNAME order on the device) -> counts -> MLP fits SUBMITTED.  Returns without waiting
+    for the fits."""
     timings: dict = {}
     tm = _Timer(timings)
     if reencode:
@@ -129,7 +150,19 @@ def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequen
         count_c = engine.counts_from_histogram(hist_c)
         norm_s = engine.normalize_indels(count_s)
         norm_c = engine.normalize_indels(count_c)
-        loci = engine.select_mutation_loci(hist_s, sample.strand_host, sequence, norm_s, norm_c, knockin)
+        finish = engine.begin_select_mutation_loci(hist_s, sample.strand_host, sequence, norm_s, norm_c, knockin)
+    return _InFlight(sample, control, knockin, order, rows, finish, timings, time.perf_counter())
+
+
+def _back(st: _InFlight, fetch_labels: bool = True) -> HotPathResult:
+    """wait for the fits -> loci -> 3-mer scores -> score rows -> clustering -> labels."""
+    dev = engine.require_cuda()
+    sample, control, knockin, timings = st.sample, st.control, st.knockin, st.timings
+    tm = _Timer(timings)
+    order, rows = st.order, st.rows
+    with tm.host("loci_host_ms"):
+        loci = st.finish_loci()
+    timings["loci_wait_ms"] = (time.perf_counter() - st.t_submit) * 1e3
     with tm.host("order_host_ms"):
         if rows is not None:
             order = rows.cpu().numpy()
@@ -156,6 +189,45 @@ def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequen
     _finish(timings)
     timings.update({"n_points": info["n_points"], "n_cols": model.n_cols})
     return HotPathResult(labels, order, sizes, pct, loci, model, timings)
+
+
+def run_many(samples, control, sequence: str, knockin: set[int] | None = None, depth: int = 4,
+             fetch_labels: bool = True, on_result=None) -> list:
+    """Several samples against one control, software-pipelined (the reference's batch mode runs samples side by side
+    in processes, ``utils/multiprocess.py:117-150``): while the MLP fits of sample i run in the host worker pool, the
+    device encodes and histograms samples i+1 .. i+depth-1 and finishes sample i-1.  ``samples`` yields
+    ``engine.EncodedReads`` (text resident in HBM) or ``ingest.HostReads`` (copied here, inside the pipeline); every
+    sample does the whole path — nothing is shared between samples except the control file's encoding, exactly as
+    ``run_device`` shares it.  Returns the ``HotPathResult`` of every sample in order (or hands each to
+    ``on_result`` and returns their count, so that finished samples can be released)."""
+    from collections import deque
+
+    if isinstance(control, HostReads):
+        control = engine.EncodedReads(control, len(sequence), validate=False, encode=False, sequence=sequence)
+    inflight: deque = deque()
+    out: list = []
+    n_done = 0
+
+    def retire():
+        nonlocal n_done
+        res = _back(inflight.popleft(), fetch_labels)
+        n_done += 1
+        if on_result is not None:
+            on_result(res)
+        else:
+            out.append(res)
+
+    first = True
+    for s in samples:
+        if isinstance(s, HostReads):
+            s = engine.EncodedReads(s, len(sequence), validate=False, encode=False, sequence=sequence)
+        inflight.append(_front(s, control, sequence, knockin, None, True if first else True))
+        first = False
+        if len(inflight) >= max(1, depth):
+            retire()
+    while inflight:
+        retire()
+    return out if on_result is None else n_done
 
 
 def run_host(sample: HostReads, control: HostReads, sequence: str, knockin: set[int] | None = None,

@@ -66,10 +66,9 @@ def extract_sequence_errors_in_strand_biased_loci(path_midsv_sample: Path, anoma
     return engine.strand_biased_loci(enc.histogram(), enc.strand_host, anomal_loci_transposed)
 
 
-def extract_mutation_loci(path_midsv_sample: Path, sequence: str, path_indels_normalized_sample: Path,
-                          path_indels_normalized_control: Path, path_knockin: Path, thresholds: dict = None,
-                          is_consensus: bool = False) -> list[set[str]]:
-    """mutation_extractor.py:28-87."""
+def _begin_extract_mutation_loci(path_midsv_sample: Path, sequence: str, path_indels_normalized_sample: Path,
+                                 path_indels_normalized_control: Path, path_knockin: Path, thresholds: dict = None,
+                                 is_consensus: bool = False):
     norm_sample = _load_pickle(path_indels_normalized_sample)
     norm_control = _load_pickle(path_indels_normalized_control)
     knockin = _load_pickle(path_knockin) if Path(path_knockin).exists() else None
@@ -82,8 +81,16 @@ def extract_mutation_loci(path_midsv_sample: Path, sequence: str, path_indels_no
         )
 
         insample = lambda norm: extract_sequence_errors_using_insample_control(norm, sigma_threshold=2.0)  # noqa: E731
-    return engine.select_mutation_loci(enc.histogram(), enc.strand_host, sequence, norm_sample, norm_control, knockin,
-                                       thresholds, is_consensus, insample)
+    return engine.begin_select_mutation_loci(enc.histogram(), enc.strand_host, sequence, norm_sample, norm_control,
+                                             knockin, thresholds, is_consensus, insample)
+
+
+def extract_mutation_loci(path_midsv_sample: Path, sequence: str, path_indels_normalized_sample: Path,
+                          path_indels_normalized_control: Path, path_knockin: Path, thresholds: dict = None,
+                          is_consensus: bool = False) -> list[set[str]]:
+    """mutation_extractor.py:28-87."""
+    return _begin_extract_mutation_loci(path_midsv_sample, sequence, path_indels_normalized_sample,
+                                        path_indels_normalized_control, path_knockin, thresholds, is_consensus)()
 
 
 def cache_indels_count(ARGS, is_control: bool = False) -> None:
@@ -108,10 +115,14 @@ def cache_indels_count(ARGS, is_control: bool = False) -> None:
 
 
 def cache_mutation_loci(ARGS, is_control: bool = False) -> None:
-    """mutation_extractor.py:126-168."""
+    """mutation_extractor.py:126-168.  The reference finishes one allele before it starts the next; here every
+    allele's file is encoded and its three MLP fits are started first, then the selections are finished in FASTA
+    order: a sample with A alleles waits for the longest of 3 A concurrent fits instead of A times the longest of 3
+    (same files, same contents)."""
     cache_indels_count(ARGS, is_control)
     if is_control:
         return None
+    begun = []
     for allele, sequence in ARGS.fasta_alleles.items():
         key = _allele_key(allele)
         path_midsv_sample = Path(ARGS.tempdir, ARGS.sample_name, "midsv", key, f"{ARGS.sample_name}_midsv.jsonl")
@@ -125,7 +136,10 @@ def cache_mutation_loci(ARGS, is_control: bool = False) -> None:
         name = f"{ARGS.sample_name}_normalized.pickle"
         if not Path(dir_control, name).exists():
             name = f"{ARGS.control_name}_normalized.pickle"
-        loci = extract_mutation_loci(path_midsv_sample, sequence, Path(dir_sample, f"{ARGS.sample_name}_normalized.pickle"),
-                                     Path(dir_control, name),
-                                     Path(ARGS.tempdir, ARGS.sample_name, "knockin_loci", key, "knockin.pickle"))
-        _save_pickle(loci, out)
+        finish = _begin_extract_mutation_loci(path_midsv_sample, sequence,
+                                              Path(dir_sample, f"{ARGS.sample_name}_normalized.pickle"),
+                                              Path(dir_control, name),
+                                              Path(ARGS.tempdir, ARGS.sample_name, "knockin_loci", key, "knockin.pickle"))
+        begun.append((finish, out))
+    for finish, out in begun:
+        _save_pickle(finish(), out)

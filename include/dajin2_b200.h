@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DJ_ABI_VERSION 1
+#define DJ_ABI_VERSION 2
 
 #define DJ_CODE_INVALID 0x7F
 #define DJ_CODE_INS 0x80
@@ -192,12 +192,15 @@ int dj_dedup_export(const void *table, uint32_t capacity, DjRowRecord *h_out, ui
  * Lloyd: sklearn/cluster/_kmeans.py:630-758, sparse kernels sklearn/cluster/_k_means_lloyd.pyx:221-420,
  * _k_means_common.pyx:55-312).  Points whose leaf[] equals `target` are split in two starting from the points
  * seed0 / seed1.  sub_label[p] in {0,1} is written for those points (untouched elsewhere).
+ * last_row[p] = position, in the row order of the matrix the reference would have built, of the LAST row equal to
+ * point p: scikit-learn's empty-cluster relocation takes the farthest row and, among rows at the same distance, the
+ * last one (np.argpartition), so ties between points are decided by it.
  * stats[0..1] = inertia of the two halves, stats[2] = iterations, stats[3..4] = weights of the halves.
  * The call that call site clustering/clustering.py:35,68 makes through scikit-learn.
  */
 int dj_bisect(const double *X, const double *weight, int32_t n_points, int32_t n_cols, const int32_t *leaf,
-              int32_t target, int32_t seed0, int32_t seed1, double tol, int32_t max_iter, int8_t *sub_label,
-              double *centers, double *stats, void *stream);
+              const int32_t *last_row, int32_t target, int32_t seed0, int32_t seed1, double tol, int32_t max_iter,
+              int8_t *sub_label, double *centers, double *stats, void *stream);
 
 /*
  * Brute-force read x centroid assignment for n_rows score rows given as value ids (no de-duplication):

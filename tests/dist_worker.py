@@ -37,8 +37,14 @@ def main():
     reduced = comm.allreduce_sum(torch.from_numpy(hist.copy()))
     expect = sum(shard_summary(r)[0].astype(np.int64) for r in range(world))
     assert np.array_equal(reduced.numpy(), expect), "allreduce"
-    loci = comm.broadcast_object(["", "+", "-*"] if rank == 0 else None)
-    assert loci == ["", "+", "-*"], "broadcast"
+    from dajin2_b200 import engine
+
+    loci_sel = [set(), {"+"}, {"-", "*"}, {"+", "-", "*"}]
+    mask = torch.zeros(len(loci_sel), dtype=torch.uint8)
+    if rank == 0:
+        mask.copy_(torch.from_numpy(engine.loci_to_mask(loci_sel)))
+    loci = engine.mask_to_loci(comm.broadcast_tensor(mask).numpy())  # one byte per locus, as run_device_sharded sends it
+    assert loci == loci_sel, "broadcast"
     merged = dj.merge_kmers(comm.allgather_object(kmers), 40)
     table = {(l, merged.names[k]): (int(merged.records["count_sample"][k]), int(merged.records["count_control"][k]))
              for l, ks in merged.per_locus.items() for k in ks}

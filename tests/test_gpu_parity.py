@@ -609,3 +609,29 @@ def test_consensus_views_of_the_code_matrix():
         assert [[k, float(v).hex()] for k, v in pwm[int(i)].items()] == want, i
     digest = hashlib.sha256(json.dumps([[[k, float(v).hex()] for k, v in d.items()] for d in pwm]).encode()).hexdigest()
     assert digest == g["consensus_percentage_sha"]
+
+
+def test_run_many_equals_run_device():
+    """pipeline.run_many (samples software-pipelined over the host MLP fits, the reference's batch mode) returns for
+    every sample exactly what pipeline.run_device returns for it alone, at every pipeline depth."""
+    from dajin2_b200 import engine, pipeline
+    from dajin2_b200.ingest import pack_rows
+
+    names = ["point_L900_N1500_f01", "point_L900_N1500", "point_L900_N1500_f50"]
+    loaded = [load_case(n)[0]["control"] for n in names]
+    sequence = loaded[0]["sequence"]
+    assert all(a["sequence"] == sequence and a["control"]["rows"] == loaded[0]["control"]["rows"] for a in loaded)
+    L = len(sequence)
+    hosts = [pack_rows(a["sample"]["rows"], a["sample"]["strands"], a["sample"]["qnames"]) for a in loaded]
+    c = loaded[0]["control"]
+    host_c = pack_rows(c["rows"], c["strands"], c["qnames"])
+    alone = []
+    for h in hosts:
+        alone.append(pipeline.run_device(engine.EncodedReads(h, L), engine.EncodedReads(host_c, L), sequence))
+    for depth in (1, 2, 4):
+        many = pipeline.run_many(list(hosts) + [hosts[0]], host_c, sequence, depth=depth)
+        assert len(many) == 4
+        for got, want in zip(many, alone + [alone[0]]):
+            assert got.mutation_loci == want.mutation_loci
+            assert got.labels.tolist() == want.labels.tolist()
+            assert got.cluster_sizes == want.cluster_sizes and got.percentages == want.percentages
