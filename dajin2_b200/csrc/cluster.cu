@@ -131,11 +131,13 @@ bisect_kernel(const double *__restrict__ X, const double *__restrict__ weight, i
               const int32_t *__restrict__ leaf, const int32_t *__restrict__ last_row, int target, int seed0, int seed1,
               double tol, int max_iter,
               int8_t *__restrict__ lab, int8_t *__restrict__ lab_old, double *__restrict__ dist,
-              double *__restrict__ centers_out, double *__restrict__ stats) {
+              double *__restrict__ centers_out, double *__restrict__ stats, double *__restrict__ big_centers) {
     extern __shared__ double smem[];
-    double *c_old = smem;                    // [2][n_cols]
-    double *c_new = smem + 2 * n_cols;       // [2][n_cols]
-    double *scratch = smem + 4 * n_cols;     // [kBisectThreads]
+    // the four centre rows live in shared memory; with more score columns than fit there (one column per selected
+    // locus: multi-kb deletions or knock-ins) they live in global memory -- one CTA, so __syncthreads orders them
+    double *c_old = big_centers ? big_centers : smem;                             // [2][n_cols]
+    double *c_new = (big_centers ? big_centers : smem) + 2 * n_cols;              // [2][n_cols]
+    double *scratch = big_centers ? smem : smem + 4 * n_cols;                     // [kBisectThreads]
     __shared__ double cn[2], wsum[2], shift[2];
     __shared__ int s_flag, s_far;
     __shared__ int s_idx[kBisectThreads];
@@ -331,11 +333,13 @@ constexpr int kSilThreads = 128;
 
 __global__ void __launch_bounds__(kSilThreads)
 silhouette_kernel(const double *__restrict__ X, const double *__restrict__ weight, const int32_t *__restrict__ label,
-                  int n_points, int n_cols, int n_clusters, int tile_rows, double *__restrict__ s_out) {
+                  int n_points, int n_cols, int n_clusters, int tile_rows, double *__restrict__ s_out,
+                  double *__restrict__ big_acc) {
     extern __shared__ double smem[];
-    double *acc = smem;                                    // [kSilThreads][n_clusters]
-    double *cw = acc + (size_t)kSilThreads * n_clusters;   // [n_clusters] cluster weights
-    double *tile = cw + n_clusters;                        // [tile_rows][n_cols]
+    // per-thread sums over the clusters: shared memory, or (many clusters) this CTA's slice of a global buffer
+    double *acc = big_acc ? big_acc + (size_t)blockIdx.x * kSilThreads * n_clusters : smem;  // [kSilThreads][n_clusters]
+    double *cw = big_acc ? smem : smem + (size_t)kSilThreads * n_clusters;                   // [n_clusters] cluster weights
+    double *tile = cw + n_clusters;                                                          // [tile_rows][n_cols]
     const int tid = threadIdx.x;
     const int i = blockIdx.x * blockDim.x + tid;
     for (int c = tid; c < n_clusters; c += blockDim.x) cw[c] = 0.0;
@@ -536,21 +540,21 @@ extern "C" int dj_bisect(const double *X, const double *weight, int32_t n_points
         dj_set_error("dj_bisect: empty problem");
         return 1;
     }
-    const size_t smem = sizeof(double) * ((size_t)4 * n_cols + kBisectThreads);
-    if (smem > 200 * 1024) {
-        dj_set_error("dj_bisect: %d score columns exceed the shared-memory budget of the single-CTA kernel", n_cols);
-        return 1;
-    }
+    size_t smem = sizeof(double) * ((size_t)4 * n_cols + kBisectThreads);
+    const bool big = smem > 200 * 1024;  // centres in global memory instead
+    if (big) smem = sizeof(double) * kBisectThreads;
     DJ_CUDA_CHECK(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int8_t *lab_old = nullptr;
-    double *dist = nullptr;
+    double *dist = nullptr, *big_centers = nullptr;
     DJ_CUDA_CHECK(cudaMallocAsync(&lab_old, (size_t)n_points, st));
     DJ_CUDA_CHECK(cudaMallocAsync(&dist, sizeof(double) * (size_t)n_points, st));
+    if (big) DJ_CUDA_CHECK(cudaMallocAsync(&big_centers, sizeof(double) * 4 * (size_t)n_cols, st));
     bisect_kernel<<<1, kBisectThreads, smem, st>>>(X, weight, n_points, n_cols, leaf, last_row, target, seed0, seed1, tol,
-                                                   max_iter, sub_label, lab_old, dist, centers, stats);
+                                                   max_iter, sub_label, lab_old, dist, centers, stats, big_centers);
     cudaError_t err = cudaGetLastError();
     cudaFreeAsync(lab_old, st);
     cudaFreeAsync(dist, st);
+    if (big_centers) cudaFreeAsync(big_centers, st);
     if (err != cudaSuccess) {
         dj_set_error("dj_bisect: %s", cudaGetErrorString(err));
         return 1;
@@ -568,17 +572,25 @@ extern "C" int dj_silhouette(const double *X, const double *weight, const int32_
     int tile_rows = 16384 / (n_cols > 0 ? n_cols : 1);
     if (tile_rows < 1) tile_rows = 1;
     if (tile_rows > 64) tile_rows = 64;
-    const size_t smem = sizeof(double) * ((size_t)kSilThreads * n_clusters + n_clusters + (size_t)tile_rows * n_cols);
-    if (smem > 200 * 1024) {
-        dj_set_error("dj_silhouette: %d clusters x %d columns exceed the shared-memory budget", n_clusters, n_cols);
-        return 1;
+    size_t smem = sizeof(double) * ((size_t)kSilThreads * n_clusters + n_clusters + (size_t)tile_rows * n_cols);
+    const bool big = smem > 200 * 1024;  // the per-thread cluster sums move to global memory
+    if (big) {
+        while (tile_rows > 1 && sizeof(double) * ((size_t)n_clusters + (size_t)tile_rows * n_cols) > 200 * 1024) tile_rows /= 2;
+        smem = sizeof(double) * ((size_t)n_clusters + (size_t)tile_rows * n_cols);
+        if (smem > 200 * 1024) {
+            dj_set_error("dj_silhouette: %d clusters x %d columns exceed the shared-memory budget", n_clusters, n_cols);
+            return 1;
+        }
     }
     DJ_CUDA_CHECK(cudaFuncSetAttribute(silhouette_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    double *s = nullptr;
+    const unsigned blocks = (unsigned)((n_points + kSilThreads - 1) / kSilThreads);
+    double *s = nullptr, *big_acc = nullptr;
     DJ_CUDA_CHECK(cudaMallocAsync(&s, sizeof(double) * (size_t)n_points, st));
-    silhouette_kernel<<<(n_points + kSilThreads - 1) / kSilThreads, kSilThreads, smem, st>>>(
-        X, weight, label, n_points, n_cols, n_clusters, tile_rows, s);
+    if (big) DJ_CUDA_CHECK(cudaMallocAsync(&big_acc, sizeof(double) * (size_t)blocks * kSilThreads * n_clusters, st));
+    silhouette_kernel<<<blocks, kSilThreads, smem, st>>>(X, weight, label, n_points, n_cols, n_clusters, tile_rows, s,
+                                                         big_acc);
     cudaError_t err = cudaGetLastError();
+    if (big_acc) cudaFreeAsync(big_acc, st);
     if (err == cudaSuccess) {
         weighted_mean_kernel<<<1, kBisectThreads, 0, st>>>(s, weight, n_points, score);
         err = cudaGetLastError();

@@ -44,10 +44,28 @@ def fit_predict(sample: np.ndarray, control: np.ndarray, threshold: float) -> np
     return fit_predict_stats(sample, control, threshold)[0]
 
 
-def fit_predict_stats(sample: np.ndarray, control: np.ndarray, threshold: float):
-    """``fit_predict`` plus what the fit did: (mask, {"n_iter", "fast_path", "seconds"})."""
+#: fits the caller expects to have in flight at once (3 per allele / sample in flight): pipeline.run_many raises it so
+#: that the element-wise passes of each fit take fewer threads and the fits do not fight for the cores
+expected_fits = 3
+
+
+def threads_per_fit() -> int:
+    """Threads of the element-wise passes of one fit: the cores this process may use, shared by the expected fits,
+    never more than ``fastmlp.default_threads()``.  The thread count cannot change a bit of the result."""
+    from .fastmlp import default_threads
+
+    usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+    return max(1, min(default_threads(), (usable - 2) // max(1, expected_fits)))
+
+
+def fit_predict_stats(sample: np.ndarray, control: np.ndarray, threshold: float, threads: int | None = None):
+    """``fit_predict`` plus what the fit did: (mask, {"n_iter", "fast_path", "seconds", "threads"})."""
     import time
 
+    if threads:
+        from .fastmlp import load_host_lib
+
+        load_host_lib().fm_set_threads(int(threads))
     t0 = time.perf_counter()
     import warnings
 
@@ -72,7 +90,7 @@ def fit_predict_stats(sample: np.ndarray, control: np.ndarray, threshold: float)
         clf.fit(X, y)
     mask = clf.predict(np.array([control, sample]).T) == 1
     return mask, {"n_iter": int(getattr(clf, "n_iter_", -1)), "fast_path": bool(getattr(clf, "fast_path_used_", False)),
-                  "seconds": time.perf_counter() - t0}
+                  "seconds": time.perf_counter() - t0, "threads": int(threads or 0)}
 
 
 def workers() -> int:
@@ -127,6 +145,7 @@ class _Worker:
         for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
             env[v] = "1"  # as the reference runs a sample (main.py:5-9): the fit is sensitive to the summation order
         env["CUDA_VISIBLE_DEVICES"] = ""
+        env["OMP_WAIT_POLICY"] = "passive"  # idle threads of one fit must not spin on cores other fits need
         root = str(Path(__file__).resolve().parent.parent)
         env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
         self.proc = subprocess.Popen([sys.executable, "-m", "dajin2_b200.mlp_pool", "--worker"], stdin=subprocess.PIPE,
@@ -197,7 +216,7 @@ def submit(sample: np.ndarray, control: np.ndarray, threshold: float) -> Future:
     if n == 0:
         fut: Future = Future()
         try:
-            mask, stats = fit_predict_stats(sample, control, threshold)
+            mask, stats = fit_predict_stats(sample, control, threshold, threads_per_fit())
             _note(stats)
             fut.set_result(mask)
         except BaseException as exc:  # noqa: BLE001 - handed to the caller through the future
@@ -208,7 +227,7 @@ def submit(sample: np.ndarray, control: np.ndarray, threshold: float) -> Future:
         _pool = _Pool(n)
         atexit.register(_shutdown)
     return _pool.submit((np.ascontiguousarray(sample, dtype=np.float64),
-                         np.ascontiguousarray(control, dtype=np.float64), float(threshold)))
+                         np.ascontiguousarray(control, dtype=np.float64), float(threshold), threads_per_fit()))
 
 
 def warm_up() -> None:

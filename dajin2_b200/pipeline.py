@@ -202,6 +202,8 @@ def run_many(samples, control, sequence: str, knockin: set[int] | None = None, d
     ``on_result`` and returns their count, so that finished samples can be released)."""
     from collections import deque
 
+    from . import mlp_pool
+
     if isinstance(control, HostReads):
         control = engine.EncodedReads(control, len(sequence), validate=False, encode=False, sequence=sequence)
     inflight: deque = deque()
@@ -217,16 +219,19 @@ def run_many(samples, control, sequence: str, knockin: set[int] | None = None, d
         else:
             out.append(res)
 
-    first = True
-    for s in samples:
-        if isinstance(s, HostReads):
-            s = engine.EncodedReads(s, len(sequence), validate=False, encode=False, sequence=sequence)
-        inflight.append(_front(s, control, sequence, knockin, None, True if first else True))
-        first = False
-        if len(inflight) >= max(1, depth):
+    saved = mlp_pool.expected_fits
+    mlp_pool.expected_fits = 3 * max(1, depth)  # the fits of `depth` samples share the host cores
+    try:
+        for s in samples:
+            if isinstance(s, HostReads):
+                s = engine.EncodedReads(s, len(sequence), validate=False, encode=False, sequence=sequence)
+            inflight.append(_front(s, control, sequence, knockin, None, True))
+            if len(inflight) >= max(1, depth):
+                retire()
+        while inflight:
             retire()
-    while inflight:
-        retire()
+    finally:
+        mlp_pool.expected_fits = saved
     return out if on_result is None else n_done
 
 

@@ -68,7 +68,7 @@ def test_flow_matches_the_reference(name, tmp_path):
 
     golden = cases.load_golden(name)["samples"]
     samples = _inputs(name)
-    assert list(samples) == list(golden)
+    assert sorted(samples) == sorted(golden)  # (the golden file is written with sorted keys; the run order is the case's)
     cname = "ctrl"
     cache.clear()
     first = next(iter(samples.values()))["alleles"]

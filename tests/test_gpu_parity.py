@@ -635,3 +635,38 @@ def test_run_many_equals_run_device():
             assert got.mutation_loci == want.mutation_loci
             assert got.labels.tolist() == want.labels.tolist()
             assert got.cluster_sizes == want.cluster_sizes and got.percentages == want.percentages
+
+
+def test_clustering_kernels_beyond_shared_memory():
+    """dj_bisect with more score columns than fit shared memory (one column per selected locus: multi-kb deletions,
+    knock-ins) and dj_silhouette with hundreds of clusters keep their operands in global memory and return what the
+    shared-memory path / scikit-learn return."""
+    from sklearn.metrics import silhouette_score
+
+    from dajin2_b200 import clusterer
+
+    rng = np.random.default_rng(7)
+    n, k = 300, 120
+    small = np.where(rng.random((n, k)) < 0.1, rng.integers(1, 6, (n, k)) / 10.0, 0.0)
+    small[:150, 3] += 2.0  # two well separated groups
+    wide = np.zeros((n, 7000))
+    wide[:, rng.choice(7000, k, replace=False)] = small[:, np.argsort(rng.random(k))]
+    w = rng.integers(1, 4, n).astype(np.float64)
+    leaf = np.zeros(n, dtype=np.int32)
+    last = torch.arange(n, dtype=torch.int32, device="cuda")
+    out = []
+    for X in (small, wide):
+        X_d = torch.as_tensor(np.ascontiguousarray(X), device="cuda")
+        sub, stats = clusterer._bisect(X_d, torch.as_tensor(w, device="cuda"), leaf, last, 0, 5, 200)
+        out.append((sub.tolist(), stats[:5].tolist()))
+    assert out[0][0] == out[1][0]
+    assert out[0][1][2:] == out[1][1][2:]  # iterations and weights; the inertia sums run over another column order
+    assert np.allclose(out[0][1][:2], out[1][1][:2], rtol=1e-12)
+    assert 0 < sum(out[0][0]) < n
+    # silhouette: 260 clusters (> what 128 x n_clusters doubles of shared memory hold next to a tile)
+    n_c = 260
+    pts = rng.normal(size=(n_c * 3, 6)) + np.repeat(rng.normal(scale=20, size=(n_c, 6)), 3, axis=0)
+    labels = np.repeat(np.arange(n_c), 3)
+    got = clusterer._silhouette(torch.as_tensor(pts, device="cuda"), torch.ones(len(pts), dtype=torch.float64, device="cuda"),
+                                labels, n_c)
+    assert got == pytest.approx(silhouette_score(pts, labels), abs=1e-12)
