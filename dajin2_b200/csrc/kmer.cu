@@ -1,6 +1,12 @@
 // 3-mer counting at the selected loci (dj_kmer_count), score-row annotation (dj_annotate) and raw token
 // retrieval (dj_fetch_tokens).
 //
+// Counting is staged through shared memory: a selected locus sees a few dozen distinct 3-mers however many reads
+// there are, so every CTA of the persistent grid counts into its own 1024-slot table (fingerprint, payload, count,
+// smallest read) with shared-memory atomics and adds its entries to the global table ONCE, when it has run out of
+// reads: a 25 %-allele locus costs (CTAs x distinct 3-mers) global atomics instead of one per read.  A 3-mer that
+// finds no room in the CTA's table (32 probes) goes to the global table directly.
+//
 // Only tokens whose operation is listed in mutation_loci[i] form a k-mer other than "@,@,@"
 // (src/DAJIN2/core/clustering/kmer_generator.py:40-54), so both kernels read three code bytes per
 // (read, selected locus) -- lanes run over consecutive selected loci of one read so that neighbouring loci share
@@ -12,12 +18,58 @@
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kLocalSlots = 1024;  // per-CTA staging table (24 KB of shared memory)
+constexpr int kLocalProbes = 32;
+
+// find or claim the slot of fp in a CTA-local table; kLocalSlots when 32 probes found neither
+__device__ __forceinline__ uint32_t local_insert(unsigned long long *fps, unsigned long long fp, bool *claimed) {
+    uint32_t slot = (uint32_t)(dj_mix64(fp) & (kLocalSlots - 1));
+    *claimed = false;
+    for (int probe = 0; probe < kLocalProbes; ++probe) {
+        const unsigned long long cur = *((volatile unsigned long long *)&fps[slot]);
+        if (cur == fp) return slot;
+        if (cur == 0ULL) {
+            const unsigned long long old = atomicCAS(&fps[slot], 0ULL, fp);
+            if (old == 0ULL) {
+                *claimed = true;
+                return slot;
+            }
+            if (old == fp) return slot;
+        }
+        slot = (slot + 1) & (kLocalSlots - 1);
+    }
+    return kLocalSlots;
+}
+
+__device__ __forceinline__ void global_count(DjKmerTableView &tb, unsigned long long fp, unsigned long long payload,
+                                             uint32_t count, uint32_t example, int which, uint32_t *overflow) {
+    bool claimed;
+    const uint32_t slot = dj_table_insert(tb.fp, tb.capacity, fp, &claimed);
+    if (slot == tb.capacity) {
+        atomicAdd(overflow, count);
+        return;
+    }
+    if (claimed) {
+        tb.payload[slot] = payload;
+        atomicAdd(tb.n_entries, 1u);
+    }
+    atomicAdd(which == 0 ? &tb.cnt0[slot] : &tb.cnt1[slot], count);
+    atomicMin(&tb.example[slot], example);
+}
 
 __global__ void __launch_bounds__(kThreads)
 kmer_count_kernel(const uint8_t *__restrict__ codes, int code_pitch, const int32_t *__restrict__ rows,
                   int64_t n_rows, DjTextRef tr, const uint8_t *__restrict__ locimask,
                   const int32_t *__restrict__ sel, int n_sel, int which, DjKmerTableView tb,
                   uint32_t *__restrict__ overflow) {
+    __shared__ unsigned long long l_fp[kLocalSlots], l_payload[kLocalSlots];
+    __shared__ uint32_t l_cnt[kLocalSlots], l_example[kLocalSlots];
+    for (int e = threadIdx.x; e < kLocalSlots; e += blockDim.x) {
+        l_fp[e] = 0ULL;
+        l_cnt[e] = 0u;
+        l_example[e] = 0xFFFFFFFFu;
+    }
+    __syncthreads();
     const int64_t n_items = n_rows * (int64_t)n_sel;
     for (int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; item < n_items;
          item += (int64_t)gridDim.x * blockDim.x) {
@@ -26,19 +78,20 @@ kmer_count_kernel(const uint8_t *__restrict__ codes, int code_pitch, const int32
         const int64_t r = rows ? rows[t] : t;
         const DjKmerKey key = dj_kmer_key(codes + r * (int64_t)code_pitch, sel[s], locimask, s, tr, r);
         if (key.at) continue;
+        const uint32_t example = ((uint32_t)which << 31) | (uint32_t)r;
         bool claimed;
-        const uint32_t slot = dj_table_insert(tb.fp, tb.capacity, key.fp, &claimed);
-        if (slot == tb.capacity) {
-            atomicAdd(overflow, 1u);
+        const uint32_t slot = local_insert(l_fp, key.fp, &claimed);
+        if (slot == kLocalSlots) {  // no room in this CTA's table
+            global_count(tb, key.fp, key.payload, 1u, example, which, overflow);
             continue;
         }
-        if (claimed) {
-            tb.payload[slot] = key.payload;
-            atomicAdd(tb.n_entries, 1u);
-        }
-        atomicAdd(which == 0 ? &tb.cnt0[slot] : &tb.cnt1[slot], 1u);
-        atomicMin(&tb.example[slot], ((uint32_t)which << 31) | (uint32_t)r);
+        if (claimed) l_payload[slot] = key.payload;
+        atomicAdd(&l_cnt[slot], 1u);
+        atomicMin(&l_example[slot], example);
     }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kLocalSlots; e += blockDim.x)
+        if (l_fp[e] != 0ULL) global_count(tb, l_fp[e], l_payload[e], l_cnt[e], l_example[e], which, overflow);
 }
 
 __global__ void kmer_export_kernel(DjKmerTableView tb, DjKmerRecord *out, uint32_t max_records, uint32_t *n_out) {

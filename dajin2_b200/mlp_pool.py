@@ -97,7 +97,7 @@ def workers() -> int:
     raw = os.environ.get("DAJIN2_B200_MLP_WORKERS")
     if raw is not None:
         return max(0, int(raw))
-    return max(3, min(12, (os.cpu_count() or 3) - 1))
+    return max(3, min(16, (os.cpu_count() or 4) - 2))
 
 
 # ---------------------------------------------------------------------------------------------------------
