@@ -283,9 +283,32 @@ def window_cosine(sample: np.ndarray, control: np.ndarray) -> tuple[np.ndarray, 
     return d.cpu().numpy(), dt.cpu().numpy()
 
 
+def _cosine_distance_numpy(x: np.ndarray, y: np.ndarray) -> float:
+    """``cosine_distance`` with the reference's own numpy calls (``anomaly_detector.py:11-25``): np.dot / np.linalg.norm
+    sum in BLAS order, the device kernel left to right -- the two agree to ~1e-16, which only matters AT a threshold."""
+    if x.size == 0 or y.size == 0:
+        return 0.0
+    den = np.linalg.norm(x) * np.linalg.norm(y)
+    if den == 0 or np.isnan(den):
+        return 1.0
+    sim = float(np.dot(x, y) / (den + np.finfo(float).eps))
+    return 1 - np.clip(sim, -1.0, 1.0)
+
+
 def dissimilar_mask(sample: np.ndarray, control: np.ndarray, is_consensus: bool = False) -> np.ndarray:
-    """``is_dissimilar_loci`` for every locus (reference ``anomaly_detector.py:28-58``)."""
+    """``is_dissimilar_loci`` for every locus (reference ``anomaly_detector.py:28-58``).  The ten-wide window
+    distances come from the device (``dj_window_cosine``); a locus whose distance or ratio lies within 1e-9 of a
+    decision threshold (0.05, 0.9) is recomputed with the reference's own numpy calls, so that the decision is the
+    reference's whatever the summation order."""
     d, dt = window_cosine(sample, control)
+    den0 = d + dt
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio0 = np.where(den0 != 0, d / np.where(den0 != 0, den0, 1.0), 0.0)
+    near = np.flatnonzero((np.abs(d - 0.05) < 1e-9) | ((d > 0.05 - 1e-9) & (np.abs(ratio0 - 0.9) < 1e-9)))
+    for i in near.tolist():
+        x, y = sample[i : i + 10], control[i : i + 10]
+        d[i] = _cosine_distance_numpy(x, y)
+        dt[i] = _cosine_distance_numpy(x[1:], y[1:])
     big = (sample - control) > 20
     big_ok = np.ones_like(big) if not is_consensus else sample > 50
     den = d + dt
