@@ -21,6 +21,9 @@ FLAG_TOKEN_COUNT = 1
 FLAG_BAD_TOKEN = 2
 ENC_CHUNK = 1536
 HIST_ROWS = 10
+# rows of dj_hist (include/dajin2_b200.h: DJ_HIST_*)
+HIST_MATCH, HIST_INS, HIST_DEL, HIST_SUB = 0, 1, 2, 3
+HIST_SW_INS_P, HIST_SW_DEL_P, HIST_SW_SUB_P, HIST_SW_INS_M, HIST_SW_DEL_M, HIST_SW_SUB_M = 4, 5, 6, 7, 8, 9
 MASK_INS, MASK_DEL, MASK_SUB = 1, 2, 4
 KMER_AT, KMER_RAW = 256, 257
 
@@ -45,6 +48,7 @@ class RowRecord(ctypes.Structure):
         ("count", ctypes.c_uint32),
         ("count_plus", ctypes.c_uint32),
         ("first_row", ctypes.c_uint32),
+        ("last_row", ctypes.c_uint32),
     ]
 
 

@@ -42,6 +42,7 @@ class RowSet:
     first_row: np.ndarray  # int64[U]
     point_ids: np.ndarray  # uint16[U, n_cols] value ids of each point
     point_of_slot: np.ndarray  # int32[capacity] slot -> point (-1 elsewhere)
+    last_row: np.ndarray = None  # int64[U] last row of each point (scikit-learn's tie rule, dj_bisect)
 
 
 def dedup_rows(ids: torch.Tensor, strand: torch.Tensor, rows: torch.Tensor | None) -> RowSet:
@@ -78,7 +79,7 @@ def dedup_rows(ids: torch.Tensor, strand: torch.Tensor, rows: torch.Tensor | Non
     point_of_slot = np.full(capacity, -1, dtype=np.int32)
     point_of_slot[rec["slot"]] = np.arange(len(rec), dtype=np.int32)
     return RowSet(n_rows, slot_of_row[:n_rows], rec["slot"], rec["count"].astype(np.int64),
-                  rec["count_plus"].astype(np.int64), first, point_ids, point_of_slot)
+                  rec["count_plus"].astype(np.int64), first, point_ids, point_of_slot, rec["last_row"].astype(np.int64))
 
 
 def uniform_choice2(rng: np.random.RandomState, n: int) -> np.ndarray:
@@ -110,13 +111,11 @@ def last_rows_of_points(row_points: np.ndarray, n_points: int) -> np.ndarray:
 
 
 def last_rows(rs: RowSet) -> np.ndarray:
-    """Last row (in the row order ``rs`` was built in) of every point of a device row set."""
-    dev = rs.slot_of_row.device
-    last = torch.full((int(rs.point_of_slot.shape[0]),), -1, dtype=torch.int64, device=dev)
-    if rs.n_rows:
-        last.scatter_reduce_(0, rs.slot_of_row.long(), torch.arange(rs.n_rows, dtype=torch.int64, device=dev),
-                             reduce="amax")
-    return last[torch.as_tensor(rs.slots.astype(np.int64), device=dev)].cpu().numpy()
+    """Last row (in the row order ``rs`` was built in) of every point of a device row set: recorded by the
+    de-duplication kernel next to the first row."""
+    if rs.last_row is None:
+        raise ValueError("this RowSet was built without last rows")
+    return np.asarray(rs.last_row, dtype=np.int64)
 
 
 def _bisect(X_d, w_d, leaf_host: np.ndarray, last_row_d, target: int, seed0: int, seed1: int):

@@ -86,6 +86,81 @@ def onehot_by_mutations(midsv_sample) -> dict[str, np.ndarray]:
     return {mut: m.astype(np.int64) for mut, m in _op_classes(codes_host).items()}
 
 
+def _startswith_class_table() -> np.ndarray:
+    """class of every code byte for ``token.startswith(mut)``: 0 '+', 1 '-', 2 '*', 3 neither."""
+    t = np.full(256, 3, dtype=np.uint8)
+    for code in range(256):
+        anchor = code & 0x7F
+        if code & 0x80:
+            t[code] = 0
+        elif 10 <= anchor < 20:
+            t[code] = 1
+        elif 20 <= anchor < 70:
+            t[code] = 2
+    return t
+
+
+def _masked_row_sums(codes_host: np.ndarray, n_loci: int, mask: dict[str, np.ndarray]) -> dict[str, np.ndarray]:
+    """``(onehot * mask).sum(axis=1)`` per mutation type, summed the way numpy sums a row (hostc/fastmlp.c)."""
+    import os
+
+    from .fastmlp import load_host_lib
+
+    lib = load_host_lib()
+    table = _startswith_class_table()
+    codes_host = np.ascontiguousarray(codes_host)
+    n = int(codes_host.shape[0])
+    out = {}
+    for cls, mut in enumerate("+-*"):
+        m = np.ascontiguousarray(mask[mut], dtype=np.float64)
+        res = np.empty(n, dtype=np.float64)
+        lib.dj_masked_row_sums(codes_host.ctypes.data, int(codes_host.strides[0]), n, n_loci, table.ctypes.data, cls,
+                               m.ctypes.data, res.ctypes.data, min(8, os.cpu_count() or 1))
+        out[mut] = res
+    return out
+
+
+def filter_control(ARGS, path_consensus_control: Path, path_consensus_sample: Path, allele: str,
+                   no_filter: bool = False) -> list[bool]:
+    """similarity_searcher.py:82-110 (``filter_control``: onehot_by_mutations of both files, calculate_percentage,
+    get_values_to_mask, apply_mask, identify_normal_reads) without materialising the reads x loci one-hot matrices:
+    the per-locus counts are the startswith rows of the device histogram, the masked row sums come straight from the
+    code matrix (summed in numpy's order), and ``LocalOutlierFactor`` is scikit-learn's, called as the reference calls
+    it on the n x 1 row sums.  (The reference also pickles the control's one-hot matrices next to the control file for
+    the next cluster; the encoded control file is cached on the device instead.)"""
+    from sklearn.neighbors import LocalOutlierFactor
+
+    from . import _cabi
+
+    enc_s = encoded_file(path_consensus_sample, None)
+    enc_c = encoded_file(path_consensus_control, enc_s.n_loci)
+    L = enc_s.n_loci
+    hist = enc_s.histogram().astype(np.int64)
+    rows = {"+": (_cabi.HIST_SW_INS_P, _cabi.HIST_SW_INS_M), "-": (_cabi.HIST_SW_DEL_P, _cabi.HIST_SW_DEL_M),
+            "*": (_cabi.HIST_SW_SUB_P, _cabi.HIST_SW_SUB_M)}
+    count = {mut: hist[a] + hist[b] for mut, (a, b) in rows.items()}
+    coverage_match = enc_s.n_reads - (count["+"] + count["-"] + count["*"])  # tokens that start with '='
+    mask = {}
+    for mut in "+-*":
+        with np.errstate(divide="ignore", invalid="ignore"):
+            x = count[mut] / coverage_match
+        pct = np.where(np.isnan(x), 0, x)
+        mask[mut] = np.where(pct > 0.5, 0, pct)
+    sums_s = _masked_row_sums(enc_s.codes[: enc_s.n_reads, :L].cpu().numpy(), L, mask)
+    sums_c = _masked_row_sums(enc_c.codes[: enc_c.n_reads, :L].cpu().numpy(), L, mask)
+    ok = None
+    for mut in "+-*":
+        vs, vc = sums_s[mut].reshape(-1, 1), sums_c[mut].reshape(-1, 1)
+        if no_filter and len(vs) <= 1:
+            cmp = np.ones(len(vc), dtype=bool)
+        else:
+            n_neighbors = min(len(vs), max(1, len(vs) - 1))
+            clf = LocalOutlierFactor(novelty=True, n_neighbors=n_neighbors).fit(vs)
+            cmp = clf.predict(vc) == 1
+        ok = cmp if ok is None else ok & cmp
+    return ok.tolist()
+
+
 def call_percentage(midsv_tags: list[list[str]], mutation_loci: list[set[str]], sequence: str) -> list[dict[str, float]]:
     """consensus/consensus.py:19-75 (convert_to_percentage, remove_all_n, adjust_to_100_percent) — the position weight
     matrix of a cluster.  Token identities come from the code matrix (the raw text is fetched only for insertions);

@@ -61,6 +61,7 @@ dedup_kernel(const uint16_t *__restrict__ ids, int64_t n_rows, int n_cols, const
             if (n_plus) atomicAdd(&tb.plus[slot], (uint32_t)n_plus);
             atomicMin(&tb.first[slot], (uint32_t)t);  // the leader holds the smallest t of its group
         }
+        if (lane == 31 - __clz(same)) atomicMax(&tb.last[slot], (uint32_t)t);  // ... this lane the largest
     }
 }
 
@@ -74,6 +75,7 @@ __global__ void dedup_export_kernel(DjRowTableView tb, DjRowRecord *out, uint32_
         rec.count = tb.count[slot];
         rec.count_plus = tb.plus[slot];
         rec.first_row = tb.first[slot];
+        rec.last_row = tb.last[slot];
         out[k] = rec;
     }
 }
@@ -469,7 +471,7 @@ assign_rows_kernel(const uint16_t *__restrict__ ids, int64_t n_rows, int n_cols,
 
 }  // namespace
 
-extern "C" int64_t dj_row_table_bytes(uint32_t capacity) { return 64 + (int64_t)capacity * 20; }
+extern "C" int64_t dj_row_table_bytes(uint32_t capacity) { return 64 + (int64_t)capacity * 24; }
 
 extern "C" int dj_row_table_clear(void *table, uint32_t capacity, void *stream) {
     if (capacity == 0 || (capacity & (capacity - 1)) != 0) {
@@ -480,6 +482,7 @@ extern "C" int dj_row_table_clear(void *table, uint32_t capacity, void *stream) 
     DjRowTableView tb = dj_row_view(table, capacity);
     DJ_CUDA_CHECK(cudaMemsetAsync(table, 0, 64 + (size_t)capacity * 16, st));
     DJ_CUDA_CHECK(cudaMemsetAsync(tb.first, 0xFF, (size_t)capacity * 4, st));
+    DJ_CUDA_CHECK(cudaMemsetAsync(tb.last, 0, (size_t)capacity * 4, st));
     return 0;
 }
 

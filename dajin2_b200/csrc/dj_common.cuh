@@ -230,6 +230,7 @@ struct DjRowTableView {
     uint32_t *count;
     uint32_t *plus;
     uint32_t *first;
+    uint32_t *last;
     uint32_t capacity;
 };
 
@@ -245,6 +246,8 @@ __host__ __device__ inline DjRowTableView dj_row_view(void *base, uint32_t capac
     v.plus = (uint32_t *)p;
     p += (size_t)capacity * 4;
     v.first = (uint32_t *)p;
+    p += (size_t)capacity * 4;
+    v.last = (uint32_t *)p;
     v.capacity = capacity;
     return v;
 }

@@ -126,35 +126,43 @@ def merge_kmers(payloads: list[list[tuple[int, str, int, int]]], n_loci: int) ->
     return MergedKmers(n_loci, names, per_locus, records)
 
 
-def merge_points(payloads: list[tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]]):
+def merge_points(payloads: list[tuple]):
     """Union of the shards' distinct score rows.  Each payload = (point_ids [U, K] uint16, count [U], count_plus [U],
-    first global position [U]).  Returns (point_ids, count, count_plus, first, maps) with the points ordered by
-    first global position — the order ``dedup_rows`` gives an unsharded run — and, per shard, local -> merged."""
-    index: dict[bytes, int] = {}
-    rows, count, plus, first = [], [], [], []
-    for ids, c, p, f in payloads:
-        for u in range(ids.shape[0]):
-            key = ids[u].tobytes()
-            k = index.get(key)
-            if k is None:
-                index[key] = len(rows)
-                rows.append(ids[u])
-                count.append(int(c[u]))
-                plus.append(int(p[u]))
-                first.append(int(f[u]))
-            else:
-                count[k] += int(c[u])
-                plus[k] += int(p[u])
-                first[k] = min(first[k], int(f[u]))
-    order = np.argsort(np.array(first, dtype=np.int64), kind="stable") if rows else np.zeros(0, dtype=np.int64)
-    new_of_old = np.empty(len(rows), dtype=np.int64)
-    new_of_old[order] = np.arange(len(rows))
+    first global position [U][, last global position [U]]).  Returns (point_ids, count, count_plus, first, maps, last)
+    with the points ordered by first global position — the order ``dedup_rows`` gives an unsharded run — and, per
+    shard, local -> merged.  Vectorised: one ``np.unique`` over the stacked rows instead of a Python dict per row."""
+    payloads = [tuple(p) if len(p) == 5 else (*p, p[3]) for p in payloads]
     n_cols = payloads[0][0].shape[1] if payloads else 0
-    ids_m = np.stack([rows[i] for i in order]) if rows else np.zeros((0, n_cols), dtype=np.uint16)
-    maps = [np.array([new_of_old[index[ids[u].tobytes()]] for u in range(ids.shape[0])], dtype=np.int32)
-            for ids, _, _, _ in payloads]
-    return (ids_m, np.array(count, dtype=np.int64)[order], np.array(plus, dtype=np.int64)[order],
-            np.array(first, dtype=np.int64)[order], maps)
+    sizes = [int(p[0].shape[0]) for p in payloads]
+    if sum(sizes) == 0:
+        z = np.zeros(0, dtype=np.int64)
+        return np.zeros((0, n_cols), dtype=np.uint16), z, z, z, [np.zeros(0, dtype=np.int32) for _ in payloads], z
+    ids = np.concatenate([np.ascontiguousarray(p[0], dtype=np.uint16).reshape(-1, n_cols) for p in payloads], axis=0)
+    cnt = np.concatenate([np.asarray(p[1], dtype=np.int64) for p in payloads])
+    plus = np.concatenate([np.asarray(p[2], dtype=np.int64) for p in payloads])
+    first = np.concatenate([np.asarray(p[3], dtype=np.int64) for p in payloads])
+    last = np.concatenate([np.asarray(p[4], dtype=np.int64) for p in payloads])
+    if n_cols:
+        keys = np.ascontiguousarray(ids).view(np.dtype((np.void, 2 * n_cols))).ravel()
+        _, rep, inv = np.unique(keys, return_index=True, return_inverse=True)
+    else:  # no score column: every row is the same (empty) point
+        rep, inv = np.zeros(1, dtype=np.int64), np.zeros(len(ids), dtype=np.int64)
+    n_u = len(rep)
+    count_u = np.bincount(inv, weights=cnt, minlength=n_u).astype(np.int64)
+    plus_u = np.bincount(inv, weights=plus, minlength=n_u).astype(np.int64)
+    first_u = np.full(n_u, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(first_u, inv, first)
+    last_u = np.full(n_u, -1, dtype=np.int64)
+    np.maximum.at(last_u, inv, last)
+    order = np.argsort(first_u, kind="stable")
+    new_of_old = np.empty(n_u, dtype=np.int64)
+    new_of_old[order] = np.arange(n_u)
+    merged_of_row = new_of_old[inv].astype(np.int32)
+    maps, start = [], 0
+    for n in sizes:
+        maps.append(merged_of_row[start : start + n])
+        start += n
+    return ids[rep][order], count_u[order], plus_u[order], first_u[order], maps, last_u[order]
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -231,7 +239,10 @@ class ShardRun:
 
         first_global = (self.gpos_sorted[torch.as_tensor(self.rs.first_row, device=self.dev)].cpu().numpy()
                         if len(self.rs.first_row) else np.zeros(0, dtype=np.int64))
-        return (self.rs.point_ids, self.rs.count, self.rs.count_plus, first_global)
+        # local rows are in global order, so the last local row of a point is its last global position on this shard
+        last_global = (self.gpos_sorted[torch.as_tensor(self.rs.last_row, device=self.dev)].cpu().numpy()
+                       if len(self.rs.first_row) else np.zeros(0, dtype=np.int64))
+        return (self.rs.point_ids, self.rs.count, self.rs.count_plus, first_global, last_global)
 
     # phase 4 -> all-gather of (global position, merged point) per read
     def points_of_reads(self, point_payloads: list, shard_index: int):
@@ -251,12 +262,12 @@ class ShardRun:
 
         from . import clusterer
 
-        ids_m, count, plus, first, _ = self.merged_points
+        ids_m, count, plus, first, _, last = self.merged_points
         n_points = int(ids_m.shape[0])
         point_of_global_row = torch.empty(self.n_total, dtype=torch.int32, device=self.dev)
         point_of_global_row[gpos_all.long()] = point_all
         rs_global = clusterer.RowSet(self.n_total, point_of_global_row, np.arange(n_points, dtype=np.uint32), count, plus,
-                                     first, ids_m, np.arange(n_points, dtype=np.int32))
+                                     first, ids_m, np.arange(n_points, dtype=np.int32), last)
         final_pts, info = clusterer.cluster_points(rs_global, self.ids_c, self.control.strand, self.model,
                                                    {"+": self.n_plus, "-": self.n_total - self.n_plus})
         labels_d = torch.as_tensor(final_pts, device=self.dev)[self.point_of_row.long()]

@@ -178,6 +178,8 @@ def load_host_lib():
         lib.dj_gather_fixed.restype = None
         lib.dj_midsv_postfix.argtypes = [vp, vp, vp, i64, vp, i64, ctypes.c_int32, cd, vp, vp, vp, ci]
         lib.dj_midsv_postfix.restype = i64
+        lib.dj_masked_row_sums.argtypes = [vp, i64, i64, ctypes.c_int32, vp, ctypes.c_int32, vp, vp, ci]
+        lib.dj_masked_row_sums.restype = None
         lib.fm_set_threads(default_threads())
         if os.environ.get("DAJIN2_B200_MLP_VMATH", "1") != "0":
             tables = _libm_tables()

@@ -70,6 +70,25 @@ static double pairwise_sum(const double *a, int64_t n) {
     }
 }
 
+/* (onehot * mask).sum(axis=1) of the consensus control filter (reference consensus/similarity_searcher.py:45-62):
+ * row r of the implicit matrix holds mask[i] where the code byte of read r at locus i is of class `cls` (class_of[256]:
+ * 0 '+', 1 '-', 2 '*', 3 none) and 0.0 elsewhere; each row is summed the way numpy sums a contiguous float64 row. */
+void dj_masked_row_sums(const uint8_t *codes, int64_t pitch, int64_t n_rows, int32_t n_loci, const uint8_t *class_of,
+                        int32_t cls, const double *mask, double *out, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+#pragma omp parallel num_threads(n_threads)
+    {
+        double *tmp = (double *)malloc(sizeof(double) * (size_t)(n_loci > 0 ? n_loci : 1));
+#pragma omp for schedule(static)
+        for (int64_t r = 0; r < n_rows; r++) {
+            const uint8_t *row = codes + r * pitch;
+            for (int32_t i = 0; i < n_loci; i++) tmp[i] = class_of[row[i]] == cls ? mask[i] : 0.0;
+            out[r] = pairwise_sum(tmp, n_loci);
+        }
+        free(tmp);
+    }
+}
+
 /* np.maximum(v, 0): v unless v < 0 (NaN and -0.0 pass through, as numpy's loop does) */
 static inline double relu(double v) { return v < 0.0 ? 0.0 : v; }
 

@@ -66,6 +66,7 @@ _PATCHES = [
     ("DAJIN2.core.consensus.consensus_mutation_analyzer", "extract_path_n_filtered_control",
      consensus.extract_path_n_filtered_control),
     ("DAJIN2.core.consensus.similarity_searcher", "onehot_by_mutations", consensus.onehot_by_mutations),
+    ("DAJIN2.core.consensus.similarity_searcher", "filter_control", consensus.filter_control),
     ("DAJIN2.core.consensus.consensus", "call_percentage", consensus.call_percentage),
     # the candidate-loci step with its three concurrent, bit-identical MLP fits (anomaly_detector.py:99-109), for the
     # consensus stage (one call per cluster, is_consensus=True) and for anyone else who imported it by value

@@ -84,6 +84,7 @@ typedef struct {
     uint32_t count;      /* number of rows equal to this one                                    */
     uint32_t count_plus; /* ... of which '+' strand                                             */
     uint32_t first_row;  /* smallest row position (in the order given to dj_dedup_rows)         */
+    uint32_t last_row;   /* largest row position: decides scikit-learn's ties between points (dj_bisect) */
 } DjRowRecord;
 
 int dj_abi_version(void);

@@ -405,6 +405,20 @@ def run_reference_sv(case: dict) -> dict:
         from DAJIN2.core.consensus.consensus import call_percentage
         from DAJIN2.core.consensus.similarity_searcher import onehot_by_mutations
 
+        # the control filter of the consensus stage (similarity_searcher.py:82-110): which N-filtered control reads
+        # resemble the cluster (one-hot matrices, masked row sums, LocalOutlierFactor)
+        from DAJIN2.core.consensus.similarity_searcher import filter_control
+
+        g["consensus_filter_control"] = [int(bool(x)) for x in filter_control(args, p_nf, p_cluster, "control")]
+        # ... and on a control that also holds 60 reads of the sample's OTHER alleles, which the filter must drop
+        # (another sample name: filter_control pickles the control's one-hot matrices per sample name)
+        others = [i for i in range(len(recs)) if i not in set(members)][:60]
+        p_mixed = tmp / cname / "consensus" / key / "mixed_control.jsonl"
+        p_mixed.write_text(p_nf.read_text() + "".join(json.dumps(recs[i]) + "\n" for i in others))
+        args_mixed = SimpleNamespace(tempdir=tmp, sample_name=sname + "_mixed", control_name=cname,
+                                     fasta_alleles=args.fasta_alleles)
+        g["consensus_filter_control_mixed_extra"] = others
+        g["consensus_filter_control_mixed"] = [int(bool(x)) for x in filter_control(args_mixed, p_mixed, p_cluster, "control")]
         cluster_recs = [recs[i] for i in members]
         onehot = onehot_by_mutations(iter(cluster_recs))
         g["consensus_onehot_sha"] = {k: hashlib.sha256(__import__("numpy").ascontiguousarray(v, dtype="int64").tobytes()).hexdigest()

@@ -26,7 +26,8 @@ def shard_summary(rank: int):
     count = np.array([5, 2, 1] if rank == 0 else [4, 1, 6])
     plus = np.array([2, 1, 0] if rank == 0 else [3, 0, 2])
     first = np.array([0, 3, 9] if rank == 0 else [1, 2, 4])
-    return hist, kmers, (ids, count, plus, first)
+    last = np.array([20, 3, 9] if rank == 0 else [30, 2, 25])
+    return hist, kmers, (ids, count, plus, first, last)
 
 
 def main():
@@ -50,7 +51,8 @@ def main():
              for l, ks in merged.per_locus.items() for k in ks}
     assert table[(3, "@,-G,@")] == (5 + 6 + 1, 4), table  # counts of one shard add up, the replicated control does not
     assert table[(9, "@,-T,+A|=C")] == (4, 0) and table[(7, "=A,+I=C,@")] == (2, 1), table
-    ids_m, count, plus, first, maps = dj.merge_points(comm.allgather_object(points))
+    ids_m, count, plus, first, maps, last = dj.merge_points(comm.allgather_object(points))
+    assert last.tolist() == [25, 30, 2, 9]  # last global position of every merged point
     assert ids_m.tolist() == [[0, 0], [1, 0], [0, 3], [1, 2]], ids_m.tolist()  # ordered by first global position
     assert count.tolist() == [11, 6, 1, 1] and plus.tolist() == [4, 4, 0, 0] and first.tolist() == [0, 1, 2, 9]
     assert maps[0].tolist() == [0, 1, 3] and maps[1].tolist() == [1, 2, 0]

@@ -55,7 +55,7 @@ def test_merge_points_matches_global_dedup():
             cnt[u] += 1; plus[u] += int(strand_plus[p]); idx.append(u)
         payloads.append((np.array(ids), np.array(cnt), np.array(plus), np.array(first)))
         local_index.append((pos, np.array(idx)))
-    ids_m, count, plus_m, first_m, maps = dj.merge_points(payloads)
+    ids_m, count, plus_m, first_m, maps, _ = dj.merge_points(payloads)
     table, order = {}, []
     for p in range(n):
         key = rows[p].tobytes()

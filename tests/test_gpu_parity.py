@@ -670,3 +670,41 @@ def test_clustering_kernels_beyond_shared_memory():
     got = clusterer._silhouette(torch.as_tensor(pts, device="cuda"), torch.ones(len(pts), dtype=torch.float64, device="cuda"),
                                 labels, n_c)
     assert got == pytest.approx(silhouette_score(pts, labels), abs=1e-12)
+
+
+def test_consensus_filter_control(tmp_path):
+    """filter_control (similarity_searcher.py:82-110): which N-filtered control reads resemble a cluster -- masked
+    one-hot row sums from the code matrix (numpy's summation order) + scikit-learn's LocalOutlierFactor as the reference
+    calls it: the real reference's list, read for read."""
+    from dajin2_b200 import cache, consensus
+    from dajin2_b200.preprocess import _allele_key
+
+    cache.clear()
+    alleles, golden = load_case("sv_like")
+    a, g = alleles["control"], golden["alleles"]["control"]
+    args = _write_tree(tmp_path, alleles)
+    key = _allele_key("control")
+    p_c = tmp_path / "ctrl" / "midsv" / key / "ctrl_midsv.jsonl"
+    p_nf = consensus.extract_path_n_filtered_control(tmp_path, "ctrl", "sample", p_c, "control")
+    clean = set(g["sample_without_error"])
+    keep = [i for i, q in enumerate(a["sample"]["qnames"]) if q in clean]
+    members = [keep[i] for i in g["consensus_cluster_reads"]]
+    p_cluster = tmp_path / "sample" / "consensus" / key / "1" / "sample_sample.jsonl"
+    p_cluster.parent.mkdir(parents=True, exist_ok=True)
+    with open(p_cluster, "w") as f:
+        for i in members:
+            f.write(json.dumps({"QNAME": a["sample"]["qnames"][i], "RNAME": "control", "MIDSV": a["sample"]["rows"][i],
+                                "STRAND": a["sample"]["strands"][i], "PRESET": "map-ont"}) + "\n")
+    got = consensus.filter_control(args, p_nf, p_cluster, "control")
+    want = [bool(x) for x in g["consensus_filter_control"]]
+    assert len(got) == len(want) == g["control_n_filtered_reads"]
+    assert got == want
+    # a control that also holds 60 reads of the sample's other alleles
+    p_mixed = p_nf.parent / "mixed_control.jsonl"
+    lines = p_nf.read_text()
+    for i in g["consensus_filter_control_mixed_extra"]:
+        j = keep[i]
+        lines += json.dumps({"QNAME": a["sample"]["qnames"][j], "RNAME": "control", "MIDSV": a["sample"]["rows"][j],
+                             "STRAND": a["sample"]["strands"][j], "PRESET": "map-ont"}) + "\n"
+    p_mixed.write_text(lines)
+    assert consensus.filter_control(args, p_mixed, p_cluster, "control") == [bool(x) for x in g["consensus_filter_control_mixed"]]

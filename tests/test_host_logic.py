@@ -411,3 +411,21 @@ def test_encode_unit_arithmetic_on_host(tmp_path):
     out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.strip().endswith("OK")
+
+
+def test_masked_row_sums_are_numpys():
+    """consensus._masked_row_sums (hostc/fastmlp.c: dj_masked_row_sums) returns (onehot * mask).sum(axis=1) of the
+    reference's control filter (similarity_searcher.py:45-62) bit for bit: numpy's pairwise summation of every row."""
+    from dajin2_b200 import consensus
+
+    rng = np.random.default_rng(11)
+    table = consensus._startswith_class_table()
+    for n, L in ((7, 5), (50, 127), (33, 128), (64, 129), (40, 1000), (25, 5000)):
+        codes = rng.choice(np.array([0, 1, 2, 3, 4, 10, 13, 25, 44, 0x80, 0x83, 0x8A, 0x99], dtype=np.uint8), size=(n, L + 3))
+        mask = {m: np.where(rng.random(L) < 0.3, 0.0, rng.random(L) * 0.5) for m in "+-*"}
+        got = consensus._masked_row_sums(codes[:, :L], L, mask)
+        cls = table[codes[:, :L]]
+        for k, m in enumerate("+-*"):
+            onehot = (cls == k).astype(np.int64)
+            want = (onehot * mask[m]).sum(axis=1)
+            assert got[m].tobytes() == want.tobytes(), (n, L, m)
