@@ -27,7 +27,7 @@ def test_build_and_symbols():
     assert lib.dj_code_pitch(5000) == 5024 and lib.dj_code_pitch(32) == 32
     assert lib.dj_ckpt_pitch(15200) >= (15200 + 15) // _cabi.ENC_CHUNK + 1  # one checkpoint per trip of the encoder
     assert lib.dj_kmer_table_bytes(1024) == 64 + 1024 * 28
-    assert lib.dj_row_table_bytes(1024) == 64 + 1024 * 20
+    assert lib.dj_row_table_bytes(1024) == 64 + 1024 * 24
 
 
 def test_no_cpu_fallback():
