@@ -390,6 +390,10 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     enc_ms = float(np.mean([a.elapsed_time(b) for a, b in enc_events]))
+    stage_by_rank = None
+    if dist is not None:  # outside the timed region: every rank's phase times, to see who waits for whom
+        stage_by_rank = [None] * world
+        dist.all_gather_object(stage_by_rank, {k: round(v / args.steps, 2) for k, v in stage.items()})
     fits = list(mlp_pool.STATS)
     mlp_block = {"fits": len(fits), "lbfgs_iterations": [f["n_iter"] for f in fits[-9:]],
                  "fast_path_taken": bool(fits) and all(f["fast_path"] for f in fits),
@@ -516,6 +520,8 @@ def run_ours(args):
         "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage.items()},
         "mlp": mlp_block,
     }
+    if stage_by_rank is not None:
+        line["stage_ms_per_step_by_rank"] = stage_by_rank
     if pipelined is not None:
         line["pipelined"] = pipelined
     if pipelined_e2e is not None:
