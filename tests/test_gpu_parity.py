@@ -708,3 +708,59 @@ def test_consensus_filter_control(tmp_path):
                              "STRAND": a["sample"]["strands"][j], "PRESET": "map-ont"}) + "\n"
     p_mixed.write_text(lines)
     assert consensus.filter_control(args, p_mixed, p_cluster, "control") == [bool(x) for x in g["consensus_filter_control_mixed"]]
+
+
+def test_optimize_labels_many_points_and_columns():
+    """optimize_labels (clustering.py:29-55) where de-duplication does not help: ~10^4 distinct score rows over 120
+    columns (an R9-profile sample with many informative loci) and a search that runs past k = 8.  The device path
+    (weighted points, scikit-learn's tie rules) against scikit-learn itself through the oracle: same labels."""
+    from scipy.sparse import csr_matrix
+
+    from dajin2_b200 import clustering
+    from oracle import dajin2_oracle as orc
+
+    rng = np.random.default_rng(21)
+    n_s, n_c, k = 12_000, 1_000, 120
+    centres = np.where(rng.random((9, k)) < 0.08, rng.integers(2, 9, (9, k)) / 10.0, 0.0)
+    alleles = rng.choice(9, size=n_s, p=[0.3, 0.2, 0.15, 0.1, 0.08, 0.07, 0.05, 0.03, 0.02])
+    noise = np.where(rng.random((n_s, k)) < 0.03, rng.integers(1, 4, (n_s, k)) / 10.0, 0.0)
+    Xs = centres[alleles] + noise
+    Xc = np.where(rng.random((n_c, k)) < 0.03, rng.integers(1, 4, (n_c, k)) / 10.0, 0.0)
+    X = np.vstack([Xs, Xc])
+    assert len(np.unique(Xs, axis=0)) > 8_000
+    want = orc.optimize_labels(csr_matrix(X), n_s, n_c)
+    got = clustering.optimize_labels(csr_matrix(X), n_s, n_c)
+    assert len(set(got)) == len(set(want)) and len(set(want)) >= 5
+    assert _ari(want, got) >= 0.99
+
+
+def test_encoder_never_writes_past_a_row():
+    """a row with more tokens than the code pitch (malformed line, wrong `sequence` length) is flagged
+    BEFORE anything is staged or stored: the rows around it and the memory behind the code matrix stay untouched, in
+    the unit encoder and in the round-1 kernel."""
+    from dajin2_b200 import _cabi, engine
+    from dajin2_b200.ingest import pack_rows
+
+    L = 700
+    good = ",".join(["=A", "=C", "=G", "=T"] * (L // 4))
+    rows = [good, ",".join(["=A"] * (2 * L + 37)), good, ",".join(["*AG"] * (3 * L)), ",".join(["=T"] * (2 * L))]
+    enc = engine.EncodedReads(pack_rows(rows), L, validate=False, encode=False)
+    n, pitch = len(rows), enc.pitch
+    for which in ("unit", "v1"):
+        big = torch.full((n + 3, pitch), 0xAB, dtype=torch.uint8, device="cuda")
+        enc.codes = big[:n]
+        if which == "unit":
+            enc.encode()
+        else:
+            ms = torch.empty(n, dtype=torch.int32, device="cuda")
+            nt = torch.empty(n, dtype=torch.int32, device="cuda")
+            fl = torch.zeros(n, dtype=torch.int32, device="cuda")
+            _cabi.call("dj_encode_v1", engine._p(enc.text), engine._p(enc.row_off), engine._p(enc.row_len), n, L, pitch,
+                       engine._p(big), engine._p(ms), engine._p(nt), engine._p(fl), engine._stream())
+            enc.flags = fl
+        torch.cuda.synchronize()
+        assert bool((big[n:] == 0xAB).all()), which  # nothing behind the matrix
+        want = torch.as_tensor(encode_rows([good])[0], device="cuda")
+        assert torch.equal(big[0, :L], want) and torch.equal(big[2, :L], want), which  # the neighbours are intact
+        flags = enc.flags[:n].cpu().numpy()
+        assert flags[0] == 0 and flags[2] == 0 and all(flags[i] != 0 for i in (1, 3, 4)), (which, flags)
