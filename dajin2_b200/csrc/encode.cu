@@ -53,9 +53,7 @@ constexpr int kStageBytes = 64 + kMaxTokensPerTrip;  // 31 carried bytes + the t
 constexpr int kListBytes = kU * 32;                // unit ids of the slow path, compacted
 constexpr int kCntBytes = kU * 32 * 4;             // per unit: commas of its three chunks (one byte each)
 constexpr int kExclBytes = kU * 32 * 2;            // per unit: rank of its first token inside the trip
-constexpr int kCkptSlots = 16;                     // checkpoints buffered per warp (a 15 KB row has 10), stored together
-constexpr int kCkptBytes = kCkptSlots * 4;
-constexpr int kWarpBytes = kStages * kSlotBytes + kStageBytes + kListBytes + kCntBytes + kExclBytes + kCkptBytes;
+constexpr int kWarpBytes = kStages * kSlotBytes + kStageBytes + kListBytes + kCntBytes + kExclBytes;
 constexpr int kPatOffset = kLutSize * 4;           // four phase entries (uint4)
 constexpr int kBarOffset = kPatOffset + 64;
 constexpr int kWarpOffset = (kBarOffset + kWarps * kStages * 8 + 127) & ~127;
@@ -63,7 +61,6 @@ constexpr int kSmemBytes = kWarpOffset + kWarps * kWarpBytes;
 static_assert(kWarpBytes % 16 == 0 && kSlotBytes % 16 == 0 && kStageBytes % 16 == 0, "16-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory of the unit encoder");
 static_assert(kU >= 1 && kU <= 2, "units per lane");
-static_assert(kCkptSlots <= 32 && kCkptSlots % kU == 0, "one store per lane empties the checkpoint buffer");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -148,7 +145,6 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     uint8_t *list = stage + kStageBytes;
     uint8_t *cntbuf = list + kListBytes;
     uint16_t *exclbuf = reinterpret_cast<uint16_t *>(cntbuf + kCntBytes);
-    uint32_t *ckbuf = reinterpret_cast<uint32_t *>(cntbuf + kCntBytes + kExclBytes);
     const uint32_t ring_s = smem_u32(wbase);
     const uint32_t stage_s = smem_u32(stage);
     const uint32_t lut_s = smem_u32(lut);
@@ -216,8 +212,6 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
         uint32_t carry_w = kFill;         // the word in front of the trip's first byte
         uint8_t *outp = out + lane * 16;  // where this lane's 16 bytes of the next flush go
         bool broken = false;
-        int n_ck = 0;                     // checkpoints buffered in shared memory
-        const int n_ck_row = nbytes / kHalf + 1;  // checkpoints of this row: one per kHalf bytes of its span
 
 #pragma unroll 1
         for (int t = 0; t < geom.n_trips; ++t) {
@@ -349,21 +343,13 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                 __syncwarp();
                 continue;
             }
-            // checkpoints: tokens that START before byte j * DJ_ENC_CHUNK of the span (dj_find_token resumes there);
-            // buffered in shared memory, stored to the row's checkpoint array 32 at a time
             if (lane == 0) {
-                ckbuf[n_ck] = t == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
-                if (kU == 2) ckbuf[n_ck + 1] = (uint32_t)(tokbase + total0) + (sb[16 + kHalf - 1] == ',' ? 0u : 1u);
+                // checkpoints: tokens that START before byte j * DJ_ENC_CHUNK of the span (dj_find_token resumes there)
+                ck[0] = t == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
+                if (kU == 2 && g0 + kHalf <= nbytes)
+                    ck[1] = (uint32_t)(tokbase + total0) + (sb[16 + kHalf - 1] == ',' ? 0u : 1u);
             }
-            n_ck += kU;
-            if (n_ck == kCkptSlots) {
-                const int left = n_ck_row - (int)(ck - (ckpt + r * (int64_t)ckpt_pitch));
-                __syncwarp();
-                if (lane < left && lane < kCkptSlots) ck[lane] = ckbuf[lane];
-                ck += kCkptSlots;
-                n_ck = 0;
-                __syncwarp();
-            }
+            ck += kU;
             const uint32_t t0 = (uint32_t)tokbase & 31u;  // stage[0] holds locus (tokbase & ~31) of the row
 
             // ---- plain units: sixteen code bytes as whole words (the word shared with a plain neighbour is merged
@@ -444,11 +430,6 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             __syncwarp();
         }
 
-        if (!broken) {  // the row's last checkpoints (only those inside the row: the last trip may hold one too many)
-            const int left = min(n_ck, n_ck_row - (int)(ck - (ckpt + r * (int64_t)ckpt_pitch)));
-            __syncwarp();
-            if (lane < left) ck[lane] = ckbuf[lane];
-        }
         if (!broken) {  // what is left is less than one sector: pad it (deterministically) and store it
             const int staged = tokbase & 31;
             if (lane < 32 - staged) stage[staged + lane] = 0;  // reads as a plain match: dj_hist looks at every byte of the pitch

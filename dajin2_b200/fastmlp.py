@@ -312,7 +312,29 @@ class FastMLPClassifier(MLPClassifier):
     def _fit_lbfgs(self, X, y, sample_weight, activations, deltas, coef_grads, intercept_grads, layer_units):
         self._fm_mode = None
         start = [c.copy() for c in self.coefs_], [b.copy() for b in self.intercepts_]
-        super()._fit_lbfgs(X, y, sample_weight, activations, deltas, coef_grads, intercept_grads, layer_units)
+        self.lean_driver_used_ = False
+        if os.environ.get("DAJIN2_B200_MLP_LEAN", "1") != "0" and _lean_selftest():
+            # scikit-learn's _fit_lbfgs looks `scipy.optimize.minimize` up at call time: for the duration of this fit it
+            # finds the lean driver (same compiled L-BFGS-B, same loop; self-tested against scipy's above)
+            import scipy.optimize
+
+            stock = scipy.optimize.minimize
+
+            def lean(fun, x0, method=None, jac=None, options=None, args=(), **kw):
+                opts = dict(options or {})
+                if method != "L-BFGS-B" or jac is not True or kw or set(opts) - {"maxfun", "maxiter", "gtol", "iprint"} \
+                        or opts.get("iprint", -1) not in (-1, None):
+                    return stock(fun, x0, method=method, jac=jac, options=options, args=args, **kw)
+                self.lean_driver_used_ = True
+                return _lean_lbfgsb(fun, x0, args, opts.get("maxfun", 15000), opts.get("maxiter", 15000), opts.get("gtol", 1e-5))
+
+            scipy.optimize.minimize = lean
+            try:
+                super()._fit_lbfgs(X, y, sample_weight, activations, deltas, coef_grads, intercept_grads, layer_units)
+            finally:
+                scipy.optimize.minimize = stock
+        else:
+            super()._fit_lbfgs(X, y, sample_weight, activations, deltas, coef_grads, intercept_grads, layer_units)
         self.fast_path_used_ = self._fm_mode == "fast"
         if self._fm_mode == "fast":
             # check the last evaluated point as well (late iterates exercise the clipped / saturated branches)
@@ -330,6 +352,112 @@ class FastMLPClassifier(MLPClassifier):
                 MLPClassifier._fit_lbfgs(self, X, y, sample_weight, activations, deltas, coef_grads, intercept_grads,
                                          layer_units)
         self._fm = None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# scipy's L-BFGS-B driver loop without its per-evaluation Python machinery
+# ---------------------------------------------------------------------------------------------------------
+_LEAN_OK: bool | None = None  # None: not self-tested yet
+
+
+def _lean_lbfgsb(fun, x0, args, maxfun, maxiter, gtol, maxcor=10, ftol=2.220446049250313e-09, maxls=20):
+    """``scipy.optimize.minimize(fun, x0, method="L-BFGS-B", jac=True, args=args, options={maxfun, maxiter, gtol})``
+    with the SAME compiled routine (``scipy.optimize._lbfgsb.setulb``), the same workspace and the same driver loop
+    as ``scipy/optimize/_lbfgsb_py.py:_minimize_lbfgsb`` -- minus ``ScalarFunction`` / ``MemoizeJac``, which spend
+    ~0.1 ms of pure Python per evaluation (a fifth of a fit of the reference's MLP).  The iterates only depend on
+    what ``setulb`` is fed, so they are scipy's; ``_lean_selftest`` compares whole runs bit for bit before this is used."""
+    from scipy.optimize import OptimizeResult, _lbfgsb
+    from scipy.optimize._lbfgsb_py import status_messages, task_messages
+
+    m = maxcor
+    factr = ftol / np.finfo(float).eps
+    x0 = np.asarray(x0).ravel()
+    (n,) = x0.shape
+    int_dtype = _lbfgsb_int_dtype()
+    nbd = np.zeros(n, dtype=int_dtype)
+    low_bnd = np.zeros(n, dtype=np.float64)
+    upper_bnd = np.zeros(n, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64)
+    f = np.array(0.0, dtype=np.float64)
+    g = np.zeros((n,), dtype=np.float64)
+    wa = np.zeros(2 * m * n + 5 * n + 11 * m * m + 8 * m, np.float64)
+    iwa = np.zeros(3 * n, dtype=int_dtype)
+    task = np.zeros(2, dtype=int_dtype)
+    ln_task = np.zeros(2, dtype=int_dtype)
+    lsave = np.zeros(4, dtype=int_dtype)
+    isave = np.zeros(44, dtype=int_dtype)
+    dsave = np.zeros(29, dtype=np.float64)
+    n_iterations = 0
+    nfev = 0
+    while True:
+        g = g.astype(np.float64)
+        _lbfgsb.setulb(m, x, low_bnd, upper_bnd, nbd, f, g, factr, gtol, wa, iwa, task, lsave, isave, dsave, maxls, ln_task)
+        if task[0] == 3:
+            # ScalarFunction hands the objective a copy of x and keeps f as a Python float, g as a float64 array
+            f, g = fun(np.copy(x), *args)
+            nfev += 1
+            f = float(f)
+            g = np.atleast_1d(np.asarray(g, dtype=np.float64))
+        elif task[0] == 1:
+            n_iterations += 1
+            if n_iterations >= maxiter:
+                task[0] = 5
+                task[1] = 504
+            elif nfev > maxfun:
+                task[0] = 5
+                task[1] = 502
+        else:
+            break
+    if task[0] == 4:
+        warnflag = 0
+    elif nfev > maxfun or n_iterations >= maxiter:
+        warnflag = 1
+    else:
+        warnflag = 2
+    msg = status_messages[task[0]] + ": " + task_messages[task[1]]
+    return OptimizeResult(fun=f, jac=g, nfev=nfev, njev=nfev, nit=n_iterations, status=warnflag, message=msg, x=x,
+                          success=(warnflag == 0))
+
+
+def _lbfgsb_int_dtype():
+    from scipy.optimize import _lbfgsb_py
+
+    return np.int64 if getattr(_lbfgsb_py, "HAS_ILP64", False) else np.int32
+
+
+def _lean_selftest() -> bool:
+    """Whole runs of the lean driver against ``scipy.optimize.minimize`` on three small problems: x, f, g, nit, nfev,
+    status and message must agree exactly.  Any exception (another scipy with another ``setulb``) switches it off."""
+    global _LEAN_OK
+    if _LEAN_OK is not None:
+        return _LEAN_OK
+    try:
+        import scipy.optimize
+
+        rng = np.random.default_rng(7)
+        ok = True
+        for n, scale, maxiter in ((27, 1.0, 1000), (9, 30.0, 1000), (27, 5.0, 7)):
+            A = rng.normal(size=(n, n))
+            A = A @ A.T / n + np.eye(n) * 0.1
+            b = rng.normal(size=n) * scale
+
+            def fun(x, A=A, b=b):
+                r = A @ x - b
+                q = np.tanh(x)
+                return 0.5 * float(r @ r) + float(np.sum(np.log1p(q * q))), A.T @ r + 2 * q * (1 - q * q) / (1 + q * q)
+
+            x0 = rng.normal(size=n)
+            ref = scipy.optimize.minimize(fun, x0.copy(), method="L-BFGS-B", jac=True,
+                                          options={"maxfun": 15000, "maxiter": maxiter, "gtol": 1e-4})
+            got = _lean_lbfgsb(fun, x0.copy(), (), 15000, maxiter, 1e-4)
+            ok = ok and (np.array_equal(ref.x.view(np.uint64), got.x.view(np.uint64)) and float(ref.fun) == float(got.fun)
+                         and np.array_equal(np.asarray(ref.jac).view(np.uint64), np.asarray(got.jac).view(np.uint64))
+                         and ref.nit == got.nit and ref.nfev == got.nfev and ref.status == got.status
+                         and ref.message == got.message)
+        _LEAN_OK = bool(ok)
+    except Exception:  # noqa: BLE001
+        _LEAN_OK = False
+    return _LEAN_OK
 
 
 def _same_bits(ref, got) -> bool:

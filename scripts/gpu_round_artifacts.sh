@@ -11,7 +11,7 @@ $B > gpurun_out/${R}_prebench.json 2> gpurun_out/${R}_prebench.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv \
   $B > gpurun_out/${R}_ncu_launches.log 2>&1
 for k in encode_unit_kernel hist_tile_kernel kmer_count_kernel annotate_kernel; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -o gpurun_out/${R}_$k -f \
+  ncu --set full --clock-control none --import-source on -k regex:$k -s $([ $k = hist_tile_kernel ] && echo 3 || echo 2) -c 1 -o gpurun_out/${R}_$k -f \
     $B > gpurun_out/${R}_ncu_$k.log 2>&1
   python scripts/ncu_summary.py gpurun_out/${R}_$k.ncu-rep > gpurun_out/${R}_ncu_$k.summary.txt 2>&1
 done
