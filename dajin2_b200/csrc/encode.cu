@@ -25,11 +25,13 @@
 //
 // Reference behaviour covered here: the tokenisation every pass of the reference starts with
 // (`json.loads` + `MIDSV.split(",")`, src/DAJIN2/utils/fileio.py:49-52) and calc_match.
+#include <type_traits>
+
 #include "encode_common.cuh"
 #include "encode_unit.cuh"
 
 #ifndef DJ_ENC_WARPS
-#define DJ_ENC_WARPS 24  // warps per CTA, one CTA per SM (80 registers)
+#define DJ_ENC_WARPS 24  // warps per CTA, one CTA per SM (80 registers; 28 warps at 72 registers measured the same)
 #endif
 #ifndef DJ_ENC_STAGES
 #define DJ_ENC_STAGES 2  // slots of the per-warp text ring (one trip in flight while one is translated)
@@ -60,7 +62,7 @@ constexpr int kWarpOffset = (kBarOffset + kWarps * kStages * 8 + 127) & ~127;
 constexpr int kSmemBytes = kWarpOffset + kWarps * kWarpBytes;
 static_assert(kWarpBytes % 16 == 0 && kSlotBytes % 16 == 0 && kStageBytes % 16 == 0, "16-byte alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory of the unit encoder");
-static_assert(kU >= 1 && kU <= 2, "units per lane");
+static_assert(kU >= 1 && kU <= 4, "units per lane");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -91,12 +93,34 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
         : "memory");
 }
 
-// comma flags of one 16-byte chunk in the layout emit_chunk expects (bit 7-k of byte j <=> byte j of word k), exact
-__device__ __forceinline__ uint32_t chunk_commas_exact(const uint4 &c, uint32_t &high) {
-    high |= c.x | c.y;
-    high |= c.z | c.w;
-    return dju::comma_flags_exact(c.x) | (dju::comma_flags_exact(c.y) >> 1) | (dju::comma_flags_exact(c.z) >> 2) |
-           (dju::comma_flags_exact(c.w) >> 3);
+// comma flags of a piece of kW words in the layout emit_piece expects (bit 7-k of byte j <=> byte j of word k), exact
+template <int kW>
+__device__ __forceinline__ uint32_t piece_commas_exact(const uint32_t (&w)[kW], uint32_t &high) {
+    uint32_t zz = 0;
+#pragma unroll
+    for (int k = 0; k < kW; ++k) {
+        high |= w[k];
+        zz |= dju::comma_flags_exact(w[k]) >> k;
+    }
+    return zz;
+}
+
+// The text of the slow path is cut into PIECES: 16-byte thirds of a unit (kW = 4 words, eight comma slots) or, when a
+// trip has more thirds than lanes but not more halves, 24-byte halves (kW = 6, twelve slots): one pass at 1.5 times
+// the cost instead of two passes (on the benchmark profile a trip has 31 thirds on average; 43 % of the trips have
+// 33..48).
+template <int kW>
+__device__ __forceinline__ void load_piece(const uint8_t *p, uint32_t (&w)[kW]) {
+    if constexpr (kW == 4) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(p);
+        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kW; k += 2) {
+            const uint2 q = *reinterpret_cast<const uint2 *>(p + 4 * k);
+            w[k] = q.x; w[k + 1] = q.y;
+        }
+    }
 }
 
 // inclusive warp scan, one shuffle and one predicated add per step
@@ -128,7 +152,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1)
 encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ row_off,
                    const int32_t *__restrict__ row_len, int64_t n_reads, int n_loci, int code_pitch, int ckpt_pitch,
                    uint8_t *__restrict__ codes, int32_t *__restrict__ match_score, int32_t *__restrict__ n_tokens,
-                   uint32_t *__restrict__ flags, uint32_t *__restrict__ ckpt, uint32_t c_four, uint32_t c_shift) {
+                   uint32_t *__restrict__ flags, uint32_t *__restrict__ ckpt, uint32_t c_four, uint32_t c_shift,
+                   dju::Muls muls) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
     uint4 *pat = reinterpret_cast<uint4 *>(smem + kPatOffset);
@@ -260,7 +285,7 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                 const uint4 pe = pat[dju::phase_index(w[0])];
                 dju::Phase ph;
                 ph.shift = pe.x; ph.trail = pe.y; ph.bad = pe.z; ph.n0 = pe.w;
-                const dju::UnitOut uo = dju::decode_unit(wprev, w, ph);
+                const dju::UnitOut uo = dju::decode_unit(wprev, w, ph, muls);
                 const int g = g0 + h * kHalf + dju::kUnitBytes * lane;
                 dead[h] = g > nbytes;  // past the virtual closing comma
                 tail[h] = g + dju::kUnitBytes > nbytes;
@@ -274,7 +299,8 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             //      lanes and counted (the same compaction translates them further down) ------------------------------
             uint32_t plain_mask[kU], slow_mask[kU], cnt[kU];
             uint32_t zz_first = 0;
-            int n_chunks = 0;
+            int n_pieces = 0;
+            bool halves = false;  // the pieces of this trip are 24-byte halves of units (else 16-byte thirds)
             bool force = false;
 #pragma unroll 1
             for (;;) {
@@ -287,22 +313,31 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                     if (!p && !dead[h]) list[n_slow + __popc(slow_mask[h] & lanes_below)] = (uint8_t)(h * 32 + lane);
                     n_slow += __popc(slow_mask[h]);
                 }
-                n_chunks = 3 * n_slow;
+                halves = 3 * n_slow > 32 && 2 * n_slow <= 32;
+                n_pieces = (halves ? 2 : 3) * n_slow;
                 if (n_slow > 0) {
                     __syncwarp();
+                    auto count_pass = [&](auto kw_tag) {
+                        constexpr int kW = decltype(kw_tag)::value;
+                        constexpr int kPer = 12 / kW;  // pieces per unit
 #pragma unroll 1
-                    for (int j0 = 0; j0 < n_chunks; j0 += 32) {
-                        const int j = j0 + lane;
-                        if (j < n_chunks) {
-                            const int ui = (j * 171) >> 9;  // j / 3 for j < 192
-                            const int c = j - 3 * ui;
-                            const int u = list[ui];
-                            const uint4 ch = *reinterpret_cast<const uint4 *>(sb + 16 + dju::kUnitBytes * u + 16 * c);
-                            const uint32_t zz = chunk_commas_exact(ch, high);
-                            cntbuf[4 * u + c] = (uint8_t)__popc(zz);
-                            if (j0 == 0) zz_first = zz;
+                        for (int j0 = 0; j0 < n_pieces; j0 += 32) {
+                            const int j = j0 + lane;
+                            if (j < n_pieces) {
+                                const int ui = kPer == 2 ? j >> 1 : (int)(((uint32_t)j * 43691u) >> 17);  // j / kPer
+                                const int c = j - kPer * ui;
+                                const int u = list[ui];
+                                uint32_t w[kW];
+                                load_piece<kW>(sb + 16 + dju::kUnitBytes * u + 4 * kW * c, w);
+                                const uint32_t zz = piece_commas_exact<kW>(w, high);
+                                cntbuf[4 * u + c] = (uint8_t)__popc(zz);
+                                if (kPer == 2 && c == 1) cntbuf[4 * u + 2] = 0;
+                                if (j0 == 0) zz_first = zz;
+                            }
                         }
-                    }
+                    };
+                    if (halves) count_pass(std::integral_constant<int, 6>{});
+                    else count_pass(std::integral_constant<int, 4>{});
                     __syncwarp();
                 }
                 bool small = false;
@@ -325,15 +360,25 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                 force = true;
             }
 
-            uint32_t packed = cnt[0];
-            if (kU == 2) packed |= cnt[kU - 1] << 16;
-            const uint32_t incl = warp_scan_incl(packed);
-            const uint32_t totals = __shfl_sync(0xffffffffu, incl, 31);
-            const int total0 = (int)(totals & 0xFFFFu);
-            const int total = total0 + (kU == 2 ? (int)(totals >> 16) : 0);
+            // inclusive scans of the units' token counts over the lanes, two 16-bit fields per word; unit (h, lane)
+            // follows every unit of the rows h' < h and the lanes below it in its own row
+            constexpr int kScanWords = (kU + 1) / 2;
+            uint32_t incl[kScanWords];
+#pragma unroll
+            for (int q = 0; q < kScanWords; ++q)
+                incl[q] = warp_scan_incl(cnt[2 * q] | (2 * q + 1 < kU ? cnt[(2 * q + 1) % kU] << 16 : 0u));
+            uint32_t row_totals[kScanWords];
+#pragma unroll
+            for (int q = 0; q < kScanWords; ++q) row_totals[q] = __shfl_sync(0xffffffffu, incl[q], 31);
+            int row_base[kU];  // tokens the rows of units in front of row h close
+            int total = 0;
             uint32_t excl[kU];
-            excl[0] = (incl & 0xFFFFu) - cnt[0];
-            if (kU == 2) excl[kU - 1] = (uint32_t)total0 + (incl >> 16) - cnt[kU - 1];
+#pragma unroll
+            for (int h = 0; h < kU; ++h) {
+                row_base[h] = total;
+                excl[h] = (uint32_t)total + ((h & 1) ? incl[h / 2] >> 16 : incl[h / 2] & 0xFFFFu) - cnt[h];
+                total += (int)((h & 1) ? row_totals[h / 2] >> 16 : row_totals[h / 2] & 0xFFFFu);
+            }
             // not MIDSV: more commas than a trip of tokens can hold, or more tokens than the row has room for (tested
             // BEFORE anything is staged or stored: a row never writes past its own row of the code matrix)
             if (total > kMaxTokensPerTrip || tokbase + total > code_pitch) {
@@ -346,8 +391,10 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             if (lane == 0) {
                 // checkpoints: tokens that START before byte j * DJ_ENC_CHUNK of the span (dj_find_token resumes there)
                 ck[0] = t == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
-                if (kU == 2 && g0 + kHalf <= nbytes)
-                    ck[1] = (uint32_t)(tokbase + total0) + (sb[16 + kHalf - 1] == ',' ? 0u : 1u);
+#pragma unroll
+                for (int h = 1; h < kU; ++h)
+                    if (g0 + h * kHalf <= nbytes)
+                        ck[h] = (uint32_t)(tokbase + row_base[h]) + (sb[16 + h * kHalf - 1] == ',' ? 0u : 1u);
             }
             ck += kU;
             const uint32_t t0 = (uint32_t)tokbase & 31u;  // stage[0] holds locus (tokbase & ~31) of the row
@@ -389,29 +436,37 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             }
             __syncwarp();
 
-            // ---- slow path: the 16-byte chunks of the other units go through the generic comma slots ------------
+            // ---- slow path: the pieces of the other units go through the generic comma slots --------------------
+            auto translate_pass = [&](auto kw_tag) {
+                constexpr int kW = decltype(kw_tag)::value;
+                constexpr int kPer = 12 / kW;
 #pragma unroll 1
-            for (int j0 = 0; j0 < n_chunks; j0 += 32) {
-                const int j = j0 + lane;
-                if (j < n_chunks) {
-                    const int ui = (j * 171) >> 9;
-                    const int c = j - 3 * ui;
-                    const int u = list[ui];
-                    const uint8_t *cp = sb + 16 + dju::kUnitBytes * u + 16 * c;
-                    const uint4 ch = *reinterpret_cast<const uint4 *>(cp);
-                    const uint32_t wp = *reinterpret_cast<const uint32_t *>(cp - 4);
-                    const uint32_t zz = j0 == 0 ? zz_first : chunk_commas_exact(ch, high);
-                    const uint32_t cb = reinterpret_cast<const uint32_t *>(cntbuf)[u];
-                    const uint32_t rel = exclbuf[u] + (c == 0 ? 0u : (c == 1 ? cb & 0xFFu : (cb & 0xFFu) + ((cb >> 8) & 0xFFu)));
-                    uint32_t acc = 0;
-                    const uint32_t wrote = emit_chunk(acc, stage_s + t0 + rel, lut_s, wp, ch, zz, c_four, c_shift);
-                    // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV: bits
-                    // 0..3; the table's "special" counter: bits 8..12
-                    sticky |= (wrote ^ (uint32_t)__popc(zz)) | ((acc >> 15) & 0x1F00u);
-                    mism += (acc >> kStatShift) & 0x3Fu;
-                    n_sub += (acc >> 18) & 0x1Fu;
+                for (int j0 = 0; j0 < n_pieces; j0 += 32) {
+                    const int j = j0 + lane;
+                    if (j < n_pieces) {
+                        const int ui = kPer == 2 ? j >> 1 : (int)(((uint32_t)j * 43691u) >> 17);
+                        const int c = j - kPer * ui;
+                        const int u = list[ui];
+                        const uint8_t *cp = sb + 16 + dju::kUnitBytes * u + 4 * kW * c;
+                        uint32_t w[kW];
+                        load_piece<kW>(cp, w);
+                        const uint32_t wp = *reinterpret_cast<const uint32_t *>(cp - 4);
+                        const uint32_t zz = j0 == 0 ? zz_first : piece_commas_exact<kW>(w, high);
+                        const uint32_t cb = reinterpret_cast<const uint32_t *>(cntbuf)[u];
+                        const uint32_t rel =
+                            exclbuf[u] + (c == 0 ? 0u : (c == 1 ? cb & 0xFFu : (cb & 0xFFu) + ((cb >> 8) & 0xFFu)));
+                        uint32_t acc = 0;
+                        const uint32_t wrote = emit_piece<kW>(acc, stage_s + t0 + rel, lut_s, wp, w, zz, c_four, c_shift);
+                        // two commas among bytes 1..3 of a word (an empty or one-character token) are not MIDSV: bits
+                        // 0..3; the table's "special" counter: bits 8..12
+                        sticky |= (wrote ^ (uint32_t)__popc(zz)) | ((acc >> 15) & 0x1F00u);
+                        mism += (acc >> kStatShift) & 0x3Fu;
+                        n_sub += (acc >> 18) & 0x1Fu;
+                    }
                 }
-            }
+            };
+            if (halves) translate_pass(std::integral_constant<int, 6>{});
+            else translate_pass(std::integral_constant<int, 4>{});
             __syncwarp();
 
             // ---- complete 32-byte sectors leave; the incomplete one moves to the front of the staging buffer ---
@@ -489,7 +544,7 @@ extern "C" int dj_encode(const uint8_t *text, const int64_t *row_off, const int3
     if (ctas > sms) ctas = sms;  // persistent: one CTA of kWarps warps per SM
     encode_unit_kernel<<<(unsigned)ctas, kWarps * 32, kSmemBytes, (cudaStream_t)stream>>>(
         text, row_off, row_len, n_reads, n_loci, code_pitch, ckpt_pitch, codes, match_score, n_tokens, flags, ckpt, 4u,
-        (uint32_t)kLutSize);
+        (uint32_t)kLutSize, dju::Muls{1u << 28, 10u << 28});
     DJ_LAUNCH_CHECK();
     return 0;
 }

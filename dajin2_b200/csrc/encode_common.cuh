@@ -236,4 +236,22 @@ __device__ __forceinline__ uint32_t emit_chunk(uint32_t &acc, uint32_t sp, uint3
     return sp - sp0;
 }
 
+// The same for a piece of kW <= 8 words (w[0..kW-1], wp the word in front): zz holds the comma flags of word k in
+// bit 7-k of every byte (piece_commas_exact).
+template <int kW>
+__device__ __forceinline__ uint32_t emit_piece(uint32_t &acc, uint32_t sp, uint32_t lut_s, uint32_t wp,
+                                               const uint32_t (&w)[kW], uint32_t zz, uint32_t c_four, uint32_t c_shift) {
+    static_assert(kW == 4 || kW == 6, "piece sizes of the unit encoder");
+    const uint32_t sp0 = sp;
+    emit_word<0>(acc, sp, lut_s, wp, w[0], zz, c_four, c_shift);
+    emit_word<1>(acc, sp, lut_s, w[0], w[1], zz, c_four, c_shift);
+    emit_word<2>(acc, sp, lut_s, w[1], w[2], zz, c_four, c_shift);
+    emit_word<3>(acc, sp, lut_s, w[2], w[3], zz, c_four, c_shift);
+    if constexpr (kW == 6) {
+        emit_word<4>(acc, sp, lut_s, w[3], w[4], zz, c_four, c_shift);
+        emit_word<5>(acc, sp, lut_s, w[4], w[5], zz, c_four, c_shift);
+    }
+    return sp - sp0;
+}
+
 }  // namespace

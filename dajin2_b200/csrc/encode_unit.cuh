@@ -27,6 +27,10 @@
 #define DJU_HD static inline
 #endif
 
+#ifndef DJ_ENC_FMA
+#define DJ_ENC_FMA 0  // 1: the shift-and-add steps of a group as multiply-adds with run-time multipliers (see Muls)
+#endif
+
 namespace dju {
 
 constexpr int kUnitBytes = 48;
@@ -114,14 +118,35 @@ DJU_HD uint32_t phase_index(uint32_t w0) {
     return ((f >> 7) | (f >> 14)) & 3u;
 }
 
+// Multipliers that arrive as kernel arguments (DJ_ENC_FMA = 1): with a multiplier it cannot see, ptxas keeps the
+// two shift-and-add steps of a group on the multiply-add pipe (IMAD.HI) instead of turning them into LEA.HI on the
+// ALU pipe, which is the pipe that bounds the kernel (profiles/: ALU 78 %, FMA 20 % busy).
+struct Muls {
+    uint32_t fold;  // 1 << 28: mad.hi(x, fold, x) = x + (x >> 4)
+    uint32_t del;   // 10 << 28: mad.hi(d, del, c) = c + ((d * 10) >> 4)
+};
+
 // idx + (idx >> 4): byte 0 = i0 | i1 << 4, byte 2 = i2 | i3 << 4 (a multiply-add, off the ALU pipe on the device)
-DJU_HD uint32_t fold_nibbles(uint32_t idx) {
-#ifdef __CUDA_ARCH__
+DJU_HD uint32_t fold_nibbles(uint32_t idx, const Muls &m) {
+#if defined(__CUDA_ARCH__) && DJ_ENC_FMA
     uint32_t r;
-    asm("mad.hi.u32 %0, %1, 0x10000000, %1;" : "=r"(r) : "r"(idx));
+    asm("mad.hi.u32 %0, %1, %2, %1;" : "=r"(r) : "r"(idx), "r"(m.fold));
     return r;
 #else
+    (void)m;
     return idx + (idx >> 4);
+#endif
+}
+
+// code + ((dels * 10) >> 4): dels holds 0x10 in every byte whose operator is '-' ("-X" = 10 + base)
+DJU_HD uint32_t add_deletions(uint32_t code, uint32_t dels, const Muls &m) {
+#if defined(__CUDA_ARCH__) && DJ_ENC_FMA
+    uint32_t r;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(dels), "r"(m.del), "r"(code));
+    return r;
+#else
+    (void)m;
+    return code + ((dels * 10u) >> 4);
 #endif
 }
 
@@ -143,18 +168,18 @@ struct GroupOut {
 };
 
 // one aligned group: v0 = "=X,=", v1 = "X,=X", v2 = ",=X,"
-DJU_HD GroupOut decode_group(uint32_t v0, uint32_t v1, uint32_t v2) {
+DJU_HD GroupOut decode_group(uint32_t v0, uint32_t v1, uint32_t v2, const Muls &m) {
     GroupOut g;
     const uint32_t x = prmt_raw(prmt_raw(v0, v1, 0x0741u), v2, 0x6210u);   // bases: v0.b1 v1.b0 v1.b3 v2.b2
     const uint32_t op = prmt_raw(prmt_raw(v0, v1, 0x0630u), v2, 0x5210u);  // operators: v0.b0 v0.b3 v1.b2 v2.b1
     const uint32_t cm = prmt_raw(prmt_raw(v0, v1, 0x0052u), v2, 0x7410u);  // commas: v0.b2 v1.b1 v2.b0 v2.b3
     const uint32_t idx = x & 0x07070707u;                                   // A 1, C 3, T 4, N 6, G 7
-    const uint32_t sel = prmt_raw(fold_nibbles(idx), 0u, 0x4420u);
+    const uint32_t sel = prmt_raw(fold_nibbles(idx, m), 0u, 0x4420u);
     const uint32_t code = prmt_raw(0x01FF00FFu, 0x0204FF03u, sel);          // index -> code, 0xFF for 0 / 2 / 5
     const uint32_t back = prmt_raw(0x43004100u, 0x474E0054u, sel);          // index -> letter
     g.dels = ~op & 0x10101010u;                                             // '-' = 0x2D, '=' = 0x3D
     g.bad = (cm ^ 0x2C2C2C2Cu) | ((op | 0x10101010u) ^ 0x3D3D3D3Du) | (back ^ x);
-    g.codes = code + ((g.dels * 10u) >> 4);                                 // "-X" = 10 + base
+    g.codes = add_deletions(code, g.dels, m);                               // "-X" = 10 + base
     return g;
 }
 
@@ -167,7 +192,7 @@ struct UnitOut {
 };
 
 // prev is the word in front of the unit; ph = phase_entry(phase_index(w[0]))
-DJU_HD UnitOut decode_unit(uint32_t prev, const uint32_t *w, const Phase &ph) {
+DJU_HD UnitOut decode_unit(uint32_t prev, const uint32_t *w, const Phase &ph, const Muls &m = Muls{1u << 28, 10u << 28}) {
     const uint32_t shift = ph.shift;
     uint32_t v[12];
     v[0] = shr_pair(prev, w[0], shift);
@@ -185,7 +210,7 @@ DJU_HD UnitOut decode_unit(uint32_t prev, const uint32_t *w, const Phase &ph) {
 #pragma unroll
 #endif
     for (int g = 0; g < 4; ++g) {
-        const GroupOut o = decode_group(v[3 * g], v[3 * g + 1], v[3 * g + 2]);
+        const GroupOut o = decode_group(v[3 * g], v[3 * g + 1], v[3 * g + 2], m);
         u.c[g] = o.codes;
         if (g < 2) u.bad_head |= o.bad; else u.bad |= o.bad;
         dsum += o.dels << g;  // 0x10, 0x20, 0x40, 0x80: one bit per (group, byte)
