@@ -39,6 +39,9 @@
 #ifndef DJ_ENC_UNITS
 #define DJ_ENC_UNITS 2   // units per lane and trip
 #endif
+#ifndef DJ_ENC_BULK
+#define DJ_ENC_BULK 1    // 1: the ring is filled by bulk copies (cp.async.bulk + mbarrier); 0: by per-lane 16-byte cp.async
+#endif
 
 static_assert(DJ_ENC_CHUNK == dju::kTripBytes, "the checkpoint grid is one unit per lane of the unit encoder");
 
@@ -93,6 +96,12 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
         : "memory");
 }
 
+// DJ_ENC_BULK = 0: every lane copies 16 bytes global -> shared (LDGSTS, L1 bypassed); completion is tracked per thread
+// in commit groups
+__device__ __forceinline__ void lane_copy16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
 // comma flags of a piece of kW words in the layout emit_piece expects (bit 7-k of byte j <=> byte j of word k), exact
 template <int kW>
 __device__ __forceinline__ uint32_t piece_commas_exact(const uint32_t (&w)[kW], uint32_t &high) {
@@ -105,10 +114,12 @@ __device__ __forceinline__ uint32_t piece_commas_exact(const uint32_t (&w)[kW], 
     return zz;
 }
 
-// The text of the slow path is cut into PIECES: 16-byte thirds of a unit (kW = 4 words, eight comma slots) or, when a
-// trip has more thirds than lanes but not more halves, 24-byte halves (kW = 6, twelve slots): one pass at 1.5 times
-// the cost instead of two passes (on the benchmark profile a trip has 31 thirds on average; 43 % of the trips have
-// 33..48).
+// The text of the slow path is cut into PIECES, one per lane and pass: 16-byte thirds of a unit (kW = 4 words, eight
+// comma slots) or 24-byte halves (kW = 6, twelve slots).  A pass costs about 50 + 30 instructions per slot whatever
+// the number of busy lanes, so the size is chosen per trip from the number of slow units: whichever of thirds /
+// halves needs fewer slot rounds (halves for 11..16 units: one pass at 1.4 times the cost instead of two).  On the
+// benchmark profile a trip has 10.3 slow units on average.  Measured and dropped: 12-byte quarters for trips with at
+// most eight slow units (0.603 against 0.616 of peak).
 template <int kW>
 __device__ __forceinline__ void load_piece(const uint8_t *p, uint32_t (&w)[kW]) {
     if constexpr (kW == 4) {
@@ -174,6 +185,8 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     const uint32_t stage_s = smem_u32(stage);
     const uint32_t lut_s = smem_u32(lut);
     const uint32_t bar_s = smem_u32(smem + kBarOffset) + (uint32_t)wid * (kStages * 8);
+#pragma unroll
+    for (int h = 0; h < kU; ++h) reinterpret_cast<uint32_t *>(cntbuf)[h * 32 + lane] = 0u;
     if (lane == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(bar_s + 8u * s, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -205,9 +218,31 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     };
     if (p_row < n_reads) p_open(row_off[p_row], row_len[p_row]);
     auto produce = [&]() {
-        if (p_trips == 0) return;
+        if (p_trips == 0) {
+#if !DJ_ENC_BULK
+            asm volatile("cp.async.commit_group;" ::: "memory");  // the consumer counts groups: one per call
+#endif
+            return;
+        }
         const int bytes = p_left > kTrip ? kTrip : (p_left < 16 ? 16 : p_left);
+#if DJ_ENC_BULK
         bulk_load(ring_s + (uint32_t)(p_slot * kSlotBytes + 16), p_src, (uint32_t)bytes, bar_s + 8u * p_slot);
+#else
+        {
+            const uint32_t dst = ring_s + (uint32_t)(p_slot * kSlotBytes + 16 + 16 * lane);
+            const uint8_t *src = p_src + 16 * lane;
+            if (bytes == kTrip) {
+#pragma unroll
+                for (int k = 0; k < kTrip / 512; ++k) lane_copy16(dst + 512 * k, src + 512 * k);
+            } else {
+#pragma unroll 1
+                for (int b = 16 * lane; b < bytes; b += 512) lane_copy16(dst + (uint32_t)(b - 16 * lane), src + (b - 16 * lane));
+            }
+        }
+#endif
+#if !DJ_ENC_BULK
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
         p_slot = p_slot + 1 == kStages ? 0 : p_slot + 1;
         p_src += kTrip;
         p_left -= kTrip;
@@ -220,7 +255,9 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
     for (int s = 0; s < kStages - 1; ++s) produce();
 
     int c_slot = 0;
+#if DJ_ENC_BULK
     uint32_t c_phase = 0;  // bit s: parity the consumer waits for on slot s
+#endif
 
     for (int64_t r = warp; r < n_reads; r += n_warps) {
         const int64_t off = row_off[r];
@@ -241,9 +278,13 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
 #pragma unroll 1
         for (int t = 0; t < geom.n_trips; ++t) {
             produce();  // refills the slot the previous trip read (all of its reads are behind a __syncwarp)
+#if DJ_ENC_BULK
             mbar_wait(bar_s + 8u * c_slot, (c_phase >> c_slot) & 1u);
-            uint8_t *sb = wbase + c_slot * kSlotBytes;
             c_phase ^= 1u << c_slot;
+#else
+            asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");  // this trip's group has landed
+#endif
+            uint8_t *sb = wbase + c_slot * kSlotBytes;
             c_slot = c_slot + 1 == kStages ? 0 : c_slot + 1;
             if (broken) {
                 __syncwarp();
@@ -300,7 +341,7 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             uint32_t plain_mask[kU], slow_mask[kU], cnt[kU];
             uint32_t zz_first = 0;
             int n_pieces = 0;
-            bool halves = false;  // the pieces of this trip are 24-byte halves of units (else 16-byte thirds)
+            int per_unit = 3;  // pieces per slow unit in this trip: 3 thirds or 2 halves
             bool force = false;
 #pragma unroll 1
             for (;;) {
@@ -313,8 +354,10 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                     if (!p && !dead[h]) list[n_slow + __popc(slow_mask[h] & lanes_below)] = (uint8_t)(h * 32 + lane);
                     n_slow += __popc(slow_mask[h]);
                 }
-                halves = 3 * n_slow > 32 && 2 * n_slow <= 32;
-                n_pieces = (halves ? 2 : 3) * n_slow;
+                // halves where ceil(2 n / 32) passes of halves cost less than ceil(3 n / 32) passes of thirds (cost ratio
+                // 10 : 7): n = 11..16, 22..32, 43..48, 54..64 -- bit n of the masks (n - 32 in the second word)
+                per_unit = (((n_slow < 32 ? 0xFFC1F800u : 0xFFC1F801u) >> (n_slow & 31)) & 1u) != 0u ? 2 : 3;
+                n_pieces = per_unit * n_slow;
                 if (n_slow > 0) {
                     __syncwarp();
                     auto count_pass = [&](auto kw_tag) {
@@ -336,8 +379,8 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                             }
                         }
                     };
-                    if (halves) count_pass(std::integral_constant<int, 6>{});
-                    else count_pass(std::integral_constant<int, 4>{});
+                    if (per_unit == 3) count_pass(std::integral_constant<int, 4>{});
+                    else count_pass(std::integral_constant<int, 6>{});
                     __syncwarp();
                 }
                 bool small = false;
@@ -345,7 +388,7 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                 for (int h = 0; h < kU; ++h) {
                     const bool p = plain[h] && !force;
                     const uint32_t cb = reinterpret_cast<const uint32_t *>(cntbuf)[h * 32 + lane];
-                    const uint32_t slow_cnt = (cb & 0xFFu) + ((cb >> 8) & 0xFFu) + ((cb >> 16) & 0xFFu);
+                    const uint32_t slow_cnt = __dp4a(cb, 0x01010101u, 0u);  // the fourth byte is never written (zero)
                     cnt[h] = dead[h] ? 0u : (p ? 16u : slow_cnt);
                     small = small || (!tail[h] && !p && slow_cnt < 4u);
                 }
@@ -384,17 +427,22 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             if (total > kMaxTokensPerTrip || tokbase + total > code_pitch) {
                 sticky |= kStickyBroken;
                 broken = true;
+#if DJ_ENC_BULK
                 if (edge_trip) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
                 __syncwarp();
                 continue;
             }
-            if (lane == 0) {
-                // checkpoints: tokens that START before byte j * DJ_ENC_CHUNK of the span (dj_find_token resumes there)
-                ck[0] = t == 0 ? 0u : (uint32_t)tokbase + ((carry_w >> 24) == ',' ? 0u : 1u);
+            if (lane < kU) {
+                // checkpoints: tokens that START before byte j * DJ_ENC_CHUNK of the span (dj_find_token resumes there);
+                // lane h writes the one of row h of units: the tokens closed in front of it, and one more unless the byte
+                // in front of the row is a comma (for h = 0 that byte is the last of the previous trip, at sb + 15)
+                int before = tokbase;
 #pragma unroll
                 for (int h = 1; h < kU; ++h)
-                    if (g0 + h * kHalf <= nbytes)
-                        ck[h] = (uint32_t)(tokbase + row_base[h]) + (sb[16 + h * kHalf - 1] == ',' ? 0u : 1u);
+                    if (lane == h) before = tokbase + row_base[h];
+                const uint32_t v = (uint32_t)before + (sb[15 + lane * kHalf] == ',' ? 0u : 1u);
+                if (lane == 0 ? true : g0 + lane * kHalf <= nbytes) ck[lane] = lane == 0 && t == 0 ? 0u : v;
             }
             ck += kU;
             const uint32_t t0 = (uint32_t)tokbase & 31u;  // stage[0] holds locus (tokbase & ~31) of the row
@@ -465,8 +513,8 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                     }
                 }
             };
-            if (halves) translate_pass(std::integral_constant<int, 6>{});
-            else translate_pass(std::integral_constant<int, 4>{});
+            if (per_unit == 3) translate_pass(std::integral_constant<int, 4>{});
+            else translate_pass(std::integral_constant<int, 6>{});
             __syncwarp();
 
             // ---- complete 32-byte sectors leave; the incomplete one moves to the front of the staging buffer ---
@@ -481,7 +529,9 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
             if (lane < staged - flush_bytes) stage[lane] = b;
             tokbase += total;
             outp += flush_bytes;
+#if DJ_ENC_BULK
             if (edge_trip) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // padded words were written
+#endif
             __syncwarp();
         }
 
