@@ -52,6 +52,18 @@ class RowRecord(ctypes.Structure):
     ]
 
 
+class ClusterStepOut(ctypes.Structure):
+    _fields_ = [
+        ("inertia", ctypes.c_double * 2),
+        ("weight", ctypes.c_double * 2),
+        ("silhouette", ctypes.c_double),
+        ("iterations", ctypes.c_int32),
+        ("control_clusters", ctypes.c_int32),
+        ("sample_labels_distinct", ctypes.c_int32),
+        ("seed_point", ctypes.c_int32 * 2),
+    ]
+
+
 # name -> (restype, argtypes); every name here must be exported by the library (tests/test_cabi.py)
 SIGNATURES = {
     "dj_abi_version": (c_int32, []),
@@ -88,6 +100,9 @@ SIGNATURES = {
     "dj_assign_rows": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
     "dj_silhouette": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "dj_cluster_step": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                  c_double, c_double, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dj_member_counts": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_void_p, c_void_p]),
     "dj_member_locate": (c_int32, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "dj_gather_labels": (c_int32, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -104,7 +119,7 @@ _NO_STATUS = {"dj_abi_version", "dj_last_error", "dj_code_pitch", "dj_ckpt_pitch
 KERNELS_PER_CALL = {
     "dj_encode": 1, "dj_encode_v1": 1, "dj_encode_ref": 1, "dj_hist": 2, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
     "dj_fetch_tokens": 1, "dj_dedup_rows": 1, "dj_dedup_export": 1, "dj_bisect": 1, "dj_assign_rows": 1,
-    "dj_silhouette": 2, "dj_member_counts": 1, "dj_member_locate": 1, "dj_gather_labels": 1,
+    "dj_silhouette": 2, "dj_cluster_step": 6, "dj_member_counts": 1, "dj_member_locate": 1, "dj_gather_labels": 1,
     "dj_read_n_features": 1, "dj_sv_scan": 1,
 }
 launch_count = 0

@@ -4,9 +4,10 @@
 The N score rows are collapsed to U distinct weighted points by ``dj_dedup_rows``; scikit-learn's
 BisectingKMeans / silhouette arithmetic then runs on those points in float64 inside ``dj_bisect`` /
 ``dj_silhouette``.  What stays on the host is control flow that is O(U) or O(k): the bisecting tree, the greedy
-silhouette stop rule, numpy's legacy ``RandomState`` (the seeds scikit-learn draws are row *indices*, so the
-draws are mapped back to points with ``dj_member_counts`` / ``dj_member_locate``), Fisher tests and the rare
-decision-tree re-allocation of strand-biased clusters.
+silhouette stop rule, numpy's legacy ``RandomState`` (the seeds scikit-learn draws are row *indices*: their ranks
+go to the device, which finds the rows), Fisher tests and the rare decision-tree re-allocation of strand-biased
+clusters.  One iteration of ``optimize_labels`` is ONE call (``dj_cluster_step``: seed location, 2-means of the leaf,
+labels, control-share rule, silhouette) with one device -> host copy.
 """
 
 from __future__ import annotations
@@ -163,7 +164,7 @@ class _Tree:
                 best, best_score = leaf, s
         return best
 
-    def split(self, node: int, scores) -> tuple[int, int]:
+    def split(self, node: int, scores=(0.0, 0.0)) -> tuple[int, int]:
         a, b = self.next_id, self.next_id + 1
         self.next_id += 2
         self.nodes[a] = {"score": float(scores[0]), "left": None, "right": None}
@@ -171,30 +172,8 @@ class _Tree:
         self.nodes[node]["left"], self.nodes[node]["right"] = a, b
         return a, b
 
-
-class _MemberSelector:
-    """j-th member (in row order) of a leaf among the sample rows, then among the control-subset rows."""
-
-    def __init__(self, sample: RowSet, point_leaf_sample, control_rows_points: np.ndarray):
-        self.sample = sample
-        self.control_points = control_rows_points  # point id (in the control part) of each control-subset row
-
-    def sample_member(self, leaf_of_slot_d: torch.Tensor, target: int, rank: int) -> int:
-        dev = leaf_of_slot_d.device
-        n = self.sample.n_rows
-        n_blocks = (n + 1023) // 1024
-        counts = torch.empty(n_blocks, dtype=torch.int32, device=dev)
-        _cabi.call("dj_member_counts", _p(self.sample.slot_of_row), n, _p(leaf_of_slot_d), target, _p(counts), _stream())
-        cum = np.cumsum(counts.cpu().numpy().astype(np.int64))
-        block = int(np.searchsorted(cum, rank, side="right"))
-        before = int(cum[block - 1]) if block else 0
-        out = torch.full((1,), -1, dtype=torch.int32, device=dev)
-        _cabi.call("dj_member_locate", _p(self.sample.slot_of_row), n, _p(leaf_of_slot_d), target, block, rank - before,
-                   _p(out), _stream())
-        row = int(out.item())
-        if row < 0:
-            raise RuntimeError("member selection failed")
-        return row
+    def set_scores(self, a: int, b: int, scores) -> None:
+        self.nodes[a]["score"], self.nodes[b]["score"] = float(scores[0]), float(scores[1])
 
 
 def _values_matrix(point_ids: np.ndarray, value_of_id: np.ndarray) -> np.ndarray:
@@ -253,46 +232,56 @@ def optimize_labels_points(Xs: np.ndarray, ws: np.ndarray, Xc: np.ndarray, wc: n
         TRACE.append(trace)
     rng = np.random.RandomState(1)
     tree = _Tree()
-    leaf = np.zeros(n_s_pts + n_c_pts, dtype=np.int32)
+    n_pts = n_s_pts + n_c_pts
+    leaf = np.zeros(n_pts, dtype=np.int32)                       # host mirror of leaf_d
+    leaf_d = torch.zeros(n_pts, dtype=torch.int32, device=dev)   # moved to the child leaves by every step
+    on_device_rows = sample_row_points is None
+    if on_device_rows:
+        point_of_slot_d = torch.as_tensor(sample.point_of_slot, device=dev)
+        slot_of_row_p, n_rows, point_of_slot_p = _p(sample.slot_of_row), sample.n_rows, _p(point_of_slot_d)
+    else:
+        slot_of_row_p, n_rows, point_of_slot_p = None, 0, None
+    sub = np.empty(n_pts, dtype=np.int8)
+    out = _cabi.ClusterStepOut()
+    given = (ctypes.c_int32 * 2)()
+    rank = (ctypes.c_int64 * 2)()
     for n_clusters in range(2, coverage_sample):
         target = tree.pick()
         members = leaf == target
         ns_leaf = int(ws[members[:n_s_pts]].sum())
         nc_leaf = int(wc[members[n_s_pts:]].sum()) if n_c_pts else 0
         n_sub = ns_leaf + nc_leaf
+        # scikit-learn seeds the bisection with two ROWS of the leaf (sklearn/cluster/_kmeans.py:1030-1037); a sample
+        # row is found on the device from its rank among the leaf's rows, a control row here (<= 1000 rows)
         seeds = uniform_choice2(rng, n_sub)
-        seed_points = []
-        leaf_of_slot_d = None
-        for j in seeds.tolist():
+        for i, j in enumerate(seeds.tolist()):
+            given[i], rank[i] = -1, 0
             if j < ns_leaf:
-                if sample_row_points is not None:
-                    rows_in = np.flatnonzero(members[:n_s_pts][sample_row_points])
-                    seed_points.append(int(sample_row_points[rows_in[j]]))
+                if on_device_rows:
+                    rank[i] = j
                 else:
-                    if leaf_of_slot_d is None:
-                        los = np.full(sample.point_of_slot.shape[0], -1, dtype=np.int32)
-                        los[sample.slots] = leaf[:n_s_pts]
-                        leaf_of_slot_d = torch.as_tensor(los, device=dev)
-                    row = _MemberSelector(sample, None, control_row_points).sample_member(leaf_of_slot_d, target, j)
-                    slot = int(sample.slot_of_row[row].item())
-                    seed_points.append(int(sample.point_of_slot[slot]))
+                    rows_in = np.flatnonzero(members[:n_s_pts][sample_row_points])
+                    given[i] = int(sample_row_points[rows_in[j]])
             else:
                 ctrl_members = np.flatnonzero(members[n_s_pts:][control_row_points])
-                seed_points.append(n_s_pts + int(control_row_points[ctrl_members[j - ns_leaf]]))
-        sub, stats = _bisect(X_d, w_d, leaf, last_row_d, target, seed_points[0], seed_points[1])
-        a, b = tree.split(target, stats[:2])
+                given[i] = n_s_pts + int(control_row_points[ctrl_members[j - ns_leaf]])
+        a, b = tree.split(target)
+        order_of_leaf = np.full(tree.next_id, -1, dtype=np.int32)
+        for k, node in enumerate(tree.leaves()):
+            order_of_leaf[node] = k
+        located = given[0] < 0 or given[1] < 0
+        _cabi.call("dj_cluster_step", _p(X_d), _p(w_d), n_pts, n_s_pts, int(X.shape[1]), _p(leaf_d), _p(last_row_d),
+                   slot_of_row_p, n_rows, point_of_slot_p, target, a, b, ctypes.cast(given, ctypes.c_void_p),
+                   ctypes.cast(rank, ctypes.c_void_p), order_of_leaf.ctypes.data, int(order_of_leaf.shape[0]), n_clusters,
+                   float(coverage_control if n_c_pts else 0), TOL, MAX_ITER, 1, sub.ctypes.data,
+                   ctypes.cast(ctypes.pointer(out), ctypes.c_void_p), _stream())
+        if not located:
+            _cabi.launch_count -= 1  # no member count pass
+        tree.set_scores(a, b, out.inertia)
         leaf = np.where(members, np.where(sub == 1, b, a), leaf).astype(np.int32)
-        order = {node: k for k, node in enumerate(tree.leaves())}
-        labels = np.array([order[n] for n in leaf.tolist()], dtype=np.int64)
-        lab_s, lab_c = labels[:n_s_pts], labels[n_s_pts:]
-        ctrl_clusters = 0
-        if n_c_pts:
-            per = np.bincount(lab_c, weights=wc, minlength=n_clusters)
-            ctrl_clusters = int((per / coverage_control > 0.01).sum())
-        if len(set(lab_s.tolist())) > 1:
-            cur = _silhouette(X_d, w_d, labels, n_clusters)
-        else:
-            cur = -1.0
+        lab_s = order_of_leaf[leaf[:n_s_pts]].astype(np.int64)
+        ctrl_clusters = int(out.control_clusters) if n_c_pts else 0
+        cur = float(out.silhouette) if out.sample_labels_distinct else -1.0
         trace["silhouette"].append((n_clusters, cur))
         if prev >= cur or ctrl_clusters > 1:
             break

@@ -9,6 +9,7 @@
 //   silhouette_score sklearn/metrics/cluster/_unsupervised.py:59-300
 // which is what the reference calls at src/DAJIN2/core/clustering/clustering.py:35,42,68.
 #include <float.h>
+#include <string.h>
 
 #include "dj_common.cuh"
 
@@ -130,10 +131,17 @@ constexpr int kBisectThreads = 512;
 // (each column sums its points in point order, so the result does not depend on the thread count).
 __global__ void __launch_bounds__(kBisectThreads)
 bisect_kernel(const double *__restrict__ X, const double *__restrict__ weight, int n_points, int n_cols,
-              const int32_t *__restrict__ leaf, const int32_t *__restrict__ last_row, int target, int seed0, int seed1,
+              int32_t *leaf, const int32_t *__restrict__ last_row, int target, int seed0, int seed1,
               double tol, int max_iter,
               int8_t *__restrict__ lab, int8_t *__restrict__ lab_old, double *__restrict__ dist,
-              double *__restrict__ centers_out, double *__restrict__ stats, double *__restrict__ big_centers) {
+              double *__restrict__ centers_out, double *__restrict__ stats, double *__restrict__ big_centers,
+              const int32_t *__restrict__ seed_dev, int child_a, int child_b) {
+    // dj_cluster_step: the seeds were located on the device (seed_dev[0..1]) and the members of the bisected leaf move
+    // to the two child leaves at the end (child_a / child_b >= 0); dj_bisect passes seeds as arguments and keeps `leaf`
+    if (seed_dev) {
+        seed0 = seed_dev[0];
+        seed1 = seed_dev[1];
+    }
     extern __shared__ double smem[];
     // the four centre rows live in shared memory; with more score columns than fit there (one column per selected
     // locus: multi-kb deletions or knock-ins) they live in global memory -- one CTA, so __syncthreads orders them
@@ -318,13 +326,19 @@ bisect_kernel(const double *__restrict__ X, const double *__restrict__ weight, i
     in1 = block_sum(in1, scratch);
     w0 = block_sum(w0, scratch);
     w1 = block_sum(w1, scratch);
-    for (int k = tid; k < 2 * n_cols; k += blockDim.x) centers_out[k] = c_old[k];
+    if (centers_out)
+        for (int k = tid; k < 2 * n_cols; k += blockDim.x) centers_out[k] = c_old[k];
     if (tid == 0) {
         stats[0] = in0;
         stats[1] = in1;
         stats[2] = (double)iter;
         stats[3] = w0;
         stats[4] = w1;
+    }
+    if (child_a >= 0) {
+        __syncthreads();
+        for (int p = tid; p < n_points; p += blockDim.x)
+            if (leaf[p] == target) leaf[p] = lab[p] ? child_b : child_a;
     }
 }
 
@@ -469,6 +483,105 @@ assign_rows_kernel(const uint16_t *__restrict__ ids, int64_t n_rows, int n_cols,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// dj_cluster_step: one iteration of optimize_labels without a host round trip in between
+// ---------------------------------------------------------------------------------------------------------
+// members of leaf `target` among the sample rows, counted per 1024 rows; a row belongs to the leaf of its point
+__global__ void __launch_bounds__(1024)
+step_member_count_kernel(const int32_t *__restrict__ slot_of_row, int64_t n_rows, const int32_t *__restrict__ point_of_slot,
+                         const int32_t *__restrict__ leaf, int target, int32_t *__restrict__ block_counts) {
+    const int64_t t = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int member = (t < n_rows && leaf[point_of_slot[slot_of_row[t]]] == target) ? 1 : 0;
+    const int n = __syncthreads_count(member);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = n;
+}
+
+// CTA i resolves seed i: a point given by the host (seed_given[i] >= 0), or the point of the seed_rank[i]-th member
+// row of the leaf (scikit-learn draws ROW indices; rows are in file order)
+__global__ void __launch_bounds__(1024)
+step_seed_kernel(const int32_t *__restrict__ slot_of_row, int64_t n_rows, const int32_t *__restrict__ point_of_slot,
+                 const int32_t *__restrict__ leaf, int target, const int32_t *__restrict__ block_counts, int n_blocks,
+                 int given0, int given1, long long rank0, long long rank1, int32_t *__restrict__ seed_out) {
+    __shared__ long long s_before[1024];
+    __shared__ int s_block, s_rank;
+    __shared__ int warp_counts[32];
+    const int given = blockIdx.x == 0 ? given0 : given1;
+    const long long rank = blockIdx.x == 0 ? rank0 : rank1;
+    if (given >= 0) {
+        if (threadIdx.x == 0) seed_out[blockIdx.x] = given;
+        return;
+    }
+    // strips of the block counts: thread q owns blocks [q * per, (q + 1) * per)
+    const int per = (n_blocks + 1023) / 1024;
+    long long mine = 0;
+    for (int b = threadIdx.x * per; b < min(n_blocks, (threadIdx.x + 1) * per); ++b) mine += block_counts[b];
+    s_before[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        int q = 0;
+        for (; q < 1024; ++q) {
+            if (acc + s_before[q] > rank) break;
+            acc += s_before[q];
+        }
+        int b = q * per;
+        for (; b < n_blocks; ++b) {
+            const int c = block_counts[b];
+            if (acc + c > rank) break;
+            acc += c;
+        }
+        s_block = b;
+        s_rank = (int)(rank - acc);
+    }
+    __syncthreads();
+    if (s_block >= n_blocks) return;  // rank beyond the members: seed_out stays -1 and the host raises
+    const int64_t t = (int64_t)s_block * 1024 + threadIdx.x;
+    const int pt = t < n_rows ? point_of_slot[slot_of_row[t]] : -1;
+    const int member = (pt >= 0 && leaf[pt] == target) ? 1 : 0;
+    const unsigned ballot = __ballot_sync(0xffffffffu, member);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_counts[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += warp_counts[w];
+    before += __popc(ballot & ((1u << lane) - 1u));
+    if (member && before == s_rank) seed_out[blockIdx.x] = pt;
+}
+
+// labels = position of each point's leaf in the left-to-right order of the leaves; clusters that hold more than 1 %
+// of the control rows (clustering.py:43-45); whether the sample points carry more than one label
+__global__ void __launch_bounds__(kBisectThreads)
+step_relabel_kernel(const int32_t *__restrict__ leaf, const int32_t *__restrict__ order_of_leaf, int n_points,
+                    int n_sample_points, const double *__restrict__ weight, int n_clusters, double control_coverage,
+                    int32_t *__restrict__ label, double *__restrict__ ctrl_weight, int32_t *__restrict__ out_flags) {
+    __shared__ int s_distinct, s_ctrl;
+    const int tid = threadIdx.x;
+    if (tid == 0) { s_distinct = 0; s_ctrl = 0; }
+    for (int c = tid; c < n_clusters; c += blockDim.x) ctrl_weight[c] = 0.0;
+    __syncthreads();
+    const int first = n_sample_points > 0 ? order_of_leaf[leaf[0]] : -1;
+    for (int p = tid; p < n_points; p += blockDim.x) {
+        const int lab = order_of_leaf[leaf[p]];
+        label[p] = lab;
+        if (p < n_sample_points) {
+            if (lab != first) s_distinct = 1;
+        } else {
+            atomicAdd(&ctrl_weight[lab], weight[p]);  // integer-valued weights: the sum is exact in any order
+        }
+    }
+    __syncthreads();
+    int n = 0;
+    if (control_coverage > 0.0)
+        for (int c = tid; c < n_clusters; c += blockDim.x)
+            if (ctrl_weight[c] / control_coverage > 0.01) ++n;
+    if (n) atomicAdd(&s_ctrl, n);
+    __syncthreads();
+    if (tid == 0) {
+        out_flags[0] = s_ctrl;
+        out_flags[1] = s_distinct;
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t dj_row_table_bytes(uint32_t capacity) { return 64 + (int64_t)capacity * 24; }
@@ -552,8 +665,9 @@ extern "C" int dj_bisect(const double *X, const double *weight, int32_t n_points
     DJ_CUDA_CHECK(cudaMallocAsync(&lab_old, (size_t)n_points, st));
     DJ_CUDA_CHECK(cudaMallocAsync(&dist, sizeof(double) * (size_t)n_points, st));
     if (big) DJ_CUDA_CHECK(cudaMallocAsync(&big_centers, sizeof(double) * 4 * (size_t)n_cols, st));
-    bisect_kernel<<<1, kBisectThreads, smem, st>>>(X, weight, n_points, n_cols, leaf, last_row, target, seed0, seed1, tol,
-                                                   max_iter, sub_label, lab_old, dist, centers, stats, big_centers);
+    bisect_kernel<<<1, kBisectThreads, smem, st>>>(X, weight, n_points, n_cols, const_cast<int32_t *>(leaf), last_row,
+                                                   target, seed0, seed1, tol, max_iter, sub_label, lab_old, dist, centers,
+                                                   stats, big_centers, nullptr, -1, -1);
     cudaError_t err = cudaGetLastError();
     cudaFreeAsync(lab_old, st);
     cudaFreeAsync(dist, st);
@@ -652,5 +766,149 @@ extern "C" int dj_assign_rows(const uint16_t *ids, int64_t n_rows, int32_t n_col
     assign_rows_kernel<<<grid_for(n_rows, kThreads), kThreads, smem, st>>>(ids, n_rows, n_cols, value_of_id, centers,
                                                                          n_centers, label, sums, counts);
     DJ_LAUNCH_CHECK();
+    return 0;
+}
+
+// One iteration of the reference's optimize_labels loop (clustering/clustering.py:29-55) as one stream of launches
+// and ONE device -> host copy: the two random seeds of the bisection located among the sample rows (or given as
+// points), the 2-means of the leaf (dj_bisect's kernel), the left-to-right cluster labels, the control-share rule and
+// the silhouette score.  `leaf` (device, int32 per point) is updated in place: members of `target` move to child_a /
+// child_b.  Host outputs: sub_host[p] (0 / 1 for the members of the leaf as they were split, untouched elsewhere) and
+// out (DjClusterStepOut).
+extern "C" int dj_cluster_step(const double *X, const double *weight, int32_t n_points, int32_t n_sample_points,
+                               int32_t n_cols, int32_t *leaf, const int32_t *last_row, const int32_t *slot_of_row,
+                               int64_t n_rows, const int32_t *point_of_slot, int32_t target, int32_t child_a,
+                               int32_t child_b, const int32_t *seed_given, const int64_t *seed_rank,
+                               const int32_t *order_of_leaf_host, int32_t n_leaf_ids, int32_t n_clusters,
+                               double control_coverage, double tol, int32_t max_iter, int32_t want_silhouette,
+                               int8_t *sub_host, DjClusterStepOut *out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_points <= 0 || n_cols <= 0 || n_clusters <= 0 || n_leaf_ids <= 0) {
+        dj_set_error("dj_cluster_step: empty problem");
+        return 1;
+    }
+    const bool locate = seed_given[0] < 0 || seed_given[1] < 0;
+    if (locate && (slot_of_row == nullptr || point_of_slot == nullptr || n_rows <= 0)) {
+        dj_set_error("dj_cluster_step: a seed is given as a row rank but there are no rows");
+        return 1;
+    }
+    // pinned staging for the step's inputs and results (grown on demand, kept for the life of the process)
+    static uint8_t *h_pin = nullptr;
+    static size_t h_pin_bytes = 0;
+    const size_t order_bytes = sizeof(int32_t) * (size_t)n_leaf_ids;
+    const size_t res_off = (order_bytes + 15) & ~(size_t)15;
+    const size_t res_bytes = 64 + (((size_t)n_points + 15) & ~(size_t)15);  // stats[5], score, flags[2], seeds[2]; sub labels
+    const size_t need = res_off + res_bytes;
+    if (need > h_pin_bytes) {
+        if (h_pin) cudaFreeHost(h_pin);
+        h_pin = nullptr;
+        h_pin_bytes = 0;
+        DJ_CUDA_CHECK(cudaMallocHost(&h_pin, need * 2));
+        h_pin_bytes = need * 2;
+    }
+    memcpy(h_pin, order_of_leaf_host, order_bytes);
+
+    const int64_t n_blocks = locate ? (n_rows + 1023) / 1024 : 0;
+    // one device allocation for everything the step needs
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_order = take(order_bytes), o_res = take(res_bytes), o_labold = take((size_t)n_points),
+                 o_dist = take(sizeof(double) * (size_t)n_points), o_label = take(sizeof(int32_t) * (size_t)n_points),
+                 o_ctrl = take(sizeof(double) * (size_t)n_clusters), o_counts = take(sizeof(int32_t) * (size_t)(n_blocks + 1)),
+                 o_sil = take(sizeof(double) * (size_t)n_points);
+    size_t bis_smem = sizeof(double) * ((size_t)4 * n_cols + kBisectThreads);
+    const bool bis_big = bis_smem > 200 * 1024;
+    if (bis_big) bis_smem = sizeof(double) * kBisectThreads;
+    const size_t o_bigc = take(bis_big ? sizeof(double) * 4 * (size_t)n_cols : 0);
+    int tile_rows = 16384 / n_cols;
+    if (tile_rows < 1) tile_rows = 1;
+    if (tile_rows > 64) tile_rows = 64;
+    size_t sil_smem = sizeof(double) * ((size_t)kSilThreads * n_clusters + n_clusters + (size_t)tile_rows * n_cols);
+    const bool sil_big = sil_smem > 200 * 1024;
+    const unsigned sil_blocks = (unsigned)((n_points + kSilThreads - 1) / kSilThreads);
+    if (sil_big) {
+        while (tile_rows > 1 && sizeof(double) * ((size_t)n_clusters + (size_t)tile_rows * n_cols) > 200 * 1024) tile_rows /= 2;
+        sil_smem = sizeof(double) * ((size_t)n_clusters + (size_t)tile_rows * n_cols);
+        if (sil_smem > 200 * 1024) {
+            dj_set_error("dj_cluster_step: %d clusters x %d columns exceed the shared-memory budget", n_clusters, n_cols);
+            return 1;
+        }
+    }
+    const size_t o_bigacc = take(sil_big ? sizeof(double) * (size_t)sil_blocks * kSilThreads * n_clusters : 0);
+    uint8_t *ws = nullptr;
+    DJ_CUDA_CHECK(cudaMallocAsync(&ws, off + 256, st));
+    int32_t *d_order = reinterpret_cast<int32_t *>(ws + o_order);
+    uint8_t *d_res = ws + o_res;
+    double *d_stats = reinterpret_cast<double *>(d_res);           // [0..4] bisect, [5] silhouette
+    int32_t *d_flags = reinterpret_cast<int32_t *>(d_res + 48);    // ctrl clusters, distinct sample labels
+    int32_t *d_seeds = reinterpret_cast<int32_t *>(d_res + 56);    // the two seed points
+    int8_t *d_sub = reinterpret_cast<int8_t *>(d_res + 64);
+    int32_t *d_label = reinterpret_cast<int32_t *>(ws + o_label);
+
+    cudaError_t err = cudaMemcpyAsync(d_order, h_pin, order_bytes, cudaMemcpyHostToDevice, st);
+    if (err == cudaSuccess) err = cudaMemsetAsync(d_res, 0xFF, res_bytes, st);  // seeds = -1, sub labels = 0xFF
+    if (err == cudaSuccess && locate) {
+        step_member_count_kernel<<<(unsigned)n_blocks, 1024, 0, st>>>(slot_of_row, n_rows, point_of_slot, leaf, target,
+                                                                      reinterpret_cast<int32_t *>(ws + o_counts));
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) {
+        step_seed_kernel<<<2, 1024, 0, st>>>(slot_of_row, n_rows, point_of_slot, leaf, target,
+                                             reinterpret_cast<int32_t *>(ws + o_counts), (int)n_blocks, seed_given[0],
+                                             seed_given[1], (long long)seed_rank[0], (long long)seed_rank[1], d_seeds);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bis_smem);
+    if (err == cudaSuccess) {
+        bisect_kernel<<<1, kBisectThreads, bis_smem, st>>>(
+            X, weight, n_points, n_cols, leaf, last_row, target, 0, 0, tol, max_iter, d_sub,
+            reinterpret_cast<int8_t *>(ws + o_labold), reinterpret_cast<double *>(ws + o_dist), nullptr, d_stats,
+            bis_big ? reinterpret_cast<double *>(ws + o_bigc) : nullptr, d_seeds, child_a, child_b);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) {
+        step_relabel_kernel<<<1, kBisectThreads, 0, st>>>(leaf, d_order, n_points, n_sample_points, weight, n_clusters,
+                                                          control_coverage, d_label,
+                                                          reinterpret_cast<double *>(ws + o_ctrl), d_flags);
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess && want_silhouette) {
+        err = cudaFuncSetAttribute(silhouette_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sil_smem);
+        if (err == cudaSuccess) {
+            silhouette_kernel<<<sil_blocks, kSilThreads, sil_smem, st>>>(
+                X, weight, d_label, n_points, n_cols, n_clusters, tile_rows, reinterpret_cast<double *>(ws + o_sil),
+                sil_big ? reinterpret_cast<double *>(ws + o_bigacc) : nullptr);
+            err = cudaGetLastError();
+        }
+        if (err == cudaSuccess) {
+            weighted_mean_kernel<<<1, kBisectThreads, 0, st>>>(reinterpret_cast<double *>(ws + o_sil), weight, n_points,
+                                                               d_stats + 5);
+            err = cudaGetLastError();
+        }
+    }
+    if (err == cudaSuccess) err = cudaMemcpyAsync(h_pin + res_off, d_res, res_bytes, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(ws, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) {
+        dj_set_error("dj_cluster_step: %s", cudaGetErrorString(err));
+        return 1;
+    }
+    const double *h_stats = reinterpret_cast<const double *>(h_pin + res_off);
+    const int32_t *h_flags = reinterpret_cast<const int32_t *>(h_pin + res_off + 48);
+    out->inertia[0] = h_stats[0];
+    out->inertia[1] = h_stats[1];
+    out->weight[0] = h_stats[3];
+    out->weight[1] = h_stats[4];
+    out->silhouette = h_stats[5];
+    out->iterations = (int32_t)h_stats[2];
+    out->control_clusters = h_flags[0];
+    out->sample_labels_distinct = h_flags[1];
+    out->seed_point[0] = h_flags[2];
+    out->seed_point[1] = h_flags[3];
+    memcpy(sub_host, h_pin + res_off + 64, (size_t)n_points);
+    if (out->seed_point[0] < 0 || out->seed_point[1] < 0) {
+        dj_set_error("dj_cluster_step: a seed rank lies beyond the members of leaf %d", target);
+        return 1;
+    }
     return 0;
 }

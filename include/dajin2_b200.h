@@ -219,6 +219,32 @@ int dj_assign_rows(const uint16_t *ids, int64_t n_rows, int32_t n_cols, const do
 int dj_silhouette(const double *X, const double *weight, const int32_t *label, int32_t n_points,
                   int32_t n_cols, int32_t n_clusters, double *score, void *stream);
 
+/*
+ * One iteration of optimize_labels (clustering/clustering.py:29-55) without a host round trip in between: locates the
+ * two seeds scikit-learn draws for the bisection (seed_given[i] >= 0: a point; else the seed_rank[i]-th row, in file
+ * order, of the sample rows whose point lies in leaf `target`: slot_of_row / point_of_slot as dj_dedup_rows made them),
+ * runs the 2-means of that leaf (as dj_bisect), moves its members to child_a / child_b in `leaf` (device, in place),
+ * labels every point with order_of_leaf_host[leaf] (left-to-right order of the leaves after the split), counts the
+ * clusters that hold more than 1 % of the control weight (points >= n_sample_points; control_coverage = their total)
+ * and, if want_silhouette, computes the weighted silhouette score (as dj_silhouette).  One device -> host copy.
+ * sub_host[p] (host, n_points bytes) = 0 / 1 for the members of the split leaf, 0xFF elsewhere.
+ */
+typedef struct {
+    double inertia[2];   /* of the two halves: the next leaf to split is the one with the largest */
+    double weight[2];
+    double silhouette;   /* undefined unless want_silhouette */
+    int32_t iterations;
+    int32_t control_clusters;
+    int32_t sample_labels_distinct; /* 0: every sample point carries the same label (the reference then scores -1) */
+    int32_t seed_point[2];
+} DjClusterStepOut;
+int dj_cluster_step(const double *X, const double *weight, int32_t n_points, int32_t n_sample_points, int32_t n_cols,
+                    int32_t *leaf, const int32_t *last_row, const int32_t *slot_of_row, int64_t n_rows,
+                    const int32_t *point_of_slot, int32_t target, int32_t child_a, int32_t child_b,
+                    const int32_t *seed_given, const int64_t *seed_rank, const int32_t *order_of_leaf_host,
+                    int32_t n_leaf_ids, int32_t n_clusters, double control_coverage, double tol, int32_t max_iter,
+                    int32_t want_silhouette, int8_t *sub_host, DjClusterStepOut *out, void *stream);
+
 /* j-th member selection for sklearn's random init: members of leaf `target` in row order. */
 int dj_member_counts(const int32_t *slot_of_row, int64_t n_rows, const int32_t *leaf_of_slot, int32_t target,
                      int32_t *block_counts, void *stream); /* one count per 1024 rows */

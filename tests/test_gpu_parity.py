@@ -332,6 +332,36 @@ def test_encoder_chunk_boundaries():
             assert enc.fetch_tokens([k] * len(idx), idx) == [want[i] for i in idx]
 
 
+def test_encoder_event_density_sweep():
+    """Rows from all-plain to all-events: the number of slow units per trip of the unit encoder runs from 0 to 64, which
+    takes it through both piece sizes of its slow path (16-byte thirds, 24-byte halves) and through one to six passes."""
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+    from oracle import dajin2_oracle as orc
+
+    rng = np.random.default_rng(23)
+    plain = ["=A", "=C", "=G", "=T", "-A", "-C", "-G", "-T"]
+    # (midsv lowercases whole tokens of an inverted segment, so the inserted bases and the anchor of a token share
+    # their case; calc_match of a mixed-case insertion is outside what the encoder promises, DESIGN.md §4.1)
+    events = ["*AG", "*TC", "*CA", "+A|=C", "+T|+G|=A", "+C|+C|+C|+C|+C|=G", "=a", "-t", "*ag", "=N", "+a|*ct", "+g|+t|=c"]
+    n_tok = 4000
+    for rate in (0.0, 0.002, 0.008, 0.012, 0.02, 0.035, 0.06, 0.1, 0.3, 1.0):
+        rows = []
+        for _ in range(24):
+            is_event = rng.random(n_tok) < rate
+            toks = np.where(is_event, rng.choice(events, size=n_tok), rng.choice(plain, size=n_tok, p=[.23, .23, .23, .23, .02, .02, .02, .02]))
+            rows.append(",".join(toks))
+        enc = engine.EncodedReads(pack_rows(rows), n_tok)
+        assert np.array_equal(enc.codes[: len(rows), :n_tok].cpu().numpy(), encode_rows(rows)), rate
+        assert enc.match_scores().tolist() == [orc.calc_match(r) for r in rows], rate
+        codes_v1, ms_v1, nt_v1, fl_v1 = enc.encode_v1()
+        assert torch.equal(enc.codes, codes_v1) and torch.equal(enc.match_score, ms_v1), rate
+        assert torch.equal(enc.n_tokens, nt_v1) and torch.equal(enc.flags, fl_v1), rate
+        want = rows[5].split(",")
+        idx = [0, 1, 511, 512, 1023, 1024, 1025, 2047, 3999]
+        assert enc.fetch_tokens([5] * len(idx), idx) == [want[i] for i in idx], rate
+
+
 def test_first_token_raw_insertion_quirk():
     """Token 0 is never a k-mer centre, so as 'prev' of locus 1 it stays uncompressed (kmer_generator.py:40-52)."""
     from dajin2_b200 import engine
