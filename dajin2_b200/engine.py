@@ -38,6 +38,19 @@ def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+#: piece size of the overlapped host -> device copy (EncodedReads(encode="overlap")): large enough that a piece's copy
+#: (5 ms at PCIe Gen5 x16) dwarfs the launch of its dj_encode
+OVERLAP_CHUNK_BYTES = 256 << 20
+_COPY_STREAM: dict = {}
+
+
+def _copy_stream() -> torch.cuda.Stream:
+    dev = torch.cuda.current_device()
+    if dev not in _COPY_STREAM:
+        _COPY_STREAM[dev] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAM[dev]
+
+
 def _to_device(arr: np.ndarray | torch.Tensor, device) -> torch.Tensor:
     t = torch.from_numpy(arr) if isinstance(arr, np.ndarray) else arr
     return t.to(device, non_blocking=True)
@@ -80,7 +93,7 @@ def order_of_keys(keys: torch.Tensor) -> torch.Tensor:
 class EncodedReads:
     """One MIDSV file on the device: text, row index, read x locus code matrix and per-read scalars."""
 
-    def __init__(self, host: HostReads, n_loci: int, validate: bool = True, encode: bool = True,
+    def __init__(self, host: HostReads, n_loci: int, validate: bool = True, encode: bool | str = True,
                  sequence: str | None = None, assisted: bool | None = None):
         """``sequence`` / ``assisted`` select the ``dj_encode_ref`` entry point (round 1: plain stretches verified
         against the rendered reference).  The unit encoder behind ``dj_encode`` verifies plain stretches against
@@ -95,7 +108,8 @@ class EncodedReads:
         self.h2d_bytes = int(host.text.nbytes + host.row_off.nbytes + host.row_len.nbytes + host.strand.nbytes
                              + host.qnames.nbytes)
         self.name_keys = qname_keys(host.qnames, dev)  # int64[N, ceil(W / 8)]: the label order is the QNAME order
-        self.text = _to_device(host.text, dev)
+        overlap = encode == "overlap" and self.n_reads > 0 and host.text.nbytes > 2 * OVERLAP_CHUNK_BYTES
+        self.text = torch.empty(host.text.shape[0], dtype=torch.uint8, device=dev) if overlap else _to_device(host.text, dev)
         self.row_off = _to_device(host.row_off, dev)
         self.row_len = _to_device(host.row_len, dev)
         self.strand = _to_device(host.strand, dev)
@@ -113,20 +127,49 @@ class EncodedReads:
             assisted = os.environ.get("DAJIN2_B200_ENCODE_REF", "0") == "1"
         if assisted and sequence is not None and len(sequence) == self.n_loci:
             self.ref = torch.from_numpy(np.frombuffer(sequence.encode("ascii", "replace"), dtype=np.uint8).copy()).to(dev)
-        if encode:
+        self.encoded = False
+        if overlap:
+            self._copy_text_and_encode(host)
+        elif encode:
             self.encode()
-            if validate:
-                self.validate()
+        if encode and validate:
+            self.validate()
+
+    def _copy_text_and_encode(self, host: HostReads) -> None:
+        """The text goes to the device in pieces of whole rows (>= OVERLAP_CHUNK_BYTES each) on a copy stream and the
+        rows of a piece are encoded as soon as it has landed: all but the last piece's ``dj_encode`` hide behind the
+        copy of the next piece.  (The encoder may read up to 30 bytes past a row's end -- the start of the next piece,
+        possibly not there yet: those bytes are never interpreted.)"""
+        text_h = torch.from_numpy(host.text) if isinstance(host.text, np.ndarray) else host.text
+        total = int(text_h.shape[0])
+        cuts = np.searchsorted(host.row_off, np.arange(OVERLAP_CHUNK_BYTES, total, OVERLAP_CHUNK_BYTES), side="left")
+        first_rows = [0] + sorted(set(int(c) for c in cuts if 0 < c < self.n_reads)) + [self.n_reads]
+        main, copy = torch.cuda.current_stream(), _copy_stream()
+        copy.wait_stream(main)  # the buffers were allocated (and row_off / row_len queued) on the main stream
+        for r0, r1 in zip(first_rows[:-1], first_rows[1:]):
+            b0 = 0 if r0 == 0 else int(host.row_off[r0])
+            b1 = total if r1 == self.n_reads else int(host.row_off[r1])
+            with torch.cuda.stream(copy):
+                self.text[b0:b1].copy_(text_h[b0:b1], non_blocking=True)
+                landed = copy.record_event()
+            main.wait_event(landed)
+            _cabi.call("dj_encode", _p(self.text), _p(self.row_off[r0:]), _p(self.row_len[r0:]), r1 - r0, self.n_loci,
+                       self.pitch, self.ckpt_pitch, _p(self.codes[r0:]), _p(self.match_score[r0:]),
+                       _p(self.n_tokens[r0:]), _p(self.flags[r0:]), _p(self.ckpt[r0:]), _stream())
+        self.text.record_stream(copy)
+        self.encoded = True
 
     def encode(self) -> None:
         if self.ref is not None:
             _cabi.call("dj_encode_ref", _p(self.text), _p(self.row_off), _p(self.row_len), self.n_reads, self.n_loci,
                        self.pitch, self.ckpt_pitch, _p(self.ref), _p(self.codes), _p(self.match_score),
                        _p(self.n_tokens), _p(self.flags), _p(self.ckpt), _stream())
+            self.encoded = True
             return
         _cabi.call("dj_encode", _p(self.text), _p(self.row_off), _p(self.row_len), self.n_reads, self.n_loci,
                    self.pitch, self.ckpt_pitch, _p(self.codes), _p(self.match_score), _p(self.n_tokens),
                    _p(self.flags), _p(self.ckpt), _stream())
+        self.encoded = True
 
     def encode_v1(self):
         """The round-1 generic kernel on the same text (cross-check of the unit encoder): codes, match_score,
