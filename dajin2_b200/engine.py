@@ -369,21 +369,24 @@ def mlp_candidates(sample: np.ndarray, control: np.ndarray, threshold: float) ->
     return mlp_pool.submit(sample, control, threshold).result()
 
 
-def submit_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False):
+def submit_anomal_loci(norm_sample, norm_control, thresholds, is_consensus: bool = False, defer_checks: bool = False):
     """First half of ``extract_anomal_loci`` (reference ``anomaly_detector.py:99-109``): start the three MLP fits in
     the worker pool and compute the window distances on the device; returns a zero-argument function that waits for
-    the fits and returns the loci.  The fits of several alleles / samples can be in flight at once."""
+    the fits and returns the loci.  The fits of several alleles / samples can be in flight at once.
+    ``defer_checks``: the fits' comparisons with scikit-learn's own evaluation run beside them in other workers
+    (``mlp_pool``); the caller then calls ``finish.verify()`` before its result is final (False: redo, not deferred)."""
     from . import mlp_pool
 
     pending = {}
     for op in MUTS:
         s = np.asarray(norm_sample[op], dtype=float)
         c = np.asarray(norm_control[op], dtype=float)
-        pending[op] = (mlp_pool.submit(s, c, thresholds[op]), dissimilar_mask(s, c, is_consensus))
+        pending[op] = (mlp_pool.submit(s, c, thresholds[op], defer_checks), dissimilar_mask(s, c, is_consensus))
 
     def finish() -> dict[str, set[int]]:
         return {op: set(np.flatnonzero(fut.result() & mask).tolist()) for op, (fut, mask) in pending.items()}
 
+    finish.verify = lambda: all([mlp_pool.verified(fut) for fut, _ in pending.values()])
     return finish
 
 
@@ -485,14 +488,14 @@ def transpose_loci(loci: dict[str, set[int]], n_loci: int) -> list[set[str]]:
 
 def begin_select_mutation_loci(hist_sample: np.ndarray, strand_host: np.ndarray, sequence: str, norm_sample,
                                norm_control_raw, knockin: set[int] | None = None, thresholds=None,
-                               is_consensus: bool = False, insample_filter=None):
+                               is_consensus: bool = False, insample_filter=None, defer_checks: bool = False):
     """``extract_mutation_loci`` (reference ``mutation_processing/mutation_extractor.py:28-87``) in two halves: this
     call starts the MLP fits (host worker processes) and returns a zero-argument function that waits for them and
     applies the rest of the selection.  Callers with several alleles or samples begin all of them before finishing
     the first: the fits are independent (``mutation_extractor.py:126-168`` loops over alleles one after the other)."""
     thresholds = thresholds or {"*": 0.1, "-": 0.1, "+": 0.1}
     norm_control = {op: np.minimum(norm_control_raw[op], norm_sample[op]) for op in MUTS}
-    finish_anomal = submit_anomal_loci(norm_sample, norm_control, thresholds, is_consensus)
+    finish_anomal = submit_anomal_loci(norm_sample, norm_control, thresholds, is_consensus, defer_checks)
 
     def finish() -> list[set[str]]:
         loci = finish_anomal()
@@ -507,6 +510,7 @@ def begin_select_mutation_loci(hist_sample: np.ndarray, strand_host: np.ndarray,
             loci = {op: loci[op] - extra[op] for op in MUTS}
         return transpose_loci(merge_consecutive_indels(loci), len(sequence))
 
+    finish.verify = finish_anomal.verify
     return finish
 
 
@@ -586,6 +590,9 @@ class KmerCounts:
     per_locus: dict  # locus -> record indices
 
 
+_KMER_RECORD_BUFFERS: dict = {}  # capacity -> host array dj_kmer_export writes into (copied out right away)
+
+
 def count_kmers(sample: EncodedReads, rows_sample: torch.Tensor | None, control: EncodedReads | None,
                 loci_t: list[set[str]], capacity: int = 1 << 18) -> KmerCounts:
     """generate_mutation_kmers + call_count (reference ``kmer_generator.py:35-56``, ``score_handler.py:15-16``) for
@@ -603,7 +610,9 @@ def count_kmers(sample: EncodedReads, rows_sample: torch.Tensor | None, control:
         _count_kmers(sample, rows_sample, n_s, mask_d, sel_d, len(sel), 0, table, capacity)
         if control is not None:
             _count_kmers(control, None, control.n_reads, mask_d, sel_d, len(sel), 1, table, capacity)
-        recs = (_cabi.KmerRecord * capacity)()
+        recs = _KMER_RECORD_BUFFERS.get(capacity)
+        if recs is None:  # 7 MB at the default capacity: allocated (zeroed, page-faulted) once, not per call
+            recs = _KMER_RECORD_BUFFERS.setdefault(capacity, (_cabi.KmerRecord * capacity)())
         n_rec = ctypes.c_uint32(0)
         try:
             _cabi.call("dj_kmer_export", _p(table), capacity, ctypes.cast(recs, ctypes.c_void_p), capacity,

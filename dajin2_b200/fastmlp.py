@@ -206,6 +206,11 @@ class FastMLPClassifier(MLPClassifier):
 
     fast_path_used_: bool = False
     fast_validation_used_: bool = False
+    #: True: the two comparisons with scikit-learn's own evaluation (first and last evaluated point) are NOT made inside
+    #: the fit; the points and the fused results are left in ``deferred_checks_`` for the caller, who has them evaluated
+    #: by scikit-learn elsewhere (``mlp_pool``: another worker process, beside the fit) and compares the bits
+    defer_checks: bool = False
+    deferred_checks_: list | None = None
 
     def _validate_input(self, X, y, incremental, reset):
         """scikit-learn's input validation spends several ms per fit in the generic label machinery (sparse label
@@ -289,7 +294,15 @@ class FastMLPClassifier(MLPClassifier):
         mode = getattr(self, "_fm_mode", None)
         if mode is None:  # first evaluation of this fit: decide, and check against scikit-learn's own evaluation
             mode = "sklearn"
-            if self._fast_applicable(X, y, sample_weight):
+            if self._fast_applicable(X, y, sample_weight) and self.defer_checks:
+                try:
+                    self._fast_setup(X, y)
+                    loss, grad = self._fast_loss_grad(packed_coef_inter, X)
+                    self.deferred_checks_ = [(packed_coef_inter.copy(), float(loss), grad.copy())]
+                    mode = "fast"
+                except Exception:  # noqa: BLE001
+                    mode = "sklearn"
+            elif self._fast_applicable(X, y, sample_weight):
                 self._fast_setup(X, y)
                 ref = super()._loss_grad_lbfgs(packed_coef_inter.copy(), X, y, sample_weight, activations, deltas,
                                                coef_grads, intercept_grads)
@@ -336,7 +349,13 @@ class FastMLPClassifier(MLPClassifier):
         else:
             super()._fit_lbfgs(X, y, sample_weight, activations, deltas, coef_grads, intercept_grads, layer_units)
         self.fast_path_used_ = self._fm_mode == "fast"
-        if self._fm_mode == "fast":
+        if self._fm_mode == "fast" and self.defer_checks:
+            last = self._fm_last
+            final = [c.copy() for c in self.coefs_], [b.copy() for b in self.intercepts_]
+            loss, grad = self._fast_loss_grad(last, X)
+            self.deferred_checks_.append((last.copy(), float(loss), grad.copy()))
+            self.coefs_, self.intercepts_ = final
+        elif self._fm_mode == "fast":
             # check the last evaluated point as well (late iterates exercise the clipped / saturated branches)
             last = self._fm_last
             final = [c.copy() for c in self.coefs_], [b.copy() for b in self.intercepts_]
@@ -467,3 +486,39 @@ def _same_bits(ref, got) -> bool:
     return bool(a[0] == b[0]) and g0.shape == g1.shape and bool(
         np.array_equal(np.ascontiguousarray(g0, dtype=np.float64).view(np.uint64),
                        np.ascontiguousarray(g1, dtype=np.float64).view(np.uint64)))
+
+
+class ProbeMLPClassifier(MLPClassifier):
+    """scikit-learn's own loss / gradient (``_loss_grad_lbfgs``) at given parameter vectors of the model a fit on
+    (X, y) would start from: ``fit`` runs scikit-learn's validation, initialisation and buffer set-up, then evaluates
+    instead of optimising.  ``points_`` = [(packed, loss, grad), ...]; ``None`` among ``points`` stands for the
+    initial parameters (random_state decides them, so a fit elsewhere starts from the same ones)."""
+
+    def __init__(self, points=(None,), **kw):
+        super().__init__(**kw)
+        self.points = points
+
+    def _fit_lbfgs(self, X, y, sample_weight, activations, deltas, coef_grads, intercept_grads, layer_units):
+        from sklearn.neural_network._multilayer_perceptron import _pack
+
+        self._coef_indptr, self._intercept_indptr = [], []
+        start = 0
+        for i in range(self.n_layers_ - 1):  # as MLPClassifier._fit_lbfgs lays the packed vector out
+            n_fan_in, n_fan_out = layer_units[i], layer_units[i + 1]
+            end = start + (n_fan_in * n_fan_out)
+            self._coef_indptr.append((start, end, (n_fan_in, n_fan_out)))
+            start = end
+        for i in range(self.n_layers_ - 1):
+            end = start + layer_units[i + 1]
+            self._intercept_indptr.append((start, end))
+            start = end
+        x0 = _pack(self.coefs_, self.intercepts_)
+        self.points_ = []
+        for p in self.points:
+            packed = x0.copy() if p is None else np.array(p, dtype=np.float64)
+            loss, grad = MLPClassifier._loss_grad_lbfgs(self, packed.copy(), X, y, sample_weight, activations, deltas,
+                                                        coef_grads, intercept_grads)
+            self.points_.append((packed, float(loss), np.array(grad, dtype=np.float64)))
+        self._unpack(x0)
+        self.n_iter_ = 0
+        self.loss_ = float("nan")

@@ -58,19 +58,11 @@ def threads_per_fit() -> int:
     return max(1, min(default_threads(), (usable - 2) // max(1, expected_fits)))
 
 
-def fit_predict_stats(sample: np.ndarray, control: np.ndarray, threshold: float, threads: int | None = None):
-    """``fit_predict`` plus what the fit did: (mask, {"n_iter", "fast_path", "seconds", "threads"})."""
-    import time
+MLP_KW = dict(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
 
-    if threads:
-        from .fastmlp import load_host_lib
 
-        load_host_lib().fm_set_threads(int(threads))
-    t0 = time.perf_counter()
-    import warnings
-
-    from .fastmlp import FastMLPClassifier  # scikit-learn's MLPClassifier with a fused, bit-identical loss/gradient
-
+def training_set(control: np.ndarray, threshold: float):
+    """The training set of ``detect_anomalies`` (``anomaly_detector.py:61-88``), rebuilt exactly as the reference does."""
     rng = np.random.default_rng(seed=1)
     n_rand, n_ctrl = 10_000, len(control)
     base = rng.uniform(0, 100, n_rand)
@@ -84,13 +76,51 @@ def fit_predict_stats(sample: np.ndarray, control: np.ndarray, threshold: float,
     # the reference passes the labels as a Python list ([0] * n + [1] * n); the same labels as an array spare
     # scikit-learn's input validation the element-wise conversion (several ms per fit) and change nothing else
     y = np.repeat(np.array([0, 1]), n_rand + n_ctrl)
-    clf = FastMLPClassifier(solver="lbfgs", alpha=1e-5, hidden_layer_sizes=(5, 2), random_state=1, max_iter=1000)
+    return X, y
+
+
+def fit_predict_stats(sample: np.ndarray, control: np.ndarray, threshold: float, threads: int | None = None,
+                      defer_checks: bool = False):
+    """``fit_predict`` plus what the fit did: (mask, {"n_iter", "fast_path", "seconds", "threads"}).  With
+    ``defer_checks`` the fit does not compare itself with scikit-learn's evaluation; the points and fused results to
+    compare are returned as ``stats["checks"]`` (see ``check_points``)."""
+    import time
+
+    if threads:
+        from .fastmlp import load_host_lib
+
+        load_host_lib().fm_set_threads(int(threads))
+    t0 = time.perf_counter()
+    import warnings
+
+    from .fastmlp import FastMLPClassifier  # scikit-learn's MLPClassifier with a fused, bit-identical loss/gradient
+
+    X, y = training_set(control, threshold)
+    clf = FastMLPClassifier(**MLP_KW)
+    clf.defer_checks = bool(defer_checks)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")  # ConvergenceWarning, as the reference silences it (utils/config.py:79-83)
         clf.fit(X, y)
     mask = clf.predict(np.array([control, sample]).T) == 1
-    return mask, {"n_iter": int(getattr(clf, "n_iter_", -1)), "fast_path": bool(getattr(clf, "fast_path_used_", False)),
-                  "seconds": time.perf_counter() - t0, "threads": int(threads or 0)}
+    stats = {"n_iter": int(getattr(clf, "n_iter_", -1)), "fast_path": bool(getattr(clf, "fast_path_used_", False)),
+             "seconds": time.perf_counter() - t0, "threads": int(threads or 0)}
+    if defer_checks:
+        stats["checks"] = clf.deferred_checks_ if clf.fast_path_used_ else []
+    return mask, stats
+
+
+def check_points(control: np.ndarray, threshold: float, points) -> list:
+    """scikit-learn's own loss and gradient at ``points`` (packed parameter vectors; ``None`` = the initial ones) of
+    the model ``fit_predict_stats`` fits for this control profile and threshold: [(packed, loss, grad), ...]."""
+    import warnings
+
+    from .fastmlp import ProbeMLPClassifier
+
+    X, y = training_set(control, threshold)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        probe = ProbeMLPClassifier(points=list(points), **MLP_KW).fit(X, y)
+    return probe.points_
 
 
 def workers() -> int:
@@ -134,7 +164,10 @@ def _worker_main() -> None:
         except EOFError:
             return
         try:
-            _send(stdout, ("ok", fit_predict_stats(*req)))
+            if req[0] == "check":
+                _send(stdout, ("ok", check_points(*req[1:])))
+            else:
+                _send(stdout, ("ok", fit_predict_stats(*req[1:])))
         except BaseException as exc:  # noqa: BLE001 - reported to the parent
             _send(stdout, ("error", repr(exc)))
 
@@ -172,29 +205,95 @@ class _Worker:
 
 
 class _Pool:
+    """n worker interpreters.  While fits with deferred self-checks are in flight (``submit(defer=True)``), up to three
+    of the workers are kept free of fits so that scikit-learn's loss / gradient at the first and the last point of
+    those fits is evaluated beside them: the fit's two self-checks leave its critical path.  Without such fits every
+    worker takes fits."""
+
     def __init__(self, n: int):
         self.n = n
-        self.idle: queue.Queue = queue.Queue()
         self.all = [_Worker() for _ in range(n)]  # start every interpreter now: their imports run concurrently
-        for w in self.all:
-            self.idle.put(w)
+        self.free = list(self.all)
+        self.cv = threading.Condition()
+        self.n_checkers = 3 if n >= 9 else (2 if n >= 6 else 0)
+        self.deferred_in_flight = 0
         self.threads = ThreadPoolExecutor(max_workers=n, thread_name_prefix="dj-mlp")
-        self.lock = threading.Lock()
+        self.check_threads = ThreadPoolExecutor(max_workers=max(1, self.n_checkers), thread_name_prefix="dj-mlp-check")
 
-    def _run(self, args):
-        w = self.idle.get()
+    def _acquire(self, for_check: bool) -> _Worker:
+        with self.cv:
+            while True:
+                reserve = 0 if for_check or self.deferred_in_flight == 0 else self.n_checkers
+                if len(self.free) > reserve:
+                    return self.free.pop()
+                self.cv.wait()
+
+    def _release(self, w: _Worker) -> None:
+        with self.cv:
+            self.free.append(w)
+            self.cv.notify_all()
+
+    def _check(self, control, threshold, points):
+        w = self._acquire(True)
         try:
-            mask, stats = w.call(args)
+            return w.call(("check", control, threshold, points))
         finally:
-            self.idle.put(w)
+            self._release(w)
+
+    def _run(self, args, verdict: Future | None):
+        first = None
+        if verdict is not None:  # scikit-learn's evaluation of the initial point starts beside the fit
+            first = self.check_threads.submit(self._check, args[1], args[2], [None])
+        w = self._acquire(False)
+        try:
+            mask, stats = w.call(("fit",) + args + (verdict is not None,))
+        except BaseException as exc:
+            if verdict is not None:
+                self._deferred_done()
+                verdict.set_exception(exc)
+            raise
+        finally:
+            self._release(w)
+        checks = stats.pop("checks", None)
         _note(stats)
+        if verdict is not None:
+            verdict.add_done_callback(lambda _v: self._deferred_done())
+            if not stats.get("fast_path"):
+                verdict.set_result(True)  # the fit ran on scikit-learn's own evaluation: nothing to compare
+            else:
+                last = self.check_threads.submit(self._check, args[1], args[2], [checks[1][0]])
+
+                def settle(_done, first=first, last=last, checks=checks):
+                    try:
+                        from .fastmlp import _same_bits
+
+                        ref = [first.result()[0], last.result()[0]]
+                        ok = all(np.array_equal(r[0].view(np.uint64), c[0].view(np.uint64))
+                                 and _same_bits((r[1], r[2]), (c[1], c[2])) for r, c in zip(ref, checks))
+                        verdict.set_result(bool(ok))
+                    except BaseException as exc:  # noqa: BLE001
+                        verdict.set_exception(exc)
+
+                last.add_done_callback(settle)
         return mask
 
-    def submit(self, args) -> Future:
-        return self.threads.submit(self._run, args)
+    def _deferred_done(self) -> None:
+        with self.cv:
+            self.deferred_in_flight -= 1
+            self.cv.notify_all()
+
+    def submit(self, args, defer: bool = False) -> Future:
+        verdict: Future | None = Future() if (defer and self.n_checkers) else None
+        if verdict is not None:
+            with self.cv:
+                self.deferred_in_flight += 1
+        fut = self.threads.submit(self._run, args, verdict)
+        fut.verdict = verdict
+        return fut
 
     def close(self):
         self.threads.shutdown(wait=False, cancel_futures=True)
+        self.check_threads.shutdown(wait=False, cancel_futures=True)
         for w in self.all:
             w.close()
 
@@ -209,12 +308,20 @@ def _shutdown() -> None:
         _pool = None
 
 
-def submit(sample: np.ndarray, control: np.ndarray, threshold: float) -> Future:
-    """Start one fit; ``.result()`` gives the boolean candidate mask."""
+#: cleared when a deferred comparison fails on this host: fits then check themselves inline again (and fall back to
+#: scikit-learn's evaluation by themselves)
+deferred_checks_ok = True
+
+
+def submit(sample: np.ndarray, control: np.ndarray, threshold: float, defer_checks: bool = False) -> Future:
+    """Start one fit; ``.result()`` gives the boolean candidate mask.  With ``defer_checks`` (and a pool with checker
+    workers) the fit's comparisons with scikit-learn's own evaluation run in other workers and the caller MUST call
+    ``verified(future)`` before it lets a result depend on the mask for good; False means: redo without deferral."""
     global _pool
     n = workers()
     if n == 0:
         fut: Future = Future()
+        fut.verdict = None
         try:
             mask, stats = fit_predict_stats(sample, control, threshold, threads_per_fit())
             _note(stats)
@@ -227,7 +334,21 @@ def submit(sample: np.ndarray, control: np.ndarray, threshold: float) -> Future:
         _pool = _Pool(n)
         atexit.register(_shutdown)
     return _pool.submit((np.ascontiguousarray(sample, dtype=np.float64),
-                         np.ascontiguousarray(control, dtype=np.float64), float(threshold), threads_per_fit()))
+                         np.ascontiguousarray(control, dtype=np.float64), float(threshold), threads_per_fit()),
+                        defer=defer_checks and deferred_checks_ok)
+
+
+def verified(fut: Future) -> bool:
+    """Outcome of the deferred comparisons of one fit (True when nothing was deferred).  Waits for them."""
+    global deferred_checks_ok
+    fut.result()
+    verdict = getattr(fut, "verdict", None)
+    if verdict is None:
+        return True
+    ok = bool(verdict.result())
+    if not ok:
+        deferred_checks_ok = False
+    return ok
 
 
 def warm_up() -> None:

@@ -110,7 +110,7 @@ def run_device(sample: engine.EncodedReads, control: engine.EncodedReads, sequen
             sample.validate()
             control.validate()
         return distributed.run_device_sharded(sample, control, sequence, knockin, comm, gpos, fetch_labels)
-    return _back(_front(sample, control, sequence, knockin, order, reencode), fetch_labels)
+    return _back(_front(sample, control, sequence, knockin, order, reencode, defer_checks=True), fetch_labels)
 
 
 @dataclass
@@ -126,6 +126,7 @@ class _InFlight:
     finish_loci: object
     timings: dict
     t_submit: float
+    redo_loci: object = None  # the selection once more with the fits checking themselves (a deferred check failed)
 
 
 _SIDE: dict = {}
@@ -138,7 +139,7 @@ def _side_stream() -> torch.cuda.Stream:
     return _SIDE[dev]
 
 
-def _front(sample, control, sequence, knockin, order, reencode) -> _InFlight:
+def _front(sample, control, sequence, knockin, order, reencode, defer_checks: bool = False) -> _InFlight:
     """encode -> histograms -> (QNAME order on the device) -> counts -> MLP fits SUBMITTED.  Returns without waiting
     for the fits."""
     timings: dict = {}
@@ -168,19 +169,41 @@ def _front(sample, control, sequence, knockin, order, reencode) -> _InFlight:
         count_c = engine.counts_from_histogram(hist_c)
         norm_s = engine.normalize_indels(count_s)
         norm_c = engine.normalize_indels(count_c)
-        finish = engine.begin_select_mutation_loci(hist_s, sample.strand_host, sequence, norm_s, norm_c, knockin)
-    return _InFlight(sample, control, knockin, order, rows, finish, timings, time.perf_counter())
+        # one sample at a time: the fits' comparisons with scikit-learn's own evaluation run beside them in other
+        # worker processes and are collected at the end of _back (several samples in flight keep every worker busy
+        # with fits, there is nothing to gain)
+        finish = engine.begin_select_mutation_loci(hist_s, sample.strand_host, sequence, norm_s, norm_c, knockin,
+                                                   defer_checks=defer_checks)
+        redo = lambda: engine.select_mutation_loci(hist_s, sample.strand_host, sequence, norm_s, norm_c, knockin)  # noqa: E731
+    return _InFlight(sample, control, knockin, order, rows, finish, timings, time.perf_counter(), redo)
 
 
 def _back(st: _InFlight, fetch_labels: bool = True) -> HotPathResult:
     """wait for the fits -> loci -> 3-mer scores -> score rows -> clustering -> labels."""
+    timings = st.timings
+    tm = _Timer(timings)
+    with tm.host("loci_host_ms"):
+        loci = st.finish_loci()
+    timings["loci_wait_ms"] = (time.perf_counter() - st.t_submit) * 1e3
+    res = _after_loci(st, loci, fetch_labels)
+    verify = getattr(st.finish_loci, "verify", None)
+    if verify is not None:
+        with tm.host("mlp_verify_wait_ms"):
+            ok = verify()
+        if not ok:  # the fused MLP evaluation is not scikit-learn's on this host: the selection again, self-checking
+            with tm.host("loci_host_ms"):
+                loci2 = st.redo_loci()
+            if loci2 != loci:
+                res = _after_loci(st, loci2, fetch_labels)
+    _finish(timings)
+    return res
+
+
+def _after_loci(st: _InFlight, loci, fetch_labels: bool) -> HotPathResult:
     dev = engine.require_cuda()
     sample, control, knockin, timings = st.sample, st.control, st.knockin, st.timings
     tm = _Timer(timings)
     order, rows = st.order, st.rows
-    with tm.host("loci_host_ms"):
-        loci = st.finish_loci()
-    timings["loci_wait_ms"] = (time.perf_counter() - st.t_submit) * 1e3
     with tm.host("order_host_ms"):
         if rows is not None:
             order = rows.cpu().numpy()
@@ -189,7 +212,6 @@ def _back(st: _InFlight, fetch_labels: bool = True) -> HotPathResult:
     n = sample.n_reads
     if all(not m for m in loci) or n < 5:
         labels = np.ones(n, dtype=np.int32) if fetch_labels else None
-        _finish(timings)
         return HotPathResult(labels, order, [n], [100.0], loci, None, timings)
     with tm.host("score_ms"):
         model = engine.build_kmer_model(sample, rows, control, loci, knockin)
@@ -204,7 +226,6 @@ def _back(st: _InFlight, fetch_labels: bool = True) -> HotPathResult:
         labels = labels_d.cpu().numpy() if fetch_labels else None
     sizes = info["cluster_sizes"]
     pct = [round(s / n * 100, 3) for s in sizes]
-    _finish(timings)
     timings.update({"n_points": info["n_points"], "n_cols": model.n_cols})
     return HotPathResult(labels, order, sizes, pct, loci, model, timings)
 

@@ -238,3 +238,58 @@ def test_avx512_passes_return_the_avx2_bits():
                     assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (n, trial)
     finally:
         lib.fm_set_avx512(1)
+
+
+def test_deferred_checks_leave_the_fit_and_the_verdict_unchanged():
+    """defer_checks: the fit does not call scikit-learn's evaluation itself; ProbeMLPClassifier (scikit-learn's own
+    _loss_grad_lbfgs after scikit-learn's own initialisation) returns the same bits at the first and the last
+    evaluated point as the fused evaluation recorded, and the fitted parameters are those of the self-checking fit."""
+    X, y, _ = training_set(700, 3)
+    y = np.asarray(y)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = fastmlp.FastMLPClassifier(**KW)
+        a.defer_checks = True
+        a.fit(X, y)
+        b = fastmlp.FastMLPClassifier(**KW).fit(X, y)
+        assert a.fast_path_used_ and len(a.deferred_checks_) == 2
+        assert all(np.array_equal(p.view(np.uint64), q.view(np.uint64)) for p, q in zip(a.coefs_ + a.intercepts_,
+                                                                                        b.coefs_ + b.intercepts_))
+        probe = fastmlp.ProbeMLPClassifier(points=[None, a.deferred_checks_[1][0]], **KW).fit(X, y)
+    for (p0, l0, g0), (p1, l1, g1) in zip(a.deferred_checks_, probe.points_):
+        assert np.array_equal(p0.view(np.uint64), p1.view(np.uint64))
+        assert fastmlp._same_bits((l0, g0), (l1, g1))
+    # a wrong fused value is caught by the comparison
+    assert not fastmlp._same_bits((a.deferred_checks_[1][1] + 1e-16 * abs(a.deferred_checks_[1][1]) + 5e-324,
+                                   a.deferred_checks_[1][2]), (probe.points_[1][1], probe.points_[1][2]))
+
+
+def test_pool_defers_checks_to_other_workers(monkeypatch):
+    """mlp_pool.submit(defer_checks=True): same masks as the self-checking fits, verdict True; a tampered fused result
+    gives verdict False and switches deferral off for the process."""
+    from dajin2_b200 import mlp_pool
+
+    monkeypatch.setenv("DAJIN2_B200_MLP_WORKERS", "6")
+    g = np.random.default_rng(5)
+    control = np.abs(g.normal(0.5, 0.3, 600))
+    sample = control.copy()
+    sample[[100, 200]] = [30.0, 12.0]
+    plain = [mlp_pool.submit(sample, control, th) for th in (0.1, 0.2)]
+    deferred = [mlp_pool.submit(sample, control, th, defer_checks=True) for th in (0.1, 0.2)]
+    for p, d in zip(plain, deferred):
+        assert np.array_equal(p.result(), d.result())
+        assert mlp_pool.verified(p) and mlp_pool.verified(d)
+        assert d.verdict is not None and p.verdict is None
+    assert mlp_pool.deferred_checks_ok
+    real = fastmlp._same_bits
+    try:
+        fastmlp._same_bits = lambda ref, got: False
+        bad = mlp_pool.submit(sample, control, 0.1, defer_checks=True)
+        assert not mlp_pool.verified(bad)
+        assert not mlp_pool.deferred_checks_ok
+        again = mlp_pool.submit(sample, control, 0.1, defer_checks=True)  # not deferred any more
+        assert again.verdict is None and np.array_equal(again.result(), plain[0].result())
+    finally:
+        fastmlp._same_bits = real
+        mlp_pool.deferred_checks_ok = True
+        mlp_pool._shutdown()
