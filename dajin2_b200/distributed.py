@@ -203,7 +203,7 @@ class ShardRun:
         return torch.cat([hist, tail])
 
     # rank 0 between phase 1 and 2
-    def select_loci(self, reduced, while_waiting=None) -> list[set[str]]:
+    def select_loci(self, reduced, while_waiting=None, defer_checks: bool = False) -> list[set[str]]:
         eng = self.engine
         L = self.sample.n_loci
         host = reduced.cpu().numpy()
@@ -212,8 +212,13 @@ class ShardRun:
         hist_c = self.control.histogram()
         norm_s = eng.normalize_indels(eng.counts_from_histogram(hist_s))
         norm_c = eng.normalize_indels(eng.counts_from_histogram(hist_c))
-        return eng.select_mutation_loci(hist_s, (n_plus, n_total - n_plus), self.sequence, norm_s, norm_c, self.knockin,
-                                        while_waiting=while_waiting)
+        finish = eng.begin_select_mutation_loci(hist_s, (n_plus, n_total - n_plus), self.sequence, norm_s, norm_c,
+                                                self.knockin, defer_checks=defer_checks)
+        if while_waiting is not None:
+            while_waiting()
+        loci = finish()
+        self.verify_loci = finish.verify  # deferred self-checks of the fits (mlp_pool): True when nothing was deferred
+        return loci
 
     # phase 2 -> all-gather of 3-mer payloads
     def count_kmers(self, reduced, loci_t: list[set[str]]):
@@ -275,7 +280,7 @@ class ShardRun:
 
 
 def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, gpos=None,
-                       fetch_labels: bool = True):
+                       fetch_labels: bool = True, defer_checks: bool = True):
     """Drive one shard through the phases with real collectives.  Returns a ``pipeline.HotPathResult`` whose labels
     refer to the local reads in global order (``order`` = the local read index of each label).  Without ``gpos`` the
     global label order (QNAME order over all shards) is established here, on every rank while rank 0 waits for the
@@ -308,7 +313,9 @@ def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, g
 
     mask_t = torch.zeros(sample.n_loci, dtype=torch.uint8, device=comm.device)
     if comm.rank == 0:
-        loci_sel = run.select_loci(reduced, while_waiting=positions)
+        # the fits' comparisons with scikit-learn's own evaluation run beside them; their verdict is collected (and
+        # broadcast) at the end of the step, see below
+        loci_sel = run.select_loci(reduced, while_waiting=positions, defer_checks=defer_checks)
         mask_t.copy_(torch.from_numpy(engine.loci_to_mask(loci_sel)))
     else:
         positions()
@@ -331,6 +338,14 @@ def run_device_sharded(sample, control, sequence, knockin, comm: Communicator, g
     mark("points_allgather_ms")
     labels_d, info = run.cluster(gpos_all, point_all)
     mark("cluster_ms")
+    if defer_checks:
+        verdict = torch.ones(1, dtype=torch.uint8, device=comm.device)
+        if comm.rank == 0 and not run.verify_loci():
+            verdict.zero_()
+        if int(comm.broadcast_tensor(verdict).item()) == 0:
+            # the fused MLP evaluation is not scikit-learn's on rank 0's host: the whole step again, fits self-checking
+            return run_device_sharded(sample, control, sequence, knockin, comm, gpos, fetch_labels, defer_checks=False)
+        mark("mlp_verify_ms")
     labels = labels_d.cpu().numpy() if fetch_labels else None
     sizes_c = info["cluster_sizes"]
     pct = [round(s / n_total * 100, 3) for s in sizes_c]

@@ -230,6 +230,18 @@ def _after_loci(st: _InFlight, loci, fetch_labels: bool) -> HotPathResult:
     return HotPathResult(labels, order, sizes, pct, loci, model, timings)
 
 
+def freeze_startup_objects() -> None:
+    """Move everything allocated so far to the garbage collector's permanent generation (``gc.freeze``).  A process
+    that has imported torch, scikit-learn and scipy holds ~10^6 long-lived objects; every full collection walks them
+    (≈ 60 ms on a B200 host, triggered every few samples by the containers a sample allocates), in the middle of a
+    sample.  Call once after start-up (``plugin.install(freeze_gc=True)`` does); later allocations are collected as
+    usual."""
+    import gc
+
+    gc.collect()
+    gc.freeze()
+
+
 def run_many(samples, control, sequence: str, knockin: set[int] | None = None, depth: int = 4,
              fetch_labels: bool = True, on_result=None) -> list:
     """Several samples against one control, software-pipelined (the reference's batch mode runs samples side by side

@@ -86,8 +86,13 @@ _PATCHES = [
 _saved: list[tuple] = []
 
 
-def install(strict: bool = False) -> list[str]:
-    """Patch the reference in place; returns the list of ``module.attribute`` names that were rebound."""
+def install(strict: bool = False, freeze_gc: bool = False) -> list[str]:
+    """Patch the reference in place; returns the list of ``module.attribute`` names that were rebound.
+    ``freeze_gc``: also ``pipeline.freeze_startup_objects()`` (no 60 ms full-collection pauses inside samples)."""
+    if freeze_gc:
+        from .pipeline import freeze_startup_objects
+
+        freeze_startup_objects()
     done = []
     for mod_name, attr, repl in _PATCHES:
         try:
