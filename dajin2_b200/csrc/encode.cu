@@ -338,7 +338,7 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
 
             // ---- ranks: a plain unit closes sixteen tokens; the chunks of the other units are compacted over the
             //      lanes and counted (the same compaction translates them further down) ------------------------------
-            uint32_t plain_mask[kU], slow_mask[kU], cnt[kU];
+            uint32_t slow_mask[kU], cnt[kU];
             uint32_t zz_first = 0;
             int n_pieces = 0;
             int per_unit = 3;  // pieces per slow unit in this trip: 3 thirds or 2 halves
@@ -349,7 +349,6 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
 #pragma unroll
                 for (int h = 0; h < kU; ++h) {
                     const bool p = plain[h] && !force;
-                    plain_mask[h] = __ballot_sync(0xffffffffu, p);
                     slow_mask[h] = __ballot_sync(0xffffffffu, !p && !dead[h]);
                     if (!p && !dead[h]) list[n_slow + __popc(slow_mask[h] & lanes_below)] = (uint8_t)(h * 32 + lane);
                     n_slow += __popc(slow_mask[h]);
@@ -396,10 +395,10 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
                 // it shares with its neighbours: such a trip goes through the slow path as a whole (the unit that holds
                 // the row's end has no neighbour behind it)
                 if (force || !__any_sync(0xffffffffu, small)) break;
-                bool any_plain = false;
+                bool mine_plain = false;
 #pragma unroll
-                for (int h = 0; h < kU; ++h) any_plain = any_plain || plain_mask[h] != 0u;
-                if (!any_plain) break;
+                for (int h = 0; h < kU; ++h) mine_plain = mine_plain || plain[h];
+                if (!__any_sync(0xffffffffu, mine_plain)) break;
                 force = true;
             }
 
@@ -449,38 +448,40 @@ encode_unit_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__
 
             // ---- plain units: sixteen code bytes as whole words (the word shared with a plain neighbour is merged
             //      through a shuffle; a word shared with another unit is overwritten by the slow path afterwards) -------
-            uint32_t last_spill = 0;
-            bool last_plain = false;
+            uint32_t last_spill = 0;  // spill word of lane 31 of the previous row of units (zero unless it is plain)
 #pragma unroll
             for (int h = 0; h < kU; ++h) {
                 const bool p = plain[h] && !force;
                 const uint32_t o = t0 + excl[h];
                 uint32_t rot[5];
                 dju::rotate_codes(cw[h], o & 3u, rot);
-                const uint32_t spill = __shfl_up_sync(0xffffffffu, rot[4], 1);
-                if (lane == 0) {
-                    if (h == 0) rot[0] |= *reinterpret_cast<const uint32_t *>(stage + (t0 & ~3u)) & ((1u << (8u * (t0 & 3u))) - 1u);
-                    else if (last_plain) rot[0] |= last_spill;
-                } else if ((plain_mask[h] >> (lane - 1)) & 1u) {
-                    rot[0] |= spill;
+                const uint32_t spill_out = p ? rot[4] : 0u;
+                // the bytes in front of this unit inside its first word: the spill of the plain unit in front of it
+                // (lane - 1, or lane 31 of the previous row), the codes carried over from the previous trip for the
+                // trip's first unit, nothing behind a unit of the slow path (it writes its own bytes later)
+                uint32_t before = __shfl_up_sync(0xffffffffu, spill_out, 1);
+                if (h == 0) {
+                    const uint32_t carried =
+                        *reinterpret_cast<const uint32_t *>(stage + (t0 & ~3u)) & ((1u << (8u * (t0 & 3u))) - 1u);
+                    if (lane == 0) before = carried;
+                } else if (lane == 0) {
+                    before = last_spill;
                 }
-                const bool next_plain = lane < 31 ? ((plain_mask[h] >> (lane + 1)) & 1u) != 0u
-                                                  : (h + 1 < kU ? (plain_mask[(h + 1) % kU] & 1u) != 0u : false);
+                uint32_t *dst = reinterpret_cast<uint32_t *>(stage + (o & ~3u));
+                // the spill word first: if the next unit is plain too, its first word (the same word, merged with this
+                // spill) is stored behind the __syncwarp and stands
+                if (p) dst[4] = rot[4];
+                __syncwarp();
                 if (p) {
-                    uint32_t *dst = reinterpret_cast<uint32_t *>(stage + (o & ~3u));
-                    dst[0] = rot[0];
+                    dst[0] = rot[0] | before;
                     dst[1] = rot[1];
                     dst[2] = rot[2];
                     dst[3] = rot[3];
-                    if (!next_plain) dst[4] = rot[4];
                     mism += n_del[h];
                 } else if (!dead[h]) {
                     exclbuf[h * 32 + lane] = (uint16_t)excl[h];
                 }
-                if (h + 1 < kU) {
-                    last_spill = __shfl_sync(0xffffffffu, rot[4], 31);
-                    last_plain = (plain_mask[h] >> 31) != 0u;
-                }
+                if (h + 1 < kU) last_spill = __shfl_sync(0xffffffffu, spill_out, 31);
             }
             __syncwarp();
 

@@ -323,7 +323,16 @@ def submit(sample: np.ndarray, control: np.ndarray, threshold: float, defer_chec
         fut: Future = Future()
         fut.verdict = None
         try:
-            mask, stats = fit_predict_stats(sample, control, threshold, threads_per_fit())
+            # as the pool's workers (and the reference, main.py:5-9): BLAS pinned to one thread for the fit, whose
+            # result depends on the summation order
+            try:
+                from threadpoolctl import threadpool_limits
+            except ImportError:  # the environment variables of the process decide
+                import contextlib
+
+                threadpool_limits = lambda **kw: contextlib.nullcontext()  # noqa: E731
+            with threadpool_limits(limits=1, user_api="blas"):
+                mask, stats = fit_predict_stats(sample, control, threshold, threads_per_fit())
             _note(stats)
             fut.set_result(mask)
         except BaseException as exc:  # noqa: BLE001 - handed to the caller through the future

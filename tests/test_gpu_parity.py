@@ -572,6 +572,35 @@ def test_sv_scan_edge_cases():
             assert got == [orc.index_and_sv_size(r, name, loci) for r in rows], (L, name)
 
 
+def test_deferred_mlp_checks_and_their_failure_path():
+    """pipeline.run_device defers the fits' comparisons with scikit-learn's evaluation to other pool workers and waits
+    for the verdicts at the end; when a verdict is False (forced here) the selection is repeated with self-checking
+    fits and the step still returns the reference's result; deferral is then off for the process."""
+    from dajin2_b200 import engine, fastmlp, mlp_pool, pipeline
+    from dajin2_b200.ingest import pack_rows
+
+    a = load_case("point_L900_N1500")[0]["control"]
+    sequence = a["sequence"]
+    L = len(sequence)
+    host_s = pack_rows(a["sample"]["rows"], a["sample"]["strands"], a["sample"]["qnames"])
+    host_c = pack_rows(a["control"]["rows"], a["control"]["strands"], a["control"]["qnames"])
+    es, ec = engine.EncodedReads(host_s, L), engine.EncodedReads(host_c, L)
+    mlp_pool.deferred_checks_ok = True
+    want = pipeline.run_device(es, ec, sequence)
+    deferred = mlp_pool._pool is not None and mlp_pool._pool.n_checkers > 0
+    assert "mlp_verify_wait_ms" in want.timings
+    real = fastmlp._same_bits
+    try:
+        fastmlp._same_bits = lambda ref, got: False  # the parent's comparison of the deferred checks
+        got = pipeline.run_device(es, ec, sequence)
+        assert mlp_pool.deferred_checks_ok == (not deferred)
+    finally:
+        fastmlp._same_bits = real
+        mlp_pool.deferred_checks_ok = True
+    assert got.mutation_loci == want.mutation_loci and got.labels.tolist() == want.labels.tolist()
+    assert got.cluster_sizes == want.cluster_sizes and got.percentages == want.percentages
+
+
 def test_consensus_n_filter_on_files(tmp_path):
     """extract_path_n_filtered_control (consensus_mutation_analyzer.py:75-102): the file the real reference wrote."""
     import hashlib
