@@ -166,6 +166,8 @@ def load_host_lib():
         lib.fm_set_avx512(int(os.environ.get("DAJIN2_B200_MLP_AVX512", "1") != "0"))
         lib.fm_backward_packed.argtypes = [vp, i64, i64, i64, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, cd, cd, vp]
         lib.fm_backward_packed.restype = ci
+        lib.fm_eval.argtypes = [vp, vp, vp, vp]
+        lib.fm_eval.restype = cd
         lib.fm_uniform_choice.argtypes = [i64, vp, ci, vp]
         lib.fm_uniform_choice.restype = ci
         lib.fm_uniform_cumsum_term.argtypes = [i64, i64]
@@ -191,6 +193,70 @@ def load_host_lib():
         lib.fm_pairwise_sum.restype = ctypes.c_double
         _lib = lib
     return _lib
+
+
+class _EvalCtx(ctypes.Structure):  # FmEvalCtx of hostc/fastmlp.c
+    _fields_ = [("X", ctypes.c_void_p), ("xs_row", ctypes.c_int64), ("xs_col", ctypes.c_int64), ("n", ctypes.c_int64),
+                ("n_in", ctypes.c_int32), ("h1", ctypes.c_int32), ("h2", ctypes.c_int32), ("vec", ctypes.c_int32),
+                ("y", ctypes.c_void_p), ("a1", ctypes.c_void_p), ("a2", ctypes.c_void_p), ("a3", ctypes.c_void_p),
+                ("d3", ctypes.c_void_p), ("d2", ctypes.c_void_p), ("d1", ctypes.c_void_p), ("terms", ctypes.c_void_p),
+                ("alpha", ctypes.c_double), ("dgemv", ctypes.c_void_p), ("ddot", ctypes.c_void_p)]
+
+
+_BLAS: tuple | None | bool = False  # False: not looked for yet; None: not usable; (lib, dgemv address, ddot address)
+
+
+def _numpy_blas():
+    """Entry points of the OpenBLAS instance numpy itself is linked against (``cblas_dgemv`` / ``cblas_ddot`` under the
+    names its build exports), for ``fm_eval``: the two matrix-vector products and the three dot products of one
+    evaluation are then made by the same code numpy would run, with the arguments numpy's ``matmul`` / ``dot`` pass.
+    Used only if, on random matrices of the shapes of a fit, both products and the dot return numpy's bits; ``None``
+    otherwise (the evaluation then goes through numpy as before).  ``DAJIN2_B200_MLP_ONECALL=0`` switches it off."""
+    global _BLAS
+    if _BLAS is not False:
+        return _BLAS
+    _BLAS = None
+    if os.environ.get("DAJIN2_B200_MLP_ONECALL", "1") == "0":
+        return None
+    try:
+        from threadpoolctl import threadpool_info
+
+        paths = [i["filepath"] for i in threadpool_info() if i.get("user_api") == "blas" and "numpy" in i["filepath"]]
+        if len(paths) != 1:
+            return None
+        lib = ctypes.CDLL(paths[0])
+        i64, dbl, vp, ci = ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_int
+        for prefix, suffix in (("scipy_", "64_"), ("", "64_"), ("scipy_", ""), ("", "")):
+            if hasattr(lib, f"{prefix}cblas_dgemv{suffix}") and hasattr(lib, f"{prefix}cblas_ddot{suffix}"):
+                break
+        else:
+            return None
+        if suffix != "64_":  # fm_eval passes 64-bit integers (numpy's wheels are built against the ILP64 interface)
+            return None
+        dgemv, ddot = getattr(lib, f"{prefix}cblas_dgemv{suffix}"), getattr(lib, f"{prefix}cblas_ddot{suffix}")
+        dgemv.argtypes = [ci, ci, i64, i64, dbl, vp, i64, vp, i64, dbl, vp, i64]
+        dgemv.restype = None
+        ddot.argtypes = [i64, vp, i64, vp, i64]
+        ddot.restype = dbl
+        rng = np.random.default_rng(11)
+        for trial in range(24):
+            n, h = int(rng.integers(500, 40_000)), int(rng.integers(2, 7))  # h = 1 takes other routes inside numpy
+            a2 = np.maximum(rng.normal(size=(n, h)), 0) * rng.uniform(0.01, 60)
+            packed = rng.normal(size=64)
+            w3 = packed[7:7 + h].reshape(h, 1)
+            d3 = rng.normal(size=(n, 1)) * 10.0 ** rng.integers(-6, 1)
+            y1, y2 = np.empty((n, 1)), np.empty((h, 1))
+            dgemv(102, 112, h, n, 1.0, a2.ctypes.data, h, w3.ctypes.data, 1, 0.0, y1.ctypes.data, 1)
+            dgemv(101, 112, n, h, 1.0, a2.ctypes.data, h, d3.ctypes.data, 1, 0.0, y2.ctypes.data, 1)
+            sl = packed[3:3 + int(rng.integers(1, 30))]
+            if not (np.array_equal((a2 @ w3).view(np.uint64), y1.view(np.uint64))
+                    and np.array_equal((a2.T @ d3).view(np.uint64), y2.view(np.uint64))
+                    and float(np.dot(sl, sl)) == ddot(sl.shape[0], sl.ctypes.data, 1, sl.ctypes.data, 1)):
+                return None
+        _BLAS = (lib, ctypes.cast(dgemv, vp).value, ctypes.cast(ddot, vp).value)
+    except Exception:  # noqa: BLE001 - anything unexpected: the evaluation keeps going through numpy
+        _BLAS = None
+    return _BLAS
 
 
 def _ptr(a: np.ndarray) -> int:
@@ -259,6 +325,17 @@ class FastMLPClassifier(MLPClassifier):
             fm["vec"] = 2 if (lib.fm_get_avx512() and lib.fm512_vmath_ready()) else int(bool(lib.fm_vmath_ready()))
         fm["a2T"] = fm["a2"].T
         fm["ptr"] = {k: _ptr(fm[k]) for k in ("a1", "a2", "d3", "d2", "d1", "terms", "sum3", "y", "X")}
+        fm["ctx"] = None
+        blas = _numpy_blas()
+        if blas is not None and h2 >= 2:  # one C call per evaluation (fm_eval), the products by numpy's own OpenBLAS
+            fm["a3"] = f(n, 1)
+            ptr = fm["ptr"]
+            fm["ctx"] = _EvalCtx(ptr["X"], X.strides[0] // 8, X.strides[1] // 8, n, n_in, h1, h2, fm["vec"], ptr["y"],
+                                 ptr["a1"], ptr["a2"], _ptr(fm["a3"]), ptr["d3"], ptr["d2"], ptr["d1"], ptr["terms"],
+                                 float(self.alpha), blas[1], blas[2])
+            fm["ctx_ref"] = ctypes.addressof(fm["ctx"])
+            fm["status"] = ctypes.c_int(0)
+            fm["status_ref"] = ctypes.addressof(fm["status"])
         self._fm = fm
 
     def _fast_loss_grad(self, packed, X):
@@ -269,6 +346,14 @@ class FastMLPClassifier(MLPClassifier):
         if X is not fm["X"] or packed.dtype != np.float64 or not packed.flags.c_contiguous or packed.shape[0] != fm["n_par"]:
             raise RuntimeError("unexpected arguments for the fused evaluation")
         pp = _ptr(packed)
+        if fm["ctx"] is not None:
+            if fm["ctx"].vec != fm["vec"]:
+                fm["ctx"].vec = fm["vec"]
+            grad = np.empty(fm["n_par"], dtype=np.float64)
+            loss = np.float64(lib.fm_eval(fm["ctx_ref"], pp, _ptr(grad), fm["status_ref"]))
+            if fm["status"].value != 0:
+                raise RuntimeError("layer too wide for the fused evaluation")
+            return loss, grad
         o_w3, o_b3 = fm["o_w3"], fm["o_b3"]
         if lib.fm_forward_packed(ptr["X"], xs_row, xs_col, n, n_in, h1, h2, pp, ptr["a1"], ptr["a2"]) != 0:
             raise RuntimeError("layer too wide for the fused evaluation")

@@ -537,3 +537,56 @@ int fm_backward_packed(const double *X, int64_t xs_row, int64_t xs_col, int64_t 
 }
 
 double fm_pairwise_sum(const double *a, int64_t n) { return pairwise_sum(a, n); }
+
+/* ---- one call per evaluation ------------------------------------------------------------------------------------
+ * _fast_loss_grad (dajin2_b200/fastmlp.py) made three calls into this file per evaluation and, between them, two
+ * matrix-vector products and three dot products through numpy (numpy -> OpenBLAS): ~70 us of interpreter time around
+ * 0.3 ms of arithmetic.  fm_eval does the same sequence in one call.  The two products and the dots are NOT restated:
+ * they are made by the very OpenBLAS instance numpy is linked against, through its own entry points (cblas_dgemv /
+ * cblas_ddot, handed over as function pointers), with the arguments numpy's matmul / dot pass for these shapes
+ * (numpy/_core/src/umath/matmul.c.src, DOUBLE_gemv: a C-contiguous (n, h) matrix times a column goes out as
+ * ColMajor / Trans with lda = h; its transposed view times a column as RowMajor / Trans with lda = h) -- same code,
+ * same arguments, same bits; fastmlp.py compares both against numpy at load time and keeps the three-call path
+ * otherwise, and every fit still compares its evaluation with scikit-learn's. */
+typedef void (*fm_dgemv_fn)(int order, int trans, int64_t m, int64_t n, double alpha, const double *a, int64_t lda,
+                            const double *x, int64_t incx, double beta, double *y, int64_t incy);
+typedef double (*fm_ddot_fn)(int64_t n, const double *x, int64_t incx, const double *y, int64_t incy);
+
+typedef struct {
+    const double *X;
+    int64_t xs_row, xs_col, n;
+    int32_t n_in, h1, h2, vec;
+    const double *y;
+    double *a1, *a2, *a3, *d3, *d2, *d1, *terms;
+    double alpha;
+    fm_dgemv_fn dgemv;
+    fm_ddot_fn ddot;
+} FmEvalCtx;
+
+/* loss (return value) and packed gradient of MLPClassifier._loss_grad_lbfgs for the 2-hidden-layer logistic model */
+double fm_eval(const FmEvalCtx *c, const double *packed, double *grad, int *status) {
+    const int n_in = c->n_in, h1 = c->h1, h2 = c->h2;
+    const int64_t n = c->n;
+    const int o_w3 = n_in * h1 + h1 * h2, o_b3 = o_w3 + h2 + h1 + h2;
+    *status = fm_forward_packed(c->X, c->xs_row, c->xs_col, n, n_in, h1, h2, packed, c->a1, c->a2);
+    if (*status) return 0.0;
+    /* a3 = a2 @ W3 */
+    c->dgemv(102 /* ColMajor */, 112 /* Trans */, h2, n, 1.0, c->a2, h2, packed + o_w3, 1, 0.0, c->a3, 1);
+    double sum3 = 0.0;
+    double loss = fm_output(c->a3, packed[o_b3], c->y, n, c->d3, c->terms, &sum3, c->vec);
+    /* values = 0; for s in coefs_: values += np.dot(s.ravel(), s.ravel());  loss += (0.5 * alpha) * values / n */
+    double values = 0.0;
+    const int sizes[3] = {n_in * h1, h1 * h2, h2};
+    int lo = 0;
+    for (int k = 0; k < 3; k++) {
+        values += 0.0 + c->ddot(sizes[k], packed + lo, 1, packed + lo, 1); /* numpy: sum = 0.0; sum += cblas_ddot(...) */
+        lo += sizes[k];
+    }
+    loss += (0.5 * c->alpha) * values / (double)n;
+    /* g3_raw = a2.T @ d3 */
+    double g3_raw[FM_MAX_H];
+    c->dgemv(101 /* RowMajor */, 112 /* Trans */, n, h2, 1.0, c->a2, h2, c->d3, 1, 0.0, g3_raw, 1);
+    *status = fm_backward_packed(c->X, c->xs_row, c->xs_col, n, n_in, h1, h2, packed, c->a1, c->a2, c->d3, c->d2, c->d1,
+                                 g3_raw, sum3, c->alpha, grad);
+    return loss;
+}

@@ -293,3 +293,25 @@ def test_pool_defers_checks_to_other_workers(monkeypatch):
         fastmlp._same_bits = real
         mlp_pool.deferred_checks_ok = True
         mlp_pool._shutdown()
+
+
+def test_one_call_evaluation_returns_the_three_call_bits():
+    """fm_eval (one C call per evaluation; the two matrix-vector products and the dots made by numpy's own OpenBLAS
+    through its cblas entry points) is in use here, and a fit through it equals a fit through the three-call path
+    (products through numpy) in every parameter bit and in the number of evaluations."""
+    X, y, _ = training_set(900, 4)
+    y = np.asarray(y)
+    assert fastmlp._numpy_blas() is not None
+    saved = fastmlp._BLAS
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            one = fastmlp.FastMLPClassifier(**KW).fit(X, y)
+            fastmlp._BLAS = None
+            three = fastmlp.FastMLPClassifier(**KW).fit(X, y)
+    finally:
+        fastmlp._BLAS = saved
+    assert one.fast_path_used_ and three.fast_path_used_ and one.n_iter_ == three.n_iter_
+    assert all(np.array_equal(p.view(np.uint64), q.view(np.uint64))
+               for p, q in zip(one.coefs_ + one.intercepts_, three.coefs_ + three.intercepts_))
+    assert float(one.loss_) == float(three.loss_)
