@@ -110,6 +110,10 @@ SIGNATURES = {
     "dj_loci_words": (c_int32, [c_int32]),
     "dj_sv_scan": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_void_p, c_void_p]),
+    "dj_cs_midsv_measure": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                      c_void_p, c_void_p]),
+    "dj_cs_midsv_write": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
 }
 
 _NO_STATUS = {"dj_abi_version", "dj_last_error", "dj_code_pitch", "dj_ckpt_pitch", "dj_encode_ref_smem_bytes",
@@ -120,7 +124,7 @@ KERNELS_PER_CALL = {
     "dj_encode": 1, "dj_encode_v1": 1, "dj_encode_ref": 1, "dj_hist": 2, "dj_window_cosine": 1, "dj_kmer_count": 1, "dj_kmer_export": 1, "dj_annotate": 1,
     "dj_fetch_tokens": 1, "dj_dedup_rows": 1, "dj_dedup_export": 1, "dj_bisect": 1, "dj_assign_rows": 1,
     "dj_silhouette": 2, "dj_cluster_step": 6, "dj_member_counts": 1, "dj_member_locate": 1, "dj_gather_labels": 1,
-    "dj_read_n_features": 1, "dj_sv_scan": 1,
+    "dj_read_n_features": 1, "dj_sv_scan": 1, "dj_cs_midsv_measure": 1, "dj_cs_midsv_write": 1,
 }
 launch_count = 0
 

@@ -1,16 +1,26 @@
-"""Host mirrors of the post-fixes ``generate_midsv`` applies to freshly transformed MIDSV records
-(reference ``preprocess/alignment/midsv_caller.py:88-220``, chained at ``:267-272``): SURVEY.md §8f rank 4, the
-part of it the reference's own tests pin (``tests/src/preprocess/test_midsv_caller.py``).  Same names, arguments
-and in-place effects as the reference's generators — each mutates the dicts it is given and yields them — but a
-call consumes its input and fixes every read in one multi-threaded byte-level pass (``hostc/midsvfix.c``) instead
-of splitting and re-joining ~L tokens per read in the interpreter.  The SAM → MIDSV transformation itself
-(third-party ``midsv.transform``, ``midsv_caller.py:84-85``) is not restated: parity unpinned, see DESIGN.md.
+"""Host mirrors of the alignment stage's seams (reference ``preprocess/alignment/midsv_caller.py``), SURVEY.md §8f
+rank 4.
+
+* ``transform_to_midsv_format(path_sam)`` (``midsv_caller.py:84-85``, the call into third-party ``midsv.transform``):
+  SAM records are read and grouped on the host, the per-read string work -- cs tag (long form) -> MIDSV tokens, split
+  reads joined in position order, inverted pieces in lowercase, gaps / introns / flanks as ``=N`` -- runs on the
+  device (``dj_cs_midsv_measure`` / ``dj_cs_midsv_write``, ``csrc/cstag.cu``) and leaves the text in HBM in the layout
+  ``dj_encode`` takes (``midsv_text_on_device``).  ``midsv`` is absent here: PARITY UNPINNED, the rules are those
+  ``oracle/midsv_transform.py`` states and checks with the reference's own inverse
+  (``utils/midsv_handler.py:158-161``).  There is no CPU fallback.
+* the post-fixes ``generate_midsv`` chains after it (``midsv_caller.py:88-220``, chained at ``:267-272``), the part
+  the reference's own tests pin (``tests/src/preprocess/test_midsv_caller.py``).  Same names, arguments and in-place
+  effects as the reference's generators -- each mutates the dicts it is given and yields them -- but a call consumes
+  its input and fixes every read in one multi-threaded byte-level pass (``hostc/midsvfix.c``) instead of splitting
+  and re-joining ~L tokens per read in the interpreter.
 """
 
 from __future__ import annotations
 
 import os
 from collections.abc import Iterable, Iterator
+from dataclasses import dataclass
+from pathlib import Path
 
 import numpy as np
 
@@ -120,3 +130,133 @@ def postprocess_midsv(midsv_chain: Iterable[dict], sequence: str, best_preset: d
         if qname in best_preset:
             samp["PRESET"] = best_preset[qname]
         yield samp
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SAM (cs tag) -> MIDSV on the device
+# ---------------------------------------------------------------------------------------------------------
+
+CS_OVERLAP, CS_GRAMMAR, CS_TOO_LONG = 1, 2, 4  # row_status bits of dj_cs_midsv_measure
+
+
+@dataclass
+class PackedAlignments:
+    """The alignments of one reference sequence, grouped by read (reads in QNAME order, alignments of a read in POS
+    order) and packed as ``dj_cs_midsv_*`` take them."""
+
+    rname: str
+    ref_len: int
+    cs: np.ndarray  # uint8, 16 bytes of slack after the last tag
+    aln_off: np.ndarray  # int64[A + 1]
+    aln_pos: np.ndarray  # int32[A], 0-based
+    aln_lower: np.ndarray  # uint8[A]
+    read_first: np.ndarray  # int64[R + 1]
+    qnames: list[str]
+    flags: list[int]  # FLAG of each read's first alignment
+
+    @property
+    def n_reads(self) -> int:
+        return len(self.qnames)
+
+
+def read_sam_records(path_sam: str | Path) -> tuple[dict[str, int], list[tuple]]:
+    """``@SQ`` lengths and (QNAME, FLAG, RNAME, POS, cs) of the mapped records of a SAM file.  Like ``midsv``, a
+    mapped record without a long-form ``cs:Z:`` tag is an error (the reference maps with ``cs=True, cs long``,
+    ``preprocess/alignment/mapping.py``)."""
+    sq: dict[str, int] = {}
+    records = []
+    with open(path_sam) as fh:
+        for line in fh:
+            if line.startswith("@"):
+                if line.startswith("@SQ"):
+                    tags = dict(t.split(":", 1) for t in line.rstrip("\n").split("\t")[1:] if ":" in t)
+                    sq[tags["SN"]] = int(tags["LN"])
+                continue
+            f = line.rstrip("\n").split("\t")
+            if len(f) < 11:
+                continue
+            flag = int(f[1])
+            if flag & 4 or f[2] == "*":
+                continue
+            cs = next((t[5:] for t in f[11:] if t.startswith("cs:Z:")), None)
+            if cs is None:
+                raise ValueError(f"{path_sam}: {f[0]} has no cs tag (map with the long-form cs tag)")
+            records.append((f[0], flag, f[2], int(f[3]), cs))
+    return sq, records
+
+
+def pack_alignments(sq: dict[str, int], records: list[tuple]) -> list[PackedAlignments]:
+    """Group the records by reference sequence and read; one ``PackedAlignments`` per reference sequence."""
+    by_rname: dict[str, list[tuple]] = {}
+    for rec in records:
+        by_rname.setdefault(rec[2], []).append(rec)
+    packed = []
+    for rname, recs in by_rname.items():
+        if rname not in sq:
+            raise ValueError(f"no @SQ line for {rname}")
+        recs.sort(key=lambda r: (r[0], r[3]))
+        qnames, flags, read_first, lower = [], [], [], []
+        for k, (qname, flag, _, _, _) in enumerate(recs):
+            if not qnames or qname != qnames[-1]:
+                qnames.append(qname)
+                flags.append(flag)
+                read_first.append(k)
+            lower.append(int(bool(flag & 16) != bool(flags[-1] & 16)))
+        read_first.append(len(recs))
+        tags = [r[4].encode("ascii") for r in recs]
+        lens = np.fromiter(map(len, tags), dtype=np.int64, count=len(tags))
+        aln_off = np.zeros(len(tags) + 1, dtype=np.int64)
+        np.cumsum(lens, out=aln_off[1:])
+        cs = np.zeros(int(aln_off[-1]) + 16, dtype=np.uint8)
+        cs[: int(aln_off[-1])] = np.frombuffer(b"".join(tags), dtype=np.uint8)
+        packed.append(PackedAlignments(rname, int(sq[rname]), cs, aln_off,
+                                       np.array([r[3] - 1 for r in recs], dtype=np.int32),
+                                       np.array(lower, dtype=np.uint8), np.array(read_first, dtype=np.int64),
+                                       qnames, flags))
+    return packed
+
+
+def midsv_text_on_device(pa: PackedAlignments):
+    """MIDSV text of every read of ``pa`` in HBM: (text uint8, row_off int64[R], row_len int32[R], status int32[R]) as
+    device tensors, rows of dropped reads (status != 0: overlapping alignments, not a long-form cs tag, longer than
+    the reference) with ``row_len`` 0.  ``text`` / ``row_off`` / ``row_len`` are what ``dj_encode`` takes."""
+    import torch
+
+    from . import _cabi
+    from .engine import _p, _stream, require_cuda
+    from .ingest import SLACK
+
+    dev = require_cuda()
+    n = pa.n_reads
+    up = [torch.from_numpy(a).to(dev, non_blocking=True) for a in (pa.cs, pa.aln_off, pa.aln_pos, pa.aln_lower,
+                                                                   pa.read_first)]
+    row_len = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    status = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    _cabi.call("dj_cs_midsv_measure", *(_p(t) for t in up), n, pa.ref_len, _p(row_len), _p(status), _stream())
+    span = torch.where(row_len > 0, row_len.to(torch.int64) + 1, torch.zeros((), dtype=torch.int64, device=dev))
+    ends = torch.cumsum(span, 0)
+    row_off = ends - span
+    total = int(ends[-1].item()) if n else 0
+    text = torch.full((total + SLACK,), ord("\n"), dtype=torch.uint8, device=dev)
+    _cabi.call("dj_cs_midsv_write", *(_p(t) for t in up), n, pa.ref_len, _p(row_off), _p(row_len), _p(text), _stream())
+    return text, row_off[:n], row_len[:n], status[:n]
+
+
+def transform_to_midsv_format(path_sam: str | Path) -> list[dict]:
+    """``midsv_caller.py:84-85``: ``midsv.transform(path_sam, qscore=False, keep={"FLAG"})`` -- one dict per read with
+    QNAME, RNAME, MIDSV and FLAG, in QNAME order."""
+    sq, records = read_sam_records(path_sam)
+    out = []
+    for pa in pack_alignments(sq, records):
+        text, row_off, row_len, status = midsv_text_on_device(pa)
+        status_h = status.cpu().numpy()
+        if (status_h & CS_GRAMMAR).any():
+            bad = int(np.flatnonzero(status_h & CS_GRAMMAR)[0])
+            raise ValueError(f"{path_sam}: the cs tag of {pa.qnames[bad]} is not in the long format")
+        buf = text.cpu().numpy().tobytes()
+        for qname, flag, o, m in zip(pa.qnames, pa.flags, row_off.tolist(), row_len.tolist()):
+            if m > 0:
+                out.append({"QNAME": qname, "RNAME": pa.rname, "MIDSV": buf[o : o + m].decode("ascii"), "FLAG": flag})
+    if len({r[2] for r in records}) > 1:  # several reference sequences in one file: back to one QNAME order
+        out.sort(key=lambda d: d["QNAME"])
+    return out

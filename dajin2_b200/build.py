@@ -14,7 +14,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libdajin2_b200.so"
-SOURCES = ["cabi.cu", "encode.cu", "encode_v1.cu", "hist.cu", "kmer.cu", "cluster.cu", "readstat.cu"]
+SOURCES = ["cabi.cu", "encode.cu", "encode_v1.cu", "hist.cu", "kmer.cu", "cluster.cu", "readstat.cu", "cstag.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

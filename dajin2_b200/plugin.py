@@ -83,18 +83,31 @@ _PATCHES = [
     ("DAJIN2.core.preprocess.alignment.midsv_caller", "convert_consecutive_indels", alignment.convert_consecutive_indels),
 ]
 
+# SURVEY.md §8f rank 4, the unpinned part: ``transform_to_midsv_format`` (midsv_caller.py:84-85) wraps third-party
+# ``midsv.transform``, which is not available to hold the device path to.  Rebound only on request
+# (``install(sam_to_midsv=True)`` or DAJIN2_B200_SAM_TO_MIDSV=1): a default install changes nothing whose output the
+# real reference could not confirm.
+_OPT_IN_PATCHES = [
+    ("DAJIN2.core.preprocess.alignment.midsv_caller", "transform_to_midsv_format", alignment.transform_to_midsv_format),
+]
+
 _saved: list[tuple] = []
 
 
-def install(strict: bool = False, freeze_gc: bool = False) -> list[str]:
+def install(strict: bool = False, freeze_gc: bool = False, sam_to_midsv: bool | None = None) -> list[str]:
     """Patch the reference in place; returns the list of ``module.attribute`` names that were rebound.
-    ``freeze_gc``: also ``pipeline.freeze_startup_objects()`` (no 60 ms full-collection pauses inside samples)."""
+    ``freeze_gc``: also ``pipeline.freeze_startup_objects()`` (no 60 ms full-collection pauses inside samples).
+    ``sam_to_midsv``: also rebind ``transform_to_midsv_format`` to the device path (parity unpinned, see above)."""
+    import os
+
     if freeze_gc:
         from .pipeline import freeze_startup_objects
 
         freeze_startup_objects()
+    if sam_to_midsv is None:
+        sam_to_midsv = os.environ.get("DAJIN2_B200_SAM_TO_MIDSV", "0") == "1"
     done = []
-    for mod_name, attr, repl in _PATCHES:
+    for mod_name, attr, repl in _PATCHES + (_OPT_IN_PATCHES if sam_to_midsv else []):
         try:
             mod = importlib.import_module(mod_name)
         except Exception:

@@ -285,6 +285,30 @@ int dj_sv_scan(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, in
                int32_t ckpt_pitch, const uint32_t *del_loci, const uint32_t *ins_loci, int32_t min_size,
                int32_t *records, uint32_t capacity, uint32_t *n_records, void *stream);
 
+/*
+ * SAM alignments (cs tag, long form) -> MIDSV text on the device: the per-read string
+ * work of midsv.transform(path_sam, qscore=False, keep={"FLAG"}) as preprocess/alignment/midsv_caller.py:84-85 calls
+ * it (third-party midsv >= 0.13.1, absent from the reference tree: PARITY UNPINNED; rules as restated in
+ * oracle/midsv_transform.py and checked with the reference's own inverse, utils/midsv_handler.py:158-161).
+ *   cs          the cs tags (without "cs:Z:") back to back; 16-byte aligned, >= 16 readable bytes after the last one
+ *   aln_off     n_alignments + 1 offsets into cs
+ *   aln_pos     0-based reference position of each alignment (POS - 1)
+ *   aln_lower   1: the alignment is on the other strand than the first alignment of its read -> lowercase tokens
+ *   read_first  n_reads + 1: alignments read_first[r] .. read_first[r+1]-1 belong to read r, ordered by position
+ * "=ACG" -> "=A,=C,=G"; "*ag" -> "*AG"; "-ac" -> "-A,-C"; "+ac" joins the next token as "+A|+C|<next>";
+ * "~gt123ag" -> 123 x "=N"; gaps between the alignments of a read and the flanks up to ref_len tokens -> "=N".
+ * dj_cs_midsv_measure: row_len[r] = bytes of read r's MIDSV string, 0 for a dropped read; row_status[r] = 0 or
+ *   1 (two alignments share a reference base) | 2 (not a long-form cs tag) | 4 (longer than ref_len tokens / 2 GB).
+ * dj_cs_midsv_write: writes the string of every read with row_len[r] > 0 at text + row_off[r], followed by '\n'
+ *   (row_len[r] + 1 bytes); the result is the text / row_off / row_len triple dj_encode takes.
+ */
+int dj_cs_midsv_measure(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
+                        const int64_t *read_first, int64_t n_reads, int32_t ref_len, int32_t *row_len,
+                        int32_t *row_status, void *stream);
+int dj_cs_midsv_write(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
+                      const int64_t *read_first, int64_t n_reads, int32_t ref_len, const int64_t *row_off,
+                      const int32_t *row_len, uint8_t *text, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

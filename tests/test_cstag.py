@@ -1,0 +1,263 @@
+"""SAM (cs tag) -> MIDSV, SURVEY.md §8f rank 4 (reference call site ``preprocess/alignment/midsv_caller.py:84-85``).
+
+``midsv`` itself is absent (parity unpinned, ``oracle/midsv_transform.py``); what IS held here:
+
+* CPU: the oracle reproduces ``tests/golden/cs_midsv.json.gz`` (rows that ``oracle/make_cs_golden.py`` checked with
+  the reference's own inverse ``convert_midsvs_to_cstag`` and CIGAR length, on the reference's SAM fixtures and on
+  random split / spliced / inverted / overlapping reads); the device routine ``csrc/cstag_core.cuh`` itself, executed
+  on the host with 32 threads as the lanes of a warp (``scripts/cstag_host_test.cpp``), returns those rows byte for
+  byte and writes nothing outside them;
+* GPU: ``alignment.transform_to_midsv_format`` through the C ABI returns the golden rows; chained with the post-fix
+  pass it returns what the REAL reference's chain (``midsv_caller.py:267-271``) made of them; the text it leaves in
+  HBM encodes to the same code matrix as the same rows shipped from the host.
+"""
+from __future__ import annotations
+
+import ctypes
+import gzip
+import json
+import os
+import random
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from dajin2_b200 import alignment
+from oracle import midsv_transform as mt
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def golden():
+    with gzip.open(ROOT / "tests" / "golden" / "cs_midsv.json.gz", "rt") as f:
+        return json.load(f)
+
+
+def write_sam(case: dict, path: Path) -> Path:
+    lines = [f"@SQ\tSN:{sn}\tLN:{ln}" for sn, ln in case["sq"].items()]
+    for r in case["records"]:
+        lines.append("\t".join([r["QNAME"], str(r["FLAG"]), r["RNAME"], str(r["POS"]), "60", r["CIGAR"], "*", "0", "0",
+                                "*", "*", "NM:i:0", "cs:Z:" + r["CSTAG"]]))
+    path.write_text("\n".join(lines) + "\n")
+    return path
+
+
+def big_case(seed: int, ref_len: int, n_reads: int) -> dict:
+    """Reads of ~ref_len bases with substitutions, indels, an intron or a split now and then (all in the grammar)."""
+    rng = random.Random(seed)
+    ref = "".join(rng.choice("ACGT") for _ in range(ref_len))
+    records = []
+    for r in range(n_reads):
+        cuts = [0, ref_len]
+        if r % 5 == 0:
+            a = rng.randrange(100, ref_len - 100)
+            cuts = [rng.randrange(0, 30), a, a + rng.randrange(0, 80), ref_len - rng.randrange(0, 30)]
+        flag0 = 16 if rng.random() < 0.5 else 0
+        for k in range(0, len(cuts), 2):
+            lo, hi = cuts[k], cuts[k + 1]
+            parts, i, prev = [], lo, ""
+            while i < hi:
+                u = rng.random()
+                if i == lo or i >= hi - 2 or u > 0.03 or prev != "=":
+                    n = min(rng.randrange(1, 120), hi - i)
+                    parts.append(("" if prev == "=" else "=") + ref[i : i + n])
+                    i, prev = i + n, "="
+                elif u < 0.01:
+                    parts.append("*" + ref[i].lower() + rng.choice("acgt"))
+                    i, prev = i + 1, "*"
+                elif u < 0.018:
+                    n = min(rng.choice([1, 2, 9, 300]), hi - 2 - i)
+                    parts.append("-" + ref[i : i + n].lower())
+                    i, prev = i + n, "-"
+                elif u < 0.027:
+                    parts.append("+" + "".join(rng.choice("acgt") for _ in range(rng.choice([1, 3, 70]))))
+                    prev = "+"
+                else:
+                    n = min(rng.randrange(1, 2000), hi - 2 - i)
+                    parts.append(f"~gt{n}ag")
+                    i, prev = i + n, "~"
+            flag = (flag0 ^ (16 if (k == 2 and r % 10 == 0) else 0)) | (2048 if k else 0)
+            records.append({"QNAME": f"r{r:05d}_{seed}", "FLAG": flag, "RNAME": "allele", "POS": lo + 1, "CIGAR": "*",
+                            "CSTAG": "".join(parts)})
+    return {"sq": {"allele": ref_len}, "records": records, "sequence": ref}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU: the oracle against the golden rows; the device routine executed on the host
+# ---------------------------------------------------------------------------------------------------------
+
+
+def test_oracle_reproduces_golden_rows(golden, tmp_path):
+    for case in golden:
+        assert mt.transform(write_sam(case, tmp_path / "case.sam")) == case["transform"], case["name"]
+        for row in case["transform"]:
+            assert len(row["MIDSV"].split(",")) == case["sq"][row["RNAME"]]
+
+
+def test_oracle_known_answers():
+    assert mt.cs_to_tokens("=AC+gt=T-ac*ag=C")[0] == ["=A", "=C", "+G|+T|=T", "-A", "-C", "*AG", "=C"]
+    assert mt.cs_to_tokens("=AC~gt3ag=T", lower=True)[0] == ["=a", "=c", "=n", "=n", "=n", "=t"]
+    aln = [{"FLAG": 0, "POS": 3, "CSTAG": "=AC"}, {"FLAG": 2064, "POS": 7, "CSTAG": "=G*ct"}]
+    assert mt.join_alignments(aln, 10) == ["=N", "=N", "=A", "=C", "=N", "=N", "=g", "*ct", "=N", "=N"]
+    assert mt.join_alignments([aln[0], {"FLAG": 0, "POS": 4, "CSTAG": "=CG"}], 10) is None  # shared reference base
+    assert mt.join_alignments([{"FLAG": 0, "POS": 9, "CSTAG": "=ACG"}], 10) is None  # past the end
+    with pytest.raises(ValueError):
+        mt.cs_to_tokens(":10*ag:5")  # short-form cs tag
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    so = tmp_path_factory.mktemp("cstag") / "libcstag_host.so"
+    subprocess.run([gxx, "-O1", "-std=c++17", "-pthread", "-shared", "-fPIC", "-Wno-unknown-pragmas",
+                    *os.environ.get("DJ_CSTAG_HOST_CXXFLAGS", "").split(), "-o", str(so),
+                    str(ROOT / "scripts" / "cstag_host_test.cpp")], check=True)
+    lib = ctypes.CDLL(str(so))
+    vp = ctypes.c_void_p
+    lib.cs_host_measure.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp, vp]
+    lib.cs_host_write.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp, vp, vp]
+    return lib
+
+
+def run_on_host(lib, pa: alignment.PackedAlignments, lead: int = 0):
+    """measure + write with the device routine on host threads; the text buffer starts ``lead`` bytes into a
+    16-byte aligned allocation and is surrounded by sentinel bytes."""
+    n = pa.n_reads
+    cs = np.zeros(pa.cs.shape[0] + 16, dtype=np.uint8)
+    shift = (-cs.ctypes.data) % 16
+    cs = cs[shift : shift + pa.cs.shape[0]]
+    cs[:] = pa.cs
+    row_len = np.full(n, -7, dtype=np.int32)
+    status = np.full(n, -7, dtype=np.int32)
+    lib.cs_host_measure(cs.ctypes.data, pa.aln_off.ctypes.data, pa.aln_pos.ctypes.data, pa.aln_lower.ctypes.data,
+                        pa.read_first.ctypes.data, n, pa.ref_len, row_len.ctypes.data, status.ctypes.data)
+    span = np.where(row_len > 0, row_len.astype(np.int64) + 1, 0)
+    row_off = np.cumsum(span) - span
+    total = int(span.sum())
+    raw = np.full(total + 64 + 32, 0xEE, dtype=np.uint8)
+    base = (-raw.ctypes.data) % 16 + lead
+    text = raw[base : base + total]
+    lib.cs_host_write(cs.ctypes.data, pa.aln_off.ctypes.data, pa.aln_pos.ctypes.data, pa.aln_lower.ctypes.data,
+                      pa.read_first.ctypes.data, n, pa.ref_len, row_off.ctypes.data, row_len.ctypes.data,
+                      text.ctypes.data)
+    assert (raw[:base] == 0xEE).all() and (raw[base + total :] == 0xEE).all(), "bytes outside the rows were written"
+    rows = {}
+    for q, o, m in zip(pa.qnames, row_off.tolist(), row_len.tolist()):
+        if m > 0:
+            assert text[o + m] == ord("\n")
+            rows[q] = text[o : o + m].tobytes().decode("ascii")
+    return rows, status
+
+
+def packed_of(case: dict, tmp_path: Path) -> alignment.PackedAlignments:
+    sq, records = alignment.read_sam_records(write_sam(case, tmp_path / "case.sam"))
+    (pa,) = alignment.pack_alignments(sq, records)
+    return pa
+
+
+def test_device_routine_on_host_threads_returns_golden_rows(golden, host_lib, tmp_path):
+    for k, case in enumerate(golden):
+        pa = packed_of(case, tmp_path)
+        rows, status = run_on_host(host_lib, pa, lead=k % 16)
+        want = {r["QNAME"]: r["MIDSV"] for r in case["transform"]}
+        assert rows == want, case["name"]
+        assert [r["FLAG"] for r in case["transform"]] == [f for q, f in zip(pa.qnames, pa.flags) if q in want]
+        dropped = [q for q, s in zip(pa.qnames, status.tolist()) if s]
+        assert sorted(dropped) == sorted(set(pa.qnames) - set(want))
+        assert all(s in (alignment.CS_OVERLAP, alignment.CS_TOO_LONG) for s in status.tolist() if s)
+
+
+def test_device_routine_on_host_threads_long_reads_and_errors(host_lib, tmp_path):
+    case = big_case(5, 5000, 24)
+    pa = packed_of(case, tmp_path)
+    rows, status = run_on_host(host_lib, pa, lead=5)
+    want = {r["QNAME"]: r["MIDSV"] for r in mt.transform(tmp_path / "case.sam")}
+    assert rows == want and len(want) >= 20
+    # grammar errors are flagged, not written: short-form tag, a substitution with one base, a trailing insertion,
+    # a tag that does not start with an operator
+    bad = {"sq": {"a": 12}, "records": [
+        {"QNAME": "q1", "FLAG": 0, "RNAME": "a", "POS": 1, "CIGAR": "*", "CSTAG": ":12"},
+        {"QNAME": "q2", "FLAG": 0, "RNAME": "a", "POS": 1, "CIGAR": "*", "CSTAG": "=ACGT*a=CGTACGT"},
+        {"QNAME": "q3", "FLAG": 0, "RNAME": "a", "POS": 1, "CIGAR": "*", "CSTAG": "=ACGTACGTACGT+ac"},
+        {"QNAME": "q4", "FLAG": 0, "RNAME": "a", "POS": 1, "CIGAR": "*", "CSTAG": "ACGTACGTACGT"},
+        {"QNAME": "q5", "FLAG": 0, "RNAME": "a", "POS": 1, "CIGAR": "*", "CSTAG": "=ACGTACGTACGT"},
+        {"QNAME": "q6", "FLAG": 16, "RNAME": "a", "POS": 2, "CIGAR": "*", "CSTAG": "=CGTA+tt"},
+    ]}
+    rows, status = run_on_host(host_lib, packed_of(bad, tmp_path), lead=3)
+    assert status.tolist() == [2, 2, 2, 2, 0, 0]
+    assert rows == {"q5": "=A,=C,=G,=T,=A,=C,=G,=T,=A,=C,=G,=T", "q6": "=N,=C,=G,=T,=A,+T|+T|=N,=N,=N,=N,=N,=N,=N"}
+
+
+def test_pack_alignments_orders_and_flags():
+    sq = {"a": 100}
+    records = [("b", 2048, "a", 50, "=AC"), ("a", 16, "a", 1, "=G"), ("b", 16, "a", 10, "=T"), ("b", 0, "a", 80, "=C")]
+    (pa,) = alignment.pack_alignments(sq, records)
+    assert pa.qnames == ["a", "b"] and pa.flags == [16, 16] and pa.read_first.tolist() == [0, 1, 4]
+    assert pa.aln_pos.tolist() == [0, 9, 49, 79] and pa.aln_lower.tolist() == [0, 0, 1, 1]
+    assert bytes(pa.cs[: int(pa.aln_off[-1])]) == b"=G=T=AC=C"
+    assert pa.cs.shape[0] == int(pa.aln_off[-1]) + 16
+
+
+def test_transform_refuses_without_cuda(tmp_path, golden):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        alignment.transform_to_midsv_format(write_sam(golden[0], tmp_path / "case.sam"))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU: through the C ABI
+# ---------------------------------------------------------------------------------------------------------
+
+
+@pytest.mark.gpu
+def test_transform_on_device_returns_golden_rows(golden, tmp_path):
+    for case in golden:
+        got = alignment.transform_to_midsv_format(write_sam(case, tmp_path / "case.sam"))
+        assert got == case["transform"], case["name"]
+
+
+@pytest.mark.gpu
+def test_transform_then_postfixes_equal_the_reference_chain(golden, tmp_path):
+    """Everything after the unpinned step is the REAL reference's output (``postfixed`` of the golden file)."""
+    for case in golden:
+        rows = alignment.transform_to_midsv_format(write_sam(case, tmp_path / "case.sam"))
+        got = list(alignment.postprocess_midsv(rows, case["sequence"], {}))
+        assert got == case["postfixed"], case["name"]
+
+
+@pytest.mark.gpu
+def test_device_text_matches_oracle_and_feeds_the_encoder(tmp_path):
+    import torch
+
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import HostReads, pack_rows
+
+    case = big_case(9, 5000, 600)
+    sam = write_sam(case, tmp_path / "case.sam")
+    want = mt.transform(sam)
+    sq, records = alignment.read_sam_records(sam)
+    (pa,) = alignment.pack_alignments(sq, records)
+    text, row_off, row_len, status = alignment.midsv_text_on_device(pa)
+    keep = (row_len > 0).cpu().numpy()
+    assert [q for q, k in zip(pa.qnames, keep) if k] == [r["QNAME"] for r in want]
+    assert set(status.cpu().numpy()[~keep].tolist()) <= {alignment.CS_OVERLAP, alignment.CS_TOO_LONG}
+    buf = text.cpu().numpy().tobytes()
+    got = [buf[o : o + m].decode("ascii") for o, m in zip(row_off.tolist(), row_len.tolist()) if m > 0]
+    assert got == [r["MIDSV"] for r in want]
+    # the text left in HBM is what dj_encode takes: same codes as the same rows packed on the host
+    sel = torch.from_numpy(np.flatnonzero(keep)).to(text.device)
+    n = int(sel.shape[0])
+    from_host = engine.EncodedReads(pack_rows(got), 5000)
+    on_device = engine.EncodedReads(HostReads(text, row_off[sel].contiguous(), row_len[sel].contiguous(),
+                                              np.full(n, ord("+"), dtype=np.uint8),
+                                              np.array([f"read{i:09d}".encode() for i in range(n)], dtype="S")), 5000)
+    assert torch.equal(from_host.codes, on_device.codes) and torch.equal(from_host.match_score, on_device.match_score)

@@ -389,6 +389,12 @@ assert list(mc.filter_samples_by_n_proportion([{{"MIDSV": "=N,=N"}}, {{"MIDSV": 
 plugin.uninstall()
 for (m, a), old in originals.items():
     assert getattr(sys.modules[m], a, None) is old, (m, a)
+from dajin2_b200 import alignment
+original = mc.transform_to_midsv_format
+assert len(plugin.install(strict=True, sam_to_midsv=True)) == len(plugin._PATCHES) + 1
+assert mc.transform_to_midsv_format is alignment.transform_to_midsv_format
+plugin.uninstall()
+assert mc.transform_to_midsv_format is original
 print("ok")
 """
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
