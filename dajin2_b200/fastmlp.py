@@ -183,6 +183,10 @@ def load_host_lib():
         lib.dj_masked_row_sums.argtypes = [vp, i64, i64, ctypes.c_int32, vp, ctypes.c_int32, vp, vp, ci]
         lib.dj_masked_row_sums.restype = None
         lib.fm_set_threads(default_threads())
+        lib.fm_set_forward_threads.argtypes = [ci]
+        lib.fm_set_forward_threads.restype = None
+        # the AVX-512 forward pass shares its rows among the fit's threads (rows are independent: same bits)
+        lib.fm_set_forward_threads(int(os.environ.get("DAJIN2_B200_MLP_FORWARD_THREADS", "1") != "0"))
         if os.environ.get("DAJIN2_B200_MLP_VMATH", "1") != "0":
             tables = _libm_tables()
             if tables is not None:  # 0 differences in the self test switches the four-wide exp / log pass on

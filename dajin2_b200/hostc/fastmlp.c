@@ -30,6 +30,8 @@
 
 static int g_threads = 1;
 void fm_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+static int g_forward_threads = 1; /* the forward pass shares its rows among the fit's threads (0: one thread) */
+void fm_set_forward_threads(int on) { g_forward_threads = on ? 1 : 0; }
 
 /* fastmlp512.c: the one-thread passes of the 2-5-2 model on AVX-512, entered only when the running CPU has it */
 int fm512_supported(void);
@@ -268,7 +270,18 @@ int fm_forward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int n
         int64_t done = 0;
         if (fm_get_avx512()) { /* eight rows per trip; the last n % 8 rows go through the four-row form */
             done = n - n % 8;
-            fm512_forward_252(X, xs_row, xs_col, done, W1, b1, W2, b2, a1, a2);
+            const int T = g_forward_threads ? g_threads : 1;
+            if (T > 1 && done >= 4096) { /* rows are independent: the same trips, shared among the fit's threads */
+                const int64_t per = ((done / 8 + T - 1) / T) * 8;
+#pragma omp parallel for num_threads(T) schedule(static)
+                for (int t = 0; t < T; t++) {
+                    const int64_t lo = t * per, hi = lo + per < done ? lo + per : done;
+                    if (lo < hi)
+                        fm512_forward_252(X + lo * xs_row, xs_row, xs_col, hi - lo, W1, b1, W2, b2, a1 + 5 * lo, a2 + 2 * lo);
+                }
+            } else {
+                fm512_forward_252(X, xs_row, xs_col, done, W1, b1, W2, b2, a1, a2);
+            }
         }
         if (done < n) forward_252(X + done * xs_row, xs_row, xs_col, n - done, W1, b1, W2, b2, a1 + 5 * done, a2 + 2 * done);
         return 0;
@@ -478,6 +491,10 @@ int fm_backward(const double *X, int64_t xs_row, int64_t xs_col, int64_t n, int 
     const int64_t step = (n + FM_CHUNKS - 1) / FM_CHUNKS;
 #ifdef FM_HAVE_252_AVX2
     if (n_in == 2 && h1 == 5 && h2 == 2) {
+        /* (The 27 chains are independent and could be walked in groups by the fit's threads without changing a bit.
+         * Measured, that loses badly -- fit 58 -> 117 ms on the 16-core Xeon of the B200 boxes, 76 -> 110 ms in the
+         * build container: every thread then pulls all of a1 / a2 / d3 out of the caches of the cores that wrote
+         * them, and the next forward pass takes the lines back.) */
         if (fm_get_avx512()) fm512_backward_252(X, xs_row, xs_col, n, a1, a2, W2, W3, d3, cs2, g2, cs1, g1);
         else backward_252(X, xs_row, xs_col, n, a1, a2, W2, W3, d3, cs2, g2, cs1, g1);
         return 0;
