@@ -23,6 +23,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) cs_midsv_kernel(const u
                                                                 int32_t *__restrict__ row_status,
                                                                 uint8_t *__restrict__ text) {
     __shared__ __align__(16) uint8_t stage_all[kWrite ? kWarps * DJ_CS_STAGE : 16];
+    __shared__ DjCsLut lut;  // the grammar's class and transition tables (cstag_core.cuh)
+    djcs_lut_fill(&lut, threadIdx.x, blockDim.x);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     uint8_t *stage = stage_all + (kWrite ? warp * DJ_CS_STAGE : 0);
@@ -31,10 +34,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) cs_midsv_kernel(const u
         if (kWrite) {
             int32_t len = row_len[r];
             if (len <= 0) continue;  // dropped by the measuring pass
-            djcs_read<true>(cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, stage,
+            djcs_read<true>(lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, stage,
                             text + row_off[r], &len, nullptr, lane);
         } else {
-            djcs_read<false>(cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, stage, nullptr,
+            djcs_read<false>(lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, stage, nullptr,
                              row_len + r, row_status + r, lane);
         }
     }

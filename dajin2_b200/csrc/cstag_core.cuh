@@ -32,6 +32,7 @@
 #define DJW_BALLOT(p) __ballot_sync(DJW_FULL, (p))
 #define DJW_SYNC() __syncwarp()
 #define DJW_CLZ(x) __clz((int)(x))
+#define DJW_VCMPEQ4(a, b) __vcmpeq4((a), (b))
 DJW_FN uint4 djw_load16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 #else
 // host emulation: provided by the including file (scripts/cstag_host_test.cpp) before this header
@@ -110,7 +111,13 @@ DJW_FN void djcs_fill(DjCsWriter<kWrite> &w, int lane, int64_t n_tokens, bool lo
     }
 }
 
-DJW_FN bool djcs_is_op(int c) { return c == '=' || c == '*' || c == '-' || c == '+' || c == '~'; }
+// 0xFF in every byte of a word that holds an operator character; '~' bytes are also ORed into *tilde
+DJW_FN uint32_t djcs_op_bytes(uint32_t word, uint32_t *tilde) {
+    const uint32_t t = DJW_VCMPEQ4(word, 0x7E7E7E7Eu);
+    *tilde |= t;
+    return DJW_VCMPEQ4(word, 0x3D3D3D3Du) | DJW_VCMPEQ4(word, 0x2A2A2A2Au) | DJW_VCMPEQ4(word, 0x2D2D2D2Du) |
+           DJW_VCMPEQ4(word, 0x2B2B2B2Bu) | t;
+}
 
 // byte mask of the word that holds bytes j0 .. j0 + 3 of a lane: 0xFF where j_lo <= j < j_hi
 DJW_FN uint32_t djcs_valid_mask(int j0, int j_lo, int j_hi) {
@@ -127,68 +134,132 @@ DJW_FN int djcs_byte(const uint4 &v, int j) {
     return (int)((word >> ((j & 3) * 8)) & 0xFFu);
 }
 
-// The bytes of this lane with absolute positions in [lo, hi): sizes only (emit == false) or sizes + bytes.
-// Returns the bytes produced; *refs / *bad collect reference tokens and grammar errors.
-template <bool kWrite>
-DJW_FN int djcs_walk(const uint4 &v, int64_t p0, int64_t lo, int64_t hi, int op, int since, bool lower, bool emit,
-                     const DjCsWriter<kWrite> &w, uint8_t *dst, int64_t dst_pos, int *refs, int *bad) {
-    int total = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int c = djcs_byte(v, j);
-        if (c == 0) {  // outside the alignment
-            ++since;
-            continue;
-        }
-        if (djcs_is_op(c)) {
-            if (op == '*' && since != 2 && !emit) *bad |= DJ_CS_GRAMMAR;  // a substitution is "*" + two letters
-            op = c;
-            since = 0;
-            continue;
-        }
-        ++since;
-        const int64_t p = p0 + j;
-        if (p < lo || p >= hi || op == '~') continue;
-        const bool letter = (unsigned)((c | 0x20) - 'a') < 26u;
-        const uint8_t L = (uint8_t)(lower ? (c | 0x20) : (c & 0xDF));
-        int n = 0;
-        if (!letter || op == 0) {
-            if (!emit) *bad |= DJ_CS_GRAMMAR;
-        } else if (op == '*') {
-            if (since == 1) {
-                n = 2;
-                if (kWrite && emit) {
-                    dst[total] = '*';
-                    dst[total + 1] = L;
-                }
-            } else if (since == 2) {
-                n = 2;
-                if (!emit) ++*refs;
-                if (kWrite && emit) {
-                    dst[total] = L;
-                    dst[total + 1] = djcs_sep(w, dst_pos + total + 1);
-                }
-            } else if (!emit) {
-                *bad |= DJ_CS_GRAMMAR;
-            }
-        } else {
-            n = 3;
-            if (op != '+' && !emit) ++*refs;
-            if (kWrite && emit) {
-                dst[total] = (uint8_t)op;
-                dst[total + 1] = L;
-                dst[total + 2] = op == '+' ? (uint8_t)'|' : djcs_sep(w, dst_pos + total + 2);
-            }
-        }
-        total += n;
-    }
-    return total;
+// ---------------------------------------------------------------------------------------------------------
+// The grammar as a table-driven state machine.  A byte has a class (cls[256]); a lane walks its sixteen bytes through
+// tr[state][class], which yields the next state and what the byte emits:
+//   code 1 "=X,"  2 "-X,"  3 "+X|"  (three bytes)   4 "*X"  5 "X,"  (the two letters of a substitution)   0 nothing
+// The codes of a lane are kept as sixteen nibbles; sizes, reference tokens and grammar errors are summed on the way,
+// so the bytes are written by a second, state-free walk over the nibbles once the warp's prefix sum has placed them.
+// ---------------------------------------------------------------------------------------------------------
+enum { DJCS_S_NONE = 0, DJCS_S_EQ, DJCS_S_DEL, DJCS_S_INS, DJCS_S_SUB0, DJCS_S_SUB1, DJCS_S_SUB2, DJCS_S_INTRON };
+enum { DJCS_C_OUT = 0, DJCS_C_EQ, DJCS_C_DEL, DJCS_C_INS, DJCS_C_SUB, DJCS_C_INTRON, DJCS_C_LETTER, DJCS_C_DIGIT,
+       DJCS_C_OTHER };
+
+struct DjCsLut {
+    uint8_t cls[256];
+    uint16_t tr[8 * 16];  // [3:0] code, [7:4] next state, [9:8] bytes emitted, [10] reference token, [11] grammar error
+};
+
+DJW_FN uint8_t djcs_class_of(int c) {
+    if (c == 0) return DJCS_C_OUT;
+    if (c == '=') return DJCS_C_EQ;
+    if (c == '-') return DJCS_C_DEL;
+    if (c == '+') return DJCS_C_INS;
+    if (c == '*') return DJCS_C_SUB;
+    if (c == '~') return DJCS_C_INTRON;
+    if ((unsigned)((c | 0x20) - 'a') < 26u) return DJCS_C_LETTER;
+    if ((unsigned)(c - '0') < 10u) return DJCS_C_DIGIT;
+    return DJCS_C_OTHER;
 }
 
-template <bool kWrite>
-DJW_FN void djcs_emit_range(const uint4 &v, int64_t p0, int64_t lo, int64_t hi, int in_op, int in_since, bool lower,
+DJW_FN uint16_t djcs_transition(int state, int cls) {
+    const int kBad = 0x800, kRef = 0x400;
+    int next = state, out = 0;
+    if (cls == DJCS_C_OUT) {
+    } else if (cls >= DJCS_C_EQ && cls <= DJCS_C_INTRON) {  // an operator: a substitution must be complete
+        if (state == DJCS_S_SUB0 || state == DJCS_S_SUB1) out |= kBad;
+        next = cls == DJCS_C_EQ ? DJCS_S_EQ : cls == DJCS_C_DEL ? DJCS_S_DEL : cls == DJCS_C_INS ? DJCS_S_INS
+             : cls == DJCS_C_SUB ? DJCS_S_SUB0 : DJCS_S_INTRON;
+    } else if (cls == DJCS_C_LETTER) {
+        if (state == DJCS_S_EQ) out = 1 | (3 << 8) | kRef;
+        else if (state == DJCS_S_DEL) out = 2 | (3 << 8) | kRef;
+        else if (state == DJCS_S_INS) out = 3 | (3 << 8);
+        else if (state == DJCS_S_SUB0) { out = 4 | (2 << 8); next = DJCS_S_SUB1; }
+        else if (state == DJCS_S_SUB1) { out = 5 | (2 << 8) | kRef; next = DJCS_S_SUB2; }
+        else if (state == DJCS_S_INTRON) out = 0;
+        else out = kBad;  // no operator yet, or a third letter of a substitution
+    } else if (cls == DJCS_C_DIGIT) {
+        if (state != DJCS_S_INTRON) out = kBad;
+    } else {
+        out = kBad;
+    }
+    return (uint16_t)(out | (next << 4));
+}
+
+// entries [first, 384) in steps of `step` (a CTA fills its shared-memory copy with all its threads)
+DJW_FN void djcs_lut_fill(DjCsLut *lut, int first, int step) {
+    for (int k = first; k < 384; k += step) {
+        if (k < 256) lut->cls[k] = djcs_class_of(k);
+        else lut->tr[k - 256] = djcs_transition((k - 256) >> 4, (k - 256) & 15);
+    }
+}
+
+// state a lane starts in, from the last operator before it and the bytes since
+DJW_FN int djcs_state_of(int op, int since) {
+    if (op == '=') return DJCS_S_EQ;
+    if (op == '-') return DJCS_S_DEL;
+    if (op == '+') return DJCS_S_INS;
+    if (op == '~') return DJCS_S_INTRON;
+    if (op == '*') return DJCS_S_SUB0 + (since < 2 ? since : 2);
+    return DJCS_S_NONE;
+}
+
+// Walk the lane's bytes through the table.  `active` (bit j = byte j counts) limits what is emitted, not the
+// states.  Returns bytes emitted | reference tokens << 16 | grammar error << 31; the codes go to *lo (bytes 0..7) and
+// *hi (bytes 8..15).
+template <bool kMasked>
+DJW_FN uint32_t djcs_classify(const DjCsLut &lut, const uint4 &v, int state, uint32_t active, uint32_t *lo,
+                              uint32_t *hi) {
+    uint32_t c_lo = 0, c_hi = 0, acc = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        uint32_t t = lut.tr[state * 16 + lut.cls[djcs_byte(v, j)]];
+        state = (t >> 4) & 15;
+        if (kMasked && !((active >> j) & 1u)) t &= 0x8F0u;  // keeps the state and the error, emits nothing
+        if (j < 8) c_lo |= (t & 15u) << (4 * j);
+        else c_hi |= (t & 15u) << (4 * (j - 8));
+        acc += ((t >> 8) & 3u) + ((t & 0x400u) << 6);
+        acc |= (t & 0x800u) << 20;
+    }
+    *lo = c_lo;
+    *hi = c_hi;
+    return acc;
+}
+
+// the bytes of the lane's codes at dst; `term` = offset (from dst) of the separator that ends the row, -1 if none
+DJW_FN void djcs_emit(const uint4 &v, uint32_t lo, uint32_t hi, bool lower, uint8_t *dst, int term) {
+    int o = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const uint32_t code = ((j < 8 ? lo : hi) >> (4 * (j & 7))) & 15u;
+        if (code == 0) continue;
+        const int c = djcs_byte(v, j);
+        const uint8_t L = (uint8_t)(lower ? (c | 0x20) : (c & 0xDF));
+        if (code <= 3) {
+            dst[o] = code == 1 ? (uint8_t)'=' : code == 2 ? (uint8_t)'-' : (uint8_t)'+';
+            dst[o + 1] = L;
+            dst[o + 2] = code == 3 ? (uint8_t)'|' : (o + 2 == term ? (uint8_t)'\n' : (uint8_t)',');
+            o += 3;
+        } else if (code == 4) {
+            dst[o] = '*';
+            dst[o + 1] = L;
+            o += 2;
+        } else {
+            dst[o] = L;
+            dst[o + 1] = o + 1 == term ? (uint8_t)'\n' : (uint8_t)',';
+            o += 2;
+        }
+    }
+}
+
+template <bool kWrite, bool kMasked>
+DJW_FN void djcs_emit_range(const DjCsLut &lut, const uint4 &v, uint32_t active, int in_state, bool lower,
                             DjCsWriter<kWrite> &w, int lane, int *refs, int *bad) {
-    const int mine = djcs_walk<kWrite>(v, p0, lo, hi, in_op, in_since, lower, false, w, nullptr, 0, refs, bad);
+    uint32_t lo, hi;
+    const uint32_t acc = djcs_classify<kMasked>(lut, v, in_state, active, &lo, &hi);
+    const int mine = (int)(acc & 0xFFFFu);
+    *refs += (int)((acc >> 16) & 0xFFu);
+    if (acc >> 31) *bad |= DJ_CS_GRAMMAR;
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -198,9 +269,8 @@ DJW_FN void djcs_emit_range(const uint4 &v, int64_t p0, int64_t lo, int64_t hi, 
     const int total = DJW_SHFL(incl, 31);
     if (kWrite) {
         const int excl = incl - mine;
-        int dummy_refs = 0, dummy_bad = 0;
-        djcs_walk<kWrite>(v, p0, lo, hi, in_op, in_since, lower, true, w, w.stage + w.fill + excl, w.row_pos + excl,
-                          &dummy_refs, &dummy_bad);
+        const int64_t to_term = w.last - (w.row_pos + excl);
+        djcs_emit(v, lo, hi, lower, w.stage + w.fill + excl, to_term >= 0 && to_term < 48 ? (int)to_term : -1);
         w.fill += total;
     }
     w.row_pos += total;
@@ -210,8 +280,8 @@ DJW_FN void djcs_emit_range(const uint4 &v, int64_t p0, int64_t lo, int64_t hi, 
 // One alignment: cs[a_off, a_end).  Adds its reference tokens to *refs (per lane: sum over the warp afterwards);
 // returns the operator the alignment ends under (warp-uniform).
 template <bool kWrite>
-DJW_FN int djcs_expand(const uint8_t *cs, int64_t a_off, int64_t a_end, bool lower, DjCsWriter<kWrite> &w, int lane,
-                       int *refs, int *bad) {
+DJW_FN int djcs_expand(const DjCsLut &lut, const uint8_t *cs, int64_t a_off, int64_t a_end, bool lower,
+                       DjCsWriter<kWrite> &w, int lane, int *refs, int *bad) {
     int c_op = 0, c_since = 0;
     for (int64_t chunk = a_off & ~(int64_t)15; chunk < a_end; chunk += DJ_CS_TRIP) {
         const int64_t p0 = chunk + lane * 16;
@@ -226,15 +296,18 @@ DJW_FN int djcs_expand(const uint8_t *cs, int64_t a_off, int64_t a_end, bool low
             v.z &= djcs_valid_mask(8, j_lo, j_hi);
             v.w &= djcs_valid_mask(12, j_lo, j_hi);
         }
+        // the last operator among the lane's bytes, four bytes at a time
+        uint32_t tilde_bytes = 0;
+        const uint32_t z0 = djcs_op_bytes(v.x, &tilde_bytes), z1 = djcs_op_bytes(v.y, &tilde_bytes);
+        const uint32_t z2 = djcs_op_bytes(v.z, &tilde_bytes), z3 = djcs_op_bytes(v.w, &tilde_bytes);
         int last_idx = -1, last_op = 0;
-        uint32_t tilde = 0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int c = djcs_byte(v, j);
-            if (djcs_is_op(c)) {
-                last_idx = j;
-                last_op = c;
-                if (c == '~') tilde |= 1u << j;
+        {
+            const uint32_t z = z3 ? z3 : z2 ? z2 : z1 ? z1 : z0;
+            const uint32_t word = z3 ? v.w : z2 ? v.z : z1 ? v.y : v.x;
+            if (z) {
+                const int b = (31 - DJW_CLZ(z)) >> 3;
+                last_idx = (z3 ? 12 : z2 ? 8 : z1 ? 4 : 0) + b;
+                last_op = (int)((word >> (8 * b)) & 0xFFu);
             }
         }
         const uint32_t has = DJW_BALLOT(last_idx >= 0);
@@ -250,11 +323,16 @@ DJW_FN int djcs_expand(const uint8_t *cs, int64_t a_off, int64_t a_end, bool low
         c_since = DJW_SHFL(out_since, 31);
 
         const int64_t trip_end = chunk + DJ_CS_TRIP < a_end ? chunk + DJ_CS_TRIP : a_end;
-        if (DJW_BALLOT(tilde != 0) == 0) {
-            djcs_emit_range<kWrite>(v, p0, a_off, trip_end, in_op, in_since, lower, w, lane, refs, bad);
+        const int in_state = djcs_state_of(in_op, in_since);
+        if (DJW_BALLOT(tilde_bytes != 0) == 0) {
+            djcs_emit_range<kWrite, false>(lut, v, 0xFFFFu, in_state, lower, w, lane, refs, bad);
             continue;
         }
         // introns in this trip: bytes up to the '~', the run of "=N", the rest
+        uint32_t tilde = 0;
+        for (int j = 0; j < 16; ++j) {
+            if (djcs_byte(v, j) == '~') tilde |= 1u << j;
+        }
         int64_t lo = a_off;
         for (;;) {
             int64_t mine = INT64_MAX;
@@ -267,8 +345,13 @@ DJW_FN int djcs_expand(const uint8_t *cs, int64_t a_off, int64_t a_end, bool low
                 const int64_t other = DJW_SHFL_XOR(first, d);
                 if (other < first) first = other;
             }
-            djcs_emit_range<kWrite>(v, p0, lo, first < trip_end ? first : trip_end, in_op, in_since, lower, w, lane, refs,
-                                    bad);
+            {
+                const int64_t hi = first < trip_end ? first : trip_end;
+                const int j_lo = lo <= p0 ? 0 : lo - p0 >= 16 ? 16 : (int)(lo - p0);
+                const int j_hi = hi <= p0 ? 0 : hi - p0 >= 16 ? 16 : (int)(hi - p0);
+                const uint32_t active = j_hi > j_lo ? ((1u << j_hi) - 1u) & ~((1u << j_lo) - 1u) : 0u;
+                djcs_emit_range<kWrite, true>(lut, v, active, in_state, lower, w, lane, refs, bad);
+            }
             if (first == INT64_MAX) break;
             int64_t n = 0;
             bool digits = false;
@@ -291,7 +374,7 @@ DJW_FN int djcs_expand(const uint8_t *cs, int64_t a_off, int64_t a_end, bool low
 // (row_len_io receives the row length, 0 for a dropped read; status its DJ_CS_* bits); kWrite == true writes the row
 // of a read whose measured length is *row_len_io (> 0) at `row`.
 template <bool kWrite>
-DJW_FN void djcs_read(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
+DJW_FN void djcs_read(const DjCsLut &lut, const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
                       int64_t first_aln, int64_t end_aln, int32_t ref_len, uint8_t *stage, uint8_t *row,
                       int32_t *row_len_io, int32_t *status, int lane) {
     DjCsWriter<kWrite> w;
@@ -320,7 +403,7 @@ DJW_FN void djcs_read(const uint8_t *cs, const int64_t *aln_off, const int32_t *
             cur = start;
         }
         int refs = 0;
-        ends = djcs_expand<kWrite>(cs, aln_off[a], aln_off[a + 1], aln_lower[a] != 0, w, lane, &refs, &bad);
+        ends = djcs_expand<kWrite>(lut, cs, aln_off[a], aln_off[a + 1], aln_lower[a] != 0, w, lane, &refs, &bad);
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
             refs += DJW_SHFL_XOR(refs, d);

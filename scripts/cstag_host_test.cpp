@@ -50,6 +50,14 @@ static inline uint32_t emu_ballot(bool p) {
 #define DJW_BALLOT(p) emu_ballot((p))
 #define DJW_SYNC() emu_wait()
 #define DJW_CLZ(x) __builtin_clz((unsigned)(x))
+static inline uint32_t emu_vcmpeq4(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int k = 0; k < 4; ++k) {
+        if (((a >> (8 * k)) & 0xFFu) == ((b >> (8 * k)) & 0xFFu)) r |= 0xFFu << (8 * k);
+    }
+    return r;
+}
+#define DJW_VCMPEQ4(a, b) emu_vcmpeq4((a), (b))
 static inline uint4 djw_load16(const uint8_t *p) {
     uint4 v;
     memcpy(&v, p, 16);
@@ -59,12 +67,14 @@ static inline uint4 djw_load16(const uint8_t *p) {
 #include "../dajin2_b200/csrc/cstag_core.cuh"
 
 alignas(16) static uint8_t g_stage[DJ_CS_STAGE];
+static DjCsLut g_lut;
 
 template <bool kWrite>
 static void run(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
                 const int64_t *read_first, int64_t n_reads, int32_t ref_len, const int64_t *row_off, int32_t *row_len,
                 int32_t *row_status, uint8_t *text) {
     pthread_barrier_init(&g_bar, nullptr, 32);
+    djcs_lut_fill(&g_lut, 0, 1);
     std::vector<std::thread> lanes;
     for (int lane = 0; lane < 32; ++lane) {
         lanes.emplace_back([=]() {
@@ -73,10 +83,10 @@ static void run(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_po
                 if (kWrite) {
                     int32_t len = row_len[r];
                     if (len <= 0) continue;
-                    djcs_read<true>(cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, g_stage,
+                    djcs_read<true>(g_lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, g_stage,
                                     text + row_off[r], &len, nullptr, lane);
                 } else {
-                    djcs_read<false>(cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, g_stage,
+                    djcs_read<false>(g_lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, g_stage,
                                      nullptr, row_len + r, row_status + r, lane);
                 }
             }

@@ -194,6 +194,49 @@ def test_device_routine_on_host_threads_long_reads_and_errors(host_lib, tmp_path
     assert rows == {"q5": "=A,=C,=G,=T,=A,=C,=G,=T,=A,=C,=G,=T", "q6": "=N,=C,=G,=T,=A,+T|+T|=N,=N,=N,=N,=N,=N,=N"}
 
 
+def test_device_routine_on_host_threads_boundary_sweep(host_lib, tmp_path):
+    """Alignments of every length from 1 to ~1100 bases packed back to back (so every offset modulo 16, events on
+    lane and trip boundaries, introns that straddle a trip, tags shorter than a lane) against the oracle."""
+    rng = random.Random(17)
+    ref_len = 1200
+    ref = "".join(rng.choice("ACGT") for _ in range(ref_len))
+    records = []
+    for k, n in enumerate(list(range(1, 70)) + list(range(480, 560, 3)) + list(range(1000, 1100, 7))):
+        lo = rng.randrange(0, ref_len - n + 1)
+        parts, i, prev = [], lo, ""
+        while i < lo + n:
+            u = rng.random()
+            room = lo + n - i
+            if prev != "=" or u > 0.12 or room < 2:
+                m = min(rng.randrange(1, 40), room)
+                parts.append(("" if prev == "=" else "=") + ref[i : i + m])
+                i, prev = i + m, "="
+            elif u < 0.03:
+                parts.append("*" + ref[i].lower() + rng.choice("acgt"))
+                i, prev = i + 1, "*"
+            elif u < 0.06:
+                m = min(rng.choice([1, 2, 20]), room - 1)
+                parts.append("-" + ref[i : i + m].lower())
+                i, prev = i + m, "-"
+            elif u < 0.09:
+                parts.append("+" + "".join(rng.choice("acgtn") for _ in range(rng.choice([1, 2, 15, 33]))))
+                prev = "+"
+            else:
+                m = min(rng.choice([1, 9, 10, 123, 1000]), room - 1)
+                parts.append(f"~{rng.choice(['gt', 'ct'])}{m}{rng.choice(['ag', 'ac'])}")
+                i, prev = i + m, "~"
+        records.append({"QNAME": f"q{k:04d}", "FLAG": 16 * (k & 1), "RNAME": "a", "POS": lo + 1, "CIGAR": "*",
+                        "CSTAG": "".join(parts)})
+    case = {"sq": {"a": ref_len}, "records": records}
+    pa = packed_of(case, tmp_path)
+    want = {r["QNAME"]: r["MIDSV"] for r in mt.transform(tmp_path / "case.sam")}
+    assert len(want) == len(records)
+    for lead in (0, 9):
+        rows, status = run_on_host(host_lib, pa, lead=lead)
+        assert not status.any()
+        assert rows == want
+
+
 def test_pack_alignments_orders_and_flags():
     sq = {"a": 100}
     records = [("b", 2048, "a", 50, "=AC"), ("a", 16, "a", 1, "=G"), ("b", 16, "a", 10, "=T"), ("b", 0, "a", 80, "=C")]
