@@ -2,18 +2,16 @@
 // reads it (text + row_off + row_len).  One warp per read, persistent grid; the per-read routine is cstag_core.cuh
 // (also executed on the host by the CPU suite, see there).  HBM-bound streaming: reads ~1 byte and writes ~3 bytes
 // per aligned base (16-byte loads, 16-byte stores out of a per-warp shared-memory stage).
-#include <stdlib.h>
-
 #include "dj_common.cuh"
 
 #include "cstag_core.cuh"
 
 namespace {
 
-constexpr int kWarps = 8;  // per CTA: 8 x DJ_CS_STAGE = 12.5 KB of shared memory
+constexpr int kWarps = 8;  // per CTA: 8 x DJ_CS_STAGE = 12.5 KB of shared memory; two CTAs per SM (128 registers)
 
-template <bool kWrite, int kMinCtas>
-__global__ void __launch_bounds__(kWarps * 32, kMinCtas) cs_midsv_kernel(const uint8_t *__restrict__ cs,
+template <bool kWrite>
+__global__ void __launch_bounds__(kWarps * 32, 2) cs_midsv_kernel(const uint8_t *__restrict__ cs,
                                                                 const int64_t *__restrict__ aln_off,
                                                                 const int32_t *__restrict__ aln_pos,
                                                                 const uint8_t *__restrict__ aln_lower,
@@ -51,15 +49,6 @@ int grid_for(int64_t n_reads) {
     return (int)(want < cap ? want : cap);
 }
 
-int occupancy_variant() {  // experiment switch: resident CTAs per SM the kernels are compiled for (register budget)
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("DJ_CS_OCC");
-        v = e ? atoi(e) : 2;
-    }
-    return v;
-}
-
 }  // namespace
 
 extern "C" int dj_cs_midsv_measure(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos,
@@ -72,15 +61,8 @@ extern "C" int dj_cs_midsv_measure(const uint8_t *cs, const int64_t *aln_off, co
     }
     const int grid = grid_for(n_reads);
     if (grid <= 0) return 1;
-#define DJ_CS_LAUNCH(K) cs_midsv_kernel<false, K><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>( \
-        cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, nullptr, row_len, row_status, nullptr)
-    switch (occupancy_variant()) {
-        case 3: DJ_CS_LAUNCH(3); break;
-        case 4: DJ_CS_LAUNCH(4); break;
-        case 6: DJ_CS_LAUNCH(6); break;
-        default: DJ_CS_LAUNCH(2); break;
-    }
-#undef DJ_CS_LAUNCH
+    cs_midsv_kernel<false><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(
+        cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, nullptr, row_len, row_status, nullptr);
     DJ_LAUNCH_CHECK();
     return 0;
 }
@@ -95,16 +77,9 @@ extern "C" int dj_cs_midsv_write(const uint8_t *cs, const int64_t *aln_off, cons
     }
     const int grid = grid_for(n_reads);
     if (grid <= 0) return 1;
-#define DJ_CS_LAUNCH(K) cs_midsv_kernel<true, K><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>( \
-        cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, row_off, const_cast<int32_t *>(row_len), nullptr, \
-        text)
-    switch (occupancy_variant()) {
-        case 3: DJ_CS_LAUNCH(3); break;
-        case 4: DJ_CS_LAUNCH(4); break;
-        case 6: DJ_CS_LAUNCH(6); break;
-        default: DJ_CS_LAUNCH(2); break;
-    }
-#undef DJ_CS_LAUNCH
+    cs_midsv_kernel<true><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(
+        cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, row_off, const_cast<int32_t *>(row_len), nullptr,
+        text);
     DJ_LAUNCH_CHECK();
     return 0;
 }
