@@ -111,9 +111,9 @@ SIGNATURES = {
     "dj_sv_scan": (c_int32, [c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_uint32, c_void_p, c_void_p]),
     "dj_cs_midsv_measure": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
-                                      c_void_p, c_void_p]),
+                                      c_void_p, c_void_p, c_void_p, c_void_p]),
     "dj_cs_midsv_write": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
-                                    c_void_p, c_void_p, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _NO_STATUS = {"dj_abi_version", "dj_last_error", "dj_code_pitch", "dj_ckpt_pitch", "dj_encode_ref_smem_bytes",

@@ -18,6 +18,7 @@ rank 4.
 from __future__ import annotations
 
 import os
+import re
 from collections.abc import Iterable, Iterator
 from dataclasses import dataclass
 from pathlib import Path
@@ -136,7 +137,7 @@ def postprocess_midsv(midsv_chain: Iterable[dict], sequence: str, best_preset: d
 # SAM (cs tag) -> MIDSV on the device
 # ---------------------------------------------------------------------------------------------------------
 
-CS_OVERLAP, CS_GRAMMAR, CS_TOO_LONG = 1, 2, 4  # row_status bits of dj_cs_midsv_measure
+CS_OVERLAP, CS_GRAMMAR, CS_TOO_LONG, CS_HAS_N = 1, 2, 4, 8  # row_status bits of dj_cs_midsv_measure
 
 
 @dataclass
@@ -216,10 +217,40 @@ def pack_alignments(sq: dict[str, int], records: list[tuple]) -> list[PackedAlig
     return packed
 
 
-def midsv_text_on_device(pa: PackedAlignments):
-    """MIDSV text of every read of ``pa`` in HBM: (text uint8, row_off int64[R], row_len int32[R], status int32[R]) as
-    device tensors, rows of dropped reads (status != 0: overlapping alignments, not a long-form cs tag, longer than
-    the reference) with ``row_len`` 0.  ``text`` / ``row_off`` / ``row_len`` are what ``dj_encode`` takes."""
+_DEL_THEN_INS = re.compile(r"-([A-Za-z]+)\+([A-Za-z]+)")
+
+
+def revert_deletion_insertion_pairs(cs: str) -> str:
+    """``convert_consecutive_indels_to_match`` (``midsv_caller.py:163-202``) applied to the cs tag instead of the MIDSV
+    string: where a deletion run is directly followed by an insertion that re-inserts its last bases ("-C,+C|=T",
+    an alignment artefact), those bases become matches and the insertion goes: ``-ttacg+acg`` -> ``-tt=acg``.  The
+    reference compares whole tokens of the string it was given, so the first deleted base does not count when its
+    token carries an insertion of its own (``+a-c+c``: the token is "+A|-C", not a deletion), whatever happens to
+    that insertion in the same pass."""
+    if "+" not in cs or "-" not in cs:
+        return cs
+
+    def fix(m: re.Match) -> str:
+        deleted, inserted = m.group(1), m.group(2)
+        k = len(inserted)
+        p = m.start() - 1  # the operator in front of the deletion run, in the ORIGINAL tag
+        while p >= 0 and cs[p].isalpha():
+            p -= 1
+        usable = len(deleted) - (1 if p >= 0 and cs[p] == "+" else 0)
+        if k > usable or deleted[len(deleted) - k:] != inserted:
+            return m.group(0)
+        keep = deleted[: len(deleted) - k]
+        return ("-" + keep if keep else "") + "=" + inserted
+
+    return _DEL_THEN_INS.sub(fix, cs)
+
+
+def midsv_text_on_device(pa: PackedAlignments, sequence: str | None = None):
+    """MIDSV text of every read of ``pa`` in HBM: (text uint8, row_off int64[R], row_len int32[R], status int32[R],
+    row_n int32[R]) as device tensors, rows of dropped reads (status & 7: overlapping alignments, not a long-form cs
+    tag, longer than the reference) with ``row_len`` 0.  ``text`` / ``row_off`` / ``row_len`` are what ``dj_encode``
+    takes.  With ``sequence`` the tokens between the pieces of a read are written as deletions of the reference bases
+    (``replace_internal_n_to_d`` applied); ``row_n`` counts the ``=N`` tokens left (the flanks)."""
     import torch
 
     from . import _cabi
@@ -230,16 +261,59 @@ def midsv_text_on_device(pa: PackedAlignments):
     n = pa.n_reads
     up = [torch.from_numpy(a).to(dev, non_blocking=True) for a in (pa.cs, pa.aln_off, pa.aln_pos, pa.aln_lower,
                                                                    pa.read_first)]
+    seq = None
+    if sequence is not None:
+        if len(sequence) != pa.ref_len or not sequence.isascii():
+            raise ValueError(f"the sequence of {pa.rname} must be {pa.ref_len} ASCII bases")
+        seq = torch.from_numpy(np.frombuffer(sequence.encode("ascii"), dtype=np.uint8).copy()).to(dev, non_blocking=True)
     row_len = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
     status = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
-    _cabi.call("dj_cs_midsv_measure", *(_p(t) for t in up), n, pa.ref_len, _p(row_len), _p(status), _stream())
+    row_n = torch.zeros(max(n, 1), dtype=torch.int32, device=dev)
+    _cabi.call("dj_cs_midsv_measure", *(_p(t) for t in up), n, pa.ref_len, _p(seq), _p(row_len), _p(status), _p(row_n),
+               _stream())
     span = torch.where(row_len > 0, row_len.to(torch.int64) + 1, torch.zeros((), dtype=torch.int64, device=dev))
     ends = torch.cumsum(span, 0)
     row_off = ends - span
     total = int(ends[-1].item()) if n else 0
     text = torch.full((total + SLACK,), ord("\n"), dtype=torch.uint8, device=dev)
-    _cabi.call("dj_cs_midsv_write", *(_p(t) for t in up), n, pa.ref_len, _p(row_off), _p(row_len), _p(text), _stream())
-    return text, row_off[:n], row_len[:n], status[:n]
+    _cabi.call("dj_cs_midsv_write", *(_p(t) for t in up), n, pa.ref_len, _p(seq), _p(row_off), _p(row_len), _p(text),
+               _stream())
+    return text, row_off[:n], row_len[:n], status[:n], row_n[:n]
+
+
+def host_reads_from_sam(path_sam: str | Path, sequence: str, threshold: int = 95):
+    """The reads ``generate_midsv`` (``midsv_caller.py:264-272``) would write for this SAM file and allele sequence,
+    as a ``HostReads`` whose text / row_off / row_len live in HBM -- ``midsv.transform`` and the post-fix chain without
+    the MIDSV text ever being on the host: deletion / insertion artefacts reverted on the cs tags
+    (``revert_deletion_insertion_pairs``), the pieces of split and spliced reads joined by deletions of the reference
+    bases (``dj_cs_midsv_write`` with the sequence), reads that are >= ``threshold`` percent ``=N`` dropped from the
+    measured flank sizes, FLAG -> STRAND.  Feed it to ``engine.EncodedReads``.  A file one of whose alignments holds
+    ``=N`` tokens of its own (an allele with N bases) takes the route through the host post-fix pass instead, whose
+    boundary rule needs the tokens (``transform_to_midsv_format`` + ``postprocess_midsv``)."""
+    import torch
+
+    from .ingest import HostReads, pack_rows
+
+    sq, records = read_sam_records(path_sam)
+    packed = pack_alignments(sq, [(q, f, r, p, revert_deletion_insertion_pairs(cs)) for q, f, r, p, cs in records])
+    if len(packed) != 1:
+        raise ValueError(f"{path_sam}: alignments against {len(packed)} reference sequences, expected one allele")
+    (pa,) = packed
+    text, row_off, row_len, status, row_n = midsv_text_on_device(pa, sequence)
+    status_h = status.cpu().numpy()
+    if (status_h & CS_GRAMMAR).any():
+        bad = int(np.flatnonzero(status_h & CS_GRAMMAR)[0])
+        raise ValueError(f"{path_sam}: the cs tag of {pa.qnames[bad]} is not in the long format")
+    strands = ["-" if f & 16 else "+" for f in pa.flags]
+    if (status_h & CS_HAS_N).any():  # rare: the tokens themselves decide what is an internal N
+        rows = list(postprocess_midsv(transform_to_midsv_format(path_sam), sequence, {}, threshold))
+        return pack_rows([r["MIDSV"] for r in rows], [r["STRAND"] for r in rows], [r["QNAME"] for r in rows])
+    n_share = row_n.cpu().numpy() / pa.ref_len * 100  # midsv_caller.py:152-154, the same float operations
+    keep = (row_len.cpu().numpy() > 0) & (n_share < threshold)
+    sel = torch.from_numpy(np.flatnonzero(keep)).to(text.device)
+    return HostReads(text, row_off[sel].contiguous(), row_len[sel].contiguous(),
+                     np.frombuffer("".join(s for s, k in zip(strands, keep) if k).encode("ascii"), dtype=np.uint8).copy(),
+                     np.array([q.encode("ascii") for q, k in zip(pa.qnames, keep) if k], dtype="S"))
 
 
 def transform_to_midsv_format(path_sam: str | Path) -> list[dict]:
@@ -248,7 +322,7 @@ def transform_to_midsv_format(path_sam: str | Path) -> list[dict]:
     sq, records = read_sam_records(path_sam)
     out = []
     for pa in pack_alignments(sq, records):
-        text, row_off, row_len, status = midsv_text_on_device(pa)
+        text, row_off, row_len, status, _ = midsv_text_on_device(pa)
         status_h = status.cpu().numpy()
         if (status_h & CS_GRAMMAR).any():
             bad = int(np.flatnonzero(status_h & CS_GRAMMAR)[0])

@@ -16,9 +16,11 @@ __global__ void __launch_bounds__(kWarps * 32, 2) cs_midsv_kernel(const uint8_t 
                                                                 const int32_t *__restrict__ aln_pos,
                                                                 const uint8_t *__restrict__ aln_lower,
                                                                 const int64_t *__restrict__ read_first, int64_t n_reads,
-                                                                int32_t ref_len, const int64_t *__restrict__ row_off,
+                                                                int32_t ref_len, const uint8_t *__restrict__ ref_seq,
+                                                                const int64_t *__restrict__ row_off,
                                                                 int32_t *__restrict__ row_len,
                                                                 int32_t *__restrict__ row_status,
+                                                                int32_t *__restrict__ row_n,
                                                                 uint8_t *__restrict__ text) {
     __shared__ __align__(16) uint8_t stage_all[kWrite ? kWarps * DJ_CS_STAGE : 16];
     __shared__ DjCsLut lut;  // the grammar's class and transition tables (cstag_core.cuh)
@@ -32,11 +34,11 @@ __global__ void __launch_bounds__(kWarps * 32, 2) cs_midsv_kernel(const uint8_t 
         if (kWrite) {
             int32_t len = row_len[r];
             if (len <= 0) continue;  // dropped by the measuring pass
-            djcs_read<true>(lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, stage,
-                            text + row_off[r], &len, nullptr, lane);
+            djcs_read<true>(lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, ref_seq,
+                            stage, text + row_off[r], &len, nullptr, nullptr, lane);
         } else {
-            djcs_read<false>(lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, stage, nullptr,
-                             row_len + r, row_status + r, lane);
+            djcs_read<false>(lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, ref_seq,
+                             stage, nullptr, row_len + r, row_status + r, row_n ? row_n + r : nullptr, lane);
         }
     }
 }
@@ -53,7 +55,8 @@ int grid_for(int64_t n_reads) {
 
 extern "C" int dj_cs_midsv_measure(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos,
                                    const uint8_t *aln_lower, const int64_t *read_first, int64_t n_reads,
-                                   int32_t ref_len, int32_t *row_len, int32_t *row_status, void *stream) {
+                                   int32_t ref_len, const uint8_t *ref_seq, int32_t *row_len, int32_t *row_status,
+                                   int32_t *row_n, void *stream) {
     if (n_reads <= 0) return 0;
     if (((uintptr_t)cs & 15) != 0) {
         dj_set_error("dj_cs_midsv_measure: the cs buffer must be 16-byte aligned");
@@ -62,14 +65,16 @@ extern "C" int dj_cs_midsv_measure(const uint8_t *cs, const int64_t *aln_off, co
     const int grid = grid_for(n_reads);
     if (grid <= 0) return 1;
     cs_midsv_kernel<false><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(
-        cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, nullptr, row_len, row_status, nullptr);
+        cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, ref_seq, nullptr, row_len, row_status, row_n,
+        nullptr);
     DJ_LAUNCH_CHECK();
     return 0;
 }
 
 extern "C" int dj_cs_midsv_write(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos,
                                  const uint8_t *aln_lower, const int64_t *read_first, int64_t n_reads, int32_t ref_len,
-                                 const int64_t *row_off, const int32_t *row_len, uint8_t *text, void *stream) {
+                                 const uint8_t *ref_seq, const int64_t *row_off, const int32_t *row_len, uint8_t *text,
+                                 void *stream) {
     if (n_reads <= 0) return 0;
     if (((uintptr_t)cs & 15) != 0) {
         dj_set_error("dj_cs_midsv_write: the cs buffer must be 16-byte aligned");
@@ -78,8 +83,8 @@ extern "C" int dj_cs_midsv_write(const uint8_t *cs, const int64_t *aln_off, cons
     const int grid = grid_for(n_reads);
     if (grid <= 0) return 1;
     cs_midsv_kernel<true><<<grid, kWarps * 32, 0, (cudaStream_t)stream>>>(
-        cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, row_off, const_cast<int32_t *>(row_len), nullptr,
-        text);
+        cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, ref_seq, row_off, const_cast<int32_t *>(row_len),
+        nullptr, nullptr, text);
     DJ_LAUNCH_CHECK();
     return 0;
 }

@@ -44,6 +44,7 @@ DJW_FN uint4 djw_load16(const uint8_t *p) { return __ldg(reinterpret_cast<const 
 #define DJ_CS_OVERLAP 1   // two alignments of the read share a reference base: dropped
 #define DJ_CS_GRAMMAR 2   // not a long-form cs tag, or an insertion with nothing after it at the end of the row
 #define DJ_CS_TOO_LONG 4  // the alignments reach past the end of the reference, or the row needs >= 2^31 bytes
+#define DJ_CS_HAS_N 8     // informational (the row is kept): an alignment holds "=N" tokens of its own
 
 template <bool kWrite>
 struct DjCsWriter {
@@ -53,6 +54,8 @@ struct DjCsWriter {
     int head_skip;
     int64_t row_pos;   // bytes of the row produced so far
     int64_t last;      // row position of the separator that ends the row ('\n' instead of ','); -1 when measuring
+    const uint8_t *seq;  // reference sequence: tokens between the pieces of a read become "-<base>" (else "=N")
+    int64_t n_tokens;  // "=N" tokens written by the run filler
 };
 
 template <bool kWrite>
@@ -89,9 +92,13 @@ DJW_FN void djcs_flush(DjCsWriter<kWrite> &w, int lane, bool final) {
     DJW_SYNC();
 }
 
-// n tokens "=N," (lower: "=n,")
+// n tokens "=N," (lower: "=n,"); with a reference sequence and inside == true (a gap between two alignments, an
+// intron) the tokens are "-<base>," of reference positions ref_pos .. ref_pos + n - 1 instead: what
+// replace_internal_n_to_d (midsv_caller.py:108-126) makes of them
 template <bool kWrite>
-DJW_FN void djcs_fill(DjCsWriter<kWrite> &w, int lane, int64_t n_tokens, bool lower) {
+DJW_FN void djcs_fill(DjCsWriter<kWrite> &w, int lane, int64_t n_tokens, bool lower, bool inside, int64_t ref_pos) {
+    const bool as_deletion = inside && w.seq != nullptr;
+    if (!as_deletion) w.n_tokens += n_tokens;
     if (!kWrite) {
         w.row_pos += 3 * n_tokens;
         return;
@@ -101,8 +108,8 @@ DJW_FN void djcs_fill(DjCsWriter<kWrite> &w, int lane, int64_t n_tokens, bool lo
         const int m = (int)(n_tokens - t0 < DJ_CS_TRIP ? n_tokens - t0 : DJ_CS_TRIP);
         for (int t = lane; t < m; t += 32) {
             uint8_t *p = w.stage + w.fill + 3 * t;
-            p[0] = '=';
-            p[1] = base;
+            p[0] = as_deletion ? (uint8_t)'-' : (uint8_t)'=';
+            p[1] = as_deletion ? w.seq[ref_pos + t0 + t] : base;
             p[2] = djcs_sep(w, w.row_pos + 3 * t + 2);
         }
         w.fill += 3 * m;
@@ -143,11 +150,12 @@ DJW_FN int djcs_byte(const uint4 &v, int j) {
 // ---------------------------------------------------------------------------------------------------------
 enum { DJCS_S_NONE = 0, DJCS_S_EQ, DJCS_S_DEL, DJCS_S_INS, DJCS_S_SUB0, DJCS_S_SUB1, DJCS_S_SUB2, DJCS_S_INTRON };
 enum { DJCS_C_OUT = 0, DJCS_C_EQ, DJCS_C_DEL, DJCS_C_INS, DJCS_C_SUB, DJCS_C_INTRON, DJCS_C_LETTER, DJCS_C_DIGIT,
-       DJCS_C_OTHER };
+       DJCS_C_OTHER, DJCS_C_LETTER_N };
 
 struct DjCsLut {
     uint8_t cls[256];
-    uint16_t tr[8 * 16];  // [3:0] code, [7:4] next state, [9:8] bytes emitted, [10] reference token, [11] grammar error
+    uint16_t tr[8 * 16];  // [3:0] code, [7:4] next state, [9:8] bytes emitted, [10] reference token, [11] grammar error,
+                          // [15] an "=N" token (is_n_tag, utils/midsv_handler.py:8-14)
 };
 
 DJW_FN uint8_t djcs_class_of(int c) {
@@ -157,6 +165,7 @@ DJW_FN uint8_t djcs_class_of(int c) {
     if (c == '+') return DJCS_C_INS;
     if (c == '*') return DJCS_C_SUB;
     if (c == '~') return DJCS_C_INTRON;
+    if ((c | 0x20) == 'n') return DJCS_C_LETTER_N;
     if ((unsigned)((c | 0x20) - 'a') < 26u) return DJCS_C_LETTER;
     if ((unsigned)(c - '0') < 10u) return DJCS_C_DIGIT;
     return DJCS_C_OTHER;
@@ -170,8 +179,8 @@ DJW_FN uint16_t djcs_transition(int state, int cls) {
         if (state == DJCS_S_SUB0 || state == DJCS_S_SUB1) out |= kBad;
         next = cls == DJCS_C_EQ ? DJCS_S_EQ : cls == DJCS_C_DEL ? DJCS_S_DEL : cls == DJCS_C_INS ? DJCS_S_INS
              : cls == DJCS_C_SUB ? DJCS_S_SUB0 : DJCS_S_INTRON;
-    } else if (cls == DJCS_C_LETTER) {
-        if (state == DJCS_S_EQ) out = 1 | (3 << 8) | kRef;
+    } else if (cls == DJCS_C_LETTER || cls == DJCS_C_LETTER_N) {
+        if (state == DJCS_S_EQ) out = 1 | (3 << 8) | kRef | (cls == DJCS_C_LETTER_N ? 0x8000 : 0);
         else if (state == DJCS_S_DEL) out = 2 | (3 << 8) | kRef;
         else if (state == DJCS_S_INS) out = 3 | (3 << 8);
         else if (state == DJCS_S_SUB0) { out = 4 | (2 << 8); next = DJCS_S_SUB1; }
@@ -218,7 +227,7 @@ DJW_FN uint32_t djcs_classify(const DjCsLut &lut, const uint4 &v, int state, uin
         if (kMasked && !((active >> j) & 1u)) t &= 0x8F0u;  // keeps the state and the error, emits nothing
         if (j < 8) c_lo |= (t & 15u) << (4 * j);
         else c_hi |= (t & 15u) << (4 * (j - 8));
-        acc += ((t >> 8) & 3u) + ((t & 0x400u) << 6);
+        acc += ((t >> 8) & 3u) + ((t & 0x8400u) << 6);
         acc |= (t & 0x800u) << 20;
     }
     *lo = c_lo;
@@ -258,7 +267,8 @@ DJW_FN void djcs_emit_range(const DjCsLut &lut, const uint4 &v, uint32_t active,
     uint32_t lo, hi;
     const uint32_t acc = djcs_classify<kMasked>(lut, v, in_state, active, &lo, &hi);
     const int mine = (int)(acc & 0xFFFFu);
-    *refs += (int)((acc >> 16) & 0xFFu);
+    *refs += (int)((acc >> 16) & 0x1Fu);
+    if ((acc >> 21) & 0x1Fu) *bad |= DJ_CS_HAS_N;
     if (acc >> 31) *bad |= DJ_CS_GRAMMAR;
     int incl = mine;
 #pragma unroll
@@ -280,7 +290,7 @@ DJW_FN void djcs_emit_range(const DjCsLut &lut, const uint4 &v, uint32_t active,
 // One alignment: cs[a_off, a_end).  Adds its reference tokens to *refs (per lane: sum over the warp afterwards);
 // returns the operator the alignment ends under (warp-uniform).
 template <bool kWrite>
-DJW_FN int djcs_expand(const DjCsLut &lut, const uint8_t *cs, int64_t a_off, int64_t a_end, bool lower,
+DJW_FN int djcs_expand(const DjCsLut &lut, const uint8_t *cs, int64_t a_off, int64_t a_end, bool lower, int64_t ref_start,
                        DjCsWriter<kWrite> &w, int lane, int *refs, int *bad) {
     int c_op = 0, c_since = 0;
     for (int64_t chunk = a_off & ~(int64_t)15; chunk < a_end; chunk += DJ_CS_TRIP) {
@@ -362,7 +372,10 @@ DJW_FN int djcs_expand(const DjCsLut &lut, const uint8_t *cs, int64_t a_off, int
                 digits = true;
             }
             if (!digits) *bad |= DJ_CS_GRAMMAR;
-            djcs_fill(w, lane, n, lower);
+            int before = *refs;  // reference tokens of this alignment in front of the intron
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) before += DJW_SHFL_XOR(before, d);
+            djcs_fill(w, lane, n, lower, true, ref_start + before);
             if (lane == 0) *refs += (int)(n > 0x3fffffff ? 0x3fffffff : n);
             lo = first + 1;
         }
@@ -371,18 +384,21 @@ DJW_FN int djcs_expand(const DjCsLut &lut, const uint8_t *cs, int64_t a_off, int
 }
 
 // One read: flank, alignments in POS order with the gaps between them, flank.  kWrite == false measures
-// (row_len_io receives the row length, 0 for a dropped read; status its DJ_CS_* bits); kWrite == true writes the row
-// of a read whose measured length is *row_len_io (> 0) at `row`.
+// (row_len_io receives the row length, 0 for a dropped read; status its DJ_CS_* bits; row_n, if not null, the number
+// of "=N" tokens the filler wrote); kWrite == true writes the row of a read whose measured length is *row_len_io
+// (> 0) at `row`.  ref_seq (may be null): see djcs_fill.
 template <bool kWrite>
 DJW_FN void djcs_read(const DjCsLut &lut, const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
-                      int64_t first_aln, int64_t end_aln, int32_t ref_len, uint8_t *stage, uint8_t *row,
-                      int32_t *row_len_io, int32_t *status, int lane) {
+                      int64_t first_aln, int64_t end_aln, int32_t ref_len, const uint8_t *ref_seq, uint8_t *stage,
+                      uint8_t *row, int32_t *row_len_io, int32_t *status, int32_t *row_n, int lane) {
     DjCsWriter<kWrite> w;
     w.stage = stage;
     w.row_pos = 0;
     w.last = -1;
     w.fill = w.head_skip = 0;
     w.gbase = nullptr;
+    w.seq = ref_seq;
+    w.n_tokens = 0;
     if (kWrite) {
         const uintptr_t addr = reinterpret_cast<uintptr_t>(row);
         w.gbase = reinterpret_cast<uint8_t *>(addr & ~(uintptr_t)15);
@@ -399,11 +415,11 @@ DJW_FN void djcs_read(const DjCsLut &lut, const uint8_t *cs, const int64_t *aln_
             break;
         }
         if (start > cur) {
-            djcs_fill(w, lane, start - cur, false);
+            djcs_fill(w, lane, start - cur, false, a > first_aln, cur);
             cur = start;
         }
         int refs = 0;
-        ends = djcs_expand<kWrite>(lut, cs, aln_off[a], aln_off[a + 1], aln_lower[a] != 0, w, lane, &refs, &bad);
+        ends = djcs_expand<kWrite>(lut, cs, aln_off[a], aln_off[a + 1], aln_lower[a] != 0, cur, w, lane, &refs, &bad);
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) {
             refs += DJW_SHFL_XOR(refs, d);
@@ -417,7 +433,7 @@ DJW_FN void djcs_read(const DjCsLut &lut, const uint8_t *cs, const int64_t *aln_
     }
     if (!(bad & (DJ_CS_OVERLAP | DJ_CS_TOO_LONG))) {
         if (cur < ref_len) {
-            djcs_fill(w, lane, (int64_t)ref_len - cur, false);
+            djcs_fill(w, lane, (int64_t)ref_len - cur, false, false, cur);
         } else if (ends == '+' || first_aln == end_aln) {
             bad |= DJ_CS_GRAMMAR;  // an insertion with nothing after it (or ref_len == 0)
         }
@@ -427,6 +443,7 @@ DJW_FN void djcs_read(const DjCsLut &lut, const uint8_t *cs, const int64_t *aln_
     } else if (lane == 0) {
         if (w.row_pos - 1 > 0x7fffffff - 64) bad |= DJ_CS_TOO_LONG;
         *status = bad;
-        *row_len_io = bad ? 0 : (int32_t)(w.row_pos - 1);
+        *row_len_io = (bad & ~DJ_CS_HAS_N) ? 0 : (int32_t)(w.row_pos - 1);
+        if (row_n) *row_n = (int32_t)(w.n_tokens > 0x7fffffff ? 0x7fffffff : w.n_tokens);
     }
 }

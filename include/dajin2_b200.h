@@ -297,17 +297,24 @@ int dj_sv_scan(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, in
  *   read_first  n_reads + 1: alignments read_first[r] .. read_first[r+1]-1 belong to read r, ordered by position
  * "=ACG" -> "=A,=C,=G"; "*ag" -> "*AG"; "-ac" -> "-A,-C"; "+ac" joins the next token as "+A|+C|<next>";
  * "~gt123ag" -> 123 x "=N"; gaps between the alignments of a read and the flanks up to ref_len tokens -> "=N".
+ *   ref_seq     NULL, or the ref_len bases of the reference sequence: the tokens filled between the pieces of a read
+ *               (gaps between alignments, introns) are then written as "-<base>" instead of "=N", i.e. with
+ *               replace_internal_n_to_d (midsv_caller.py:108-126) already applied; the flanks stay "=N"
  * dj_cs_midsv_measure: row_len[r] = bytes of read r's MIDSV string, 0 for a dropped read; row_status[r] = 0 or
- *   1 (two alignments share a reference base) | 2 (not a long-form cs tag) | 4 (longer than ref_len tokens / 2 GB).
+ *   1 (two alignments share a reference base) | 2 (not a long-form cs tag) | 4 (longer than ref_len tokens / 2 GB)
+ *   | 8 (informational, the read is kept: an alignment holds "=N" tokens of its own); row_n[r] (row_n may be NULL) =
+ *   the number of "=N" tokens the filler writes, i.e. all is_n_tag tokens of the row unless bit 8 is set -- what
+ *   filter_samples_by_n_proportion (midsv_caller.py:145-155) counts.
  * dj_cs_midsv_write: writes the string of every read with row_len[r] > 0 at text + row_off[r], followed by '\n'
- *   (row_len[r] + 1 bytes); the result is the text / row_off / row_len triple dj_encode takes.
+ *   (row_len[r] + 1 bytes); the result is the text / row_off / row_len triple dj_encode takes.  ref_seq as given to
+ *   dj_cs_midsv_measure.
  */
 int dj_cs_midsv_measure(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
-                        const int64_t *read_first, int64_t n_reads, int32_t ref_len, int32_t *row_len,
-                        int32_t *row_status, void *stream);
+                        const int64_t *read_first, int64_t n_reads, int32_t ref_len, const uint8_t *ref_seq,
+                        int32_t *row_len, int32_t *row_status, int32_t *row_n, void *stream);
 int dj_cs_midsv_write(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
-                      const int64_t *read_first, int64_t n_reads, int32_t ref_len, const int64_t *row_off,
-                      const int32_t *row_len, uint8_t *text, void *stream);
+                      const int64_t *read_first, int64_t n_reads, int32_t ref_len, const uint8_t *ref_seq,
+                      const int64_t *row_off, const int32_t *row_len, uint8_t *text, void *stream);
 
 #ifdef __cplusplus
 }

@@ -95,7 +95,7 @@ def random_case(seed: int, ref_len: int, n_reads: int, rate: float) -> dict:
     records = []
     for r in range(n_reads):
         qname = f"read{rng.randrange(10**6):06d}_{r}"
-        kind = rng.choice(["full", "full", "partial", "split", "split3", "inversion", "overlap", "splice"])
+        kind = rng.choice(["full", "full", "partial", "split", "split3", "inversion", "overlap", "splice", "tiny"])
         reverse = rng.random() < 0.5
         base_flag = 16 if reverse else 0
         if kind in ("full", "splice"):
@@ -103,6 +103,9 @@ def random_case(seed: int, ref_len: int, n_reads: int, rate: float) -> dict:
         elif kind == "partial":
             a = rng.randrange(0, ref_len // 2)
             spans = [(a, rng.randrange(a + 40, ref_len + 1), False)]
+        elif kind == "tiny":  # a read that is >= 95 % "=N": filter_samples_by_n_proportion drops it
+            a = rng.randrange(0, ref_len - 12)
+            spans = [(a, a + rng.randrange(3, max(4, ref_len // 25)), False)]
         elif kind == "split":
             a = rng.randrange(40, ref_len // 2)
             b = rng.randrange(a, ref_len - 40)
@@ -166,6 +169,32 @@ def check_and_expect(case: dict, tmp: Path) -> dict:
     return expect
 
 
+def indel_pair_vectors(n: int = 400) -> list[list[str]]:
+    """Random cs tags dense in deletion-then-insertion pairs and what the REAL reference's
+    ``convert_consecutive_indels_to_match`` (``midsv_caller.py:163-202``) makes of their tokens (upper- and lowercase):
+    known answers for the cs-level form of that fix (``dajin2_b200.alignment.revert_deletion_insertion_pairs``)."""
+    rng = random.Random(3)
+    out = []
+    for _ in range(n):
+        parts = ["=" + "".join(rng.choice("AC") for _ in range(rng.randrange(1, 4)))]
+        prev = "="
+        for _ in range(rng.randrange(1, 8)):
+            op = rng.choice([o for o in "=-+*" if o != prev])
+            if op == "=":
+                parts.append("=" + "".join(rng.choice("AC") for _ in range(rng.randrange(1, 3))))
+            elif op == "*":
+                parts.append("*" + rng.choice("ac") + rng.choice("ac"))
+            else:
+                parts.append(op + "".join(rng.choice("ac") for _ in range(rng.randrange(1, 4))))
+            prev = op
+        if prev == "+":
+            parts.append("=A")
+        cs = "".join(parts)
+        out.append([cs] + [midsv_caller.convert_consecutive_indels_to_match(",".join(mt.cs_to_tokens(cs, lower)[0]))
+                           for lower in (False, True)])
+    return out
+
+
 def main() -> None:
     import tempfile
 
@@ -181,6 +210,10 @@ def main() -> None:
     path = HERE.parent / "tests" / "golden" / "cs_midsv.json.gz"
     with gzip.open(path, "wt", compresslevel=9) as f:
         json.dump(out, f, separators=(",", ":"))
+    path_pairs = HERE.parent / "tests" / "golden" / "cs_indel_pairs.json.gz"
+    with gzip.open(path_pairs, "wt", compresslevel=9) as f:
+        json.dump(indel_pair_vectors(), f, separators=(",", ":"))
+    print(path_pairs, path_pairs.stat().st_size, "bytes")
     print(path, path.stat().st_size, "bytes")
 
 

@@ -65,9 +65,11 @@ def main() -> None:
     up = [torch.from_numpy(a).to(dev) for a in arrays]
     row_len = torch.zeros(n, dtype=torch.int32, device=dev)
     status = torch.zeros(n, dtype=torch.int32, device=dev)
+    seq = None  # no reference sequence: the plain midsv.transform output (the fused form writes the same bytes per token)
 
     def measure():
-        _cabi.call("dj_cs_midsv_measure", *(_p(t) for t in up), n, ref_len, _p(row_len), _p(status), _stream())
+        _cabi.call("dj_cs_midsv_measure", *(_p(t) for t in up), n, ref_len, _p(seq), _p(row_len), _p(status), _p(None),
+                   _stream())
 
     measure()
     torch.cuda.synchronize()
@@ -79,12 +81,13 @@ def main() -> None:
     text = torch.empty(total + 64, dtype=torch.uint8, device=dev)
 
     def write():
-        _cabi.call("dj_cs_midsv_write", *(_p(t) for t in up), n, ref_len, _p(row_off), _p(row_len), _p(text), _stream())
+        _cabi.call("dj_cs_midsv_write", *(_p(t) for t in up), n, ref_len, _p(seq), _p(row_off), _p(row_len), _p(text),
+                   _stream())
 
     write()
     torch.cuda.synchronize()
     # spot check against the one-copy result
-    t1, o1, l1, _ = alignment.midsv_text_on_device(pa)
+    t1, o1, l1, _, _ = alignment.midsv_text_on_device(pa)
     a = t1[: int(o1[-1] + l1[-1])]
     for c in (0, copies // 2, copies - 1):
         lo = int(row_off[c * base_n].item())

@@ -71,8 +71,8 @@ static DjCsLut g_lut;
 
 template <bool kWrite>
 static void run(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
-                const int64_t *read_first, int64_t n_reads, int32_t ref_len, const int64_t *row_off, int32_t *row_len,
-                int32_t *row_status, uint8_t *text) {
+                const int64_t *read_first, int64_t n_reads, int32_t ref_len, const uint8_t *ref_seq, const int64_t *row_off,
+                int32_t *row_len, int32_t *row_status, int32_t *row_n, uint8_t *text) {
     pthread_barrier_init(&g_bar, nullptr, 32);
     djcs_lut_fill(&g_lut, 0, 1);
     std::vector<std::thread> lanes;
@@ -83,11 +83,11 @@ static void run(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_po
                 if (kWrite) {
                     int32_t len = row_len[r];
                     if (len <= 0) continue;
-                    djcs_read<true>(g_lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, g_stage,
-                                    text + row_off[r], &len, nullptr, lane);
+                    djcs_read<true>(g_lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, ref_seq,
+                                    g_stage, text + row_off[r], &len, nullptr, nullptr, lane);
                 } else {
-                    djcs_read<false>(g_lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, g_stage,
-                                     nullptr, row_len + r, row_status + r, lane);
+                    djcs_read<false>(g_lut, cs, aln_off, aln_pos, aln_lower, read_first[r], read_first[r + 1], ref_len, ref_seq,
+                                     g_stage, nullptr, row_len + r, row_status + r, row_n ? row_n + r : nullptr, lane);
                 }
             }
         });
@@ -97,15 +97,17 @@ static void run(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_po
 }
 
 extern "C" int cs_host_measure(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
-                               const int64_t *read_first, int64_t n_reads, int32_t ref_len, int32_t *row_len,
-                               int32_t *row_status) {
-    run<false>(cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, nullptr, row_len, row_status, nullptr);
+                               const int64_t *read_first, int64_t n_reads, int32_t ref_len, const uint8_t *ref_seq,
+                               int32_t *row_len, int32_t *row_status, int32_t *row_n) {
+    run<false>(cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, ref_seq, nullptr, row_len, row_status, row_n,
+               nullptr);
     return 0;
 }
 
 extern "C" int cs_host_write(const uint8_t *cs, const int64_t *aln_off, const int32_t *aln_pos, const uint8_t *aln_lower,
-                             const int64_t *read_first, int64_t n_reads, int32_t ref_len, const int64_t *row_off,
-                             int32_t *row_len, uint8_t *text) {
-    run<true>(cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, row_off, row_len, nullptr, text);
+                             const int64_t *read_first, int64_t n_reads, int32_t ref_len, const uint8_t *ref_seq,
+                             const int64_t *row_off, int32_t *row_len, uint8_t *text) {
+    run<true>(cs, aln_off, aln_pos, aln_lower, read_first, n_reads, ref_len, ref_seq, row_off, row_len, nullptr, nullptr,
+              text);
     return 0;
 }

@@ -120,12 +120,12 @@ def host_lib(tmp_path_factory):
                     str(ROOT / "scripts" / "cstag_host_test.cpp")], check=True)
     lib = ctypes.CDLL(str(so))
     vp = ctypes.c_void_p
-    lib.cs_host_measure.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp, vp]
-    lib.cs_host_write.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp, vp, vp]
+    lib.cs_host_measure.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp, vp, vp, vp]
+    lib.cs_host_write.argtypes = [vp, vp, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp, vp, vp, vp]
     return lib
 
 
-def run_on_host(lib, pa: alignment.PackedAlignments, lead: int = 0):
+def run_on_host(lib, pa: alignment.PackedAlignments, lead: int = 0, sequence: str | None = None, with_n: bool = False):
     """measure + write with the device routine on host threads; the text buffer starts ``lead`` bytes into a
     16-byte aligned allocation and is surrounded by sentinel bytes."""
     n = pa.n_reads
@@ -133,10 +133,14 @@ def run_on_host(lib, pa: alignment.PackedAlignments, lead: int = 0):
     shift = (-cs.ctypes.data) % 16
     cs = cs[shift : shift + pa.cs.shape[0]]
     cs[:] = pa.cs
+    seq = np.frombuffer(sequence.encode("ascii"), dtype=np.uint8) if sequence is not None else None
+    seq_p = seq.ctypes.data if seq is not None else None
     row_len = np.full(n, -7, dtype=np.int32)
     status = np.full(n, -7, dtype=np.int32)
+    row_n = np.full(n, -7, dtype=np.int32)
     lib.cs_host_measure(cs.ctypes.data, pa.aln_off.ctypes.data, pa.aln_pos.ctypes.data, pa.aln_lower.ctypes.data,
-                        pa.read_first.ctypes.data, n, pa.ref_len, row_len.ctypes.data, status.ctypes.data)
+                        pa.read_first.ctypes.data, n, pa.ref_len, seq_p, row_len.ctypes.data, status.ctypes.data,
+                        row_n.ctypes.data)
     span = np.where(row_len > 0, row_len.astype(np.int64) + 1, 0)
     row_off = np.cumsum(span) - span
     total = int(span.sum())
@@ -144,7 +148,7 @@ def run_on_host(lib, pa: alignment.PackedAlignments, lead: int = 0):
     base = (-raw.ctypes.data) % 16 + lead
     text = raw[base : base + total]
     lib.cs_host_write(cs.ctypes.data, pa.aln_off.ctypes.data, pa.aln_pos.ctypes.data, pa.aln_lower.ctypes.data,
-                      pa.read_first.ctypes.data, n, pa.ref_len, row_off.ctypes.data, row_len.ctypes.data,
+                      pa.read_first.ctypes.data, n, pa.ref_len, seq_p, row_off.ctypes.data, row_len.ctypes.data,
                       text.ctypes.data)
     assert (raw[:base] == 0xEE).all() and (raw[base + total :] == 0xEE).all(), "bytes outside the rows were written"
     rows = {}
@@ -152,7 +156,7 @@ def run_on_host(lib, pa: alignment.PackedAlignments, lead: int = 0):
         if m > 0:
             assert text[o + m] == ord("\n")
             rows[q] = text[o : o + m].tobytes().decode("ascii")
-    return rows, status
+    return (rows, status, row_n) if with_n else (rows, status)
 
 
 def packed_of(case: dict, tmp_path: Path) -> alignment.PackedAlignments:
@@ -237,6 +241,38 @@ def test_device_routine_on_host_threads_boundary_sweep(host_lib, tmp_path):
         assert rows == want
 
 
+def test_cs_level_indel_fix_returns_the_references_tokens():
+    """``revert_deletion_insertion_pairs`` on the cs tag == the REAL reference's ``convert_consecutive_indels_to_match``
+    on the tokens (400 tags dense in deletion-then-insertion pairs, answers recorded by ``oracle/make_cs_golden.py``)."""
+    with gzip.open(ROOT / "tests" / "golden" / "cs_indel_pairs.json.gz", "rt") as f:
+        vectors = json.load(f)
+    assert len(vectors) == 400 and sum(v[1] != ",".join(mt.cs_to_tokens(v[0])[0]) for v in vectors) >= 20  # the fix applies
+    for cs, want_upper, want_lower in vectors:
+        fixed = alignment.revert_deletion_insertion_pairs(cs)
+        assert ",".join(mt.cs_to_tokens(fixed)[0]) == want_upper, cs
+        assert ",".join(mt.cs_to_tokens(fixed, lower=True)[0]) == want_lower, cs
+
+
+def test_fused_chain_on_host_threads_equals_the_reference_chain(golden, host_lib, tmp_path):
+    """The all-device form of ``generate_midsv``'s chain (``alignment.host_reads_from_sam``: cs-level indel fix,
+    deletions of the reference bases between the pieces of a read, N-share filter from the measured flanks), with the
+    kernels' routine on host threads: the rows, names and strands the REAL reference's chain returned (``postfixed``)."""
+    for case in golden:
+        sq, records = alignment.read_sam_records(write_sam(case, tmp_path / "case.sam"))
+        (pa,) = alignment.pack_alignments(sq, [(q, f, r, p, alignment.revert_deletion_insertion_pairs(cs))
+                                               for q, f, r, p, cs in records])
+        rows, status, row_n = run_on_host(host_lib, pa, lead=7, sequence=case["sequence"], with_n=True)
+        assert not (status & alignment.CS_HAS_N).any()
+        keep = {q for q, n in zip(pa.qnames, row_n.tolist()) if q in rows and n / pa.ref_len * 100 < 95}
+        got = [{"QNAME": q, "RNAME": pa.rname, "MIDSV": rows[q], "STRAND": "-" if f & 16 else "+"}
+               for q, f in zip(pa.qnames, pa.flags) if q in keep]
+        assert got == case["postfixed"], case["name"]
+    # an alignment with "=N" tokens of its own is reported (the caller then takes the host route)
+    odd = {"sq": {"a": 8}, "records": [{"QNAME": "q", "FLAG": 0, "RNAME": "a", "POS": 2, "CIGAR": "*", "CSTAG": "=ACNNGT"}]}
+    rows, status, row_n = run_on_host(host_lib, packed_of(odd, tmp_path), sequence="TACNNGTA", with_n=True)
+    assert status.tolist() == [alignment.CS_HAS_N] and row_n.tolist() == [2] and rows["q"] == "=N,=A,=C,=N,=N,=G,=T,=N"
+
+
 def test_pack_alignments_orders_and_flags():
     sq = {"a": 100}
     records = [("b", 2048, "a", 50, "=AC"), ("a", 16, "a", 1, "=G"), ("b", 16, "a", 10, "=T"), ("b", 0, "a", 80, "=C")]
@@ -289,7 +325,7 @@ def test_device_text_matches_oracle_and_feeds_the_encoder(tmp_path):
     want = mt.transform(sam)
     sq, records = alignment.read_sam_records(sam)
     (pa,) = alignment.pack_alignments(sq, records)
-    text, row_off, row_len, status = alignment.midsv_text_on_device(pa)
+    text, row_off, row_len, status, _ = alignment.midsv_text_on_device(pa)
     keep = (row_len > 0).cpu().numpy()
     assert [q for q, k in zip(pa.qnames, keep) if k] == [r["QNAME"] for r in want]
     assert set(status.cpu().numpy()[~keep].tolist()) <= {alignment.CS_OVERLAP, alignment.CS_TOO_LONG}
@@ -304,3 +340,26 @@ def test_device_text_matches_oracle_and_feeds_the_encoder(tmp_path):
                                               np.full(n, ord("+"), dtype=np.uint8),
                                               np.array([f"read{i:09d}".encode() for i in range(n)], dtype="S")), 5000)
     assert torch.equal(from_host.codes, on_device.codes) and torch.equal(from_host.match_score, on_device.match_score)
+
+
+@pytest.mark.gpu
+def test_host_reads_from_sam_equal_the_reference_chain(golden, tmp_path):
+    """SAM -> reads in HBM with the whole post-fix chain applied on the way (no MIDSV text on the host): the rows,
+    names and strands of the REAL reference's chain; and they encode like the same rows shipped from the host."""
+    import torch
+
+    from dajin2_b200 import engine
+    from dajin2_b200.ingest import pack_rows
+
+    for case in golden:
+        reads = alignment.host_reads_from_sam(write_sam(case, tmp_path / "case.sam"), case["sequence"])
+        want = case["postfixed"]
+        buf = reads.text.cpu().numpy().tobytes()
+        got = [buf[o : o + m].decode("ascii") for o, m in zip(reads.row_off.tolist(), reads.row_len.tolist())]
+        assert got == [r["MIDSV"] for r in want], case["name"]
+        assert [q.decode() for q in reads.qnames] == [r["QNAME"] for r in want]
+        assert bytes(reads.strand).decode() == "".join(r["STRAND"] for r in want)
+        n_loci = list(case["sq"].values())[0]
+        on_device = engine.EncodedReads(reads, n_loci)
+        from_host = engine.EncodedReads(pack_rows(got), n_loci)
+        assert torch.equal(on_device.codes, from_host.codes) and torch.equal(on_device.match_score, from_host.match_score)
