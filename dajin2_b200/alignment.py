@@ -217,6 +217,81 @@ def pack_alignments(sq: dict[str, int], records: list[tuple]) -> list[PackedAlig
     return packed
 
 
+def scan_sam(path_sam: str | Path, fix_indel_pairs: bool = False) -> list[PackedAlignments]:
+    """``read_sam_records`` + ``pack_alignments`` (+ ``revert_deletion_insertion_pairs`` on every tag) without a Python
+    object per record: the file is read once, ``hostc/samscan.c`` finds the field spans with threads over whole lines,
+    numpy orders the records by (QNAME, POS) and the tags are gathered in that order.  Same arrays as the Python pair
+    (``tests/test_cstag.py`` compares them); bytes the indel fix saves are NUL at the end of a tag's slot, which the
+    kernels skip."""
+    from .fastmlp import load_host_lib
+
+    lib = load_host_lib()
+    buf = np.fromfile(path_sam, dtype=np.uint8)
+    n = int(buf.shape[0])
+    threads = _threads()
+    sq: dict[str, int] = {}
+    window = 1 << 20  # header lines come first (SAM specification, section 1.3)
+    while True:
+        head = buf[: min(n, window)].tobytes()
+        end = 0
+        while end < len(head) and head[end : end + 1] == b"@" and head.find(b"\n", end) >= 0:
+            end = head.find(b"\n", end) + 1
+        if end < len(head) and head[end : end + 1] == b"@" and window < n:
+            window *= 8  # the header is longer than the window
+            continue
+        break
+    for line in head.split(b"\n"):
+        if not line.startswith(b"@"):
+            break
+        if line.startswith(b"@SQ"):
+            tags = dict(t.split(":", 1) for t in line.decode("ascii", "replace").rstrip("\r").split("\t")[1:] if ":" in t)
+            sq[tags["SN"]] = int(tags["LN"])
+    n_rec = int(lib.dj_sam_count(buf.ctypes.data, n, threads))
+    i64, i32 = np.int64, np.int32
+    q_off, r_off, c_off = np.empty(n_rec, i64), np.empty(n_rec, i64), np.empty(n_rec, i64)
+    q_len, r_len, c_len = np.empty(n_rec, i32), np.empty(n_rec, i32), np.empty(n_rec, i32)
+    flag, pos = np.empty(n_rec, i32), np.empty(n_rec, i32)
+    bad = lib.dj_sam_index(buf.ctypes.data, n, n_rec, q_off.ctypes.data, q_len.ctypes.data, flag.ctypes.data,
+                           r_off.ctypes.data, r_len.ctypes.data, pos.ctypes.data, c_off.ctypes.data, c_len.ctypes.data,
+                           threads)
+    if bad != 0:
+        raise ValueError(f"{path_sam}: {bad if bad > 0 else 'some'} alignment lines are not SAM records")
+
+    def names(off, length):
+        width = max(int(length.max()) if n_rec else 1, 1)
+        out = np.zeros((n_rec, width), dtype=np.uint8)
+        lib.dj_gather_fixed(buf.ctypes.data, off.ctypes.data, length.ctypes.data, n_rec, width, out.ctypes.data, threads)
+        return out.view(f"S{width}").reshape(n_rec)
+
+    qnames, rnames = names(q_off, q_len), names(r_off, r_len)
+    mapped = ((flag & 4) == 0) & (rnames != b"*")
+    if (mapped & (c_len < 0)).any():
+        k = int(np.flatnonzero(mapped & (c_len < 0))[0])
+        raise ValueError(f"{path_sam}: {qnames[k].decode('ascii', 'replace')} has no cs tag (map with the long-form cs tag)")
+    packed = []
+    for rname in sorted(set(rnames[mapped].tolist())):
+        name = rname.decode("ascii")
+        if name not in sq:
+            raise ValueError(f"no @SQ line for {name}")
+        idx = np.flatnonzero(mapped & (rnames == rname))
+        idx = idx[np.lexsort((pos[idx], qnames[idx]))]  # by QNAME, then POS; stable like list.sort
+        qn, fl = qnames[idx], flag[idx]
+        first = np.flatnonzero(np.concatenate([[True], qn[1:] != qn[:-1]]))
+        read_first = np.concatenate([first, [idx.shape[0]]]).astype(np.int64)
+        read_of = np.repeat(np.arange(first.shape[0]), np.diff(read_first))
+        lower = ((fl & 16) != (fl[first][read_of] & 16)).astype(np.uint8)
+        lens = c_len[idx].astype(np.int64)
+        aln_off = np.zeros(idx.shape[0] + 1, dtype=np.int64)
+        np.cumsum(lens, out=aln_off[1:])
+        cs = np.zeros(int(aln_off[-1]) + 16, dtype=np.uint8)
+        order = np.ascontiguousarray(idx, dtype=np.int64)
+        lib.dj_cs_pack(buf.ctypes.data, c_off.ctypes.data, c_len.ctypes.data, order.ctypes.data, int(order.shape[0]),
+                       int(fix_indel_pairs), cs.ctypes.data, aln_off.ctypes.data, threads)
+        packed.append(PackedAlignments(name, int(sq[name]), cs, aln_off, (pos[idx] - 1).astype(np.int32), lower,
+                                       read_first, [q.decode("ascii") for q in qn[first]], fl[first].tolist()))
+    return packed
+
+
 _DEL_THEN_INS = re.compile(r"-([A-Za-z]+)\+([A-Za-z]+)")
 
 
@@ -294,8 +369,7 @@ def host_reads_from_sam(path_sam: str | Path, sequence: str, threshold: int = 95
 
     from .ingest import HostReads, pack_rows
 
-    sq, records = read_sam_records(path_sam)
-    packed = pack_alignments(sq, [(q, f, r, p, revert_deletion_insertion_pairs(cs)) for q, f, r, p, cs in records])
+    packed = scan_sam(path_sam, fix_indel_pairs=True)
     if len(packed) != 1:
         raise ValueError(f"{path_sam}: alignments against {len(packed)} reference sequences, expected one allele")
     (pa,) = packed
@@ -319,9 +393,9 @@ def host_reads_from_sam(path_sam: str | Path, sequence: str, threshold: int = 95
 def transform_to_midsv_format(path_sam: str | Path) -> list[dict]:
     """``midsv_caller.py:84-85``: ``midsv.transform(path_sam, qscore=False, keep={"FLAG"})`` -- one dict per read with
     QNAME, RNAME, MIDSV and FLAG, in QNAME order."""
-    sq, records = read_sam_records(path_sam)
+    packed = scan_sam(path_sam)
     out = []
-    for pa in pack_alignments(sq, records):
+    for pa in packed:
         text, row_off, row_len, status, _ = midsv_text_on_device(pa)
         status_h = status.cpu().numpy()
         if (status_h & CS_GRAMMAR).any():
@@ -331,6 +405,6 @@ def transform_to_midsv_format(path_sam: str | Path) -> list[dict]:
         for qname, flag, o, m in zip(pa.qnames, pa.flags, row_off.tolist(), row_len.tolist()):
             if m > 0:
                 out.append({"QNAME": qname, "RNAME": pa.rname, "MIDSV": buf[o : o + m].decode("ascii"), "FLAG": flag})
-    if len({r[2] for r in records}) > 1:  # several reference sequences in one file: back to one QNAME order
+    if len(packed) > 1:  # several reference sequences in one file: back to one QNAME order
         out.sort(key=lambda d: d["QNAME"])
     return out

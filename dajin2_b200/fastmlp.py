@@ -41,7 +41,7 @@ import numpy as np
 from sklearn.neural_network import MLPClassifier
 
 HERE = Path(__file__).resolve().parent
-SOURCES = [HERE / "hostc" / name for name in ("fastmlp.c", "choice.c", "ingest.c", "midsvfix.c")]  # one small host library
+SOURCES = [HERE / "hostc" / name for name in ("fastmlp.c", "choice.c", "ingest.c", "midsvfix.c", "samscan.c")]  # one small host library
 VMATH = HERE / "hostc" / "vmath.c"
 AVX512 = HERE / "hostc" / "fastmlp512.c"  # compiled for AVX-512 on any x86-64 build machine, entered after a run-time check
 VMATH512 = HERE / "hostc" / "vmath512.c"
@@ -182,6 +182,12 @@ def load_host_lib():
         lib.dj_midsv_postfix.restype = i64
         lib.dj_masked_row_sums.argtypes = [vp, i64, i64, ctypes.c_int32, vp, ctypes.c_int32, vp, vp, ci]
         lib.dj_masked_row_sums.restype = None
+        lib.dj_sam_count.argtypes = [vp, i64, ci]
+        lib.dj_sam_count.restype = i64
+        lib.dj_sam_index.argtypes = [vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, ci]
+        lib.dj_sam_index.restype = i64
+        lib.dj_cs_pack.argtypes = [vp, vp, vp, vp, i64, ci, vp, vp, ci]
+        lib.dj_cs_pack.restype = None
         lib.fm_set_threads(default_threads())
         lib.fm_set_forward_threads.argtypes = [ci]
         lib.fm_set_forward_threads.restype = None

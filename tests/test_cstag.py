@@ -283,6 +283,44 @@ def test_pack_alignments_orders_and_flags():
     assert pa.cs.shape[0] == int(pa.aln_off[-1]) + 16
 
 
+def test_native_sam_scan_equals_the_python_packer(golden, tmp_path):
+    """``alignment.scan_sam`` (threads over the file, ``hostc/samscan.c``) == ``read_sam_records`` + ``pack_alignments``,
+    and with the indel fix == ``revert_deletion_insertion_pairs`` on every tag (saved bytes NUL at the slot's end)."""
+    cases = list(golden) + [big_case(21, 3000, 40)]
+    pairs = {"sq": {"a": 40}, "records": [
+        {"QNAME": f"p{k}", "FLAG": 0, "RNAME": "a", "POS": 1, "CIGAR": "*", "CSTAG": cs}
+        for k, cs in enumerate(["=AC-c+c=T", "=A-ttacg+acg=T", "=A-c+cc=T", "=A+a-c+c=T", "=A+a-gc+c=T", "=A-ac+ac-g=T",
+                                "=A-a+a-c+c=T", "=ACGT", "=A-c+c", "=A-", "=A-cg+g*ac=T"])]}
+    for case in cases + [pairs]:
+        sam = write_sam(case, tmp_path / "case.sam")
+        sq, records = alignment.read_sam_records(sam)
+        for fix in (False, True):
+            recs = [(q, f, r, p, alignment.revert_deletion_insertion_pairs(cs) if fix else cs) for q, f, r, p, cs in records]
+            (want,) = alignment.pack_alignments(sq, recs)
+            (got,) = alignment.scan_sam(sam, fix_indel_pairs=fix)
+            assert (got.rname, got.ref_len, got.qnames, got.flags) == (want.rname, want.ref_len, want.qnames, want.flags)
+            for name in ("aln_pos", "aln_lower", "read_first"):
+                assert np.array_equal(getattr(got, name), getattr(want, name)), name
+            assert got.aln_pos.dtype == np.int32 and got.aln_lower.dtype == np.uint8 and got.read_first.dtype == np.int64
+            tags_got = [bytes(got.cs[a:b]).rstrip(b"\0") for a, b in zip(got.aln_off[:-1], got.aln_off[1:])]
+            tags_want = [bytes(want.cs[a:b]) for a, b in zip(want.aln_off[:-1], want.aln_off[1:])]
+            assert tags_got == tags_want
+            assert got.cs.shape[0] == int(got.aln_off[-1]) + 16 and not got.cs[int(got.aln_off[-1]):].any()
+            if not fix:
+                assert np.array_equal(got.aln_off, want.aln_off)
+    # unmapped records and records of a second reference are kept apart; a mapped record without cs tag is an error
+    (tmp_path / "two.sam").write_text("@SQ\tSN:a\tLN:4\n@SQ\tSN:b\tLN:3\n@PG\tID:x\n"
+                                      "r1\t0\ta\t1\t60\t4M\t*\t0\t0\tACGT\t*\tNM:i:0\tcs:Z:=ACGT\n"
+                                      "r2\t4\t*\t0\t0\t*\t*\t0\t0\tACGT\t*\n"
+                                      "r0\t16\tb\t2\t60\t2M\t*\t0\t0\tAC\t*\tcs:Z:=AC\ttp:A:P\r\n")
+    a, b = alignment.scan_sam(tmp_path / "two.sam")
+    assert (a.rname, a.qnames, a.aln_pos.tolist(), bytes(a.cs[:5])) == ("a", ["r1"], [0], b"=ACGT")
+    assert (b.rname, b.qnames, b.flags, b.aln_pos.tolist(), bytes(b.cs[:3])) == ("b", ["r0"], [16], [1], b"=AC")
+    (tmp_path / "nocs.sam").write_text("@SQ\tSN:a\tLN:4\nr1\t0\ta\t1\t60\t4M\t*\t0\t0\tACGT\t*\tNM:i:0\n")
+    with pytest.raises(ValueError, match="no cs tag"):
+        alignment.scan_sam(tmp_path / "nocs.sam")
+
+
 def test_transform_refuses_without_cuda(tmp_path, golden):
     import torch
 
