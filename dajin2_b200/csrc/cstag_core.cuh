@@ -32,7 +32,6 @@
 #define DJW_BALLOT(p) __ballot_sync(DJW_FULL, (p))
 #define DJW_SYNC() __syncwarp()
 #define DJW_CLZ(x) __clz((int)(x))
-#define DJW_VCMPEQ4(a, b) __vcmpeq4((a), (b))
 DJW_FN uint4 djw_load16(const uint8_t *p) { return __ldg(reinterpret_cast<const uint4 *>(p)); }
 #else
 // host emulation: provided by the including file (scripts/cstag_host_test.cpp) before this header
@@ -118,13 +117,8 @@ DJW_FN void djcs_fill(DjCsWriter<kWrite> &w, int lane, int64_t n_tokens, bool lo
     }
 }
 
-// 0xFF in every byte of a word that holds an operator character; '~' bytes are also ORed into *tilde
-DJW_FN uint32_t djcs_op_bytes(uint32_t word, uint32_t *tilde) {
-    const uint32_t t = DJW_VCMPEQ4(word, 0x7E7E7E7Eu);
-    *tilde |= t;
-    return DJW_VCMPEQ4(word, 0x3D3D3D3Du) | DJW_VCMPEQ4(word, 0x2A2A2A2Au) | DJW_VCMPEQ4(word, 0x2D2D2D2Du) |
-           DJW_VCMPEQ4(word, 0x2B2B2B2Bu) | t;
-}
+// non-zero iff a byte of x is zero
+DJW_FN uint32_t djcs_has_zero_byte(uint32_t x) { return (x - 0x01010101u) & ~x & 0x80808080u; }
 
 // byte mask of the word that holds bytes j0 .. j0 + 3 of a lane: 0xFF where j_lo <= j < j_hi
 DJW_FN uint32_t djcs_valid_mask(int j0, int j_lo, int j_hi) {
@@ -153,9 +147,11 @@ enum { DJCS_C_OUT = 0, DJCS_C_EQ, DJCS_C_DEL, DJCS_C_INS, DJCS_C_SUB, DJCS_C_INT
        DJCS_C_OTHER, DJCS_C_LETTER_N };
 
 struct DjCsLut {
-    uint8_t cls[256];
-    uint16_t tr[8 * 16];  // [3:0] code, [7:4] next state, [9:8] bytes emitted, [10] reference token, [11] grammar error,
-                          // [15] an "=N" token (is_n_tag, utils/midsv_handler.py:8-14)
+    // one look-up per byte: entry[state * 256 + byte], addressed in bytes as (state << 10) | (byte << 2).
+    //   [3:0] code   [12:10] next state (already in address position)   [15] grammar error
+    //   [17:16] bytes emitted   [22] reference token   [27] an "=N" token (is_n_tag, utils/midsv_handler.py:8-14)
+    // so that sizes, tokens and "=N" tokens add up in one register (fields 16..21, 22..26, 27..31 for sixteen bytes)
+    uint32_t entry[8 * 256];
 };
 
 DJW_FN uint8_t djcs_class_of(int c) {
@@ -171,20 +167,21 @@ DJW_FN uint8_t djcs_class_of(int c) {
     return DJCS_C_OTHER;
 }
 
-DJW_FN uint16_t djcs_transition(int state, int cls) {
-    const int kBad = 0x800, kRef = 0x400;
-    int next = state, out = 0;
+DJW_FN uint32_t djcs_transition(int state, int cls) {
+    const uint32_t kBad = 1u << 15, kRef = 1u << 22, kIsN = 1u << 27, kThree = 3u << 16, kTwo = 2u << 16;
+    int next = state;
+    uint32_t out = 0;
     if (cls == DJCS_C_OUT) {
     } else if (cls >= DJCS_C_EQ && cls <= DJCS_C_INTRON) {  // an operator: a substitution must be complete
         if (state == DJCS_S_SUB0 || state == DJCS_S_SUB1) out |= kBad;
         next = cls == DJCS_C_EQ ? DJCS_S_EQ : cls == DJCS_C_DEL ? DJCS_S_DEL : cls == DJCS_C_INS ? DJCS_S_INS
              : cls == DJCS_C_SUB ? DJCS_S_SUB0 : DJCS_S_INTRON;
     } else if (cls == DJCS_C_LETTER || cls == DJCS_C_LETTER_N) {
-        if (state == DJCS_S_EQ) out = 1 | (3 << 8) | kRef | (cls == DJCS_C_LETTER_N ? 0x8000 : 0);
-        else if (state == DJCS_S_DEL) out = 2 | (3 << 8) | kRef;
-        else if (state == DJCS_S_INS) out = 3 | (3 << 8);
-        else if (state == DJCS_S_SUB0) { out = 4 | (2 << 8); next = DJCS_S_SUB1; }
-        else if (state == DJCS_S_SUB1) { out = 5 | (2 << 8) | kRef; next = DJCS_S_SUB2; }
+        if (state == DJCS_S_EQ) out = 1u | kThree | kRef | (cls == DJCS_C_LETTER_N ? kIsN : 0u);
+        else if (state == DJCS_S_DEL) out = 2u | kThree | kRef;
+        else if (state == DJCS_S_INS) out = 3u | kThree;
+        else if (state == DJCS_S_SUB0) { out = 4u | kTwo; next = DJCS_S_SUB1; }
+        else if (state == DJCS_S_SUB1) { out = 5u | kTwo | kRef; next = DJCS_S_SUB2; }
         else if (state == DJCS_S_INTRON) out = 0;
         else out = kBad;  // no operator yet, or a third letter of a substitution
     } else if (cls == DJCS_C_DIGIT) {
@@ -192,15 +189,12 @@ DJW_FN uint16_t djcs_transition(int state, int cls) {
     } else {
         out = kBad;
     }
-    return (uint16_t)(out | (next << 4));
+    return out | ((uint32_t)next << 10);
 }
 
-// entries [first, 384) in steps of `step` (a CTA fills its shared-memory copy with all its threads)
+// entries [first, 2048) in steps of `step` (a CTA fills its shared-memory copy with all its threads)
 DJW_FN void djcs_lut_fill(DjCsLut *lut, int first, int step) {
-    for (int k = first; k < 384; k += step) {
-        if (k < 256) lut->cls[k] = djcs_class_of(k);
-        else lut->tr[k - 256] = djcs_transition((k - 256) >> 4, (k - 256) & 15);
-    }
+    for (int k = first; k < 8 * 256; k += step) lut->entry[k] = djcs_transition(k >> 8, djcs_class_of(k & 255));
 }
 
 // state a lane starts in, from the last operator before it and the bytes since
@@ -213,26 +207,34 @@ DJW_FN int djcs_state_of(int op, int since) {
     return DJCS_S_NONE;
 }
 
+// (byte j of the lane) << 2
+DJW_FN uint32_t djcs_byte4(const uint4 &v, int j) {
+    const uint32_t word = j < 4 ? v.x : j < 8 ? v.y : j < 12 ? v.z : v.w;
+    const int b = j & 3;
+    return b == 0 ? (word << 2) & 0x3FCu : (word >> (8 * b - 2)) & 0x3FCu;
+}
+
 // Walk the lane's bytes through the table.  `active` (bit j = byte j counts) limits what is emitted, not the
-// states.  Returns bytes emitted | reference tokens << 16 | grammar error << 31; the codes go to *lo (bytes 0..7) and
-// *hi (bytes 8..15).
+// states.  Returns bytes emitted << 16 | reference tokens << 22 | "=N" tokens << 27 | grammar error << 15; the codes
+// go to *lo (bytes 0..7) and *hi (bytes 8..15).
 template <bool kMasked>
 DJW_FN uint32_t djcs_classify(const DjCsLut &lut, const uint4 &v, int state, uint32_t active, uint32_t *lo,
                               uint32_t *hi) {
-    uint32_t c_lo = 0, c_hi = 0, acc = 0;
+    const uint8_t *table = reinterpret_cast<const uint8_t *>(lut.entry);
+    uint32_t c_lo = 0, c_hi = 0, acc = 0, bad = 0;
+    uint32_t t = (uint32_t)state << 10;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        uint32_t t = lut.tr[state * 16 + lut.cls[djcs_byte(v, j)]];
-        state = (t >> 4) & 15;
-        if (kMasked && !((active >> j) & 1u)) t &= 0x8F0u;  // keeps the state and the error, emits nothing
+        t = *reinterpret_cast<const uint32_t *>(table + ((t & 0x1C00u) | djcs_byte4(v, j)));
+        if (kMasked && !((active >> j) & 1u)) t &= 0x9C00u;  // keeps the state and the error, emits nothing
         if (j < 8) c_lo |= (t & 15u) << (4 * j);
         else c_hi |= (t & 15u) << (4 * (j - 8));
-        acc += ((t >> 8) & 3u) + ((t & 0x8400u) << 6);
-        acc |= (t & 0x800u) << 20;
+        acc += t & 0xFFFF0000u;
+        bad |= t;
     }
     *lo = c_lo;
     *hi = c_hi;
-    return acc;
+    return acc | (bad & 0x8000u);
 }
 
 // the bytes of the lane's codes at dst; `term` = offset (from dst) of the separator that ends the row, -1 if none
@@ -266,10 +268,10 @@ DJW_FN void djcs_emit_range(const DjCsLut &lut, const uint4 &v, uint32_t active,
                             DjCsWriter<kWrite> &w, int lane, int *refs, int *bad) {
     uint32_t lo, hi;
     const uint32_t acc = djcs_classify<kMasked>(lut, v, in_state, active, &lo, &hi);
-    const int mine = (int)(acc & 0xFFFFu);
-    *refs += (int)((acc >> 16) & 0x1Fu);
-    if ((acc >> 21) & 0x1Fu) *bad |= DJ_CS_HAS_N;
-    if (acc >> 31) *bad |= DJ_CS_GRAMMAR;
+    const int mine = (int)((acc >> 16) & 0x3Fu);
+    *refs += (int)((acc >> 22) & 0x1Fu);
+    if (acc >> 27) *bad |= DJ_CS_HAS_N;
+    if (acc & 0x8000u) *bad |= DJ_CS_GRAMMAR;
     int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -295,9 +297,12 @@ DJW_FN int djcs_expand(const DjCsLut &lut, const uint8_t *cs, int64_t a_off, int
     int c_op = 0, c_since = 0;
     for (int64_t chunk = a_off & ~(int64_t)15; chunk < a_end; chunk += DJ_CS_TRIP) {
         const int64_t p0 = chunk + lane * 16;
+        const bool interior = chunk >= a_off && chunk + DJ_CS_TRIP <= a_end;  // every byte of the trip is a tag byte
         uint4 v;
         v.x = v.y = v.z = v.w = 0;
-        if (p0 < a_end && p0 + 16 > a_off) {
+        if (interior) {
+            v = djw_load16(cs + p0);
+        } else if (p0 < a_end && p0 + 16 > a_off) {
             v = djw_load16(cs + p0);
             const int j_lo = a_off > p0 ? (int)(a_off - p0) : 0;  // bytes outside [a_off, a_end) -> 0
             const int j_hi = a_end - p0 < 16 ? (int)(a_end - p0) : 16;
@@ -306,18 +311,35 @@ DJW_FN int djcs_expand(const DjCsLut &lut, const uint8_t *cs, int64_t a_off, int
             v.z &= djcs_valid_mask(8, j_lo, j_hi);
             v.w &= djcs_valid_mask(12, j_lo, j_hi);
         }
-        // the last operator among the lane's bytes, four bytes at a time
-        uint32_t tilde_bytes = 0;
-        const uint32_t z0 = djcs_op_bytes(v.x, &tilde_bytes), z1 = djcs_op_bytes(v.y, &tilde_bytes);
-        const uint32_t z2 = djcs_op_bytes(v.z, &tilde_bytes), z3 = djcs_op_bytes(v.w, &tilde_bytes);
+        // '~' anywhere in the lane (introns are rare; they and the trips at the ends of a tag take the byte-wise scan)
+        const uint32_t tilde_bytes = djcs_has_zero_byte(v.x ^ 0x7E7E7E7Eu) | djcs_has_zero_byte(v.y ^ 0x7E7E7E7Eu) |
+                                     djcs_has_zero_byte(v.z ^ 0x7E7E7E7Eu) | djcs_has_zero_byte(v.w ^ 0x7E7E7E7Eu);
+        const bool introns = DJW_BALLOT(tilde_bytes != 0) != 0;
+        // NUL bytes inside a tag (the slack alignment.scan_sam leaves behind a shortened tag) are no operators either
+        const uint32_t nul_bytes = djcs_has_zero_byte(v.x) | djcs_has_zero_byte(v.y) | djcs_has_zero_byte(v.z) |
+                                   djcs_has_zero_byte(v.w);
+        const bool plain_bytes = interior && !introns && c_op != '~' && DJW_BALLOT(nul_bytes != 0) == 0;
+        // the last operator among the lane's bytes
         int last_idx = -1, last_op = 0;
-        {
+        if (plain_bytes) {
+            // Outside introns a tag byte without bit 6 is an operator ('=' '*' '-' '+'; letters and '~' have the bit;
+            // digits and anything else without it are grammar errors the table flags, so a wrong carry cannot matter).
+            const uint32_t z0 = ~v.x & 0x40404040u, z1 = ~v.y & 0x40404040u, z2 = ~v.z & 0x40404040u,
+                           z3 = ~v.w & 0x40404040u;
             const uint32_t z = z3 ? z3 : z2 ? z2 : z1 ? z1 : z0;
             const uint32_t word = z3 ? v.w : z2 ? v.z : z1 ? v.y : v.x;
             if (z) {
                 const int b = (31 - DJW_CLZ(z)) >> 3;
                 last_idx = (z3 ? 12 : z2 ? 8 : z1 ? 4 : 0) + b;
                 last_op = (int)((word >> (8 * b)) & 0xFFu);
+            }
+        } else {
+            for (int j = 0; j < 16; ++j) {
+                const int c = djcs_byte(v, j);
+                if (c == '=' || c == '*' || c == '-' || c == '+' || c == '~') {
+                    last_idx = j;
+                    last_op = c;
+                }
             }
         }
         const uint32_t has = DJW_BALLOT(last_idx >= 0);
@@ -334,7 +356,7 @@ DJW_FN int djcs_expand(const DjCsLut &lut, const uint8_t *cs, int64_t a_off, int
 
         const int64_t trip_end = chunk + DJ_CS_TRIP < a_end ? chunk + DJ_CS_TRIP : a_end;
         const int in_state = djcs_state_of(in_op, in_since);
-        if (DJW_BALLOT(tilde_bytes != 0) == 0) {
+        if (!introns) {
             djcs_emit_range<kWrite, false>(lut, v, 0xFFFFu, in_state, lower, w, lane, refs, bad);
             continue;
         }

@@ -50,14 +50,6 @@ static inline uint32_t emu_ballot(bool p) {
 #define DJW_BALLOT(p) emu_ballot((p))
 #define DJW_SYNC() emu_wait()
 #define DJW_CLZ(x) __builtin_clz((unsigned)(x))
-static inline uint32_t emu_vcmpeq4(uint32_t a, uint32_t b) {
-    uint32_t r = 0;
-    for (int k = 0; k < 4; ++k) {
-        if (((a >> (8 * k)) & 0xFFu) == ((b >> (8 * k)) & 0xFFu)) r |= 0xFFu << (8 * k);
-    }
-    return r;
-}
-#define DJW_VCMPEQ4(a, b) emu_vcmpeq4((a), (b))
 static inline uint4 djw_load16(const uint8_t *p) {
     uint4 v;
     memcpy(&v, p, 16);
