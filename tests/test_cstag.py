@@ -273,6 +273,22 @@ def test_fused_chain_on_host_threads_equals_the_reference_chain(golden, host_lib
     assert status.tolist() == [alignment.CS_HAS_N] and row_n.tolist() == [2] and rows["q"] == "=N,=A,=C,=N,=N,=G,=T,=N"
 
 
+def test_smoke_sam_on_host_threads(host_lib, tmp_path):
+    """The three reads ``__graft_entry__.smoke()`` sends through the device path: the routine on host threads returns
+    what smoke() compares the device with (so smoke's assertion is the kernels', not the fixture's)."""
+    import __graft_entry__ as entry
+
+    sam = tmp_path / "smoke.sam"
+    sam.write_text(entry.SMOKE_SAM)
+    want = mt.transform(sam)
+    assert [r["QNAME"] for r in want] == ["r1", "r2", "r3"] and all(len(r["MIDSV"].split(",")) == 40 for r in want)
+    assert "=g,=g,=t,=t" in want[1]["MIDSV"] and want[2]["MIDSV"].count("=N") == 1 + 12 + 7
+    (pa,) = alignment.scan_sam(sam)
+    rows, status = run_on_host(host_lib, pa, lead=11)
+    assert not status.any()
+    assert [{"QNAME": q, "RNAME": pa.rname, "MIDSV": rows[q], "FLAG": f} for q, f in zip(pa.qnames, pa.flags)] == want
+
+
 def test_pack_alignments_orders_and_flags():
     sq = {"a": 100}
     records = [("b", 2048, "a", 50, "=AC"), ("a", 16, "a", 1, "=G"), ("b", 16, "a", 10, "=T"), ("b", 0, "a", 80, "=C")]
