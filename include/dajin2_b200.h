@@ -290,7 +290,8 @@ int dj_sv_scan(const uint8_t *codes, int32_t code_pitch, const int32_t *rows, in
  * work of midsv.transform(path_sam, qscore=False, keep={"FLAG"}) as preprocess/alignment/midsv_caller.py:84-85 calls
  * it (third-party midsv >= 0.13.1, absent from the reference tree: PARITY UNPINNED; rules as restated in
  * oracle/midsv_transform.py and checked with the reference's own inverse, utils/midsv_handler.py:158-161).
- *   cs          the cs tags (without "cs:Z:") back to back; 16-byte aligned, >= 16 readable bytes after the last one
+ *   cs          the cs tags (without "cs:Z:") back to back; 16-byte aligned, >= 16 readable bytes after the last one;
+ *               NUL bytes inside a tag are skipped (slack behind a tag the caller has shortened in place)
  *   aln_off     n_alignments + 1 offsets into cs
  *   aln_pos     0-based reference position of each alignment (POS - 1)
  *   aln_lower   1: the alignment is on the other strand than the first alignment of its read -> lowercase tokens

@@ -22,7 +22,8 @@ what the reference itself holds:
 
 Rules restated (each is a choice midsv documents or the reference depends on):
 
-1. Records without a mapped position (``FLAG & 4`` or RNAME ``*``) or without a ``cs:Z:`` tag are skipped.
+1. Records without a mapped position (``FLAG & 4`` or RNAME ``*``) are skipped.  (A mapped record without a
+   ``cs:Z:`` tag is skipped here and an error in the product, as it is in midsv's own validation.)
 2. Alignments are grouped by QNAME and ordered by POS; the output is ordered by QNAME (a sort + groupby).
 3. A read any two of whose alignments share a reference base is dropped (midsv's ``remove_overlapped``).
 4. ``=ACG`` -> ``=A,=C,=G``; ``*ag`` -> ``*AG``; ``-acg`` -> ``-A,-C,-G``; ``+acg`` joins the NEXT token as
